@@ -1,0 +1,185 @@
+"""ctypes images of include/proxsdp_b200_types.h and marshalling helpers.
+
+Used by the product binding (proxsdp_b200/solver.py) and by the oracle binding
+(oracle/oracle.py) — both libraries export a `…_solve(problem*, options*, result*)`
+with the same POD layouts.
+"""
+from __future__ import annotations
+
+import ctypes
+from ctypes import POINTER, c_char, c_double, c_int64
+
+import numpy as np
+import scipy.sparse as sp
+
+from .options import Options, OptionsPOD
+from .structs import AffineSets, ConicSets, Result
+
+STATUS_STRING_LEN = 256
+TRACE_COLS = 12
+TRACE_NAMES = [
+    "iter", "prim_obj", "dual_obj", "gap", "feasibility", "primal_res", "dual_res",
+    "primal_step", "beta", "sum_target_rank", "sum_current_rank", "min_eig",
+]
+
+_pd = POINTER(c_double)
+_pi = POINTER(c_int64)
+
+
+class ProblemPOD(ctypes.Structure):
+    _fields_ = [
+        ("n", c_int64), ("p", c_int64), ("m", c_int64), ("index_base", c_int64),
+        ("A_colptr", _pi), ("A_rowval", _pi), ("A_nzval", _pd),
+        ("G_colptr", _pi), ("G_rowval", _pi), ("G_nzval", _pd),
+        ("b", _pd), ("h", _pd), ("c", _pd),
+        ("n_sdp", c_int64), ("sdp_side", _pi), ("sdp_ptr", _pi), ("sdp_idx", _pi),
+        ("n_soc", c_int64), ("soc_ptr", _pi), ("soc_idx", _pi),
+        ("eig_resid", _pd),
+    ]
+
+
+class ResultPOD(ctypes.Structure):
+    _fields_ = [
+        ("status", c_int64),
+        ("status_string", c_char * STATUS_STRING_LEN),
+        ("primal", _pd), ("dual_cone", _pd), ("dual_eq", _pd), ("dual_in", _pd),
+        ("slack_eq", _pd), ("slack_in", _pd),
+        ("primal_residual", c_double), ("dual_residual", c_double),
+        ("objval", c_double), ("dual_objval", c_double), ("gap", c_double), ("time", c_double),
+        ("iter", c_int64), ("final_rank", c_int64),
+        ("primal_feasible_user_tol", c_int64), ("dual_feasible_user_tol", c_int64),
+        ("certificate_found", c_int64), ("result_count", c_int64),
+        ("final_primal_res", c_double), ("final_dual_res", c_double),
+        ("time_setup", c_double), ("time_loop", c_double), ("time_psd_proj", c_double),
+        ("n_psd_proj", c_int64), ("lanczos_matvecs", c_int64), ("lanczos_calls", c_int64),
+        ("full_eig_calls", c_int64), ("linesearch_trials", c_int64), ("gpu_launches", c_int64),
+        ("target_rank", _pi),
+        ("trace", _pd), ("trace_len", c_int64),
+    ]
+
+
+def _f64(a) -> np.ndarray:
+    return np.ascontiguousarray(np.asarray(a, dtype=np.float64).ravel())
+
+
+def _i64(a) -> np.ndarray:
+    return np.ascontiguousarray(np.asarray(a, dtype=np.int64).ravel())
+
+
+def _ptr_d(a: np.ndarray):
+    return a.ctypes.data_as(_pd) if a.size else ctypes.cast(None, _pd)
+
+
+def _ptr_i(a: np.ndarray):
+    return a.ctypes.data_as(_pi) if a.size else ctypes.cast(None, _pi)
+
+
+class MarshalledProblem:
+    """Owns the numpy buffers a ProblemPOD points into."""
+
+    def __init__(self, aff: AffineSets, con: ConicSets, eig_resid=None):
+        n, p, m = int(aff.n), int(aff.p), int(aff.m)
+        A = sp.csc_matrix(aff.A, shape=(p, n)) if p > 0 else sp.csc_matrix((0, n))
+        G = sp.csc_matrix(aff.G, shape=(m, n)) if m > 0 else sp.csc_matrix((0, n))
+        A.sort_indices()
+        G.sort_indices()
+        A.sum_duplicates()
+        G.sum_duplicates()
+        self.bufs = dict(
+            A_colptr=_i64(A.indptr), A_rowval=_i64(A.indices), A_nzval=_f64(A.data),
+            G_colptr=_i64(G.indptr), G_rowval=_i64(G.indices), G_nzval=_f64(G.data),
+            b=_f64(aff.b), h=_f64(aff.h), c=_f64(aff.c),
+        )
+        sides = [int(s.sq_side) for s in con.sdpcone]
+        sdp_ptr = np.zeros(len(sides) + 1, dtype=np.int64)
+        for k, s in enumerate(con.sdpcone):
+            assert len(s.vec_i) == s.tri_len == s.sq_side * (s.sq_side + 1) // 2
+            sdp_ptr[k + 1] = sdp_ptr[k] + s.tri_len
+        soc_ptr = np.zeros(len(con.socone) + 1, dtype=np.int64)
+        for k, s in enumerate(con.socone):
+            soc_ptr[k + 1] = soc_ptr[k] + len(s.idx)
+        self.bufs.update(
+            sdp_side=_i64(sides), sdp_ptr=sdp_ptr,
+            sdp_idx=_i64(np.concatenate([s.vec_i for s in con.sdpcone]) if sides else []),
+            soc_ptr=soc_ptr,
+            soc_idx=_i64(np.concatenate([s.idx for s in con.socone]) if con.socone else []),
+        )
+        if eig_resid is not None:
+            self.bufs["eig_resid"] = _f64(eig_resid)
+        pod = ProblemPOD()
+        pod.n, pod.p, pod.m, pod.index_base = n, p, m, 0
+        for name in ("A_colptr", "A_rowval", "G_colptr", "G_rowval", "sdp_side", "sdp_ptr", "sdp_idx",
+                     "soc_ptr", "soc_idx"):
+            setattr(pod, name, _ptr_i(self.bufs[name]))
+        for name in ("A_nzval", "G_nzval", "b", "h", "c"):
+            setattr(pod, name, _ptr_d(self.bufs[name]))
+        pod.n_sdp = len(sides)
+        pod.n_soc = len(con.socone)
+        pod.eig_resid = _ptr_d(self.bufs["eig_resid"]) if eig_resid is not None else ctypes.cast(None, _pd)
+        self.pod = pod
+        self.n, self.p, self.m, self.n_sdp = n, p, m, len(sides)
+
+
+class MarshalledResult:
+    def __init__(self, n: int, p: int, m: int, n_sdp: int, trace_cap: int = 0):
+        self.primal = np.zeros(n)
+        self.dual_cone = np.zeros(n)
+        self.dual_eq = np.zeros(p)
+        self.dual_in = np.zeros(m)
+        self.slack_eq = np.zeros(p)
+        self.slack_in = np.zeros(m)
+        self.target_rank = np.zeros(max(n_sdp, 1), dtype=np.int64)
+        self.trace = np.zeros((max(trace_cap, 1), TRACE_COLS))
+        self.n_sdp = n_sdp
+        pod = ResultPOD()
+        pod.primal = _ptr_d(self.primal)
+        pod.dual_cone = _ptr_d(self.dual_cone)
+        pod.dual_eq = _ptr_d(self.dual_eq)
+        pod.dual_in = _ptr_d(self.dual_in)
+        pod.slack_eq = _ptr_d(self.slack_eq)
+        pod.slack_in = _ptr_d(self.slack_in)
+        pod.target_rank = _ptr_i(self.target_rank)
+        pod.trace = _ptr_d(self.trace) if trace_cap > 0 else ctypes.cast(None, _pd)
+        pod.trace_len = 0
+        self.pod = pod
+
+    def to_result(self) -> Result:
+        q = self.pod
+        return Result(
+            status=int(q.status),
+            status_string=q.status_string.decode("utf-8", "replace"),
+            primal=self.primal, dual_cone=self.dual_cone, dual_eq=self.dual_eq, dual_in=self.dual_in,
+            slack_eq=self.slack_eq, slack_in=self.slack_in,
+            primal_residual=q.primal_residual, dual_residual=q.dual_residual,
+            objval=q.objval, dual_objval=q.dual_objval, gap=q.gap, time=q.time,
+            iter=int(q.iter), final_rank=int(q.final_rank),
+            primal_feasible_user_tol=bool(q.primal_feasible_user_tol),
+            dual_feasible_user_tol=bool(q.dual_feasible_user_tol),
+            certificate_found=bool(q.certificate_found), result_count=int(q.result_count),
+            final_primal_res=q.final_primal_res, final_dual_res=q.final_dual_res,
+            time_setup=q.time_setup, time_loop=q.time_loop, time_psd_proj=q.time_psd_proj,
+            n_psd_proj=int(q.n_psd_proj), lanczos_matvecs=int(q.lanczos_matvecs),
+            lanczos_calls=int(q.lanczos_calls), full_eig_calls=int(q.full_eig_calls),
+            linesearch_trials=int(q.linesearch_trials), gpu_launches=int(q.gpu_launches),
+            target_rank=self.target_rank[: self.n_sdp].copy(),
+            trace=self.trace[: int(q.trace_len)].copy(),
+        )
+
+
+def call_solve(fn, aff: AffineSets, con: ConicSets, opt: Options, eig_resid=None, err_fn=None) -> Result:
+    """Invoke a `int solve(const proxsdp_problem_t*, const proxsdp_options_t*, proxsdp_result_t*)`."""
+    mp = MarshalledProblem(aff, con, eig_resid)
+    mr = MarshalledResult(mp.n, mp.p, mp.m, mp.n_sdp, int(opt.trace_cap))
+    opod = opt.to_pod()
+    rc = fn(ctypes.byref(mp.pod), ctypes.byref(opod), ctypes.byref(mr.pod))
+    if rc != 0:
+        msg = err_fn().decode() if err_fn is not None else ""
+        raise RuntimeError(f"solve failed with code {rc}: {msg}")
+    return mr.to_result()
+
+
+def bind_solve(lib, name: str):
+    fn = getattr(lib, name)
+    fn.argtypes = [POINTER(ProblemPOD), POINTER(OptionsPOD), POINTER(ResultPOD)]
+    fn.restype = ctypes.c_int
+    return fn
