@@ -1,0 +1,83 @@
+/*
+ * proxsdp_b200.h — C ABI of the B200-native ProxSDP hot path (libproxsdp_b200.so).
+ *
+ * The reference (mariohsouto/ProxSDP.jl) exposes no FFI; the drop-in boundary is the
+ * plain Julia call `chambolle_pock(aff, con, opt)::Result` (reference src/pdhg.jl:1-5,
+ * called only from src/MOI_wrapper.jl:310).  A Julia maintainer binds these entry
+ * points with `ccall`; the Python host mirror binds them with
+ * ctypes (proxsdp_b200/solver.py).  Plain pointers and sizes only.
+ *
+ * Return value of every function: 0 on success, negative on failure
+ *   -1  invalid argument            -2  unsupported option (equilibration, exact svd norm)
+ *   -3  malformed cones             -4  out of device/host memory
+ *   -5  no CUDA device / extension  <= -100  CUDA runtime error (-100 - cudaError_t)
+ * The solver's own outcome (optimal, limits, infeasible, ...) is NOT an error: it is
+ * reported in proxsdp_result_t.status like the reference does (src/structs.jl:60-81,
+ * src/MOI_wrapper.jl:381-399).  proxsdp_b200_last_error() gives the message of the last
+ * failure on the calling thread.
+ *
+ * Threading: like the reference (global TimerOutputs / logger, src/MOI_wrapper.jl:304-315)
+ * a solve is synchronous and one solve runs per process at a time.  Host arrays are
+ * borrowed for the duration of the call only; the library never retains them and never
+ * calls back into the host language.
+ */
+#ifndef PROXSDP_B200_H
+#define PROXSDP_B200_H
+
+#include "proxsdp_b200_types.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Whole `chambolle_pock` (reference src/pdhg.jl:1-530): setup (preprocess!, norm_scaling,
+ * step size), the PDHG loop with every per-iteration array operation on the GPU, the
+ * reference's control logic on the host, and result assembly (cache_solution). */
+int proxsdp_b200_solve(const proxsdp_problem_t* problem, const proxsdp_options_t* options,
+                       proxsdp_result_t* result);
+
+/* One `psd_projection!` (reference src/prox_operators.jl:33-66) over concatenated svec
+ * blocks.  x: in/out (sum of tri_len doubles, working-space scaling: off-diagonals carry
+ * sqrt(2)).  mode 0 = the reference's dispatch (Krylov when eligible), 1 = force the full
+ * eigendecomposition.  resid: optional concatenated Lanczos start vectors (NULL = library
+ * default).  Outputs per cone: current_rank, min_eig, converged (KrylovKit info.converged;
+ * -1 when the full path ran); numops = total Lanczos mat-vecs.  The projection is executed
+ * `repeat` (>= 1) times on device-resident data and *ms_per_call (may be NULL) receives the
+ * mean CUDA-event time of one call — the "ms per eig-projection" metric. */
+int proxsdp_b200_psd_project(int64_t n_sdp, const int64_t* sides, double* x,
+                             const int64_t* target_rank, const proxsdp_options_t* options,
+                             int64_t iter, int64_t mode, const double* resid,
+                             int64_t* current_rank, double* min_eig, int64_t* converged,
+                             int64_t* numops, int64_t repeat, double* ms_per_call);
+
+/* `soc_projection!` (reference src/prox_operators.jl:138-158) over concatenated SOC blocks
+ * (lens[k] entries each, the first being t).  x: in/out. */
+int proxsdp_b200_soc_project(int64_t n_soc, const int64_t* lens, double* x);
+
+/* Kernel-level seam of the eigen back-end: KrylovKit.eigsolve(A, x0, howmany, :LR,
+ * Lanczos(orth, krylovdim, maxiter, tol)) as used at reference src/eigsolver.jl:802-812.
+ * A: n x n column-major, both triangles valid.  vals: krylovdim doubles; vecs: n x krylovdim
+ * column-major.  `repeat` as above; *ms_per_call = mean device time of one eigsolve. */
+int proxsdp_b200_lanczos(int64_t n, const double* A, const double* x0, int64_t howmany,
+                         int64_t krylovdim, int64_t maxiter, double tol,
+                         double* vals, double* vecs, int64_t* nvals, int64_t* converged,
+                         int64_t* numops, int64_t* numiter, int64_t repeat, double* ms_per_call);
+
+/* Full symmetric eigendecomposition on the device (replaces LinearAlgebra.eigen!, reference
+ * src/prox_operators.jl:113, src/pdhg.jl:685).  A: n x n column-major (both triangles).
+ * w: n eigenvalues ascending; Z: n x n eigenvectors (may be NULL). */
+int proxsdp_b200_eigh(int64_t n, const double* A, double* w, double* Z);
+
+/* Library / device information. */
+int proxsdp_b200_device_count(void);
+const char* proxsdp_b200_last_error(void);
+const char* proxsdp_b200_version(void);
+/* sizeof() of the three PODs, so a binding can verify its struct layout at load time. */
+int64_t proxsdp_b200_sizeof_problem(void);
+int64_t proxsdp_b200_sizeof_options(void);
+int64_t proxsdp_b200_sizeof_result(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PROXSDP_B200_H */

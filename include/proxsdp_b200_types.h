@@ -165,7 +165,7 @@ typedef struct proxsdp_options {
 /* ---- Result (structs.jl:60-81) ------------------------------------------
  * Vector outputs are caller-allocated with the sizes shown; any may be NULL. */
 #define PROXSDP_STATUS_STRING_LEN 256
-#define PROXSDP_TRACE_COLS 12
+#define PROXSDP_TRACE_COLS 14
 typedef struct proxsdp_result {
     int64_t status;       /* 0 not called, 1 optimal, 2 time limit, 3 iteration limit,
                              5 dual infeasible/unbounded, 6 infeasible (MOI_wrapper.jl:381-399) */
@@ -203,7 +203,8 @@ typedef struct proxsdp_result {
     int64_t* target_rank;      /* (n_sdp) final target rank per cone, may be NULL         */
     /* optional per-iteration trace, row-major (trace_cap x PROXSDP_TRACE_COLS):
        iter, prim_obj, dual_obj, gap, feasibility, primal_res, dual_res,
-       primal_step, beta, sum(target_rank), sum(current_rank), min(min_eig) */
+       primal_step, beta, sum(target_rank), sum(current_rank), min(min_eig),
+       lanczos mat-vecs this iteration, linesearch trials this iteration */
     double* trace;
     int64_t trace_len;
 } proxsdp_result_t;

@@ -257,6 +257,7 @@ typedef struct {
     int* eig_converged; int64_t* eig_converged_eigs;
     /* stats */
     double time_psd; int64_t n_psd, lanczos_matvecs, lanczos_calls, full_eig_calls, linesearch_trials;
+    int64_t trace_mv0, trace_ls0;
 } state_t;
 
 typedef proxsdp_options_t opts_t;
@@ -687,7 +688,7 @@ static int cmp_i64(const void* a, const void* b) {
     return (x > y) - (x < y);
 }
 
-static void record_trace(const state_t* s, proxsdp_result_t* out, int64_t cap) {
+static void record_trace(state_t* s, proxsdp_result_t* out, int64_t cap) {
     if (!out->trace || out->trace_len >= cap) return;
     double* row = out->trace + out->trace_len * PROXSDP_TRACE_COLS;
     int64_t k = s->iter;
@@ -706,6 +707,7 @@ static void record_trace(const state_t* s, proxsdp_result_t* out, int64_t cap) {
     row[7] = s->primal_step;
     row[8] = s->beta;
     row[9] = tr; row[10] = cr; row[11] = me;
+    row[12] = (double)(s->lanczos_matvecs - s->trace_mv0); row[13] = (double)(s->linesearch_trials - s->trace_ls0);
     out->trace_len++;
 }
 
@@ -888,6 +890,7 @@ int proxsdp_oracle_solve(const proxsdp_problem_t* prob, const proxsdp_options_t*
     int64_t kmax = 2 * opt->max_iter_local;
     for (int64_t k = 1; k <= kmax; ++k) {
         s->iter = k;
+        s->trace_mv0 = s->lanczos_matvecs; s->trace_ls0 = s->linesearch_trials;
         primal_step(s, opt);
         if (opt->line_search_flag) linesearch(s, opt); else dual_step(s);
         compute_residual(s);

@@ -16,10 +16,10 @@ from .options import Options, OptionsPOD
 from .structs import AffineSets, ConicSets, Result
 
 STATUS_STRING_LEN = 256
-TRACE_COLS = 12
+TRACE_COLS = 14
 TRACE_NAMES = [
     "iter", "prim_obj", "dual_obj", "gap", "feasibility", "primal_res", "dual_res",
-    "primal_step", "beta", "sum_target_rank", "sum_current_rank", "min_eig",
+    "primal_step", "beta", "sum_target_rank", "sum_current_rank", "min_eig", "matvecs", "ls_trials",
 ]
 
 _pd = POINTER(c_double)

@@ -1,0 +1,415 @@
+// kernels_vec.cuh — fused HBM-bound vector kernels of the PDHG iteration.
+//
+//   k_svec_to_mat<1>   K1+K2  x - tau*(Mty + c) -> full symmetric matrix  (pdhg.jl:622, prox_operators.jl:1-16)
+//   k_primal_tail      K1     same update for the SOC / free tail of x     (pdhg.jl:622)
+//   k_soc_project      K11    second-order-cone projection                 (prox_operators.jl:138-158)
+//   k_spmv_csr         K12    Mx = M x                                     (pdhg.jl:634)
+//   k_dual_trial       K14-16 over-relaxed dual step + box projection      (pdhg.jl:544-553, prox_operators.jl:160-170)
+//   k_spmv_mt_norm     K13+17 Mty = M' y fused with the linesearch norms   (pdhg.jl:556-566)
+//   k_residual_primal  K18+21 primal fixed-point residual + c'x            (residuals.jl:41-48,22)
+//   k_residual_dual    K18+20+21 dual residual, feasibility, b'y, h'y      (residuals.jl:52-59,5-29)
+//
+// All reductions are two-phase (per-block partials folded by the last block in a
+// fixed order), hence bit-reproducible run to run for a fixed grid.
+#pragma once
+#include "common.cuh"
+
+namespace pb {
+
+// ---------------------------------------------------------------------------
+// per-iteration scalar record shared between kernels and the host control loop
+// ---------------------------------------------------------------------------
+enum ScalarSlot {
+    S_LS_ACCEPTED = 0,  // 1.0 once a linesearch trial has been accepted
+    S_LS_TRIAL,         // index of the accepted trial
+    S_TAU,              // accepted primal step
+    S_YNORM2,           // ||y_new - y||^2 of the last evaluated trial
+    S_MTYNORM2,         // ||Mty_new - Mty||^2 of the last evaluated trial
+    S_LS_EVALS,         // number of trials actually evaluated
+    S_RES_P_NUM,        // max |(x - tau Mty) - (x_old - tau Mty_old)|
+    S_RES_P_DEN,        // max |x_old - tau Mty_old|
+    S_RES_D_NUM,
+    S_RES_D_DEN,
+    S_EQ_MAX,           // max |Mx - b|
+    S_IN_MAX,           // max(0, max(Mx - h))
+    S_PRIM_OBJ,         // c'x
+    S_BY,               // b'y_eq
+    S_HY,               // h'y_in
+    S_SOC_GAP,          // max over SOC cones of ||v|| - t
+    S_POISON,           // != 0: a Lanczos call did not converge; the rest of the iteration was skipped
+    S_NUMOPS,           // Lanczos mat-vecs performed this iteration
+    S_HEADER            // per-cone records follow: current_rank, min_eig, converged (3 doubles each)
+};
+
+struct ReduceWs {
+    double* partials;        // [slots][max_blocks]
+    unsigned int* counters;  // one per kernel kind
+    int max_blocks;
+};
+
+__device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double sub_rn(double a, double b) { return __dsub_rn(a, b); }
+
+// ---------------------------------------------------------------------------
+// K1+K2: X = mat(x - tau*(Mty + c)) for one PSD cone, full n x n (both triangles).
+// 32x32 tiles of the upper triangle; the mirrored tile goes through shared memory so
+// that both global writes are coalesced.  svec order: k(i,j) = j(j+1)/2 + i, i <= j.
+// grid = (#tile pairs with bi <= bj), block = (32, 8)
+// ---------------------------------------------------------------------------
+template <bool PRIMAL>
+__global__ void __launch_bounds__(256)
+k_svec_to_mat(const double* __restrict__ x, const double* __restrict__ Mty, const double* __restrict__ c,
+              double tau, double scale, int n, int ld, double* __restrict__ X) {
+    __shared__ double tile[32][33];
+    // decode tile pair index t -> (bi, bj), bi <= bj, column-major over the upper triangle of tiles
+    int t = blockIdx.x;
+    int bj = (int)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
+    while ((bj + 1) * (bj + 2) / 2 <= t) ++bj;
+    while (bj * (bj + 1) / 2 > t) --bj;
+    int bi = t - bj * (bj + 1) / 2;
+    const double sqrt2 = 1.41421356237309504880;
+    int i = bi * 32 + threadIdx.x;
+#pragma unroll
+    for (int jj = threadIdx.y; jj < 32; jj += 8) {
+        int j = bj * 32 + jj;
+        double v = 0.0;
+        if (i < n && j < n && i <= j) {
+            size_t k = (size_t)j * (size_t)(j + 1) / 2 + (size_t)i;
+            double u;
+            if (PRIMAL) u = sub_rn(x[k], mul_rn(tau, add_rn(Mty[k], c[k])));   // x .-= tau .* (Mty .+ c)
+            else u = x[k] * scale;
+            v = (i != j) ? u / sqrt2 : u;                                      // off-diagonals / sqrt(2)
+            X[(size_t)i + (size_t)j * ld] = v;
+        }
+        tile[jj][threadIdx.x] = v;   // tile[j_local][i_local]
+    }
+    __syncthreads();
+    // mirrored element (j, i): write X[j + i*ld]; thread x runs over j (contiguous)
+    int j2 = bj * 32 + threadIdx.x;
+#pragma unroll
+    for (int ii = threadIdx.y; ii < 32; ii += 8) {
+        int i2 = bi * 32 + ii;
+        if (i2 < n && j2 < n && i2 < j2) X[(size_t)j2 + (size_t)i2 * ld] = tile[threadIdx.x][ii];
+    }
+}
+
+// K1 for the non-PSD tail (SOC blocks and free variables): x_new = x - tau*(Mty + c)
+__global__ void k_primal_tail(const double* __restrict__ x, const double* __restrict__ Mty,
+                              const double* __restrict__ c, double tau, long long begin, long long end,
+                              double* __restrict__ x_new) {
+    long long i = begin + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < end; i += stride) x_new[i] = sub_rn(x[i], mul_rn(tau, add_rn(Mty[i], c[i])));
+}
+
+// ---------------------------------------------------------------------------
+// K11: SOC projection, one block per cone.  x[off] = t, x[off+1 .. off+len) = v.
+// Also records max(||v|| - t) AFTER projection (soc_convergence, residuals.jl:73-86).
+// ---------------------------------------------------------------------------
+__global__ void k_soc_project(double* __restrict__ x, const long long* __restrict__ soc_off,
+                              const int* __restrict__ soc_len, double* __restrict__ soc_gap,
+                              const double* __restrict__ poison) {
+    __shared__ double red[40];
+    if (poison && *poison != 0.0) return;
+    int k = blockIdx.x;
+    double* t = x + soc_off[k];
+    double* v = t + 1;
+    int len = soc_len[k] - 1;
+    double s = 0.0;
+    for (int i = threadIdx.x; i < len; i += blockDim.x) s += v[i] * v[i];
+    double nv = sqrt(block_sum(s, red));
+    double t0 = t[0];
+    __syncthreads();
+    double nv_after, t_after;
+    if (nv <= -t0) {
+        for (int i = threadIdx.x; i < len; i += blockDim.x) v[i] = 0.0;
+        if (threadIdx.x == 0) t[0] = 0.0;
+        nv_after = 0.0; t_after = 0.0;
+    } else if (nv <= t0) {
+        nv_after = nv; t_after = t0;
+    } else {
+        double val = 0.5 * (1.0 + t0 / nv);
+        for (int i = threadIdx.x; i < len; i += blockDim.x) v[i] *= val;
+        if (threadIdx.x == 0) t[0] = val * nv;
+        // the reference re-evaluates norm(v) - s on the projected data; recompute exactly
+        __syncthreads();
+        double s2 = 0.0;
+        for (int i = threadIdx.x; i < len; i += blockDim.x) s2 += v[i] * v[i];
+        nv_after = sqrt(block_sum(s2, red));
+        t_after = val * nv;
+    }
+    if (threadIdx.x == 0) soc_gap[k] = nv_after - t_after;
+}
+
+// ---------------------------------------------------------------------------
+// K12: y = A x for a CSR matrix, GROUP lanes per row (GROUP in {1,2,4,8,16,32}).
+// Rows flagged long (handled by k_spmv_long) are skipped through row_skip.
+// ---------------------------------------------------------------------------
+template <int GROUP>
+__global__ void k_spmv_csr(int nrows, const int* __restrict__ rowptr, const int* __restrict__ colidx,
+                           const double* __restrict__ val, const double* __restrict__ x,
+                           double* __restrict__ y, int long_threshold, const double* __restrict__ poison) {
+    if (poison && *poison != 0.0) return;
+    long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    int row = (int)(gid / GROUP);
+    int lane = (int)(gid % GROUP);
+    bool active = row < nrows;
+    int b = 0, e = 0;
+    if (active) { b = rowptr[row]; e = rowptr[row + 1]; }
+    if (e - b > long_threshold) { active = false; e = b; }
+    double s = 0.0;
+    for (int k = b + lane; k < e; k += GROUP) s += val[k] * x[colidx[k]];
+#pragma unroll
+    for (int o = GROUP / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o, GROUP);
+    if (active && lane == 0) y[row] = s;
+}
+
+// one block per long row (deterministic block reduction)
+__global__ void k_spmv_long(const int* __restrict__ long_rows, const int* __restrict__ rowptr,
+                            const int* __restrict__ colidx, const double* __restrict__ val,
+                            const double* __restrict__ x, double* __restrict__ y,
+                            const double* __restrict__ poison) {
+    __shared__ double red[40];
+    if (poison && *poison != 0.0) return;
+    int row = long_rows[blockIdx.x];
+    int b = rowptr[row], e = rowptr[row + 1];
+    double s = 0.0;
+    for (int k = b + threadIdx.x; k < e; k += blockDim.x) s += val[k] * x[colidx[k]];
+    s = block_sum(s, red);
+    if (threadIdx.x == 0) y[row] = s;
+}
+
+// ---------------------------------------------------------------------------
+// K14-K16: one linesearch trial of the dual update (also the fixed-step dual_step!).
+//   tau_t   = tau0 * decay^trial (sequential products, as pdhg.jl:569 does)
+//   theta   = tau_t / tau_old ; sigma = beta * tau_t
+//   y_half  = y + sigma*((1+theta)*Mx - theta*Mx_old)
+//   proj    = [ b ; min(y_half/sigma, h) ] ;  y_new = y_half - sigma*proj
+// fixed-step variant (use_theta=0): y_half = y + sigma*(2 Mx - Mx_old), sigma given.
+// Accumulates ||y_new - y||^2.  Skipped when an earlier trial was accepted.
+// ---------------------------------------------------------------------------
+struct DualArgs {
+    const double* y; const double* Mx; const double* Mx_old; const double* b; const double* h;
+    double* y_new;
+    int p, m;
+    double tau0, decay, tau_old, beta, sigma_fixed;
+    int trial, use_theta;
+};
+
+__global__ void __launch_bounds__(256)
+k_dual_trial(DualArgs a, double* __restrict__ scal, ReduceWs ws) {
+    __shared__ double red[40];
+    __shared__ int s_last;
+    if (scal[S_POISON] != 0.0 || scal[S_LS_ACCEPTED] != 0.0) return;
+    double tau = a.tau0;
+    for (int t = 0; t < a.trial; ++t) tau = mul_rn(tau, a.decay);
+    double sigma, w1, w2;
+    if (a.use_theta) {
+        double theta = tau / a.tau_old;
+        sigma = mul_rn(a.beta, tau);
+        w1 = add_rn(1.0, theta);
+        w2 = theta;
+    } else {
+        sigma = a.sigma_fixed;
+        w1 = 2.0; w2 = 1.0;
+    }
+    int R = a.p + a.m;
+    double acc = 0.0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < R; i += gridDim.x * blockDim.x) {
+        double yh = add_rn(a.y[i], mul_rn(sigma, sub_rn(mul_rn(w1, a.Mx[i]), mul_rn(w2, a.Mx_old[i]))));
+        double proj;
+        if (i < a.p) proj = a.b[i];
+        else proj = fmin(yh / sigma, a.h[i - a.p]);
+        double yn = sub_rn(yh, mul_rn(sigma, proj));
+        a.y_new[i] = yn;
+        double d = sub_rn(yn, a.y[i]);
+        acc += d * d;
+    }
+    acc = block_sum(acc, red);
+    if (threadIdx.x == 0) ws.partials[blockIdx.x] = acc;
+    if (last_block_arrive(ws.counters + 0, &s_last)) {
+        double s = 0.0;
+        for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) s += __ldcg(ws.partials + b);
+        s = block_sum(s, red);
+        if (threadIdx.x == 0) { scal[S_YNORM2] = s; scal[S_TAU] = tau; }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// K13+K17: Mty_new = M' y_new (CSR of M' == CSC of M, one thread per row of M'),
+// fused with ||Mty_new - Mty||^2 and the accept test
+//     sqrt(beta) * tau * ||Mty_new - Mty|| <= delta * ||y_new - y||     (pdhg.jl:566)
+// evaluated by the last block.
+// ---------------------------------------------------------------------------
+struct MtArgs {
+    int N; const int* rowptr; const int* colidx; const double* val;
+    const double* y_new; const double* Mty; double* Mty_new;
+    double beta, delta; int trial, do_test;
+};
+
+__global__ void __launch_bounds__(256)
+k_spmv_mt_norm(MtArgs a, double* __restrict__ scal, ReduceWs ws) {
+    __shared__ double red[40];
+    __shared__ int s_last;
+    if (scal[S_POISON] != 0.0 || scal[S_LS_ACCEPTED] != 0.0) return;
+    double acc = 0.0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.N; i += gridDim.x * blockDim.x) {
+        int b = a.rowptr[i], e = a.rowptr[i + 1];
+        double s = 0.0;
+        for (int k = b; k < e; ++k) s += a.val[k] * a.y_new[a.colidx[k]];
+        a.Mty_new[i] = s;
+        double d = sub_rn(s, a.Mty[i]);
+        acc += d * d;
+    }
+    acc = block_sum(acc, red);
+    if (threadIdx.x == 0) ws.partials[blockIdx.x] = acc;
+    if (last_block_arrive(ws.counters + 1, &s_last)) {
+        double s = 0.0;
+        for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) s += __ldcg(ws.partials + b);
+        s = block_sum(s, red);
+        if (threadIdx.x == 0) {
+            scal[S_MTYNORM2] = s;
+            scal[S_LS_EVALS] = (double)(a.trial + 1);
+            double tau = scal[S_TAU];
+            double lhs = mul_rn(mul_rn(sqrt(a.beta), tau), sqrt(s));
+            double rhs = mul_rn(a.delta, sqrt(scal[S_YNORM2]));
+            if (!a.do_test || lhs <= rhs) {
+                scal[S_LS_ACCEPTED] = 1.0;
+                scal[S_LS_TRIAL] = (double)a.trial;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// K18 (primal half) + K21 (c'x):  one pass over x, x_old, Mty, Mty_old, c.
+//   num = max |(x - tau*Mty) - (x_old - tau*Mty_old)| ; den = max |x_old - tau*Mty_old|
+// tau is the accepted step (scal[S_TAU]).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_residual_primal(long long N, const double* __restrict__ x, const double* __restrict__ x_old,
+                  const double* __restrict__ Mty, const double* __restrict__ Mty_old,
+                  const double* __restrict__ c, double* __restrict__ scal, ReduceWs ws) {
+    __shared__ double red[40];
+    __shared__ int s_last;
+    if (scal[S_POISON] != 0.0 || scal[S_LS_ACCEPTED] == 0.0) return;
+    const double tau = scal[S_TAU];
+    double num = 0.0, den = 0.0, obj = 0.0;
+    long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += stride) {
+        double xo = x_old[i], xn = x[i];
+        double pold = sub_rn(xo, mul_rn(tau, Mty_old[i]));
+        double pnew = sub_rn(xn, mul_rn(tau, Mty[i]));
+        num = nanmax(num, fabs(sub_rn(pnew, pold)));
+        den = nanmax(den, fabs(pold));
+        obj += c[i] * xn;
+    }
+    num = block_nanmax(num, red);
+    den = block_nanmax(den, red);
+    obj = block_sum(obj, red);
+    int nb = gridDim.x;
+    if (threadIdx.x == 0) {
+        ws.partials[blockIdx.x] = num;
+        ws.partials[nb + blockIdx.x] = den;
+        ws.partials[2 * nb + blockIdx.x] = obj;
+    }
+    if (last_block_arrive(ws.counters + 2, &s_last)) {
+        double a = 0.0, b = 0.0, o = 0.0;
+        for (int k = threadIdx.x; k < nb; k += blockDim.x) {
+            a = nanmax(a, __ldcg(ws.partials + k));
+            b = nanmax(b, __ldcg(ws.partials + nb + k));
+            o += __ldcg(ws.partials + 2 * nb + k);
+        }
+        a = block_nanmax(a, red);
+        b = block_nanmax(b, red);
+        o = block_sum(o, red);
+        if (threadIdx.x == 0) { scal[S_RES_P_NUM] = a; scal[S_RES_P_DEN] = b; scal[S_PRIM_OBJ] = o; }
+    }
+}
+
+// K18 (dual half) + K20 + K21: one pass over the R rows.
+__global__ void __launch_bounds__(256)
+k_residual_dual(int p, int m, double beta, int use_beta, double sigma_fixed,
+                const double* __restrict__ y, const double* __restrict__ y_old,
+                const double* __restrict__ Mx, const double* __restrict__ Mx_old,
+                const double* __restrict__ b, const double* __restrict__ h,
+                double* __restrict__ scal, ReduceWs ws) {
+    __shared__ double red[40];
+    __shared__ int s_last;
+    if (scal[S_POISON] != 0.0 || scal[S_LS_ACCEPTED] == 0.0) return;
+    const double sigma = use_beta ? mul_rn(beta, scal[S_TAU]) : sigma_fixed;   // p.dual_step (pdhg.jl:579)
+    int R = p + m;
+    double num = 0.0, den = 0.0, eq = 0.0, in = 0.0, by = 0.0, hy = 0.0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < R; i += gridDim.x * blockDim.x) {
+        double pold = sub_rn(y_old[i], mul_rn(sigma, Mx_old[i]));
+        double pnew = sub_rn(y[i], mul_rn(sigma, Mx[i]));
+        num = nanmax(num, fabs(sub_rn(pnew, pold)));
+        den = nanmax(den, fabs(pold));
+        if (i < p) {
+            eq = fmax(eq, fabs(Mx[i] - b[i]));
+            by += b[i] * y[i];
+        } else {
+            in = fmax(in, Mx[i] - h[i - p]);
+            hy += h[i - p] * y[i];
+        }
+    }
+    double v[6] = {num, den, eq, in, by, hy};
+    v[0] = block_nanmax(v[0], red);
+    v[1] = block_nanmax(v[1], red);
+    v[2] = block_nanmax(v[2], red);
+    v[3] = block_nanmax(v[3], red);
+    v[4] = block_sum(v[4], red);
+    v[5] = block_sum(v[5], red);
+    int nb = gridDim.x;
+    if (threadIdx.x == 0)
+        for (int q = 0; q < 6; ++q) ws.partials[q * nb + blockIdx.x] = v[q];
+    if (last_block_arrive(ws.counters + 3, &s_last)) {
+        double r[6] = {0, 0, 0, 0, 0, 0};
+        for (int k = threadIdx.x; k < nb; k += blockDim.x) {
+            r[0] = nanmax(r[0], __ldcg(ws.partials + 0 * nb + k));
+            r[1] = nanmax(r[1], __ldcg(ws.partials + 1 * nb + k));
+            r[2] = nanmax(r[2], __ldcg(ws.partials + 2 * nb + k));
+            r[3] = nanmax(r[3], __ldcg(ws.partials + 3 * nb + k));
+            r[4] += __ldcg(ws.partials + 4 * nb + k);
+            r[5] += __ldcg(ws.partials + 5 * nb + k);
+        }
+        r[0] = block_nanmax(r[0], red);
+        r[1] = block_nanmax(r[1], red);
+        r[2] = block_nanmax(r[2], red);
+        r[3] = block_nanmax(r[3], red);
+        r[4] = block_sum(r[4], red);
+        r[5] = block_sum(r[5], red);
+        if (threadIdx.x == 0) {
+            scal[S_RES_D_NUM] = r[0]; scal[S_RES_D_DEN] = r[1];
+            scal[S_EQ_MAX] = r[2]; scal[S_IN_MAX] = r[3];
+            scal[S_BY] = r[4]; scal[S_HY] = r[5];
+        }
+    }
+}
+
+// reset the per-iteration scalar record (keeps nothing from the previous iteration)
+__global__ void k_scal_reset(double* __restrict__ scal, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) scal[i] = 0.0;
+}
+
+// max over SOC cones of the stored gaps -> scal[S_SOC_GAP]  (single small block)
+__global__ void k_soc_gap_max(const double* __restrict__ soc_gap, int n_soc, double* __restrict__ scal) {
+    __shared__ double red[40];
+    if (scal[S_POISON] != 0.0) return;
+    double v = -1.0e300;
+    for (int i = threadIdx.x; i < n_soc; i += blockDim.x) v = fmax(v, soc_gap[i]);
+    // block max via nanmax tree on shifted values is unnecessary here: plain max
+    v = warp_max(v);
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) red[w] = v;
+    __syncthreads();
+    if (w == 0) {
+        double t = (lane < ((int)blockDim.x + 31) / 32) ? red[lane] : -1.0e300;
+        t = warp_max(t);
+        if (lane == 0) scal[S_SOC_GAP] = t;
+    }
+}
+
+}  // namespace pb

@@ -1,0 +1,1428 @@
+// solver.cu — host side of the B200 ProxSDP hot path: setup, per-iteration launch
+// sequence, the reference's scalar control logic, result assembly, and the C ABI.
+//
+// Restates reference src/pdhg.jl:1-530 (`chambolle_pock`) with every array operation of
+// the loop executed by the kernels in kernels_vec.cuh / lanczos.cuh / fulleig.cuh and
+// exactly one device->host read-back (the scalar record) per iteration.
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstring>
+#include <memory>
+#include <numeric>
+#include <vector>
+
+#include "../../include/proxsdp_b200.h"
+#include "common.cuh"
+#include "fulleig.cuh"
+#include "jacobi.cuh"
+#include "kernels_vec.cuh"
+#include "lanczos.cuh"
+
+namespace pb {
+
+static thread_local std::string g_last_error;
+
+static double now_s() {
+    using namespace std::chrono;
+    return duration<double>(steady_clock::now().time_since_epoch()).count();
+}
+
+// ---------------------------------------------------------------------------
+// device buffers
+// ---------------------------------------------------------------------------
+template <class T>
+struct DBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    DBuf() = default;
+    DBuf(const DBuf&) = delete;
+    DBuf& operator=(const DBuf&) = delete;
+    DBuf(DBuf&& o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+    DBuf& operator=(DBuf&& o) noexcept {
+        if (this != &o) { if (p) cudaFree(p); p = o.p; n = o.n; o.p = nullptr; o.n = 0; }
+        return *this;
+    }
+    ~DBuf() { if (p) cudaFree(p); }
+    void alloc(size_t count) {
+        if (p) { cudaFree(p); p = nullptr; }
+        n = count;
+        size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e != cudaSuccess) throw CudaError(-4, std::string("cudaMalloc failed: ") + cudaGetErrorString(e));
+        PB_CUDA(cudaMemset(p, 0, bytes));
+    }
+    void upload(const std::vector<T>& h) {
+        alloc(h.size());
+        if (!h.empty()) PB_CUDA(cudaMemcpy(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+    }
+    void upload(const T* h, size_t count) {
+        alloc(count);
+        if (count) PB_CUDA(cudaMemcpy(p, h, count * sizeof(T), cudaMemcpyHostToDevice));
+    }
+    std::vector<T> download() const {
+        std::vector<T> h(n);
+        if (n) PB_CUDA(cudaMemcpy(h.data(), p, n * sizeof(T), cudaMemcpyDeviceToHost));
+        return h;
+    }
+};
+
+struct CsrDev {
+    int nrows = 0, ncols = 0, nnz = 0, group = 1, n_long = 0, long_threshold = 1 << 30;
+    DBuf<int> rowptr, colidx, long_rows;
+    DBuf<double> val;
+};
+
+// Julia's max() propagates NaN
+static double jl_max(double a, double b) { return (a != a || b != b) ? NAN : std::max(a, b); }
+
+// CircularVector (reference src/structs.jl:2-30)
+struct Circ {
+    std::vector<double> v;
+    long long l = 0;
+    void init(long long len) { l = len; v.assign((size_t)len, 0.0); }
+    static long long mod1(long long i, long long l) { return ((i - 1) % l + l) % l; }
+    double get(long long i) const { return v[(size_t)mod1(i, l)]; }
+    void set(long long i, double x) { v[(size_t)mod1(i, l)] = x; }
+    double max_abs_diff() const {   // structs.jl:14-20 (includes the wrap seam)
+        double val = 0.0;
+        for (long long i = 1; i <= l; ++i) {
+            double d = std::fabs(get(i) - get(i - 1));
+            if (d > val) val = d;
+        }
+        return val;
+    }
+};
+
+// splitmix64 + Box-Muller substitute for Julia's MersenneTwister stream
+// (reference src/eigsolver.jl:392-411); identical to the oracle's generator.
+static void eig_resid_default(long long n, long long seed, long long init, double* out) {
+    uint64_t s = (uint64_t)seed;
+    auto next = [&]() {
+        uint64_t z = (s += 0x9E3779B97F4A7C15ULL);
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+        return z ^ (z >> 31);
+    };
+    auto uni = [&]() { return (double)(next() >> 11) * (1.0 / 9007199254740992.0); };
+    if (init == 3) {
+        double nn = 0.0;
+        for (long long i = 0; i < n; ++i) {
+            double u1 = 1.0 - uni();
+            double u2 = uni();
+            out[i] = std::sqrt(-2.0 * std::log(u1)) * std::cos(6.283185307179586476925286766559 * u2);
+        }
+        for (long long i = 0; i < n; ++i) nn += out[i] * out[i];
+        nn = std::sqrt(nn);
+        for (long long i = 0; i < n; ++i) out[i] /= nn;
+    } else if (init == 2) {
+        for (long long i = 0; i < n; ++i) out[i] = uni();
+    } else if (init == 1) {
+        for (long long i = 0; i < n; ++i) out[i] = 1.0;
+    } else {
+        for (long long i = 0; i < n; ++i) out[i] = 0.0;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// per-cone device state
+// ---------------------------------------------------------------------------
+struct ConeDev {
+    int side = 0, ld = 0;
+    long long off = 0;          // svec offset in x
+    bool small = false;
+    DBuf<double> X;             // ld x ld, large cones only
+    DBuf<double> Vfull;         // ld x ld eigenvectors for the block-Jacobi path (allocated lazily)
+    DBuf<double> Y;             // ld x (Kmax)
+    DBuf<double> resid, vcur, vals, kept_lam;
+    DBuf<int> info, kept_idx, nkept;
+};
+
+class Solver {
+  public:
+    Solver(const proxsdp_problem_t* prob, const proxsdp_options_t* opt_in, bool cones_only = false, bool force_large = false);
+    ~Solver();
+    void solve(proxsdp_result_t* out);
+    // step-level seam: one psd_projection! on x (device x_[cur_] -> x_[1-cur_]) with tau = 0
+    void psd_projection_launch(long long iter, double tau, bool force_full);
+    void sync_scalars();
+    void reset_scalars();
+    void fallback_projection(long long iter);
+    void launch_soc_only();
+    bool force_large_ = false;
+
+    // exposed for the seams
+    proxsdp_options_t opt;
+    long long n = 0, p = 0, m = 0, R = 0;
+    int n_sdp = 0, n_soc = 0;
+    std::vector<ConeDev> cones;
+    std::vector<long long> target_rank, current_rank;
+    std::vector<double> min_eig;
+    DBuf<double> x_[2], Mty_[2], y_[2], Mx_[2], c_, b_, h_;
+    int cur_ = 0;
+    double* scal_host = nullptr;
+    long long launches = 0;
+    long long lanczos_matvecs = 0, lanczos_calls = 0, full_eig_calls = 0, linesearch_trials = 0;
+    cudaStream_t stream = nullptr;
+    int scal_len = 0;
+
+    // device full eigendecomposition of the matrix currently in cone.X (destroys X):
+    // eigenvalues -> host vector (unsorted), eigenvectors in cone.Vfull
+    std::vector<double> full_eig_device(ConeDev& cd);
+    void lanczos_launch(ConeDev& cd, int cone_idx, int nev, int K, int maxiter, double tol);
+
+  private:
+    void setup_host(const proxsdp_problem_t* prob);
+    void build_csr(const std::vector<long long>& colptr, const std::vector<int>& rowidx,
+                   const std::vector<double>& val);
+    void launch_spmv(const CsrDev& A, const double* x, double* y);
+    void launch_full_projection_large(int k);
+    void launch_reconstruct(ConeDev& cd, double* x_out);
+    void launch_post_eig(double tau0, bool first_pass);
+    void launch_dual_trial(int trial, double tau0);
+    void cache_solution(const double* c_res, proxsdp_result_t* out);
+    double dual_feas_host(const std::vector<double>& y, const std::vector<double>& cvec,
+                          std::vector<double>* dual_cone_out);
+    void rank_increment_rule(int idx);
+    void record_trace(proxsdp_result_t* out);
+    bool krylov_eligible(int k, long long iter) const;
+
+    bool cones_only_ = false;
+    int dev_ = 0, num_sms_ = 148;
+    size_t smem_optin_ = 0;
+    // host problem data (permuted; scaled for the working copy)
+    std::vector<long long> ord_, var_ordering_;
+    std::vector<long long> mt_colptr_;            // CSC of M == CSR of M'
+    std::vector<int> mt_rowidx_;
+    std::vector<double> mt_val_, mt_val_orig_;    // scaled / unscaled values
+    std::vector<double> b_host_, h_host_, c_host_, c_orig_, b_orig_, h_orig_;
+    std::vector<long long> soc_off_h_;
+    std::vector<int> soc_len_h_;
+    long long psd_end_ = 0;                        // first index after the PSD blocks
+    // device problem
+    CsrDev M_, Mt_;
+    DBuf<int> cone_side_d_, small_ids_d_;
+    DBuf<long long> cone_off_d_, soc_off_d_;
+    DBuf<int> soc_len_d_;
+    DBuf<double> soc_gap_d_, scal_d_, partials_d_, lz_partials_d_, out_min_d_, offnorm_d_;
+    DBuf<unsigned int> counters_d_, bar_d_;
+    DBuf<double> bj_Q_;
+    DBuf<int> bj_pi_, bj_pj_, bj_rot_;
+    std::vector<int> small_ids_, large_ids_;
+    int max_small_side_ = 0, Kmax_ = 25;
+    ReduceWs ws_{};
+    int reduce_blocks_ = 0;
+    // Params (reference src/structs.jl:159-192)
+    long long rank_update_ = 0, update_cont_ = 0, iter_ = 0, stop_reason_ = 0;
+    std::string stop_reason_string_ = "Not optimized";
+    double primal_step_ = 0, primal_step_old_ = 0, dual_step_ = 0, theta_ = 1, beta_ = 1, adapt_level_ = 0.9;
+    long long window_ = 200;
+    double time0_ = 0, norm_c_ = 0, norm_b_ = 0, norm_h_ = 0;
+    double dual_feasibility_ = -1.0;
+    bool dual_feasibility_check_ = false, certificate_search_ = false, certificate_found_ = false;
+    long long certificate_search_min_iter_ = 0;
+    // Residuals
+    Circ dual_gap_, prim_obj_, dual_obj_, feasibility_, primal_residual_, dual_residual_, comb_residual_;
+    double equa_feasibility_ = 0, ineq_feasibility_ = 0;
+    double soc_gap_max_ = -1.0;
+    // timing
+    cudaEvent_t ev_psd0_ = nullptr, ev_psd1_ = nullptr;
+    double time_psd_ms_ = 0;
+    long long n_psd_ = 0;
+    int ladder_ = 4;
+    long long trace_mv0_ = 0, trace_ls0_ = 0;
+};
+
+// ---------------------------------------------------------------------------
+// construction / setup  (pdhg.jl:7-142)
+// ---------------------------------------------------------------------------
+Solver::Solver(const proxsdp_problem_t* prob, const proxsdp_options_t* opt_in, bool cones_only, bool force_large)
+    : opt(*opt_in), force_large_(force_large), cones_only_(cones_only) {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) throw CudaError(-5, "no CUDA device available");
+    dev_ = (int)opt.device_id;
+    if (dev_ < 0 || dev_ >= ndev) throw CudaError(-1, "device_id out of range");
+    PB_CUDA(cudaSetDevice(dev_));
+    cudaDeviceProp prop;
+    PB_CUDA(cudaGetDeviceProperties(&prop, dev_));
+    num_sms_ = prop.multiProcessorCount;
+    smem_optin_ = prop.sharedMemPerBlockOptin;
+    PB_CUDA(cudaStreamCreate(&stream));   // blocking stream: ordered against the synchronous setup copies on the legacy stream
+    PB_CUDA(cudaEventCreate(&ev_psd0_));
+    PB_CUDA(cudaEventCreate(&ev_psd1_));
+    if (const char* e = getenv("PROXSDP_B200_LADDER")) ladder_ = std::max(1, atoi(e));
+    setup_host(prob);
+}
+
+Solver::~Solver() {
+    if (scal_host) cudaFreeHost(scal_host);
+    if (ev_psd0_) cudaEventDestroy(ev_psd0_);
+    if (ev_psd1_) cudaEventDestroy(ev_psd1_);
+    if (stream) cudaStreamDestroy(stream);
+}
+
+void Solver::setup_host(const proxsdp_problem_t* prob) {
+    n = prob->n; p = prob->p; m = prob->m; R = p + m;
+    const long long base = prob->index_base;
+    n_sdp = (int)prob->n_sdp; n_soc = (int)prob->n_soc;
+    if (n < 0 || p < 0 || m < 0 || (base != 0 && base != 1)) throw CudaError(-1, "invalid problem sizes");
+    if (opt.equilibration || opt.equilibration_force)
+        throw CudaError(-2, "equilibration is not supported by the B200 path (off by default in the reference)");
+    if (!opt.approx_norm) throw CudaError(-2, "approx_norm=false (exact spectral norm) is not supported");
+    if (n >= (1LL << 31) - 64 || R >= (1LL << 31) - 64) throw CudaError(-1, "problem too large for 32-bit indices");
+
+    // norms before any permutation / scaling (pdhg.jl:14-16)
+    auto nrm2 = [](const double* v, long long len) { double s = 0; for (long long i = 0; i < len; ++i) s += v[i] * v[i]; return std::sqrt(s); };
+    norm_b_ = nrm2(prob->b, p); norm_h_ = nrm2(prob->h, m); norm_c_ = nrm2(prob->c, n);
+
+    // preprocess! (scaling.jl:2-26): ord = [sdp vars..., soc vars..., sorted remaining]
+    ord_.assign((size_t)n, 0);
+    std::vector<char> used((size_t)n, 0);
+    long long pos = 0;
+    cones.resize((size_t)n_sdp);
+    for (int k = 0; k < n_sdp; ++k) {
+        long long side = prob->sdp_side[k];
+        long long tri = side * (side + 1) / 2;
+        if (prob->sdp_ptr[k + 1] - prob->sdp_ptr[k] != tri) throw CudaError(-3, "sdp cone length mismatch");
+        cones[k].side = (int)side;
+        cones[k].off = pos;
+        for (long long q = prob->sdp_ptr[k]; q < prob->sdp_ptr[k + 1]; ++q) {
+            long long v = prob->sdp_idx[q] - base;
+            if (v < 0 || v >= n || used[(size_t)v]) throw CudaError(-3, "variable index out of range or in two cones");
+            ord_[(size_t)pos++] = v; used[(size_t)v] = 1;
+        }
+    }
+    psd_end_ = pos;
+    soc_off_h_.resize((size_t)n_soc); soc_len_h_.resize((size_t)n_soc);
+    for (int k = 0; k < n_soc; ++k) {
+        soc_off_h_[k] = pos;
+        soc_len_h_[k] = (int)(prob->soc_ptr[k + 1] - prob->soc_ptr[k]);
+        for (long long q = prob->soc_ptr[k]; q < prob->soc_ptr[k + 1]; ++q) {
+            long long v = prob->soc_idx[q] - base;
+            if (v < 0 || v >= n || used[(size_t)v]) throw CudaError(-3, "variable index out of range or in two cones");
+            ord_[(size_t)pos++] = v; used[(size_t)v] = 1;
+        }
+    }
+    for (long long v = 0; v < n; ++v) if (!used[(size_t)v]) ord_[(size_t)pos++] = v;   // ascending
+    var_ordering_.assign((size_t)n, 0);
+    for (long long j = 0; j < n; ++j) var_ordering_[(size_t)ord_[(size_t)j]] = j;       // sortperm(ord)
+
+    // column scaling factors of norm_scaling (scaling.jl:28-58)
+    std::vector<char> offdiag((size_t)n, 0);
+    {
+        long long cont = 0;
+        for (int k = 0; k < n_sdp; ++k) {
+            long long side = cones[k].side;
+            for (long long j = 0; j < side; ++j)
+                for (long long i = 0; i <= j; ++i) { if (i != j) offdiag[(size_t)cont] = 1; cont++; }
+        }
+    }
+    const double cte = std::sqrt(2.0) / 2.0;
+
+    // M = [A; G] with permuted columns, stored by column == CSR of M'
+    mt_colptr_.assign((size_t)n + 1, 0);
+    long long nnzA = (p > 0 && prob->A_colptr) ? prob->A_colptr[n] - base : 0;
+    long long nnzG = (m > 0 && prob->G_colptr) ? prob->G_colptr[n] - base : 0;
+    if (nnzA + nnzG >= (1LL << 31) - 64) throw CudaError(-1, "too many non-zeros for 32-bit indices");
+    mt_rowidx_.reserve((size_t)(nnzA + nnzG));
+    mt_val_.reserve((size_t)(nnzA + nnzG));
+    mt_val_orig_.reserve((size_t)(nnzA + nnzG));
+    for (long long j = 0; j < n; ++j) {
+        long long src = ord_[(size_t)j];
+        double sc = offdiag[(size_t)j] ? cte : 1.0;
+        if (nnzA > 0)
+            for (long long q = prob->A_colptr[src] - base; q < prob->A_colptr[src + 1] - base; ++q) {
+                mt_rowidx_.push_back((int)(prob->A_rowval[q] - base));
+                mt_val_orig_.push_back(prob->A_nzval[q]);
+                mt_val_.push_back(offdiag[(size_t)j] ? prob->A_nzval[q] * sc : prob->A_nzval[q]);
+            }
+        if (nnzG > 0)
+            for (long long q = prob->G_colptr[src] - base; q < prob->G_colptr[src + 1] - base; ++q) {
+                mt_rowidx_.push_back((int)(prob->G_rowval[q] - base + p));
+                mt_val_orig_.push_back(prob->G_nzval[q]);
+                mt_val_.push_back(offdiag[(size_t)j] ? prob->G_nzval[q] * sc : prob->G_nzval[q]);
+            }
+        mt_colptr_[(size_t)j + 1] = (long long)mt_rowidx_.size();
+    }
+    c_host_.resize((size_t)n); c_orig_.resize((size_t)n);
+    for (long long j = 0; j < n; ++j) {
+        c_orig_[(size_t)j] = prob->c[ord_[(size_t)j]];
+        c_host_[(size_t)j] = offdiag[(size_t)j] ? c_orig_[(size_t)j] * cte : c_orig_[(size_t)j];
+    }
+    b_host_.assign(prob->b, prob->b + p); h_host_.assign(prob->h, prob->h + m);
+    b_orig_ = b_host_; h_orig_ = h_host_;
+
+    // step size: 1 / ||M||_F (pdhg.jl:121-133)
+    double fro = 0.0;
+    for (double v : mt_val_) fro += v * v;
+    fro = std::sqrt(fro);
+    if (fro < 1e-10) fro = 1.0;
+    primal_step_ = 1.0 / fro; primal_step_old_ = primal_step_; dual_step_ = primal_step_;
+
+    // ---- Params (pdhg.jl:7-31) ----
+    theta_ = opt.initial_theta; adapt_level_ = opt.initial_adapt_level; window_ = opt.convergence_window;
+    beta_ = opt.initial_beta;
+    long long r0 = opt.initial_target_rank > 0 ? opt.initial_target_rank : 2;
+    target_rank.assign((size_t)n_sdp, r0); current_rank.assign((size_t)n_sdp, r0); min_eig.assign((size_t)n_sdp, 0.0);
+    if (opt.max_iter <= 0) opt.max_iter_local = (n_soc > 0 || n_sdp > 0) ? opt.max_iter_conic : opt.max_iter_lp;
+    else opt.max_iter_local = opt.max_iter;
+    for (Circ* c : {&dual_gap_, &prim_obj_, &dual_obj_, &feasibility_, &primal_residual_, &dual_residual_, &comb_residual_})
+        c->init(2 * window_);
+
+    // ---- device problem ----
+    c_.upload(c_host_); b_.upload(b_host_); h_.upload(h_host_);
+    for (int q = 0; q < 2; ++q) { x_[q].alloc((size_t)n); Mty_[q].alloc((size_t)n); y_[q].alloc((size_t)R); Mx_[q].alloc((size_t)R); }
+    if (!cones_only_) build_csr(mt_colptr_, mt_rowidx_, mt_val_);
+
+    // cones
+    long long kmax = 2 * std::max<long long>(opt.max_target_rank_krylov_eigs, r0) + 1;
+    kmax = std::max<long long>(kmax, opt.eigsolver_min_lanczos);
+    Kmax_ = (int)kmax;
+    std::vector<int> side_h((size_t)n_sdp);
+    std::vector<long long> off_h((size_t)n_sdp);
+    long long roff = 0;
+    for (int k = 0; k < n_sdp; ++k) {
+        ConeDev& cd = cones[k];
+        side_h[k] = cd.side; off_h[k] = cd.off;
+        cd.small = cd.side <= SMALL_CONE_MAX && !force_large_;
+        cd.ld = (cd.side + 63) & ~63;     // multiple of the block-Jacobi pivot size (no dummy blocks)
+        if (cd.small) {
+            small_ids_.push_back(k);
+            max_small_side_ = std::max(max_small_side_, cd.side);
+        } else {
+            large_ids_.push_back(k);
+            cd.X.alloc((size_t)cd.ld * cd.ld);
+            cd.Y.alloc((size_t)cd.ld * (size_t)(Kmax_ + 1));
+            cd.vcur.alloc((size_t)cd.ld);
+            cd.vals.alloc((size_t)cd.ld);
+            cd.kept_lam.alloc((size_t)cd.ld);
+            cd.kept_idx.alloc((size_t)cd.ld);
+            cd.info.alloc(8);
+            cd.nkept.alloc(1);
+            std::vector<double> rs((size_t)cd.side);
+            if (prob->eig_resid) std::copy(prob->eig_resid + roff, prob->eig_resid + roff + cd.side, rs.begin());
+            else eig_resid_default(cd.side, opt.eigsolver_resid_seed, opt.krylovkit_resid_init, rs.data());
+            cd.resid.upload(rs);
+        }
+        roff += cd.side;
+    }
+    cone_side_d_.upload(side_h); cone_off_d_.upload(off_h); small_ids_d_.upload(small_ids_);
+    soc_off_d_.upload(soc_off_h_); soc_len_d_.upload(soc_len_h_); soc_gap_d_.alloc((size_t)std::max(n_soc, 1));
+    out_min_d_.alloc((size_t)std::max(n_sdp, 1));
+    offnorm_d_.alloc(2);
+
+    scal_len = S_HEADER + 3 * n_sdp;
+    scal_d_.alloc((size_t)scal_len);
+    PB_CUDA(cudaMallocHost(&scal_host, sizeof(double) * (size_t)scal_len));
+    reduce_blocks_ = num_sms_ * 8;
+    partials_d_.alloc((size_t)reduce_blocks_ * 8);
+    counters_d_.alloc(16);
+    bar_d_.alloc(2);
+    lz_partials_d_.alloc((size_t)2 * (size_t)(Kmax_ + 2) * (size_t)num_sms_);
+    ws_.partials = partials_d_.p; ws_.counters = counters_d_.p; ws_.max_blocks = reduce_blocks_;
+
+    if (max_small_side_ > 1) {
+        size_t sb = small_cone_smem_bytes(max_small_side_);
+        if (sb > smem_optin_) throw CudaError(-4, "small-cone kernel needs more shared memory than the device offers");
+        PB_CUDA(cudaFuncSetAttribute(k_small_cone_proj, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb));
+    }
+    PB_CUDA(cudaFuncSetAttribute(k_lanczos, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_optin_));
+    PB_CUDA(cudaFuncSetAttribute(k_bj_pair_eig, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bj_pair_smem_bytes()));
+    PB_CUDA(cudaFuncSetAttribute(k_bj_apply<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BJ_APPLY_SMEM));
+    PB_CUDA(cudaFuncSetAttribute(k_bj_apply<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BJ_APPLY_SMEM));
+}
+
+// CSR of M (rows of M) from the by-column storage, plus device copies of both
+void Solver::build_csr(const std::vector<long long>& colptr, const std::vector<int>& rowidx,
+                       const std::vector<double>& val) {
+    const long long nnz = (long long)rowidx.size();
+    // Mt_: rows = n (columns of M)
+    {
+        std::vector<int> rp((size_t)n + 1);
+        for (long long j = 0; j <= n; ++j) rp[(size_t)j] = (int)colptr[(size_t)j];
+        Mt_.nrows = (int)n; Mt_.ncols = (int)R; Mt_.nnz = (int)nnz;
+        Mt_.rowptr.upload(rp); Mt_.colidx.upload(rowidx); Mt_.val.upload(val);
+    }
+    // M_: transpose by counting sort (keeps increasing column order inside a row)
+    std::vector<int> rp((size_t)R + 1, 0), ci((size_t)nnz);
+    std::vector<double> vv((size_t)nnz);
+    for (long long q = 0; q < nnz; ++q) rp[(size_t)rowidx[(size_t)q] + 1]++;
+    for (long long r = 0; r < R; ++r) rp[(size_t)r + 1] += rp[(size_t)r];
+    std::vector<int> next(rp.begin(), rp.end() - 1);
+    for (long long j = 0; j < n; ++j)
+        for (long long q = colptr[(size_t)j]; q < colptr[(size_t)j + 1]; ++q) {
+            int dst = next[(size_t)rowidx[(size_t)q]]++;
+            ci[(size_t)dst] = (int)j; vv[(size_t)dst] = val[(size_t)q];
+        }
+    M_.nrows = (int)R; M_.ncols = (int)n; M_.nnz = (int)nnz;
+    M_.rowptr.upload(rp); M_.colidx.upload(ci); M_.val.upload(vv);
+    // row-length statistics -> lanes per row, long rows
+    double avg = R > 0 ? (double)nnz / (double)R : 0.0;
+    M_.group = avg <= 1.5 ? 1 : avg <= 3 ? 2 : avg <= 6 ? 4 : avg <= 12 ? 8 : avg <= 24 ? 16 : 32;
+    M_.long_threshold = 4096;
+    std::vector<int> longs;
+    for (long long r = 0; r < R; ++r) if (rp[(size_t)r + 1] - rp[(size_t)r] > M_.long_threshold) longs.push_back((int)r);
+    M_.n_long = (int)longs.size();
+    M_.long_rows.upload(longs);
+}
+
+// ---------------------------------------------------------------------------
+// launches
+// ---------------------------------------------------------------------------
+void Solver::launch_spmv(const CsrDev& A, const double* x, double* y) {
+    if (A.nrows == 0) return;
+    const double* poison = scal_d_.p + S_POISON;
+    long long threads = (long long)A.nrows * A.group;
+    int blocks = ceil_div(threads, 256);
+    switch (A.group) {
+        case 1: k_spmv_csr<1><<<blocks, 256, 0, stream>>>(A.nrows, A.rowptr.p, A.colidx.p, A.val.p, x, y, A.long_threshold, poison); break;
+        case 2: k_spmv_csr<2><<<blocks, 256, 0, stream>>>(A.nrows, A.rowptr.p, A.colidx.p, A.val.p, x, y, A.long_threshold, poison); break;
+        case 4: k_spmv_csr<4><<<blocks, 256, 0, stream>>>(A.nrows, A.rowptr.p, A.colidx.p, A.val.p, x, y, A.long_threshold, poison); break;
+        case 8: k_spmv_csr<8><<<blocks, 256, 0, stream>>>(A.nrows, A.rowptr.p, A.colidx.p, A.val.p, x, y, A.long_threshold, poison); break;
+        case 16: k_spmv_csr<16><<<blocks, 256, 0, stream>>>(A.nrows, A.rowptr.p, A.colidx.p, A.val.p, x, y, A.long_threshold, poison); break;
+        default: k_spmv_csr<32><<<blocks, 256, 0, stream>>>(A.nrows, A.rowptr.p, A.colidx.p, A.val.p, x, y, A.long_threshold, poison); break;
+    }
+    launches++;
+    if (A.n_long > 0) {
+        k_spmv_long<<<A.n_long, 512, 0, stream>>>(A.long_rows.p, A.rowptr.p, A.colidx.p, A.val.p, x, y, poison);
+        launches++;
+    }
+}
+
+bool Solver::krylov_eligible(int k, long long iter) const {
+    // prox_operators.jl:46-49
+    return !opt.full_eig_decomp && target_rank[(size_t)k] <= opt.max_target_rank_krylov_eigs &&
+           cones[(size_t)k].side > opt.min_size_krylov_eigs && (iter % opt.full_eig_freq) > opt.full_eig_len;
+}
+
+void Solver::lanczos_launch(ConeDev& cd, int cone_idx, int nev, int K, int maxiter, double tol) {
+    const int nside = cd.side;
+    int G = std::min(num_sms_, std::max(1, (nside + 7) / 8));
+    int rows_max = (nside + G - 1) / G;
+    int nwarps = LZ_THREADS / 32;
+    int n2 = (nside + 1) & ~1;
+    int split = 1;
+    while (rows_max * split < 3 * nwarps && n2 / (split * 2) >= 256) split *= 2;
+    int panel = std::min((n2 + 63) & ~63, K > 64 ? 4096 : 8192);
+    size_t smem = lanczos_smem_bytes(K, rows_max, split, panel);
+    while (smem > smem_optin_ && panel > 512) { panel /= 2; smem = lanczos_smem_bytes(K, rows_max, split, panel); }
+    if (smem > smem_optin_) throw CudaError(-4, "Lanczos kernel: basis slab does not fit shared memory for this (n, K)");
+    if ((size_t)2 * (size_t)(K + 2) * (size_t)G > lz_partials_d_.n) lz_partials_d_.alloc((size_t)2 * (size_t)(K + 2) * (size_t)G);
+    if ((size_t)cd.ld * (size_t)(K + 1) > cd.Y.n) cd.Y.alloc((size_t)cd.ld * (size_t)(K + 1));
+    LanczosArgs a{};
+    a.X = cd.X.p; a.n = nside; a.ld = cd.ld; a.x0 = cd.resid.p; a.vcur = cd.vcur.p; a.Y = cd.Y.p;
+    a.partials = lz_partials_d_.p; a.bar = bar_d_.p;
+    a.nev = nev; a.K = K; a.maxiter = maxiter; a.tol = tol;
+    a.rows_max = rows_max; a.split = split; a.panel = panel;
+    a.vals = cd.vals.p; a.info = cd.info.p; a.scal = scal_d_.p; a.cone = cone_idx; a.n_cones_total = n_sdp;
+    void* args[] = {&a};
+    PB_CUDA(cudaLaunchCooperativeKernel((void*)k_lanczos, dim3(G), dim3(LZ_THREADS), args, smem, stream));
+    launches++;
+}
+
+void Solver::launch_reconstruct(ConeDev& cd, double* x_out) {
+    int nt = (cd.side + 31) / 32;
+    int tiles = nt * (nt + 1) / 2;
+    k_reconstruct_svec<<<tiles, dim3(32, 8), 0, stream>>>(cd.Y.p, cd.ld, cd.side, cd.kept_idx.p, cd.kept_lam.p,
+                                                          cd.nkept.p, x_out + cd.off, scal_d_.p + S_POISON);
+    launches++;
+}
+
+// Block-Jacobi eigendecomposition of cd.X (destroyed).  Returns the eigenvalues (unsorted);
+// eigenvectors are the columns of cd.Vfull.
+std::vector<double> Solver::full_eig_device(ConeDev& cd) {
+    const int nside = cd.side, ld = cd.ld, NP = ld;
+    if (cd.Vfull.n < (size_t)ld * ld) cd.Vfull.alloc((size_t)ld * ld);
+    int nb = NP / BJ_B;
+    int mplayers = (nb + 1) & ~1;
+    int npairs = mplayers / 2;
+    if (bj_Q_.n < (size_t)npairs * BJ_QSTRIDE) bj_Q_.alloc((size_t)npairs * BJ_QSTRIDE);
+    if (bj_pi_.n < (size_t)npairs) { bj_pi_.alloc((size_t)npairs); bj_pj_.alloc((size_t)npairs); }
+    if (bj_rot_.n < 1) bj_rot_.alloc(1);
+    {
+        long long tot = (long long)NP * NP;
+        k_bj_init<<<ceil_div(tot, 256), 256, 0, stream>>>(cd.X.p, cd.Vfull.p, ld, nside, NP);
+        launches++;
+    }
+    std::vector<int> pi((size_t)npairs), pj((size_t)npairs);
+    std::vector<double> offn(2);
+    const int chunks = (NP + BJ_P - 1) / BJ_P;
+    for (int sweep = 0; sweep < 40; ++sweep) {
+        PB_CUDA(cudaMemsetAsync(bj_rot_.p, 0, sizeof(int), stream));
+        if (nb == 1) {
+            // single block: one pivot problem on the 32x32 matrix embedded in a 64x64 pair with the dummy
+        }
+        for (int round = 0; round < std::max(1, mplayers - 1); ++round) {
+            for (int t = 0; t < npairs; ++t) {
+                int a_, b_;
+                if (mplayers == 2) { a_ = 0; b_ = 1; }
+                else if (t == 0) { a_ = mplayers - 1; b_ = round; }
+                else { a_ = (round + t) % (mplayers - 1); b_ = (round - t + (mplayers - 1)) % (mplayers - 1); }
+                int I = std::min(a_, b_), J = std::max(a_, b_);
+                if (J >= nb) { I = -1; J = -1; }
+                pi[(size_t)t] = I; pj[(size_t)t] = J;
+            }
+            PB_CUDA(cudaMemcpyAsync(bj_pi_.p, pi.data(), sizeof(int) * (size_t)npairs, cudaMemcpyHostToDevice, stream));
+            PB_CUDA(cudaMemcpyAsync(bj_pj_.p, pj.data(), sizeof(int) * (size_t)npairs, cudaMemcpyHostToDevice, stream));
+            BjPairs pr{bj_pi_.p, bj_pj_.p};
+            k_bj_pair_eig<<<npairs, 256, bj_pair_smem_bytes(), stream>>>(cd.X.p, ld, pr, bj_Q_.p, bj_rot_.p);
+            k_bj_apply<0><<<dim3(npairs, chunks, 2), 256, BJ_APPLY_SMEM, stream>>>(cd.X.p, cd.Vfull.p, ld, NP, pr, bj_Q_.p);
+            k_bj_apply<1><<<dim3(npairs, chunks, 1), 256, BJ_APPLY_SMEM, stream>>>(cd.X.p, cd.Vfull.p, ld, NP, pr, bj_Q_.p);
+            launches += 3;
+            // pi/pj host buffers are reused next round: the async copies above were issued from pageable
+            // memory (staged synchronously by the runtime), so reuse is safe.
+        }
+        k_bj_offnorm<<<std::min(reduce_blocks_, ceil_div((long long)nside * nside, 256)), 256, 0, stream>>>(
+            cd.X.p, ld, nside, offnorm_d_.p, ws_);
+        launches++;
+        PB_CUDA(cudaMemcpyAsync(offn.data(), offnorm_d_.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, stream));
+        PB_CUDA(cudaStreamSynchronize(stream));
+        if (getenv("PROXSDP_B200_DEBUG")) fprintf(stderr, "[bj] n=%d sweep %d off2=%.3e tot2=%.3e\n", nside, sweep, offn[0], offn[1]);
+        if (!(offn[0] > 1e-30 * offn[1])) break;     // off^2 <= 1e-30 * ||A||_F^2
+    }
+    DBuf<double> diag;
+    diag.alloc((size_t)nside);
+    k_bj_diag<<<ceil_div(nside, 256), 256, 0, stream>>>(cd.X.p, ld, nside, diag.p);
+    launches++;
+    PB_CUDA(cudaStreamSynchronize(stream));
+    full_eig_calls++;
+    return diag.download();
+}
+
+// full_eig! for a large cone (prox_operators.jl:111-126) on the matrix in cones[k].X
+void Solver::launch_full_projection_large(int k) {
+    ConeDev& cd = cones[(size_t)k];
+    std::vector<double> w = full_eig_device(cd);
+    std::vector<int> idx;
+    std::vector<double> lam;
+    long long rk = 0;
+    for (int i = 0; i < cd.side; ++i)
+        if (w[(size_t)i] > 0.0) { idx.push_back(i); lam.push_back(w[(size_t)i]); if (w[(size_t)i] > opt.tol_psd) rk++; }
+    int nk = (int)idx.size();
+    if (nk > 0) {
+        PB_CUDA(cudaMemcpyAsync(cd.kept_idx.p, idx.data(), sizeof(int) * (size_t)nk, cudaMemcpyHostToDevice, stream));
+        PB_CUDA(cudaMemcpyAsync(cd.kept_lam.p, lam.data(), sizeof(double) * (size_t)nk, cudaMemcpyHostToDevice, stream));
+    }
+    PB_CUDA(cudaMemcpyAsync(cd.nkept.p, &nk, sizeof(int), cudaMemcpyHostToDevice, stream));
+    double rec[3] = {(double)rk, 0.0, -1.0};
+    PB_CUDA(cudaMemcpyAsync(scal_d_.p + S_HEADER + 3 * k, rec, sizeof(rec), cudaMemcpyHostToDevice, stream));
+    int nt = (cd.side + 31) / 32;
+    int tiles = nt * (nt + 1) / 2;
+    k_reconstruct_svec<<<tiles, dim3(32, 8), 0, stream>>>(cd.Vfull.p, cd.ld, cd.side, cd.kept_idx.p, cd.kept_lam.p,
+                                                          cd.nkept.p, x_[1 - cur_].p + cd.off, nullptr);
+    launches++;
+    PB_CUDA(cudaStreamSynchronize(stream));   // idx/lam/nk/rec are stack/host temporaries
+}
+
+// psd_projection! (prox_operators.jl:33-66) fused with the primal gradient step (pdhg.jl:622)
+// reads x_[cur_], Mty_[cur_], c_ ; writes the PSD part of x_[1-cur_]
+void Solver::psd_projection_launch(long long iter, double tau, bool force_full) {
+    const double* x = x_[cur_].p; const double* Mty = Mty_[cur_].p;
+    double* xn = x_[1 - cur_].p;
+    PB_CUDA(cudaEventRecord(ev_psd0_, stream));
+    if (!small_ids_.empty()) {
+        SmallConeArgs a{};
+        a.cone_ids = small_ids_d_.p; a.cone_side = cone_side_d_.p; a.cone_off = cone_off_d_.p;
+        a.x = x; a.Mty = Mty; a.c = c_.p; a.tau = tau; a.tol_psd = opt.tol_psd; a.x_out = xn; a.scal = scal_d_.p;
+        a.mode = 0; a.scale = 1.0; a.out_min = out_min_d_.p;
+        size_t sb = max_small_side_ > 1 ? small_cone_smem_bytes(max_small_side_) : 0;
+        k_small_cone_proj<<<(int)small_ids_.size(), 256, sb, stream>>>(a);
+        launches++;
+        full_eig_calls += (long long)small_ids_.size();
+    }
+    std::vector<int> full_now;
+    for (int k : large_ids_) {
+        ConeDev& cd = cones[(size_t)k];
+        int nt = (cd.side + 31) / 32;
+        int tiles = nt * (nt + 1) / 2;
+        k_svec_to_mat<true><<<tiles, dim3(32, 8), 0, stream>>>(x + cd.off, Mty + cd.off, c_.p + cd.off, tau, 1.0,
+                                                               cd.side, cd.ld, cd.X.p);
+        launches++;
+        if (!force_full && krylov_eligible(k, iter)) {
+            int nev = (int)target_rank[(size_t)k];
+            int K = (int)std::max<long long>(2 * nev + 1, opt.eigsolver_min_lanczos);   // eigsolver.jl:794
+            lanczos_launch(cd, k, nev, K, (int)opt.krylovkit_max_iter, opt.krylovkit_tol);
+            lanczos_calls++;
+            k_lanczos_select<<<1, 32, 0, stream>>>(cd.vals.p, cd.info.p, nev, cd.kept_idx.p, cd.kept_lam.p,
+                                                   cd.nkept.p, scal_d_.p, k);
+            launches++;
+            launch_reconstruct(cd, xn);
+        } else {
+            full_now.push_back(k);
+        }
+    }
+    for (int k : full_now) launch_full_projection_large(k);
+    PB_CUDA(cudaEventRecord(ev_psd1_, stream));
+}
+
+void Solver::launch_dual_trial(int trial, double tau0) {
+    DualArgs d{};
+    d.y = y_[cur_].p; d.Mx = Mx_[1 - cur_].p; d.Mx_old = Mx_[cur_].p; d.b = b_.p; d.h = h_.p; d.y_new = y_[1 - cur_].p;
+    d.p = (int)p; d.m = (int)m;
+    d.tau0 = tau0; d.decay = opt.linsearch_decay; d.tau_old = primal_step_old_; d.beta = beta_;
+    d.sigma_fixed = dual_step_; d.trial = trial; d.use_theta = opt.line_search_flag ? 1 : 0;
+    int blocks = std::max(1, std::min(reduce_blocks_, ceil_div(R, 256)));
+    k_dual_trial<<<blocks, 256, 0, stream>>>(d, scal_d_.p, ws_);
+    MtArgs t{};
+    t.N = (int)n; t.rowptr = Mt_.rowptr.p; t.colidx = Mt_.colidx.p; t.val = Mt_.val.p;
+    t.y_new = y_[1 - cur_].p; t.Mty = Mty_[cur_].p; t.Mty_new = Mty_[1 - cur_].p;
+    t.beta = beta_; t.delta = opt.delta; t.trial = trial; t.do_test = opt.line_search_flag ? 1 : 0;
+    int blocks2 = std::max(1, std::min(reduce_blocks_, ceil_div(n, 256)));
+    k_spmv_mt_norm<<<blocks2, 256, 0, stream>>>(t, scal_d_.p, ws_);
+    launches += 2;
+}
+
+// everything after the eigen-solves: SOC projection, Mx, dual step / linesearch ladder, residuals
+void Solver::launch_post_eig(double tau0, bool first_pass) {
+    double* xn = x_[1 - cur_].p;
+    const double* poison = scal_d_.p + S_POISON;
+    if (first_pass && psd_end_ < n) {
+        long long cnt = n - psd_end_;
+        k_primal_tail<<<std::min(reduce_blocks_, ceil_div(cnt, 256)), 256, 0, stream>>>(
+            x_[cur_].p, Mty_[cur_].p, c_.p, primal_step_, psd_end_, n, xn);
+        launches++;
+    }
+    if (n_soc > 0) {
+        k_soc_project<<<n_soc, 256, 0, stream>>>(xn, soc_off_d_.p, soc_len_d_.p, soc_gap_d_.p, poison);
+        k_soc_gap_max<<<1, 256, 0, stream>>>(soc_gap_d_.p, n_soc, scal_d_.p);
+        launches += 2;
+    }
+    launch_spmv(M_, xn, Mx_[1 - cur_].p);
+    int ntr = opt.line_search_flag ? ladder_ : 1;
+    for (int t = 0; t < ntr; ++t) launch_dual_trial(t, tau0);
+    int blocksN = std::max(1, std::min(reduce_blocks_, ceil_div(n, 512)));
+    k_residual_primal<<<blocksN, 256, 0, stream>>>(n, xn, x_[cur_].p, Mty_[1 - cur_].p, Mty_[cur_].p, c_.p, scal_d_.p, ws_);
+    int blocksR = std::max(1, std::min(reduce_blocks_, ceil_div(R, 256)));
+    k_residual_dual<<<blocksR, 256, 0, stream>>>((int)p, (int)m, beta_, opt.line_search_flag ? 1 : 0, dual_step_,
+                                                 y_[1 - cur_].p, y_[cur_].p, Mx_[1 - cur_].p, Mx_[cur_].p, b_.p, h_.p,
+                                                 scal_d_.p, ws_);
+    launches += 2;
+}
+
+void Solver::launch_soc_only() {
+    if (n_soc == 0) return;
+    k_soc_project<<<n_soc, 256, 0, stream>>>(x_[1 - cur_].p, soc_off_d_.p, soc_len_d_.p, soc_gap_d_.p, scal_d_.p + S_POISON);
+    k_soc_gap_max<<<1, 256, 0, stream>>>(soc_gap_d_.p, n_soc, scal_d_.p);
+    launches += 2;
+}
+
+void Solver::reset_scalars() {
+    k_scal_reset<<<ceil_div(scal_len, 256), 256, 0, stream>>>(scal_d_.p, scal_len);
+    launches++;
+}
+
+// Krylov fallback (prox_operators.jl:55-57): cones whose eigsolve reported converged == 0 are
+// redone with the full eigendecomposition; the others only need their (skipped) reconstruction.
+void Solver::fallback_projection(long long iter) {
+    PB_CUDA(cudaMemsetAsync(scal_d_.p + S_POISON, 0, sizeof(double), stream));
+    for (int kk : large_ids_) {
+        if (!krylov_eligible(kk, iter)) continue;
+        if (scal_host[S_HEADER + 3 * kk + 2] == 0.0) {
+            launch_full_projection_large(kk);
+        } else {
+            ConeDev& cd = cones[(size_t)kk];
+            k_lanczos_select<<<1, 32, 0, stream>>>(cd.vals.p, cd.info.p, (int)target_rank[(size_t)kk], cd.kept_idx.p,
+                                                   cd.kept_lam.p, cd.nkept.p, scal_d_.p, kk);
+            launches++;
+            launch_reconstruct(cd, x_[1 - cur_].p);
+        }
+    }
+}
+
+void Solver::sync_scalars() {
+    PB_CUDA(cudaMemcpyAsync(scal_host, scal_d_.p, sizeof(double) * (size_t)scal_len, cudaMemcpyDeviceToHost, stream));
+    PB_CUDA(cudaStreamSynchronize(stream));
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) throw CudaError(-100 - (int)e, std::string("kernel launch failed: ") + cudaGetErrorString(e));
+}
+
+// ---------------------------------------------------------------------------
+// result assembly (pdhg.jl:678-787), host side
+// ---------------------------------------------------------------------------
+double Solver::dual_feas_host(const std::vector<double>& y, const std::vector<double>& cvec,
+                              std::vector<double>* dual_cone_out) {
+    // get_duals (pdhg.jl:701-710): dual_cone = c + A'y_eq + G'y_in (unscaled), off-diagonals / 2
+    std::vector<double> dc((size_t)n);
+    for (long long j = 0; j < n; ++j) {
+        double s = 0.0;
+        for (long long q = mt_colptr_[(size_t)j]; q < mt_colptr_[(size_t)j + 1]; ++q)
+            s += mt_val_orig_[(size_t)q] * y[(size_t)mt_rowidx_[(size_t)q]];
+        dc[(size_t)j] = cvec[(size_t)j] + s;
+    }
+    {
+        long long cont = 0;
+        for (int k = 0; k < n_sdp; ++k) {
+            long long side = cones[(size_t)k].side;
+            for (long long j = 0; j < side; ++j)
+                for (long long i = 0; i <= j; ++i) { if (i != j) dc[(size_t)cont] /= 2.0; cont++; }
+        }
+    }
+    if (dual_cone_out) *dual_cone_out = dc;
+    // dual_feas (pdhg.jl:716-732)
+    double ineq_viol = 0.0;
+    if (m > 0) {
+        double mn = y[(size_t)p];
+        for (long long i = 1; i < m; ++i) mn = std::min(mn, y[(size_t)(p + i)]);
+        ineq_viol = -std::min(0.0, mn);
+    }
+    // cone_feas (pdhg.jl:678-699): min eigenvalue of mat(dual_cone) with off-diagonals / sqrt(2)
+    double cone_viol = 0.0;
+    if (n_sdp > 0) {
+        DBuf<double> dcd;
+        dcd.upload(dc);
+        if (!small_ids_.empty()) {
+            SmallConeArgs a{};
+            a.cone_ids = small_ids_d_.p; a.cone_side = cone_side_d_.p; a.cone_off = cone_off_d_.p;
+            a.x = dcd.p; a.Mty = dcd.p; a.c = dcd.p; a.tau = 0.0; a.tol_psd = opt.tol_psd; a.x_out = nullptr;
+            a.scal = scal_d_.p; a.mode = 1; a.scale = 1.0; a.out_min = out_min_d_.p;
+            size_t sb = max_small_side_ > 1 ? small_cone_smem_bytes(max_small_side_) : 0;
+            k_small_cone_proj<<<(int)small_ids_.size(), 256, sb, stream>>>(a);
+            launches++;
+            PB_CUDA(cudaStreamSynchronize(stream));
+            std::vector<double> mins = out_min_d_.download();
+            for (int k : small_ids_) cone_viol = std::max(cone_viol, -std::min(0.0, mins[(size_t)k]));
+        }
+        for (int k : large_ids_) {
+            ConeDev& cd = cones[(size_t)k];
+            int nt = (cd.side + 31) / 32;
+            int tiles = nt * (nt + 1) / 2;
+            // lambda_min(Z) = -lambda_max(-Z): Lanczos (nev = 1) on the negated matrix
+            k_svec_to_mat<false><<<tiles, dim3(32, 8), 0, stream>>>(dcd.p + cd.off, nullptr, nullptr, 0.0, -1.0,
+                                                                    cd.side, cd.ld, cd.X.p);
+            launches++;
+            int K = (int)std::max<long long>(opt.eigsolver_min_lanczos, 3);
+            lanczos_launch(cd, k, 1, K, 300, 1e-10);
+            PB_CUDA(cudaStreamSynchronize(stream));
+            std::vector<double> vals = cd.vals.download();
+            double lmin = -vals[0];
+            cone_viol = std::max(cone_viol, -std::min(0.0, lmin));
+        }
+    }
+    long long cont = psd_end_;
+    for (int k = 0; k < n_soc; ++k) {
+        long long len = soc_len_h_[(size_t)k];
+        double sv = dc[(size_t)cont], nv = 0.0;
+        for (long long i = 1; i < len; ++i) nv += dc[(size_t)(cont + i)] * dc[(size_t)(cont + i)];
+        cone_viol = std::max(cone_viol, -std::min(0.0, sv - std::sqrt(nv)));
+        cont += len;
+    }
+    double zero_viol = 0.0;
+    for (long long i = cont; i < n; ++i) zero_viol = std::max(zero_viol, std::fabs(dc[(size_t)i]));
+    return std::max(cone_viol, std::max(ineq_viol, zero_viol));
+}
+
+__global__ void k_fix_diag_scaling(double* __restrict__ x, const int* __restrict__ cone_side,
+                                   const long long* __restrict__ cone_off, int n_sdp, double num) {
+    int cone = blockIdx.y;
+    if (cone >= n_sdp) return;
+    int side = cone_side[cone];
+    long long tri = (long long)side * (side + 1) / 2;
+    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < tri; k += (long long)gridDim.x * blockDim.x) {
+        long long j = (long long)((sqrt(8.0 * (double)k + 1.0) - 1.0) * 0.5);
+        while ((j + 1) * (j + 2) / 2 <= k) ++j;
+        while (j * (j + 1) / 2 > k) --j;
+        long long i = k - j * (j + 1) / 2;
+        if (i != j) x[cone_off[cone] + k] /= num;
+    }
+}
+
+// cache_solution (pdhg.jl:745-787).  Like the reference it rescales pair.x IN PLACE.
+void Solver::cache_solution(const double* c_res, proxsdp_result_t* out) {
+    if (n_sdp > 0) {
+        k_fix_diag_scaling<<<dim3(64, n_sdp), 256, 0, stream>>>(x_[cur_].p, cone_side_d_.p, cone_off_d_.p, n_sdp, std::sqrt(2.0));
+        launches++;
+    }
+    PB_CUDA(cudaStreamSynchronize(stream));
+    std::vector<double> x = x_[cur_].download(), y = y_[cur_].download();
+    std::vector<double> slack((size_t)R, 0.0);
+    for (long long j = 0; j < n; ++j) {
+        double xj = x[(size_t)j];
+        for (long long q = mt_colptr_[(size_t)j]; q < mt_colptr_[(size_t)j + 1]; ++q)
+            slack[(size_t)mt_rowidx_[(size_t)q]] += mt_val_orig_[(size_t)q] * xj;
+    }
+    std::vector<double> cvec(c_res, c_res + n), dual_cone;
+    double dfeas = dual_feas_host(y, cvec, &dual_cone);
+    out->status = stop_reason_;
+    snprintf(out->status_string, PROXSDP_STATUS_STRING_LEN, "%s", stop_reason_string_.c_str());
+    if (out->primal) for (long long i = 0; i < n; ++i) out->primal[i] = x[(size_t)var_ordering_[(size_t)i]];
+    if (out->dual_cone) for (long long i = 0; i < n; ++i) out->dual_cone[i] = dual_cone[(size_t)var_ordering_[(size_t)i]];
+    if (out->dual_eq) for (long long i = 0; i < p; ++i) out->dual_eq[i] = y[(size_t)i];
+    if (out->dual_in) for (long long i = 0; i < m; ++i) out->dual_in[i] = y[(size_t)(p + i)];
+    if (out->slack_eq) for (long long i = 0; i < p; ++i) out->slack_eq[i] = slack[(size_t)i] - b_orig_[(size_t)i];
+    if (out->slack_in) for (long long i = 0; i < m; ++i) out->slack_in[i] = slack[(size_t)(p + i)] - h_orig_[(size_t)i];
+    out->primal_residual = equa_feasibility_;
+    out->dual_residual = ineq_feasibility_;
+    out->objval = prim_obj_.get(iter_);
+    out->dual_objval = dual_obj_.get(iter_);
+    out->gap = dual_gap_.get(iter_);
+    out->time = now_s() - time0_;
+    out->iter = iter_;
+    long long fr = 0;
+    for (long long r : current_rank) fr += r;
+    out->final_rank = fr;
+    out->primal_feasible_user_tol = feasibility_.get(iter_) <= opt.tol_feasibility;
+    out->dual_feasible_user_tol = dfeas <= opt.tol_feasibility_dual;
+    out->certificate_found = certificate_found_;
+    out->result_count = 1;
+    out->final_primal_res = primal_residual_.get(iter_);
+    out->final_dual_res = dual_residual_.get(iter_);
+}
+
+void Solver::rank_increment_rule(int idx) {
+    // pdhg.jl:271-279 / 294-302
+    if (opt.freeze_target_rank) return;
+    if (current_rank[(size_t)idx] + opt.rank_slack >= target_rank[(size_t)idx]) {
+        if (min_eig[(size_t)idx] > opt.tol_psd) {
+            long long t = opt.rank_increment == 0 ? opt.rank_increment_factor * target_rank[(size_t)idx]
+                                                  : opt.rank_increment_factor + target_rank[(size_t)idx];
+            target_rank[(size_t)idx] = std::min<long long>(t, cones[(size_t)idx].side);
+        }
+    }
+}
+
+void Solver::record_trace(proxsdp_result_t* out) {
+    if (!out->trace || out->trace_len >= opt.trace_cap) return;
+    double* row = out->trace + out->trace_len * PROXSDP_TRACE_COLS;
+    double tr = 0, cr = 0, me = 0;
+    for (int i = 0; i < n_sdp; ++i) {
+        tr += (double)target_rank[(size_t)i]; cr += (double)current_rank[(size_t)i];
+        if (i == 0 || min_eig[(size_t)i] < me) me = min_eig[(size_t)i];
+    }
+    row[0] = (double)iter_; row[1] = prim_obj_.get(iter_); row[2] = dual_obj_.get(iter_); row[3] = dual_gap_.get(iter_);
+    row[4] = feasibility_.get(iter_); row[5] = primal_residual_.get(iter_); row[6] = dual_residual_.get(iter_);
+    row[7] = primal_step_; row[8] = beta_; row[9] = tr; row[10] = cr; row[11] = me;
+    row[12] = (double)(lanczos_matvecs - trace_mv0_); row[13] = (double)(linesearch_trials - trace_ls0_);
+    out->trace_len++;
+}
+
+// ---------------------------------------------------------------------------
+// chambolle_pock main loop (pdhg.jl:145-530)
+// ---------------------------------------------------------------------------
+void Solver::solve(proxsdp_result_t* out) {
+    time0_ = now_s();
+    out->trace_len = 0;
+    long long ada_count = 0;
+    bool have_cached = false;
+    auto append = [&](const char* s) { stop_reason_string_ += s; };
+
+    // advanced initialisation (pdhg.jl:138-142): x = tau*c ; Mx = M x ; Mx_old = M*0 = 0
+    if (opt.advanced_initialization) {
+        std::vector<double> x0((size_t)n);
+        for (long long i = 0; i < n; ++i) x0[(size_t)i] = primal_step_ * c_host_[(size_t)i];
+        PB_CUDA(cudaMemcpy(x_[cur_].p, x0.data(), sizeof(double) * (size_t)n, cudaMemcpyHostToDevice));
+        PB_CUDA(cudaMemsetAsync(scal_d_.p, 0, sizeof(double) * (size_t)scal_len, stream));
+        // pdhg.jl:140 writes a.Mx; the first primal_step! overwrites it, and a.Mx_old = M*x_old = 0.
+        launch_spmv(M_, x_[cur_].p, Mx_[cur_].p);
+        PB_CUDA(cudaMemsetAsync(Mx_[cur_].p, 0, sizeof(double) * (size_t)std::max<long long>(R, 1), stream));
+    }
+    out->time_setup = 0.0;   // filled by the caller (constructor time)
+    double t_loop0 = now_s();
+
+    const long long kmax = 2 * opt.max_iter_local;
+    for (long long k = 1; k <= kmax; ++k) {
+        iter_ = k;
+        trace_mv0_ = lanczos_matvecs; trace_ls0_ = linesearch_trials;
+        // ------------------------------------------------------------------ device work
+        reset_scalars();
+        double tau_primal = primal_step_;                       // pdhg.jl:622 uses the current step
+        psd_projection_launch(k, tau_primal, false);
+        double tau0 = opt.line_search_flag ? primal_step_ * std::sqrt(1.0 + theta_) : primal_step_;   // pdhg.jl:541
+        launch_post_eig(tau0, true);
+        sync_scalars();
+        if (n_sdp > 0) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, ev_psd0_, ev_psd1_) == cudaSuccess) time_psd_ms_ += ms;
+            n_psd_++;
+        }
+        // ---- Krylov fallback (prox_operators.jl:55-57): redo the failed cones exactly, then the tail
+        if (scal_host[S_POISON] != 0.0) {
+            fallback_projection(k);
+            launch_post_eig(tau0, false);
+            double keep_ops = scal_host[S_NUMOPS];
+            sync_scalars();
+            scal_host[S_NUMOPS] = keep_ops;
+        }
+        // ---- linesearch beyond the speculative ladder (pdhg.jl:543-571)
+        long long evals = (long long)scal_host[S_LS_EVALS];
+        if (opt.line_search_flag && scal_host[S_LS_ACCEPTED] == 0.0) {
+            long long t = ladder_;
+            while (scal_host[S_LS_ACCEPTED] == 0.0 && t < opt.max_linsearch_steps) {
+                launch_dual_trial((int)t, tau0);
+                sync_scalars();
+                ++t;
+            }
+            evals = t;
+            if (scal_host[S_LS_ACCEPTED] == 0.0) {
+                // loop exhausted: the reference keeps the last trial's y/Mty and the once-more decayed step
+                double tau = tau0;
+                for (long long q = 0; q < opt.max_linsearch_steps; ++q) tau *= opt.linsearch_decay;
+                double rec[3] = {1.0, (double)(opt.max_linsearch_steps - 1), tau};
+                PB_CUDA(cudaMemcpyAsync(scal_d_.p + S_LS_ACCEPTED, rec, sizeof(rec), cudaMemcpyHostToDevice, stream));
+                PB_CUDA(cudaStreamSynchronize(stream));
+            }
+            int blocksN = std::max(1, std::min(reduce_blocks_, ceil_div(n, 512)));
+            k_residual_primal<<<blocksN, 256, 0, stream>>>(n, x_[1 - cur_].p, x_[cur_].p, Mty_[1 - cur_].p, Mty_[cur_].p, c_.p, scal_d_.p, ws_);
+            int blocksR = std::max(1, std::min(reduce_blocks_, ceil_div(R, 256)));
+            k_residual_dual<<<blocksR, 256, 0, stream>>>((int)p, (int)m, beta_, 1, dual_step_, y_[1 - cur_].p, y_[cur_].p,
+                                                         Mx_[1 - cur_].p, Mx_[cur_].p, b_.p, h_.p, scal_d_.p, ws_);
+            launches += 2;
+            sync_scalars();
+        }
+        linesearch_trials += std::max<long long>(evals, 1);
+        lanczos_matvecs += (long long)scal_host[S_NUMOPS];
+
+        // ------------------------------------------------------------------ host scalars
+        // linesearch! epilogue (pdhg.jl:577-579) / dual_step! (pdhg.jl:606)
+        if (opt.line_search_flag) {
+            primal_step_ = scal_host[S_TAU];
+            theta_ = primal_step_ / primal_step_old_;
+            primal_step_old_ = primal_step_;
+            dual_step_ = beta_ * primal_step_;
+        } else {
+            primal_step_old_ = primal_step_;
+        }
+        for (int q = 0; q < n_sdp; ++q) {
+            current_rank[(size_t)q] = (long long)scal_host[S_HEADER + 3 * q + 0];
+            min_eig[(size_t)q] = scal_host[S_HEADER + 3 * q + 1];
+        }
+        soc_gap_max_ = n_soc > 0 ? scal_host[S_SOC_GAP] : -1.0;
+        // compute_residual! (residuals.jl:37-71)
+        {
+            double den = jl_max(jl_max(scal_host[S_RES_P_DEN], norm_b_), jl_max(norm_h_, 1.0));
+            double pr = std::sqrt((double)n) * scal_host[S_RES_P_NUM] / den;
+            double den2 = jl_max(jl_max(scal_host[S_RES_D_DEN], norm_c_), 1.0);
+            double dr = std::sqrt((double)R) * scal_host[S_RES_D_NUM] / den2;
+            primal_residual_.set(k, pr); dual_residual_.set(k, dr); comb_residual_.set(k, jl_max(pr, dr));
+        }
+        // compute_gap! (residuals.jl:2-35)
+        {
+            if (p > 0) equa_feasibility_ = scal_host[S_EQ_MAX] / (1.0 + norm_b_);
+            if (m > 0) ineq_feasibility_ = scal_host[S_IN_MAX] / (1.0 + norm_h_);
+            feasibility_.set(k, std::max(equa_feasibility_, ineq_feasibility_));
+            double po = scal_host[S_PRIM_OBJ], dobj = 0.0;
+            if (p > 0) dobj -= scal_host[S_BY];
+            if (m > 0) dobj -= scal_host[S_HY];
+            prim_obj_.set(k, po); dual_obj_.set(k, dobj);
+            dual_gap_.set(k, std::fabs(po - dobj) / (1.0 + std::fabs(po) + std::fabs(dobj)));
+        }
+        cur_ = 1 - cur_;    // keep-old copies (residuals.jl:65-68) are a pointer swap
+
+        if (opt.check_dual_feas && (k % opt.check_dual_feas_freq) == 0) {     // pdhg.jl:166-173
+            double f = stop_reason_ == 6 ? 0.0 : 1.0;
+            std::vector<double> cc((size_t)n);
+            for (long long i = 0; i < n; ++i) cc[(size_t)i] = f * c_orig_[(size_t)i];
+            std::vector<double> y = y_[cur_].download();
+            dual_feasibility_ = dual_feas_host(y, cc, nullptr);
+            dual_feasibility_check_ = true;
+        } else {
+            dual_feasibility_check_ = false;
+        }
+        record_trace(out);
+
+        if (iter_ < certificate_search_min_iter_) continue;                   // pdhg.jl:180-182
+
+        if (opt.certificate_search && certificate_search_) {                  // pdhg.jl:184-244
+            if (stop_reason_ == 6) {
+                if (dual_obj_.get(k) > +opt.certificate_obj_tol) {
+                    std::vector<double> cc((size_t)n, 0.0);
+                    std::vector<double> y = y_[cur_].download();
+                    dual_feasibility_ = dual_feas_host(y, cc, nullptr);
+                    dual_feasibility_check_ = true;
+                    if (dual_feasibility_ < opt.tol_feasibility_dual) {
+                        certificate_found_ = true;
+                        append(" [Dual ray found]");
+                        break;
+                    }
+                }
+            } else {
+                if (prim_obj_.get(k) < -opt.certificate_obj_tol) {
+                    if (feasibility_.get(iter_) < opt.tol_feasibility) {
+                        certificate_found_ = true;
+                        append(" [Primal ray found]");
+                        break;
+                    }
+                }
+            }
+            double cr = comb_residual_.get(k);
+            if ((prim_obj_.get(k) < -opt.certificate_fail_tol && dual_obj_.get(k) < -opt.certificate_fail_tol &&
+                 feasibility_.get(iter_) < -opt.certificate_fail_tol) || cr != cr) {
+                append(" [Failed to find certificate]");
+                break;
+            }
+        }
+
+        // convergence check (pdhg.jl:247-332)
+        rank_update_ += 1;
+        const double gap_k = dual_gap_.get(iter_), feas_k = feasibility_.get(iter_);
+        const double pr_k = primal_residual_.get(k), dr_k = dual_residual_.get(k);
+        if (gap_k <= opt.tol_gap && feas_k <= opt.tol_feasibility &&
+            (!opt.check_dual_feas || dual_feasibility_ < opt.tol_feasibility_dual)) {
+            bool conv_rank = true;                                            // residuals.jl:88-101
+            for (int q = 0; q < n_sdp; ++q)
+                if (!(cones[(size_t)q].side < opt.min_size_krylov_eigs || target_rank[(size_t)q] > opt.max_target_rank_krylov_eigs ||
+                      min_eig[(size_t)q] < opt.tol_psd)) { conv_rank = false; break; }
+            bool conv_soc = !(n_soc > 0 && soc_gap_max_ >= opt.tol_soc);      // residuals.jl:73-86
+            if (conv_rank && conv_soc && iter_ > opt.min_iter) {
+                if (!certificate_search_) {
+                    stop_reason_ = 1;
+                    stop_reason_string_ = "Optimal solution found";
+                } else {
+                    append(" [Failed to find certificate - type 2]");
+                    break;
+                }
+                break;
+            } else if (rank_update_ > window_) {
+                update_cont_ += 1;
+                if (update_cont_ > 0) {
+                    for (int q = 0; q < n_sdp; ++q) rank_increment_rule(q);
+                    rank_update_ = 0; update_cont_ = 0;
+                }
+            }
+        } else if (k > window_ && comb_residual_.get(k - window_) < comb_residual_.get(k) && rank_update_ > window_) {
+            update_cont_ += 1;
+            if (update_cont_ > opt.divergence_min_update) {
+                for (int q = 0; q < n_sdp; ++q) {
+                    if (target_rank[(size_t)q] < cones[(size_t)q].side) { rank_update_ = 0; update_cont_ = 0; }
+                    rank_increment_rule(q);
+                }
+            }
+        } else if (pr_k > opt.tol_primal && dr_k < opt.tol_dual && k > window_) {
+            ada_count += 1;
+            if (ada_count > opt.adapt_window) {
+                ada_count = 0;
+                if (opt.line_search_flag) { beta_ *= (1.0 - adapt_level_); primal_step_ /= std::sqrt(1.0 - adapt_level_); }
+                else { primal_step_ /= (1.0 - adapt_level_); dual_step_ *= (1.0 - adapt_level_); }
+                adapt_level_ *= opt.adapt_decay;
+            }
+        } else if (pr_k < opt.tol_primal && dr_k > opt.tol_dual && k > window_) {
+            ada_count += 1;
+            if (ada_count > opt.adapt_window) {
+                ada_count = 0;
+                if (opt.line_search_flag) { beta_ /= (1.0 - adapt_level_); primal_step_ *= std::sqrt(1.0 - adapt_level_); }
+                else { primal_step_ *= (1.0 - adapt_level_); dual_step_ /= (1.0 - adapt_level_); }
+                adapt_level_ *= opt.adapt_decay;
+            }
+        }
+
+        auto start_cert_infeas = [&]() {       // certificate_infeasibility (pdhg.jl:655-676)
+            std::fill(c_host_.begin(), c_host_.end(), 0.0);
+            PB_CUDA(cudaMemsetAsync(c_.p, 0, sizeof(double) * (size_t)std::max<long long>(n, 1), stream));
+            certificate_search_min_iter_ = iter_ + 2 * opt.convergence_window + iter_ / 5 + 1000;
+            certificate_search_ = true;
+            opt.time_limit *= 1.1;
+            opt.max_iter_local = opt.max_iter_local + opt.max_iter_local / 10;
+            cache_solution(c_orig_.data(), out); have_cached = true;
+        };
+        auto start_cert_dual_infeas = [&]() {  // certificate_dual_infeasibility (pdhg.jl:639-653)
+            std::fill(b_host_.begin(), b_host_.end(), 0.0);
+            std::fill(h_host_.begin(), h_host_.end(), 0.0);
+            PB_CUDA(cudaMemsetAsync(b_.p, 0, sizeof(double) * (size_t)std::max<long long>(p, 1), stream));
+            PB_CUDA(cudaMemsetAsync(h_.p, 0, sizeof(double) * (size_t)std::max<long long>(m, 1), stream));
+            certificate_search_min_iter_ = iter_ + 2 * opt.convergence_window + iter_ / 5 + 1000;
+            certificate_search_ = true;
+            opt.time_limit *= 1.1;
+            opt.max_iter_local = opt.max_iter_local + opt.max_iter_local / 10;
+            cache_solution(c_orig_.data(), out); have_cached = true;
+        };
+
+        // max_iter or time limit (pdhg.jl:335-382)
+        if (iter_ >= opt.max_iter_local || now_s() - time0_ >= opt.time_limit) {
+            if (iter_ > opt.min_iter_time_infeas && dual_gap_.max_abs_diff() < opt.infeas_stable_gap_tol &&
+                dual_gap_.get(k) > opt.infeas_limit_gap_tol) {
+                if (feasibility_.get(iter_) <= opt.tol_feasibility / 100) {
+                    stop_reason_ = 5;
+                    stop_reason_string_ = "Problem declared unbounded due to lack of improvement";
+                    if (opt.certificate_search && !certificate_search_) start_cert_dual_infeas();
+                    else if (opt.certificate_search && certificate_search_) {}
+                    else break;
+                } else if (feasibility_.get(iter_) > opt.infeas_feasibility_tol) {
+                    stop_reason_ = 6;
+                    stop_reason_string_ = "Problem declared infeasible due to lack of improvement";
+                    if (opt.certificate_search && !certificate_search_) start_cert_infeas();
+                    else if (opt.certificate_search && certificate_search_) {}
+                    else break;
+                }
+            } else if (iter_ >= opt.max_iter_local) {
+                stop_reason_ = 3;
+                stop_reason_string_ = "Iteration limit of " + std::to_string(opt.max_iter_local) + " was hit";
+            } else {
+                stop_reason_ = 2;
+                char buf[160];
+                snprintf(buf, sizeof(buf), "Time limit hit, limit: %g time: %g", opt.time_limit, now_s() - time0_);
+                stop_reason_string_ = buf;
+            }
+            if (iter_ >= opt.max_iter_local || now_s() - time0_ >= opt.time_limit) break;
+        }
+
+        if (opt.certificate_search && certificate_search_) continue;          // pdhg.jl:385-387
+
+        const double dobj_k = dual_obj_.get(k), pobj_k = prim_obj_.get(k);
+        char buf[200];
+        if ((iter_ > opt.min_iter_max_obj && dobj_k > opt.max_obj) || dobj_k != dobj_k) {        // pdhg.jl:390-405
+            stop_reason_ = 6;
+            snprintf(buf, sizeof(buf), "Infeasible: |Dual objective| = %g > maximum allowed = %g", dobj_k, opt.max_obj);
+            stop_reason_string_ = buf;
+            if (opt.certificate_search && !certificate_search_) start_cert_infeas(); else break;
+        }
+        if ((iter_ > opt.min_iter_max_obj && pobj_k < -opt.max_obj) || pobj_k != pobj_k) {        // pdhg.jl:408-422
+            stop_reason_ = 5;
+            snprintf(buf, sizeof(buf), "Unbounded: |Primal objective| = %g > maximum allowed = %g", pobj_k, opt.max_obj);
+            stop_reason_string_ = buf;
+            if (opt.certificate_search && !certificate_search_) start_cert_dual_infeas(); else break;
+        }
+        if (iter_ > opt.min_iter_max_obj && dual_gap_.get(k) > opt.infeas_limit_gap_tol &&       // pdhg.jl:425-444
+            feasibility_.get(iter_) > opt.infeas_feasibility_tol &&
+            feasibility_.max_abs_diff() < opt.infeas_stable_feasibility_tol) {
+            stop_reason_ = 6;
+            snprintf(buf, sizeof(buf), "Infeasible: feasibility stalled at %g", feasibility_.get(iter_));
+            stop_reason_string_ = buf;
+            if (opt.certificate_search && !certificate_search_) start_cert_infeas(); else break;
+        }
+        if (iter_ > opt.min_iter_max_obj && dual_gap_.get(k) > 1 - opt.infeas_gap_tol &&        // pdhg.jl:447-483
+            dual_gap_.max_abs_diff() < opt.infeas_stable_gap_tol) {
+            if (std::fabs(dobj_k) > std::fabs(pobj_k) && feasibility_.get(iter_) > opt.infeas_feasibility_tol) {
+                stop_reason_ = 6;
+                stop_reason_string_ = "Infeasible: duality gap stalled at 100 % with |Dual objective| >> |Primal objective|";
+                if (opt.certificate_search && !certificate_search_) start_cert_infeas(); else break;
+            } else if (std::fabs(pobj_k) > std::fabs(dobj_k) && feasibility_.get(iter_) <= opt.tol_feasibility) {
+                stop_reason_ = 5;
+                stop_reason_string_ = "Unbounded: duality gap stalled at 100 % with |Dual objective| << |Primal objective|";
+                if (opt.certificate_search && !certificate_search_) start_cert_dual_infeas(); else break;
+            }
+        }
+    }
+    out->time_loop = now_s() - t_loop0;
+
+    // results (pdhg.jl:486-529)
+    if (opt.certificate_search && certificate_search_) {
+        if (certificate_found_) {
+            if (stop_reason_ == 6) std::fill(c_orig_.begin(), c_orig_.end(), 0.0);
+            cache_solution(c_orig_.data(), out);
+        } else if (!have_cached) {
+            cache_solution(c_orig_.data(), out);
+        }
+    } else {
+        cache_solution(c_orig_.data(), out);
+    }
+    out->time_psd_proj = time_psd_ms_ * 1e-3;
+    out->n_psd_proj = n_psd_;
+    out->lanczos_matvecs = lanczos_matvecs;
+    out->lanczos_calls = lanczos_calls;
+    out->full_eig_calls = full_eig_calls;
+    out->linesearch_trials = linesearch_trials;
+    out->gpu_launches = launches;
+    if (out->target_rank) for (int q = 0; q < n_sdp; ++q) out->target_rank[q] = target_rank[(size_t)q];
+}
+
+}  // namespace pb
+
+// ===========================================================================
+// C ABI
+// ===========================================================================
+using namespace pb;
+
+template <class F>
+static int guarded(F&& f) {
+    try {
+        f();
+        return 0;
+    } catch (const CudaError& e) {
+        g_last_error = e.what();
+        cudaGetLastError();
+        return e.code;
+    } catch (const std::bad_alloc&) {
+        g_last_error = "host allocation failed";
+        return -4;
+    } catch (const std::exception& e) {
+        g_last_error = e.what();
+        return -1;
+    }
+}
+
+// a problem that consists of variable cones only (no rows, zero objective)
+struct ConesOnlyProblem {
+    std::vector<int64_t> sdp_ptr, sdp_idx, soc_ptr, soc_idx;
+    std::vector<double> zeros;
+    proxsdp_problem_t pr{};
+    ConesOnlyProblem(int64_t n_sdp, const int64_t* sides, int64_t n_soc, const int64_t* lens, const double* resid) {
+        int64_t N = 0;
+        sdp_ptr.assign((size_t)n_sdp + 1, 0);
+        for (int64_t k = 0; k < n_sdp; ++k) { N += sides[k] * (sides[k] + 1) / 2; sdp_ptr[(size_t)k + 1] = N; }
+        int64_t Npsd = N;
+        soc_ptr.assign((size_t)n_soc + 1, 0);
+        for (int64_t k = 0; k < n_soc; ++k) { N += lens[k]; soc_ptr[(size_t)k + 1] = N - Npsd; }
+        sdp_idx.resize((size_t)Npsd);
+        std::iota(sdp_idx.begin(), sdp_idx.end(), (int64_t)0);
+        soc_idx.resize((size_t)(N - Npsd));
+        std::iota(soc_idx.begin(), soc_idx.end(), Npsd);
+        zeros.assign((size_t)std::max<int64_t>(N, 1), 0.0);
+        pr.n = N; pr.p = 0; pr.m = 0; pr.index_base = 0;
+        pr.b = zeros.data(); pr.h = zeros.data(); pr.c = zeros.data();
+        pr.n_sdp = n_sdp; pr.sdp_side = sides; pr.sdp_ptr = sdp_ptr.data(); pr.sdp_idx = sdp_idx.data();
+        pr.n_soc = n_soc; pr.soc_ptr = soc_ptr.data(); pr.soc_idx = soc_idx.data();
+        pr.eig_resid = resid;
+    }
+};
+
+extern "C" {
+
+int proxsdp_b200_solve(const proxsdp_problem_t* problem, const proxsdp_options_t* options, proxsdp_result_t* result) {
+    if (!problem || !options || !result) { g_last_error = "null argument"; return -1; }
+    return guarded([&]() {
+        double t0 = now_s();
+        Solver s(problem, options);
+        double t_setup = now_s() - t0;
+        s.solve(result);
+        result->time_setup = t_setup;
+        result->time += t_setup;    // the reference's clock (p.time0, pdhg.jl:13) starts before the Init block
+    });
+}
+
+int proxsdp_b200_psd_project(int64_t n_sdp, const int64_t* sides, double* x, const int64_t* target_rank,
+                             const proxsdp_options_t* options, int64_t iter, int64_t mode, const double* resid,
+                             int64_t* current_rank, double* min_eig, int64_t* converged, int64_t* numops,
+                             int64_t repeat, double* ms_per_call) {
+    if (n_sdp < 0 || !sides || !x || !target_rank || !options) { g_last_error = "null argument"; return -1; }
+    return guarded([&]() {
+        ConesOnlyProblem cp(n_sdp, sides, 0, nullptr, resid);
+        proxsdp_options_t o = *options;
+        int64_t max_tr = 2;
+        for (int64_t k = 0; k < n_sdp; ++k) max_tr = std::max(max_tr, target_rank[k]);
+        o.initial_target_rank = max_tr;      // sizes the Lanczos workspaces
+        Solver s(&cp.pr, &o, /*cones_only=*/true);
+        for (int64_t k = 0; k < n_sdp; ++k) s.target_rank[(size_t)k] = target_rank[k];
+        PB_CUDA(cudaMemcpy(s.x_[0].p, x, sizeof(double) * (size_t)cp.pr.n, cudaMemcpyHostToDevice));
+        cudaEvent_t e0, e1;
+        PB_CUDA(cudaEventCreate(&e0)); PB_CUDA(cudaEventCreate(&e1));
+        int64_t reps = std::max<int64_t>(repeat, 1);
+        double total_ms = 0.0;
+        for (int64_t r = 0; r < reps; ++r) {
+            s.cur_ = 0;
+            s.reset_scalars();
+            PB_CUDA(cudaEventRecord(e0, s.stream));
+            s.psd_projection_launch(iter, 0.0, mode == 1);
+            PB_CUDA(cudaEventRecord(e1, s.stream));
+            s.sync_scalars();
+            float ms = 0.f;
+            PB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+            total_ms += ms;
+            if (s.scal_host[S_POISON] != 0.0) {
+                double ops = s.scal_host[S_NUMOPS];
+                s.fallback_projection(iter);
+                s.sync_scalars();
+                s.scal_host[S_NUMOPS] = ops;
+            }
+        }
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+        PB_CUDA(cudaMemcpy(x, s.x_[1].p, sizeof(double) * (size_t)cp.pr.n, cudaMemcpyDeviceToHost));
+        for (int64_t k = 0; k < n_sdp; ++k) {
+            if (current_rank) current_rank[k] = (int64_t)s.scal_host[S_HEADER + 3 * k + 0];
+            if (min_eig) min_eig[k] = s.scal_host[S_HEADER + 3 * k + 1];
+            if (converged) converged[k] = (int64_t)s.scal_host[S_HEADER + 3 * k + 2];
+        }
+        if (numops) *numops = (int64_t)s.scal_host[S_NUMOPS];
+        if (ms_per_call) *ms_per_call = total_ms / (double)reps;
+    });
+}
+
+int proxsdp_b200_soc_project(int64_t n_soc, const int64_t* lens, double* x) {
+    if (n_soc < 0 || (n_soc > 0 && (!lens || !x))) { g_last_error = "null argument"; return -1; }
+    return guarded([&]() {
+        ConesOnlyProblem cp(0, nullptr, n_soc, lens, nullptr);
+        proxsdp_options_t o{};
+        o.eigsolver_min_lanczos = 25; o.max_target_rank_krylov_eigs = 16; o.convergence_window = 200;
+        o.approx_norm = 1;
+        Solver s(&cp.pr, &o, /*cones_only=*/true);
+        if (n_soc == 0) return;
+        PB_CUDA(cudaMemcpy(s.x_[1].p, x, sizeof(double) * (size_t)cp.pr.n, cudaMemcpyHostToDevice));
+        s.cur_ = 0;
+        s.reset_scalars();
+        s.launch_soc_only();
+        s.sync_scalars();
+        PB_CUDA(cudaMemcpy(x, s.x_[1].p, sizeof(double) * (size_t)cp.pr.n, cudaMemcpyDeviceToHost));
+    });
+}
+
+int proxsdp_b200_lanczos(int64_t n, const double* A, const double* x0, int64_t howmany, int64_t krylovdim,
+                         int64_t maxiter, double tol, double* vals, double* vecs, int64_t* nvals,
+                         int64_t* converged, int64_t* numops, int64_t* numiter, int64_t repeat, double* ms_per_call) {
+    if (n < 1 || !A || !x0 || !vals || howmany < 1 || krylovdim < howmany) { g_last_error = "invalid argument"; return -1; }
+    return guarded([&]() {
+        int64_t side = n;
+        ConesOnlyProblem cp(1, &side, 0, nullptr, x0);
+        proxsdp_options_t o{};
+        o.eigsolver_min_lanczos = krylovdim; o.max_target_rank_krylov_eigs = howmany; o.convergence_window = 200;
+        o.approx_norm = 1; o.krylovkit_resid_init = 3;
+        Solver s(&cp.pr, &o, /*cones_only=*/true, /*force_large=*/true);
+        ConeDev& cd = s.cones[0];
+        PB_CUDA(cudaMemcpy2D(cd.X.p, sizeof(double) * (size_t)cd.ld, A, sizeof(double) * (size_t)n,
+                             sizeof(double) * (size_t)n, (size_t)n, cudaMemcpyHostToDevice));
+        cudaEvent_t e0, e1;
+        PB_CUDA(cudaEventCreate(&e0)); PB_CUDA(cudaEventCreate(&e1));
+        int64_t reps = std::max<int64_t>(repeat, 1);
+        double total_ms = 0.0;
+        for (int64_t r = 0; r < reps; ++r) {
+            s.reset_scalars();
+            PB_CUDA(cudaEventRecord(e0, s.stream));
+            s.lanczos_launch(cd, 0, (int)howmany, (int)krylovdim, (int)maxiter, tol);
+            PB_CUDA(cudaEventRecord(e1, s.stream));
+            s.sync_scalars();
+            float ms = 0.f;
+            PB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+            total_ms += ms;
+        }
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+        std::vector<int> info = cd.info.download();
+        std::vector<double> v = cd.vals.download();
+        int nv = info[0];
+        for (int i = 0; i < nv; ++i) vals[i] = v[(size_t)i];
+        if (vecs)
+            PB_CUDA(cudaMemcpy2D(vecs, sizeof(double) * (size_t)n, cd.Y.p, sizeof(double) * (size_t)cd.ld,
+                                 sizeof(double) * (size_t)n, (size_t)nv, cudaMemcpyDeviceToHost));
+        if (nvals) *nvals = nv;
+        if (converged) *converged = info[1];
+        if (numops) *numops = info[2];
+        if (numiter) *numiter = info[3];
+        if (ms_per_call) *ms_per_call = total_ms / (double)reps;
+    });
+}
+
+int proxsdp_b200_eigh(int64_t n, const double* A, double* w, double* Z) {
+    if (n < 1 || !A || !w) { g_last_error = "invalid argument"; return -1; }
+    return guarded([&]() {
+        int64_t side = n;
+        ConesOnlyProblem cp(1, &side, 0, nullptr, nullptr);
+        proxsdp_options_t o{};
+        o.eigsolver_min_lanczos = 25; o.max_target_rank_krylov_eigs = 16; o.convergence_window = 200;
+        o.approx_norm = 1; o.krylovkit_resid_init = 1;
+        Solver s(&cp.pr, &o, /*cones_only=*/true, /*force_large=*/true);
+        ConeDev& cd = s.cones[0];
+        PB_CUDA(cudaMemcpy2D(cd.X.p, sizeof(double) * (size_t)cd.ld, A, sizeof(double) * (size_t)n,
+                             sizeof(double) * (size_t)n, (size_t)n, cudaMemcpyHostToDevice));
+        std::vector<double> ev = s.full_eig_device(cd);
+        std::vector<int> order((size_t)n);
+        std::iota(order.begin(), order.end(), 0);
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return ev[(size_t)a] < ev[(size_t)b]; });
+        for (int64_t i = 0; i < n; ++i) w[i] = ev[(size_t)order[(size_t)i]];
+        if (Z) {
+            std::vector<double> V((size_t)n * (size_t)n);
+            PB_CUDA(cudaMemcpy2D(V.data(), sizeof(double) * (size_t)n, cd.Vfull.p, sizeof(double) * (size_t)cd.ld,
+                                 sizeof(double) * (size_t)n, (size_t)n, cudaMemcpyDeviceToHost));
+            for (int64_t j = 0; j < n; ++j)
+                std::memcpy(Z + j * n, V.data() + (size_t)order[(size_t)j] * (size_t)n, sizeof(double) * (size_t)n);
+        }
+    });
+}
+
+int proxsdp_b200_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+const char* proxsdp_b200_last_error(void) { return g_last_error.c_str(); }
+const char* proxsdp_b200_version(void) { return "proxsdp_b200 0.1.0 (sm_100a)"; }
+int64_t proxsdp_b200_sizeof_problem(void) { return (int64_t)sizeof(proxsdp_problem_t); }
+int64_t proxsdp_b200_sizeof_options(void) { return (int64_t)sizeof(proxsdp_options_t); }
+int64_t proxsdp_b200_sizeof_result(void) { return (int64_t)sizeof(proxsdp_result_t); }
+
+}  // extern "C"

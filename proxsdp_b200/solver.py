@@ -1,0 +1,144 @@
+"""ctypes binding of the CUDA library behind the reference's `chambolle_pock` seam.
+
+The product path has NO CPU fallback: if `libproxsdp_b200.so` is missing or no CUDA
+device is present, every entry point raises.  (The CPU oracle lives under oracle/ and
+is test infrastructure only.)
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_double, c_int, c_int64
+
+import numpy as np
+
+from ._abi import OptionsPOD, ProblemPOD, ResultPOD, bind_solve, call_solve
+from .options import Options
+from .structs import AffineSets, ConicSets, Result
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libproxsdp_b200.so")
+_lib = None
+
+_pd = POINTER(c_double)
+_pi = POINTER(c_int64)
+
+
+class ExtensionMissing(RuntimeError):
+    pass
+
+
+def lib():
+    """Load the CUDA extension; fail loudly when it is absent or its ABI does not match."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ExtensionMissing(
+            f"{LIB_PATH} not found: build it with `python -m proxsdp_b200.build` "
+            "(there is no CPU fallback for the product path)")
+    L = ctypes.CDLL(LIB_PATH)
+    L.proxsdp_b200_last_error.restype = c_char_p
+    L.proxsdp_b200_version.restype = c_char_p
+    for nm in ("problem", "options", "result"):
+        getattr(L, f"proxsdp_b200_sizeof_{nm}").restype = c_int64
+    if (L.proxsdp_b200_sizeof_problem() != ctypes.sizeof(ProblemPOD)
+            or L.proxsdp_b200_sizeof_options() != ctypes.sizeof(OptionsPOD)
+            or L.proxsdp_b200_sizeof_result() != ctypes.sizeof(ResultPOD)):
+        raise ExtensionMissing("ABI mismatch between proxsdp_b200/_abi.py and libproxsdp_b200.so")
+    L.proxsdp_b200_psd_project.argtypes = [c_int64, _pi, _pd, _pi, POINTER(OptionsPOD), c_int64, c_int64, _pd,
+                                           _pi, _pd, _pi, _pi, c_int64, _pd]
+    L.proxsdp_b200_psd_project.restype = c_int
+    L.proxsdp_b200_soc_project.argtypes = [c_int64, _pi, _pd]
+    L.proxsdp_b200_soc_project.restype = c_int
+    L.proxsdp_b200_lanczos.argtypes = [c_int64, _pd, _pd, c_int64, c_int64, c_int64, c_double, _pd, _pd,
+                                       _pi, _pi, _pi, _pi, c_int64, _pd]
+    L.proxsdp_b200_lanczos.restype = c_int
+    L.proxsdp_b200_eigh.argtypes = [c_int64, _pd, _pd, _pd]
+    L.proxsdp_b200_eigh.restype = c_int
+    L.proxsdp_b200_device_count.restype = c_int
+    _lib = L
+    return L
+
+
+def _check(rc: int):
+    if rc != 0:
+        raise RuntimeError(f"proxsdp_b200 error {rc}: {lib().proxsdp_b200_last_error().decode()}")
+
+
+def device_count() -> int:
+    return int(lib().proxsdp_b200_device_count())
+
+
+def _dp(a):
+    return a.ctypes.data_as(_pd)
+
+
+def _ip(a):
+    return a.ctypes.data_as(_pi)
+
+
+def chambolle_pock(aff: AffineSets, con: ConicSets, opt: Options, eig_resid=None) -> Result:
+    """Drop-in for reference src/pdhg.jl:1 `chambolle_pock(affine_sets, conic_sets, opt)::Result`."""
+    L = lib()
+    fn = bind_solve(L, "proxsdp_b200_solve")
+    return call_solve(fn, aff, con, opt, eig_resid, err_fn=L.proxsdp_b200_last_error)
+
+
+def psd_project(sides, x, target_rank, opt: Options, iter: int = 1, mode: int = 0, resid=None, repeat: int = 1):
+    """One `psd_projection!` (reference src/prox_operators.jl:33-66) on concatenated svec blocks.
+    Returns (x_projected, current_rank, min_eig, converged, numops, ms_per_call)."""
+    sides = np.ascontiguousarray(sides, dtype=np.int64)
+    x = np.ascontiguousarray(x, dtype=np.float64).copy()
+    tr = np.ascontiguousarray(target_rank, dtype=np.int64)
+    k = len(sides)
+    cur = np.zeros(max(k, 1), dtype=np.int64)
+    mineig = np.zeros(max(k, 1))
+    conv = np.zeros(max(k, 1), dtype=np.int64)
+    nops = c_int64(0)
+    ms = c_double(0.0)
+    opod = opt.to_pod()
+    if resid is not None:
+        resid = np.ascontiguousarray(resid, dtype=np.float64)
+        rp = _dp(resid)
+    else:
+        rp = ctypes.cast(None, _pd)
+    _check(lib().proxsdp_b200_psd_project(k, _ip(sides), _dp(x), _ip(tr), ctypes.byref(opod), iter, mode, rp,
+                                          _ip(cur), _dp(mineig), _ip(conv), ctypes.byref(nops), repeat,
+                                          ctypes.byref(ms)))
+    return x, cur[:k], mineig[:k], conv[:k], nops.value, ms.value
+
+
+def soc_project(lens, x):
+    """`soc_projection!` (reference src/prox_operators.jl:138-158)."""
+    lens = np.ascontiguousarray(lens, dtype=np.int64)
+    x = np.ascontiguousarray(x, dtype=np.float64).copy()
+    _check(lib().proxsdp_b200_soc_project(len(lens), _ip(lens), _dp(x)))
+    return x
+
+
+def lanczos(A, x0, howmany: int, krylovdim: int, maxiter: int = 100, tol: float = 1e-12, repeat: int = 1):
+    """KrylovKit-style eigsolve(:LR) on the device (reference src/eigsolver.jl:802-812)."""
+    A = np.asfortranarray(A, dtype=np.float64)
+    n = A.shape[0]
+    x0 = np.ascontiguousarray(x0, dtype=np.float64)
+    vals = np.zeros(krylovdim)
+    vecs = np.zeros((n, krylovdim), order="F")
+    nv, conv, nops, nit = (c_int64(0) for _ in range(4))
+    ms = c_double(0.0)
+    _check(lib().proxsdp_b200_lanczos(n, _dp(A), _dp(x0), howmany, krylovdim, maxiter, tol, _dp(vals), _dp(vecs),
+                                      ctypes.byref(nv), ctypes.byref(conv), ctypes.byref(nops), ctypes.byref(nit),
+                                      repeat, ctypes.byref(ms)))
+    k = nv.value
+    return vals[:k].copy(), vecs[:, :k].copy(), dict(converged=conv.value, numops=nops.value, numiter=nit.value,
+                                                     ms=ms.value)
+
+
+def eigh(A):
+    """Full symmetric eigendecomposition on the device (ascending)."""
+    A = np.asfortranarray(A, dtype=np.float64)
+    n = A.shape[0]
+    w = np.zeros(n)
+    Z = np.zeros((n, n), order="F")
+    _check(lib().proxsdp_b200_eigh(n, _dp(A), _dp(w), _dp(Z)))
+    return w, Z
