@@ -1,0 +1,303 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle.
+
+Tolerances (FP64 everywhere):
+  * kernel-level seams (eigh, lanczos, psd/soc projection): 1e-9 relative;
+  * exact-projection solves: per-iteration traces within 1e-6 relative (north_star bar);
+  * Krylov-mode solves: status identical, objective within the solver tolerance band of the
+    oracle and of the SDPLIB optimum (truncated projections are discontinuous, so trajectories
+    may differ after a near-degenerate eigen-gap — see DESIGN.md).
+"""
+import numpy as np
+import pytest
+
+from proxsdp_b200 import MAX_SENSE, MIN_SENSE, Optimizer, Options
+from proxsdp_b200.problems import (README_W, load_problem, maxcut_er_problem, maxcut_problem, mimo_problem,
+                                   sensorloc_problem, stack_problems)
+from proxsdp_b200.structs import ivec
+
+import problems_ref
+
+pytestmark = pytest.mark.gpu
+
+
+def _rand_sym(n, seed):
+    rng = np.random.default_rng(seed)
+    A = rng.standard_normal((n, n))
+    return A + A.T
+
+
+def _lowrank_plus_noise(n, r, seed, noise=0.01):
+    rng = np.random.default_rng(seed)
+    B = rng.standard_normal((n, r))
+    S = rng.standard_normal((n, n))
+    return B @ B.T - 0.1 * np.eye(n) + noise * (S + S.T)
+
+
+# ------------------------------------------------------------------ eigen back-ends
+@pytest.mark.parametrize("n", [1, 2, 5, 31, 64, 65, 101, 130, 300, 500])
+def test_eigh_parity(gpu, oracle_mod, n):
+    A = _rand_sym(n, n)
+    w, Z = gpu.eigh(A)
+    wo, _ = oracle_mod.eigh(np.triu(A))
+    assert np.abs(w - wo).max() <= 1e-9 * max(1.0, np.abs(wo).max())
+    assert np.abs(Z @ np.diag(w) @ Z.T - A).max() <= 1e-9 * np.abs(A).max() * n
+    assert np.abs(Z.T @ Z - np.eye(n)).max() <= 1e-10 * n
+
+
+@pytest.mark.parametrize("n,r,nev,K", [(101, 3, 2, 25), (150, 4, 2, 25), (300, 6, 4, 25), (500, 10, 8, 25),
+                                        (500, 20, 16, 33), (2000, 8, 6, 25), (600, 30, 25, 51)])
+def test_lanczos_parity(gpu, oracle_mod, n, r, nev, K):
+    A = _lowrank_plus_noise(n, r, n + nev)
+    x0 = oracle_mod.eig_resid(n)
+    vo, Vo, io = oracle_mod.lanczos(np.triu(A), x0, nev, K)
+    vg, Vg, ig = gpu.lanczos(A, x0, nev, K)
+    assert (ig["converged"], ig["numops"], ig["numiter"]) == (io["converged"], io["numops"], io["numiter"])
+    assert np.abs(vo - vg).max() <= 1e-9 * np.abs(vo).max()
+    assert np.abs(A @ Vg - Vg * vg).max() <= 1e-9 * np.abs(vo).max()
+    Po = (Vo[:, :nev] * vo[:nev]) @ Vo[:, :nev].T
+    Pg = (Vg[:, :nev] * vg[:nev]) @ Vg[:, :nev].T
+    assert np.abs(Po - Pg).max() <= 1e-8 * np.abs(vo).max()
+
+
+def test_lanczos_thick_restart_and_breakdown(gpu, oracle_mod):
+    n = 124
+    rng = np.random.default_rng(1)
+    Q, _ = np.linalg.qr(rng.standard_normal((n, n)))
+    x0 = oracle_mod.eig_resid(n)
+    for gap in (1e-1, 1e-5, 1e-9):
+        lam = np.concatenate([[10.0, 5.0, 5.0 - gap, 5.0 - 2 * gap, 4.0], np.linspace(3.0, -8.0, n - 5)])
+        A = (Q * lam) @ Q.T
+        A = 0.5 * (A + A.T)
+        vo, _, io = oracle_mod.lanczos(np.triu(A), x0, 2, 25)
+        vg, Vg, ig = gpu.lanczos(A, x0, 2, 25)
+        assert io["numiter"] > 1
+        assert (ig["converged"], ig["numops"], ig["numiter"]) == (io["converged"], io["numops"], io["numiter"])
+        assert np.abs(vo - vg).max() <= 1e-9
+        assert np.abs(A @ Vg - Vg * vg).max() <= 1e-9
+    # exact breakdown on the zero matrix (first PDHG iteration)
+    vg, _, ig = gpu.lanczos(np.zeros((n, n)), x0, 2, 25)
+    assert ig["converged"] == 1 and ig["numops"] == 1 and len(vg) == 1 and vg[0] == 0.0
+    # hard case: wanted eigenvalue inside a near-zero cluster -> runs into maxiter like KrylovKit would
+    lam = np.concatenate([[100.0, 80.0, 60.0, 50.0], np.linspace(1e-3, -1e-3, 20), np.linspace(-1.0, -60.0, n - 24)])
+    A = (Q * lam) @ Q.T
+    A = 0.5 * (A + A.T)
+    vo, _, io = oracle_mod.lanczos(np.triu(A), x0, 5, 25)
+    vg, _, ig = gpu.lanczos(A, x0, 5, 25)
+    assert (ig["converged"], ig["numops"], ig["numiter"]) == (io["converged"], io["numops"], io["numiter"])
+
+
+# ------------------------------------------------------------------ projections
+@pytest.mark.parametrize("sides,tr,mode", [
+    ([1, 1, 1], [2, 2, 2], 0),                  # 1x1 cones (prox_operators.jl:43-45)
+    ([2, 3, 7, 40, 65, 100], [2] * 6, 0),       # ragged batch of small cones: full eig
+    ([150], [3], 0), ([150], [3], 1),           # Krylov / forced full
+    ([600], [5], 0), ([600], [17], 0),          # target_rank > 16 -> full (prox_operators.jl:47)
+    ([120, 5, 300, 1, 64], [2, 2, 4, 2, 2], 0), # mixed large + small
+])
+def test_psd_projection_parity(gpu, oracle_mod, sides, tr, mode):
+    N = sum(s * (s + 1) // 2 for s in sides)
+    x = np.random.default_rng(N).standard_normal(N)
+    xo, co, mo, cvo, no = oracle_mod.psd_project(sides, x, tr, Options(), mode=mode)
+    xg, cg, mg, cvg, ng, _ = gpu.psd_project(sides, x, tr, Options(), mode=mode)
+    assert np.abs(xo - xg).max() <= 1e-9 * max(1.0, np.abs(xo).max())
+    assert list(co) == list(cg) and list(cvo) == list(cvg) and no == ng
+    assert np.allclose(mo, mg, rtol=1e-9, atol=1e-9)
+
+
+def test_psd_projection_zero_and_psd_inputs(gpu):
+    side = 130
+    N = side * (side + 1) // 2
+    xg, cg, mg, cvg, ng, _ = gpu.psd_project([side], np.zeros(N), [2], Options())
+    assert np.all(xg == 0) and cg[0] == 0 and cvg[0] == 1 and ng == 1
+    # a rank-2 PSD matrix is a fixed point of the rank-2 projection
+    rng = np.random.default_rng(3)
+    B = rng.standard_normal((side, 2))
+    X = B @ B.T
+    ii, jj = np.triu_indices(side)
+    order = np.lexsort((ii, jj))
+    ii, jj = ii[order], jj[order]
+    x = np.where(ii != jj, X[ii, jj] * np.sqrt(2.0), X[ii, jj])
+    xg, cg, mg, _, _, _ = gpu.psd_project([side], x, [2], Options())
+    assert np.abs(xg - x).max() <= 1e-9 * np.abs(x).max() and cg[0] == 2
+
+
+def test_soc_projection_parity(gpu, oracle_mod):
+    rng = np.random.default_rng(5)
+    lens = [1, 2, 3, 10, 257, 1000, 4, 4, 4]
+    x = rng.standard_normal(sum(lens))
+    off = np.cumsum([0] + lens)
+    x[off[6]] = 100.0        # inside the cone: untouched
+    x[off[7]] = -100.0       # inside the polar cone: zeroed
+    xo = oracle_mod.soc_project(lens, x)
+    xg = gpu.soc_project(lens, x)
+    assert np.abs(xo - xg).max() <= 1e-12
+    assert np.all(xg[off[7]:off[8]] == 0.0) and np.all(xg[off[6]:off[7]] == x[off[6]:off[7]])
+    assert gpu.soc_project([], np.zeros(0)).size == 0
+
+
+# ------------------------------------------------------------------ whole solves
+@pytest.mark.parametrize("fn", problems_ref.ALL, ids=lambda f: f.__name__)
+def test_reference_unit_problems_gpu(gpu, fn):
+    problems_ref.check(fn(Optimizer()))
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(eigsolver=1, min_size_krylov_eigs=1), dict(eigsolver=2, min_size_krylov_eigs=1),
+                                dict(full_eig_decomp=True)], ids=str)
+def test_sdp_wiki_all_eig_paths_gpu(gpu, kw):
+    problems_ref.check(problems_ref.sdp_wiki(Optimizer(**kw), MIN_SENSE))
+    problems_ref.check(problems_ref.sdp_wiki(Optimizer(**kw), MAX_SENSE))
+
+
+def test_termination_statuses_gpu(gpu):
+    o = Optimizer(max_iter=1)
+    problems_ref.sdp_wiki(o)
+    assert o.termination_status() == "ITERATION_LIMIT"
+    o = Optimizer(time_limit=0.0)
+    problems_ref.sdp_wiki(o)
+    assert o.termination_status() == "TIME_LIMIT"
+    o = Optimizer()
+    x = o.add_variables(1)
+    o.add_equal_to([(1.0, x[0])], 1.0)
+    o.add_equal_to([(1.0, x[0])], 2.0)
+    o.set_objective(MIN_SENSE, [(1.0, x[0])])
+    o.optimize()
+    assert o.termination_status() == "INFEASIBLE"
+    o = Optimizer()
+    x = o.add_variables(1)
+    o.add_greater_than([(1.0, x[0])], 0.0)
+    o.set_objective(MAX_SENSE, [(1.0, x[0])])
+    o.optimize()
+    assert o.termination_status() == "DUAL_INFEASIBLE"
+
+
+def _compare_results(rg, ro, rtol):
+    assert rg.status == ro.status and rg.iter == ro.iter
+    for name in ("objval", "dual_objval", "gap", "primal_residual", "dual_residual", "final_primal_res", "final_dual_res"):
+        a, b = getattr(rg, name), getattr(ro, name)
+        assert abs(a - b) <= rtol * max(1.0, abs(b)), (name, a, b)
+    scale = max(1.0, np.abs(ro.primal).max())
+    assert np.abs(rg.primal - ro.primal).max() <= rtol * scale
+    assert np.abs(rg.dual_eq - ro.dual_eq).max(initial=0.0) <= rtol * max(1.0, np.abs(ro.dual_eq).max(initial=0.0))
+    assert np.abs(rg.dual_in - ro.dual_in).max(initial=0.0) <= rtol * max(1.0, np.abs(ro.dual_in).max(initial=0.0))
+    assert np.abs(rg.slack_eq - ro.slack_eq).max(initial=0.0) <= rtol * max(1.0, np.abs(ro.slack_eq).max(initial=0.0))
+    assert np.abs(rg.dual_cone - ro.dual_cone).max() <= rtol * max(1.0, np.abs(ro.dual_cone).max())
+    assert rg.primal_feasible_user_tol == ro.primal_feasible_user_tol
+    assert rg.dual_feasible_user_tol == ro.dual_feasible_user_tol
+
+
+def test_solve_readme_maxcut_vs_oracle_and_golden(gpu, oracle_mod, golden_dir):
+    """Config C1."""
+    aff, con, sgn = maxcut_problem(README_W)
+    opt = Options(tol_gap=1e-4, tol_feasibility=1e-4, trace_cap=200)
+    rg = gpu.chambolle_pock(aff, con, opt)
+    ro = oracle_mod.chambolle_pock(aff, con, opt)
+    _compare_results(rg, ro, 1e-6)
+    z = np.load(f"{golden_dir}/trace_readme_maxcut.npz")
+    assert rg.iter == int(z["iters"]) and abs(rg.objval - float(z["objval"])) <= 1e-6
+    assert np.abs(rg.trace[:, 1:9] - z["trace"][:, 1:9]).max() <= 1e-6 * max(1.0, np.abs(z["trace"][:, 1:9]).max())
+
+
+def test_solve_mimo_vs_oracle(gpu, oracle_mod, golden_dir):
+    """Config C4, single instance: inequality rows + small cone -> batched Jacobi path."""
+    aff, con = mimo_problem(7, 16)
+    opt = Options(trace_cap=2000)
+    rg = gpu.chambolle_pock(aff, con, opt)
+    ro = oracle_mod.chambolle_pock(aff, con, opt)
+    _compare_results(rg, ro, 1e-6)
+    z = np.load(f"{golden_dir}/trace_mimo16.npz")
+    assert rg.iter == int(z["iters"])
+    assert np.abs(rg.primal - z["primal"]).max() <= 1e-6
+
+
+def test_solve_mimo_stacked_batch(gpu, oracle_mod):
+    """Config C4 in miniature: a batch of independent cones in one stacked problem."""
+    probs = [mimo_problem(100 + s, 8) for s in range(12)]
+    aff, con = stack_problems(probs)
+    rg = gpu.chambolle_pock(aff, con, Options())
+    ro = oracle_mod.chambolle_pock(aff, con, Options())
+    _compare_results(rg, ro, 1e-6)
+    X = ivec(rg.primal[: probs[0][0].n])
+    assert np.all((np.abs(X) > 0.99) & (np.abs(X) < 1.01))      # test/moi_mimo.jl:71-75
+
+
+def test_solve_exact_mode_trace_mcp124(gpu, oracle_mod, golden_dir):
+    """Exact-projection mode on a real SDPLIB instance (block-Jacobi full eig, n = 124):
+    per-iteration KKT residuals / objectives within 1e-6 rel of the oracle and the golden trace."""
+    aff, con = load_problem(f"{golden_dir}/sdplib_mcp124-1.npz")
+    z = np.load(f"{golden_dir}/trace_mcp124-1_exact.npz")
+    iters = int(z["iters"])
+    opt = Options(full_eig_decomp=True, max_iter=iters, trace_cap=iters)
+    rg = gpu.chambolle_pock(aff, con, opt)
+    assert rg.iter == iters and rg.status == 3
+    ref = z["trace"][:, 1:9]
+    assert np.abs(rg.trace[:, 1:9] - ref).max() <= 1e-6 * max(1.0, np.abs(ref).max())
+    assert np.abs(rg.primal - z["primal"]).max() <= 1e-6 * max(1.0, np.abs(z["primal"]).max())
+
+
+@pytest.mark.parametrize("name,optimum", [("mcp124-1", -141.9905), ("gpp124-2", 46.8623), ("mcp250-1", -317.2643)])
+def test_solve_krylov_sdplib(gpu, oracle_mod, golden_dir, name, optimum):
+    """Krylov path at real size (the only place the reference's CI exercises it, test/moi_sdplib.jl:53-56)."""
+    aff, con = load_problem(f"{golden_dir}/sdplib_{name}.npz")
+    rg = gpu.chambolle_pock(aff, con, Options(trace_cap=100))
+    ro = oracle_mod.chambolle_pock(aff, con, Options(trace_cap=100))
+    assert rg.status == ro.status == 1
+    # first iterations are bit-for-bit the same algorithm: traces agree to 1e-6 before any near-degenerate gap
+    k = 40
+    assert np.abs(rg.trace[:k, 1:9] - ro.trace[:k, 1:9]).max() <= 1e-6 * max(1.0, np.abs(ro.trace[:k, 1:9]).max())
+    assert list(rg.trace[:k, 12]) == list(ro.trace[:k, 12])          # identical Lanczos mat-vec counts
+    assert abs(rg.objval - ro.objval) <= 2e-3 * abs(ro.objval)
+    assert abs(rg.objval - optimum) <= 5e-3 * abs(optimum)
+    X = ivec(rg.primal)
+    assert (np.linalg.eigvalsh(X) < -1e-4).sum() == 0                # minus_rank == 0
+    assert abs(rg.iter - ro.iter) <= 0.25 * ro.iter
+
+
+def test_solve_gpp500_long_row(gpu, golden_dir):
+    """gpp500-1 has one constraint row with 125 250 non-zeros (SpMV long-row path)."""
+    aff, con = load_problem(f"{golden_dir}/sdplib_gpp500-1.npz")
+    rg = gpu.chambolle_pock(aff, con, Options(max_iter=400, trace_cap=400))
+    assert rg.iter == 400 and np.all(np.isfinite(rg.trace))
+    # equality feasibility of the long row is what the long-row kernel feeds
+    assert rg.trace[-1, 4] < rg.trace[5, 4]
+
+
+def test_solve_mixed_soc_psd(gpu, oracle_mod):
+    """SOC + PSD cones in one problem (config C5 variant with an added SOC block)."""
+    aff, con = sensorloc_problem(0, 10, soc_variant=True)
+    rg = gpu.chambolle_pock(aff, con, Options())
+    ro = oracle_mod.chambolle_pock(aff, con, Options())
+    _compare_results(rg, ro, 1e-6)
+
+
+def test_solve_fixed_step_variant(gpu, oracle_mod):
+    """dual_step! (line_search_flag = false, pdhg.jl:584-609)."""
+    aff, con = mimo_problem(3, 8)
+    opt = Options(line_search_flag=False, max_iter=3000)
+    rg = gpu.chambolle_pock(aff, con, opt)
+    ro = oracle_mod.chambolle_pock(aff, con, opt)
+    _compare_results(rg, ro, 1e-6)
+
+
+# ------------------------------------------------------------------ full-size properties (config C2)
+def test_c2_fullsize_properties(gpu, oracle_mod):
+    """Max-Cut n = 2000 (BASELINE config): the oracle is too slow for a whole solve here, so
+    check size-independent properties of the GPU path plus a short trace against the oracle."""
+    aff, con = maxcut_er_problem(2000, 0.01, 0)
+    opt = Options(max_iter=30, trace_cap=30)
+    rg = gpu.chambolle_pock(aff, con, opt)
+    ro = oracle_mod.chambolle_pock(aff, con, opt)
+    assert np.abs(rg.trace[:, 1:9] - ro.trace[:, 1:9]).max() <= 1e-6 * max(1.0, np.abs(ro.trace[:, 1:9]).max())
+    assert list(rg.trace[:, 12]) == list(ro.trace[:, 12])
+    # projection properties on the final iterate's scale: idempotence and positive homogeneity
+    side = 2000
+    N = side * (side + 1) // 2
+    x = np.random.default_rng(0).standard_normal(N)
+    x1, c1, m1, cv1, _, _ = gpu.psd_project([side], x, [4], Options())
+    x2, c2, _, _, _, _ = gpu.psd_project([side], x1, [4], Options())
+    assert np.abs(x2 - x1).max() <= 1e-8 * np.abs(x1).max() and c1[0] == c2[0] == 4
+    x3, _, _, _, _, _ = gpu.psd_project([side], 3.0 * x, [4], Options())
+    assert np.abs(x3 - 3.0 * x1).max() <= 1e-8 * np.abs(x3).max()
+    # the projected matrix is PSD with rank <= 4: its 5th eigenvalue vanishes
+    X1 = ivec(np.where(np.isin(np.arange(N), [j * (j + 1) // 2 + j for j in range(side)]), x1, x1 / np.sqrt(2.0)))
+    w = np.linalg.eigvalsh(X1)
+    assert w.min() >= -1e-8 * w.max() and abs(w[-5]) <= 1e-8 * w.max()

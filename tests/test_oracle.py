@@ -1,0 +1,204 @@
+"""CPU tests: the oracle against the reference's own known answers and a LAPACK mirror."""
+import numpy as np
+import pytest
+
+from proxsdp_b200 import MAX_SENSE, MIN_SENSE, Optimizer, Options
+from proxsdp_b200.problems import (README_W, load_problem, maxcut_problem, mimo_problem, randsdp_problem,
+                                   sensorloc_problem)
+from proxsdp_b200.structs import ivec
+
+import problems_ref
+
+
+def _opt(oracle_mod, **kw):
+    return Optimizer(backend=oracle_mod.chambolle_pock, **kw)
+
+
+# ---------------------------------------------------------------- eigen routines
+@pytest.mark.parametrize("n", [1, 2, 3, 10, 65, 150])
+def test_oracle_eigh_vs_lapack(oracle_mod, n):
+    rng = np.random.default_rng(n)
+    A = rng.standard_normal((n, n))
+    A = A + A.T
+    w, Z = oracle_mod.eigh(np.triu(A))
+    assert np.allclose(w, np.linalg.eigvalsh(A), atol=1e-11 * max(1, n))
+    assert np.abs(Z @ np.diag(w) @ Z.T - A).max() < 1e-11 * max(1, n)
+    assert np.abs(Z.T @ Z - np.eye(n)).max() < 1e-12 * max(1, n)
+
+
+@pytest.mark.parametrize("n,rank,nev", [(120, 3, 2), (300, 6, 4), (300, 6, 8)])
+def test_oracle_lanczos_vs_lapack(oracle_mod, n, rank, nev):
+    rng = np.random.default_rng(7)
+    B = rng.standard_normal((n, rank))
+    S = rng.standard_normal((n, n))
+    A = B @ B.T - 0.1 * np.eye(n) + 0.01 * (S + S.T)
+    vals, vecs, info = oracle_mod.lanczos(np.triu(A), oracle_mod.eig_resid(n), nev, max(2 * nev + 1, 25))
+    assert info["converged"] >= nev
+    w = np.linalg.eigvalsh(A)[::-1]
+    assert np.allclose(vals[:nev], w[:nev], atol=1e-10)
+    assert np.abs(A @ vecs - vecs * vals).max() < 1e-10
+
+
+def test_oracle_lanczos_breakdown_zero_matrix(oracle_mod):
+    """Iteration 1 of the solver projects the zero matrix: exact breakdown."""
+    n = 130
+    vals, vecs, info = oracle_mod.lanczos(np.zeros((n, n)), oracle_mod.eig_resid(n), 2, 25)
+    assert info["converged"] == 1 and info["numops"] == 1 and len(vals) == 1 and vals[0] == 0.0
+
+
+def test_oracle_lanczos_restart_cluster(oracle_mod):
+    n = 124
+    rng = np.random.default_rng(1)
+    Q, _ = np.linalg.qr(rng.standard_normal((n, n)))
+    lam = np.concatenate([[10.0, 5.0, 5.0 - 1e-5, 5.0 - 2e-5, 4.0], np.linspace(3.0, -8.0, n - 5)])
+    A = (Q * lam) @ Q.T
+    A = 0.5 * (A + A.T)
+    vals, vecs, info = oracle_mod.lanczos(np.triu(A), oracle_mod.eig_resid(n), 2, 25)
+    assert info["numiter"] > 1 and info["converged"] >= 2
+    assert np.allclose(vals[:2], lam[:2], atol=1e-10)
+
+
+# ---------------------------------------------------------------- reference known answers
+@pytest.mark.parametrize("fn", problems_ref.ALL, ids=lambda f: f.__name__)
+def test_reference_unit_problems(oracle_mod, fn):
+    problems_ref.check(fn(_opt(oracle_mod)))
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(eigsolver=1, min_size_krylov_eigs=1), dict(eigsolver=2, min_size_krylov_eigs=1),
+                                dict(full_eig_decomp=True)], ids=str)
+def test_sdp_wiki_all_eig_paths(oracle_mod, kw):
+    """test/moi_proxsdp_unit.jl:302-338 and the re-runs at :358-370."""
+    problems_ref.check(problems_ref.sdp_wiki(_opt(oracle_mod, **kw), MIN_SENSE))
+    problems_ref.check(problems_ref.sdp_wiki(_opt(oracle_mod, **kw), MAX_SENSE))
+
+
+def test_readme_maxcut(oracle_mod):
+    """README.md:58-84 (config C1)."""
+    aff, con, sgn = maxcut_problem(README_W)
+    r = oracle_mod.chambolle_pock(aff, con, Options(tol_gap=1e-4, tol_feasibility=1e-4))
+    assert r.status == 1
+    assert abs(sgn * r.objval - 18.0) < 2e-2
+    X = ivec(r.primal)
+    assert np.allclose(np.diag(X), 1.0, atol=1e-3)
+    assert np.linalg.eigvalsh(X).min() > -1e-6
+
+
+@pytest.mark.parametrize("n", [2, 3, 4, 5])
+def test_mimo_small(oracle_mod, n):
+    """test/moi_mimo.jl:71-75: every |X_ij| in (0.99, 1.01)."""
+    aff, con = mimo_problem(123 + n, n)
+    r = oracle_mod.chambolle_pock(aff, con, Options(tol_gap=1e-6, tol_feasibility=1e-6))
+    X = ivec(r.primal)
+    assert np.all((np.abs(X) > 0.99) & (np.abs(X) < 1.01))
+
+
+@pytest.mark.parametrize("name,optimum", [("mcp124-1", -141.9905), ("gpp124-2", 46.8623)])
+def test_sdplib_small(oracle_mod, golden_dir, name, optimum):
+    """test/moi_sdplib.jl:53-56 (minus_rank == 0) plus the SDPLIB optimal value as an anchor."""
+    aff, con = load_problem(f"{golden_dir}/sdplib_{name}.npz")
+    r = oracle_mod.chambolle_pock(aff, con, Options(tol_gap=1e-3, tol_feasibility=1e-3))
+    X = ivec(r.primal)
+    assert (np.linalg.eigvalsh(X) < -1e-4).sum() == 0
+    assert r.status == 1
+    assert abs(r.objval - optimum) / abs(optimum) < 5e-3
+    assert r.lanczos_calls > 0            # the Krylov path ran (n > 100)
+
+
+def test_sensorloc_runs(oracle_mod):
+    """test/moi_sensorloc.jl: runs to a status without error; X11 = X22 = 1."""
+    aff, con = sensorloc_problem(0, 10)
+    r = oracle_mod.chambolle_pock(aff, con, Options())
+    assert r.status in (1, 3)
+    X = ivec(r.primal)
+    assert abs(X[0, 0] - 1) < 1e-2 and abs(X[1, 1] - 1) < 1e-2 and abs(X[0, 1]) < 1e-2
+
+
+def test_soc_mixed_cones(oracle_mod):
+    aff, con = sensorloc_problem(0, 10, soc_variant=True)
+    assert len(con.socone) == 1
+    r = oracle_mod.chambolle_pock(aff, con, Options())
+    assert r.status == 1
+    t, u = r.primal[con.socone[0].idx[0]], r.primal[con.socone[0].idx[1:]]
+    assert np.linalg.norm(u) <= t + 1e-4
+
+
+# ---------------------------------------------------------------- statuses / options
+def test_termination_statuses(oracle_mod):
+    """test/test_terminationstatus.jl:40-72."""
+    o = _opt(oracle_mod)
+    problems_ref.sdp_from_moi(o)
+    assert o.termination_status() == "OPTIMAL"
+    o = _opt(oracle_mod, max_iter=1)
+    problems_ref.sdp_wiki(o)
+    assert o.termination_status() == "ITERATION_LIMIT"
+    o = _opt(oracle_mod, time_limit=0.0)
+    problems_ref.sdp_wiki(o)
+    assert o.termination_status() == "TIME_LIMIT"
+
+
+def test_option_errors_and_time_limit_attr():
+    """test/moitest.jl:153-171."""
+    with pytest.raises(ValueError):
+        Options(not_an_option=1)
+    o = Optimizer(backend=lambda *a: None)
+    assert o.get_time_limit_sec() is None
+    o.set_time_limit_sec(0.0)
+    assert o.get_time_limit_sec() == 0.0
+    o.set_time_limit_sec(None)
+    assert o.get_time_limit_sec() is None
+    o.set_silent(False)
+    assert o.get_attribute("log_verbose") is True
+
+
+def test_infeasible_and_unbounded_status(oracle_mod):
+    """MOI.Test conic infeasible/unbounded cases (test/moitest.jl:34-91) in miniature."""
+    o = _opt(oracle_mod)
+    x = o.add_variables(1)
+    o.add_equal_to([(1.0, x[0])], 1.0)
+    o.add_equal_to([(1.0, x[0])], 2.0)
+    o.set_objective(MIN_SENSE, [(1.0, x[0])])
+    o.optimize()
+    assert o.termination_status() == "INFEASIBLE"
+    o = _opt(oracle_mod)
+    x = o.add_variables(1)
+    o.add_greater_than([(1.0, x[0])], 0.0)
+    o.set_objective(MAX_SENSE, [(1.0, x[0])])
+    o.optimize()
+    assert o.termination_status() == "DUAL_INFEASIBLE"
+
+
+# ---------------------------------------------------------------- oracle pinned by the LAPACK mirror
+@pytest.mark.parametrize("which", ["C1", "mimo8", "mcp124-1"])
+def test_oracle_vs_numpy_mirror(oracle_mod, golden_dir, which):
+    from oracle import oracle_np
+    if which == "C1":
+        aff, con = maxcut_problem(README_W)[:2]
+    elif which == "mimo8":
+        aff, con = mimo_problem(1, 8)
+    else:
+        aff, con = load_problem(f"{golden_dir}/sdplib_mcp124-1.npz")
+    opt = Options(full_eig_decomp=True, trace_cap=400, max_iter=400)
+    ro = oracle_mod.chambolle_pock(aff, con, opt)
+    rn = oracle_np.solve_exact(aff, con, opt, 400)
+    assert ro.iter == rn["iter"]
+    k = len(rn["trace"])
+    a, b = ro.trace[:k, 1:9], rn["trace"][:k, 1:9]
+    assert np.abs(a - b).max() <= 1e-6 * max(1.0, np.abs(b).max())
+    assert np.abs(ro.primal - rn["primal"]).max() < 1e-8
+
+
+def test_oracle_matches_golden_trace(oracle_mod, golden_dir):
+    """The committed golden trace (tests/golden/make_golden_traces.py) pins the oracle."""
+    z = np.load(f"{golden_dir}/trace_mcp124-1_exact.npz")
+    aff, con = load_problem(f"{golden_dir}/sdplib_mcp124-1.npz")
+    r = oracle_mod.chambolle_pock(aff, con, Options(full_eig_decomp=True, max_iter=int(z["iters"]), trace_cap=int(z["iters"])))
+    assert np.abs(r.trace[:, 1:9] - z["trace"][:, 1:9]).max() <= 1e-7 * max(1.0, np.abs(z["trace"][:, 1:9]).max())
+
+
+def test_randsdp_mini_benchmark(oracle_mod):
+    """test/run_mini_benchmark.jl:37-40 (randsdp 10x10)."""
+    aff, con = randsdp_problem(0, 10, 10)
+    r = oracle_mod.chambolle_pock(aff, con, Options(max_iter=20000))
+    assert r.status in (1, 3)
+    X = ivec(r.primal)
+    assert np.linalg.eigvalsh(X).min() > -1e-5
