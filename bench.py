@@ -1,0 +1,336 @@
+#!/usr/bin/env python
+"""bench.py — PDHG iterations/sec of the ProxSDP hot path on Max-Cut n=2000 (BASELINE.json configs[1]).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the CPU restatement of the reference
+
+One "step" = one PDHG iteration (primal step + PSD projection + M x + linesearch/dual step + residuals,
+reference src/pdhg.jl:145-164).  All three numbers of a line cover the SAME work: iterations 1..K of the
+solve from the reference's cold start (x = tau*c, target_rank = 2):
+
+  value         device-resident: the problem is already in HBM (proxsdp_b200_create), K iterations are
+                timed with CUDA events on the solver's stream (proxsdp_b200_iterate), max over ranks.
+  e2e           the reference-facing call `chambolle_pock(aff, con, Options(max_iter=K))` on HOST numpy
+                buffers: setup, host->device copies, K iterations, result assembly and device->host
+                copies are all inside the wall-clock region.
+  cpu_baseline  the CPU oracle (oracle/, a restatement of the reference's Julia code; Julia itself is not
+                installed in this image) on the host cores, loop time only (setup/result assembly excluded,
+                which favours the CPU).
+
+N > 1: a single PSD cone does not shard (DESIGN.md "replicas only"): every rank solves an
+independent replica of the workload, `value` = N*K / max-over-ranks time, scaling = "weak".
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "pdhg_iterations_per_sec_maxcut_n2000"
+UNIT = "iterations/s"
+WORKLOAD = "maxcut_er_n2000_p0.01_seed0"
+
+
+def _peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
+    except Exception:
+        return 6550.0, "fallback from /opt/skills/guides/B200_PROFILING.md (MEASURED_PEAKS.json absent)"
+
+
+def _traffic():
+    """dram bytes per launch of the dominant kernel from the committed ncu --set full capture (or None)."""
+    path = os.path.join(ROOT, "profiles", "lanczos_traffic.json")
+    try:
+        with open(path) as fh:
+            return json.load(fh).get("dram_bytes_per_launch")
+    except Exception:
+        return None
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index: int, period: float = 0.02):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons = [], set()
+        self.max_mhz = None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.ok = True
+        except Exception:
+            self.nv = None
+
+    _NAMES = {
+        0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x10: "sync_boost",
+        0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake_slowdown",
+        0x100: "display_clock_setting",
+    }
+
+    def run(self):
+        if not self.ok:
+            return
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(int(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)))
+                r = int(self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                for bit, name in self._NAMES.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2.0)
+        s = sorted(self.samples)
+        return {
+            "sm_mhz": (s[len(s) // 2] if s else None),
+            "sm_max_mhz": self.max_mhz,
+            "reasons": sorted(self.reasons),
+            "samples": len(s),
+        }
+
+
+def _physical_gpu_index(local_rank: int) -> int:
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if vis:
+        try:
+            return int(vis.split(",")[local_rank])
+        except Exception:
+            return local_rank
+    return local_rank
+
+
+def build_workload():
+    from proxsdp_b200.problems import maxcut_er_problem
+    return maxcut_er_problem(2000, 0.01, 0)
+
+
+def config_dict(n_gpus: int, flush: bool, extra=None):
+    cfg = {
+        "workload": WORKLOAD,
+        "description": "Max-Cut SDP, Erdos-Renyi G(2000, 0.01), unit weights: one PSD cone of side 2000 "
+                       "(N = 2 001 000 svec variables), 2000 equality rows diag(X) = 1, FP64, default Options",
+        "step": "one PDHG iteration (iterations 1..K from the reference's cold start)",
+        "parallelism": "single cone: replicas only" if n_gpus > 1 else "1 GPU",
+        "l2": ("flushed before every iteration (384 MiB memset on the solver's stream, inside the timed region)"
+               if flush else "not flushed: every iteration consumes the previous iteration's outputs"),
+    }
+    if extra:
+        cfg.update(extra)
+    return cfg
+
+
+# ---------------------------------------------------------------------------------------------
+# reference arm: the CPU restatement of the reference's algorithm (oracle/), all host threads
+# ---------------------------------------------------------------------------------------------
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from oracle import oracle
+    from proxsdp_b200 import Options
+    oracle.build()
+    aff, con = build_workload()
+    cores = oracle.num_threads()
+    budget_s = float(args.cpu_budget)
+    if args.warmup > 0:
+        oracle.chambolle_pock(aff, con, Options(max_iter=min(args.warmup, 10), time_limit=budget_s))
+    r = oracle.chambolle_pock(aff, con, Options(max_iter=args.steps, time_limit=budget_s))
+    its = int(r.iter)
+    value = its / r.time_loop
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": its,
+        "warmup": min(args.warmup, 10), "ms_per_step": 1e3 * r.time_loop / its, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": config_dict(1, False, {"parallelism": "CPU, OpenMP over host cores", "l2": "n/a (CPU)"}),
+        "cpu_baseline": {
+            "value": value, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"iterations 1..{its} of the workload (requested {args.steps}, wall budget {budget_s:.0f} s), "
+                      "loop time only; oracle = C restatement of the reference (Julia is not installed here)",
+        },
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "ms_per_eig_projection": 1e3 * r.time_psd_proj / max(r.n_psd_proj, 1),
+        "lanczos_matvecs_per_step": r.lanczos_matvecs / its,
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ---------------------------------------------------------------------------------------------
+# this repo's arm
+# ---------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback "
+                         "(use --impl reference for the CPU restatement)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    from proxsdp_b200 import Options, solver
+    aff, con = build_workload()
+    K, W = args.steps, args.warmup
+    flush = not args.no_flush_l2
+    n_side = int(con.sdpcone[0].sq_side)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up: W iterations of a throw-away solve (module load, clocks, allocator)
+    opt = Options(device_id=local_rank)
+    with solver.Solve(aff, con, opt) as warm:
+        warm.iterate(max(W, 3), flush)
+
+    # ---- device-resident timing: iterations 1..K
+    with solver.Solve(aff, con, opt) as s:
+        c0 = s.counters()
+        sampler = ClockSampler(_physical_gpu_index(local_rank))
+        barrier()
+        sampler.start()
+        t0 = time.perf_counter()
+        done, finished, dev_ms = s.iterate(K, flush)
+        barrier()
+        wall_ms = 1e3 * (time.perf_counter() - t0)
+        clocks = sampler.stop()
+        c1 = s.counters()
+        res = s.finish()
+    t = torch.tensor([dev_ms, wall_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms_max, wall_ms_max = float(t[0]), float(t[1])
+    steps_done = done
+    launches = c1["launches"] - c0["launches"]
+    flush_ms = c1["l2_flush_ms"] - c0["l2_flush_ms"]
+
+    # ---- end to end through the reference-facing call, host buffers in / host buffers out
+    barrier()
+    t0 = time.perf_counter()
+    r2 = solver.chambolle_pock(aff, con, Options(device_id=local_rank, max_iter=K))
+    e2e_wall = time.perf_counter() - t0
+    te = torch.tensor([e2e_wall], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_wall = float(te[0])
+    e2e_value = world * r2.iter / e2e_wall
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the dominant kernel (k_lanczos: one launch = one eigsolve = q dense symv + CGS2)
+    peak, peak_src = _peaks()
+    lz_calls = c1["lanczos_timed_calls"] - c0["lanczos_timed_calls"]
+    lz_ms = c1["lanczos_ms"] - c0["lanczos_ms"]
+    mv = c1["lanczos_matvecs"] - c0["lanczos_matvecs"]
+    bytes_per_mv = 8.0 * n_side * n_side + 16.0 * n_side          # full-storage dense symv
+    roofline = None
+    if lz_calls > 0 and lz_ms > 0:
+        bytes_per_launch = bytes_per_mv * mv / lz_calls
+        ach = bytes_per_launch / (lz_ms / lz_calls * 1e-3) / 1e9
+        roofline = {
+            "kernel": "k_lanczos", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+            "traffic": _traffic(), "peak_source": peak_src,
+            "algorithmic_bytes_per_launch": bytes_per_launch, "launches": lz_calls, "avg_launch_ms": lz_ms / lz_calls,
+            "matvecs_per_launch": mv / lz_calls,
+            "share_of_step": lz_ms / dev_ms,
+            "note": "algorithmic bytes = mat-vecs x (8 n^2 + 16 n); the 32 MB matrix is L2-resident across the "
+                    "mat-vecs of one launch, so achieved may exceed the HBM peak — see DESIGN.md",
+        }
+
+    line = {
+        "metric": METRIC, "value": world * steps_done / (dev_ms_max * 1e-3), "unit": UNIT, "n_gpus": world,
+        "steps": steps_done, "warmup": max(W, 3), "ms_per_step": dev_ms_max / max(steps_done, 1),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": config_dict(world, flush, {"l2_flush_ms_per_step": flush_ms / max(steps_done, 1)}),
+        "clocks": clocks,
+        "e2e": {
+            "value": e2e_value, "unit": UNIT,
+            "h2d_bytes_per_step": r2.h2d_bytes / max(r2.iter, 1), "d2h_bytes_per_step": r2.d2h_bytes / max(r2.iter, 1),
+            "steps": int(r2.iter), "wall_s": e2e_wall, "setup_s": r2.time_setup, "loop_s": r2.time_loop,
+        },
+        "gpu_launches": int(launches),
+        "roofline": roofline,
+        "wall_ms_per_step": wall_ms_max / max(steps_done, 1),
+        "ms_per_eig_projection": (c1["psd_proj_ms"] - c0["psd_proj_ms"]) / max(steps_done, 1),
+        "lanczos_matvecs_per_step": mv / max(steps_done, 1),
+        "sections_ms_per_step": {
+            "psd_projection": (c1["psd_proj_ms"] - c0["psd_proj_ms"]) / max(steps_done, 1),
+            "lanczos_kernel": lz_ms / max(steps_done, 1),
+            "rest_of_iteration": (c1["rest_ms"] - c0["rest_ms"]) / max(steps_done, 1),
+            "l2_flush": flush_ms / max(steps_done, 1),
+        },
+        "objective_after_steps": res.objval,
+    }
+
+    # ---- CPU baseline beside it (rank 0, N = 1 only): bounded sample of the same iterations
+    if world == 1 and not args.no_cpu_baseline:
+        from oracle import oracle
+        oracle.build()
+        cores = oracle.num_threads()
+        budget = float(args.cpu_budget)
+        oracle.chambolle_pock(aff, con, Options(max_iter=3))
+        ro = oracle.chambolle_pock(aff, con, Options(max_iter=K, time_limit=budget))
+        line["cpu_baseline"] = {
+            "value": ro.iter / ro.time_loop, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"iterations 1..{int(ro.iter)} of the same workload on the host cores (wall budget {budget:.0f} s), "
+                      "loop time only",
+            "ms_per_eig_projection": 1e3 * ro.time_psd_proj / max(ro.n_psd_proj, 1),
+        }
+        if int(ro.iter) == int(r2.iter):
+            line["parity_vs_cpu"] = {
+                "objval_rel_diff": abs(ro.objval - r2.objval) / max(1.0, abs(ro.objval)),
+                "gap_abs_diff": abs(ro.gap - r2.gap),
+                "lanczos_matvecs": [int(ro.lanczos_matvecs), int(r2.lanczos_matvecs)],
+            }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=500)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-flush-l2", action="store_true", help="do not flush L2 between iterations")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-budget", type=float, default=60.0, help="wall-clock bound (s) of a CPU run")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_b200(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -36,6 +36,29 @@ extern "C" {
 int proxsdp_b200_solve(const proxsdp_problem_t* problem, const proxsdp_options_t* options,
                        proxsdp_result_t* result);
 
+/* The same solve in three calls, for callers that want to own the loop (the reference's
+ * `for k in 1:2*opt.max_iter_local` body, src/pdhg.jl:145-484, is one `iterate` step):
+ *   create   — everything before the loop (src/pdhg.jl:7-142): copies the problem to the device;
+ *   iterate  — up to max_steps (< 0: until termination) further PDHG iterations; *finished = 1 once the
+ *              reference's loop would have exited; *device_ms = CUDA-event time of this call on the
+ *              solver's stream; flush_l2 != 0 writes a buffer larger than L2 before every iteration
+ *              (measurement hygiene only);
+ *   finish   — result assembly (`cache_solution`, src/pdhg.jl:745-787) into caller buffers;
+ *   destroy  — releases all device memory.
+ * create + iterate(-1) + finish + destroy is exactly proxsdp_b200_solve. */
+typedef struct proxsdp_b200_handle proxsdp_b200_handle_t;
+int proxsdp_b200_create(const proxsdp_problem_t* problem, const proxsdp_options_t* options,
+                        proxsdp_b200_handle_t** handle);
+int proxsdp_b200_iterate(proxsdp_b200_handle_t* handle, int64_t max_steps, int64_t flush_l2,
+                         int64_t* steps_done, int64_t* finished, double* device_ms);
+/* Running totals since create.  counts[8]: iterations, kernel launches, Lanczos mat-vecs, Lanczos calls,
+ * Lanczos calls covered by the kernel timer, full eigendecompositions, linesearch trials, sum(target_rank).
+ * times_ms[4] (CUDA events on the solver's stream): psd_projection!, Lanczos kernel, rest of the
+ * iteration, L2 flush.  Either pointer may be NULL. */
+int proxsdp_b200_counters(proxsdp_b200_handle_t* handle, int64_t* counts, double* times_ms);
+int proxsdp_b200_finish(proxsdp_b200_handle_t* handle, proxsdp_result_t* result);
+int proxsdp_b200_destroy(proxsdp_b200_handle_t* handle);
+
 /* One `psd_projection!` (reference src/prox_operators.jl:33-66) over concatenated svec
  * blocks.  x: in/out (sum of tri_len doubles, working-space scaling: off-diagonals carry
  * sqrt(2)).  mode 0 = the reference's dispatch (Krylov when eligible), 1 = force the full

@@ -207,6 +207,14 @@ typedef struct proxsdp_result {
        lanczos mat-vecs this iteration, linesearch trials this iteration */
     double* trace;
     int64_t trace_len;
+    /* per-section device timers (CUDA events on the solver's stream; the analogue of the
+       reference's TimerOutputs sections, pdhg.jl:626 "sdp proj" > "eigs" etc.) */
+    double  time_lanczos;        /* seconds inside the Lanczos kernel (first eigsolve of each iteration) */
+    double  time_rest;           /* seconds from the end of psd_projection! to the end of the iteration's kernels */
+    double  time_l2_flush;       /* seconds spent in the optional between-iteration L2 flush (bench only) */
+    int64_t lanczos_timed_calls; /* launches covered by time_lanczos                                      */
+    int64_t h2d_bytes;           /* host->device bytes copied during this solve                           */
+    int64_t d2h_bytes;           /* device->host bytes copied during this solve                           */
 } proxsdp_result_t;
 
 #ifdef __cplusplus

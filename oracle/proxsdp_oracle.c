@@ -1133,6 +1133,8 @@ int proxsdp_oracle_solve(const proxsdp_problem_t* prob, const proxsdp_options_t*
     out->full_eig_calls = s->full_eig_calls;
     out->linesearch_trials = s->linesearch_trials;
     out->gpu_launches = 0;
+    out->time_lanczos = 0.0; out->time_rest = 0.0; out->time_l2_flush = 0.0;
+    out->lanczos_timed_calls = 0; out->h2d_bytes = 0; out->d2h_bytes = 0;
     if (out->target_rank) for (int64_t k = 0; k < nsd; ++k) out->target_rank[k] = s->target_rank[k];
 
     /* free */

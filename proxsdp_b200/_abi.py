@@ -55,6 +55,8 @@ class ResultPOD(ctypes.Structure):
         ("full_eig_calls", c_int64), ("linesearch_trials", c_int64), ("gpu_launches", c_int64),
         ("target_rank", _pi),
         ("trace", _pd), ("trace_len", c_int64),
+        ("time_lanczos", c_double), ("time_rest", c_double), ("time_l2_flush", c_double),
+        ("lanczos_timed_calls", c_int64), ("h2d_bytes", c_int64), ("d2h_bytes", c_int64),
     ]
 
 
@@ -163,6 +165,8 @@ class MarshalledResult:
             linesearch_trials=int(q.linesearch_trials), gpu_launches=int(q.gpu_launches),
             target_rank=self.target_rank[: self.n_sdp].copy(),
             trace=self.trace[: int(q.trace_len)].copy(),
+            time_lanczos=q.time_lanczos, time_rest=q.time_rest, time_l2_flush=q.time_l2_flush,
+            lanczos_timed_calls=int(q.lanczos_timed_calls), h2d_bytes=int(q.h2d_bytes), d2h_bytes=int(q.d2h_bytes),
         )
 
 

@@ -31,6 +31,9 @@ static double now_s() {
 // ---------------------------------------------------------------------------
 // device buffers
 // ---------------------------------------------------------------------------
+// host<->device traffic of the current solve (reported as h2d/d2h bytes by the bench)
+static thread_local long long g_h2d_bytes = 0, g_d2h_bytes = 0;
+
 template <class T>
 struct DBuf {
     T* p = nullptr;
@@ -55,14 +58,17 @@ struct DBuf {
     void upload(const std::vector<T>& h) {
         alloc(h.size());
         if (!h.empty()) PB_CUDA(cudaMemcpy(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+        g_h2d_bytes += (long long)(h.size() * sizeof(T));
     }
     void upload(const T* h, size_t count) {
         alloc(count);
         if (count) PB_CUDA(cudaMemcpy(p, h, count * sizeof(T), cudaMemcpyHostToDevice));
+        g_h2d_bytes += (long long)(count * sizeof(T));
     }
     std::vector<T> download() const {
         std::vector<T> h(n);
         if (n) PB_CUDA(cudaMemcpy(h.data(), p, n * sizeof(T), cudaMemcpyDeviceToHost));
+        g_d2h_bytes += (long long)(n * sizeof(T));
         return h;
     }
 };
@@ -143,6 +149,14 @@ class Solver {
     Solver(const proxsdp_problem_t* prob, const proxsdp_options_t* opt_in, bool cones_only = false, bool force_large = false);
     ~Solver();
     void solve(proxsdp_result_t* out);
+    // stepwise form of the same loop (bench / step-level seam): begin -> run(max_steps)* -> finish
+    void begin(proxsdp_result_t* out);
+    bool run(long long max_steps, bool flush_l2);   // true once the loop has terminated
+    void finish(proxsdp_result_t* out);
+    long long iterations_done() const { return iter_; }
+    double time_psd_ms() const { return time_psd_ms_; }
+    double time_lanczos_ms_ = 0, time_post_ms_ = 0, time_flush_ms_ = 0;
+    long long lanczos_timed_calls = 0;
     // step-level seam: one psd_projection! on x (device x_[cur_] -> x_[1-cur_]) with tau = 0
     void psd_projection_launch(long long iter, double tau, bool force_full);
     void sync_scalars();
@@ -231,6 +245,14 @@ class Solver {
     long long n_psd_ = 0;
     int ladder_ = 4;
     long long trace_mv0_ = 0, trace_ls0_ = 0;
+    // loop-carried state of chambolle_pock's main loop
+    long long ada_count_ = 0, k_next_ = 1;
+    bool have_cached_ = false, loop_done_ = false;
+    proxsdp_result_t* out_ = nullptr;
+    double t_loop_accum_ = 0;
+    cudaEvent_t ev_lz0_ = nullptr, ev_lz1_ = nullptr, ev_post1_ = nullptr, ev_fl0_ = nullptr, ev_fl1_ = nullptr;
+    bool lz_timed_ = false;
+    DBuf<double> flush_buf_;
 };
 
 // ---------------------------------------------------------------------------
@@ -250,7 +272,9 @@ Solver::Solver(const proxsdp_problem_t* prob, const proxsdp_options_t* opt_in, b
     PB_CUDA(cudaStreamCreate(&stream));   // blocking stream: ordered against the synchronous setup copies on the legacy stream
     PB_CUDA(cudaEventCreate(&ev_psd0_));
     PB_CUDA(cudaEventCreate(&ev_psd1_));
+    for (cudaEvent_t* e : {&ev_lz0_, &ev_lz1_, &ev_post1_, &ev_fl0_, &ev_fl1_}) PB_CUDA(cudaEventCreate(e));
     if (const char* e = getenv("PROXSDP_B200_LADDER")) ladder_ = std::max(1, atoi(e));
+    g_h2d_bytes = 0; g_d2h_bytes = 0;
     setup_host(prob);
 }
 
@@ -258,6 +282,7 @@ Solver::~Solver() {
     if (scal_host) cudaFreeHost(scal_host);
     if (ev_psd0_) cudaEventDestroy(ev_psd0_);
     if (ev_psd1_) cudaEventDestroy(ev_psd1_);
+    for (cudaEvent_t e : {ev_lz0_, ev_lz1_, ev_post1_, ev_fl0_, ev_fl1_}) if (e) cudaEventDestroy(e);
     if (stream) cudaStreamDestroy(stream);
 }
 
@@ -620,6 +645,7 @@ void Solver::psd_projection_launch(long long iter, double tau, bool force_full) 
     const double* x = x_[cur_].p; const double* Mty = Mty_[cur_].p;
     double* xn = x_[1 - cur_].p;
     PB_CUDA(cudaEventRecord(ev_psd0_, stream));
+    lz_timed_ = false;
     if (!small_ids_.empty()) {
         SmallConeArgs a{};
         a.cone_ids = small_ids_d_.p; a.cone_side = cone_side_d_.p; a.cone_off = cone_off_d_.p;
@@ -641,7 +667,10 @@ void Solver::psd_projection_launch(long long iter, double tau, bool force_full) 
         if (!force_full && krylov_eligible(k, iter)) {
             int nev = (int)target_rank[(size_t)k];
             int K = (int)std::max<long long>(2 * nev + 1, opt.eigsolver_min_lanczos);   // eigsolver.jl:794
+            const bool timed = !lz_timed_;     // the per-kernel timer covers the first eigsolve of the iteration
+            if (timed) PB_CUDA(cudaEventRecord(ev_lz0_, stream));
             lanczos_launch(cd, k, nev, K, (int)opt.krylovkit_max_iter, opt.krylovkit_tol);
+            if (timed) { PB_CUDA(cudaEventRecord(ev_lz1_, stream)); lz_timed_ = true; }
             lanczos_calls++;
             k_lanczos_select<<<1, 32, 0, stream>>>(cd.vals.p, cd.info.p, nev, cd.kept_idx.p, cd.kept_lam.p,
                                                    cd.nkept.p, scal_d_.p, k);
@@ -681,6 +710,11 @@ void Solver::launch_post_eig(double tau0, bool first_pass) {
         k_primal_tail<<<std::min(reduce_blocks_, ceil_div(cnt, 256)), 256, 0, stream>>>(
             x_[cur_].p, Mty_[cur_].p, c_.p, primal_step_, psd_end_, n, xn);
         launches++;
+    }
+    if (first_pass && iter_ == 1 && opt.advanced_initialization) {
+        // pdhg.jl:138-142 seeds pair.x = tau*c but leaves pair.x_old = 0, and compute_residual!
+        // (residuals.jl:41-48) reads x_old: once the primal step has consumed x, the old buffer becomes 0.
+        PB_CUDA(cudaMemsetAsync(x_[cur_].p, 0, sizeof(double) * (size_t)std::max<long long>(n, 1), stream));
     }
     if (n_soc > 0) {
         k_soc_project<<<n_soc, 256, 0, stream>>>(xn, soc_off_d_.p, soc_len_d_.p, soc_gap_d_.p, poison);
@@ -731,6 +765,7 @@ void Solver::fallback_projection(long long iter) {
 
 void Solver::sync_scalars() {
     PB_CUDA(cudaMemcpyAsync(scal_host, scal_d_.p, sizeof(double) * (size_t)scal_len, cudaMemcpyDeviceToHost, stream));
+    g_d2h_bytes += (long long)sizeof(double) * scal_len;
     PB_CUDA(cudaStreamSynchronize(stream));
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) throw CudaError(-100 - (int)e, std::string("kernel launch failed: ") + cudaGetErrorString(e));
@@ -899,40 +934,73 @@ void Solver::record_trace(proxsdp_result_t* out) {
 // chambolle_pock main loop (pdhg.jl:145-530)
 // ---------------------------------------------------------------------------
 void Solver::solve(proxsdp_result_t* out) {
+    begin(out);
+    run(-1, false);
+    finish(out);
+}
+
+void Solver::begin(proxsdp_result_t* out) {
     time0_ = now_s();
+    out_ = out;
     out->trace_len = 0;
-    long long ada_count = 0;
-    bool have_cached = false;
-    auto append = [&](const char* s) { stop_reason_string_ += s; };
+    ada_count_ = 0; have_cached_ = false; loop_done_ = false; k_next_ = 1; t_loop_accum_ = 0;
 
     // advanced initialisation (pdhg.jl:138-142): x = tau*c ; Mx = M x ; Mx_old = M*0 = 0
     if (opt.advanced_initialization) {
         std::vector<double> x0((size_t)n);
         for (long long i = 0; i < n; ++i) x0[(size_t)i] = primal_step_ * c_host_[(size_t)i];
         PB_CUDA(cudaMemcpy(x_[cur_].p, x0.data(), sizeof(double) * (size_t)n, cudaMemcpyHostToDevice));
+        g_h2d_bytes += (long long)sizeof(double) * n;
         PB_CUDA(cudaMemsetAsync(scal_d_.p, 0, sizeof(double) * (size_t)scal_len, stream));
         // pdhg.jl:140 writes a.Mx; the first primal_step! overwrites it, and a.Mx_old = M*x_old = 0.
         launch_spmv(M_, x_[cur_].p, Mx_[cur_].p);
         PB_CUDA(cudaMemsetAsync(Mx_[cur_].p, 0, sizeof(double) * (size_t)std::max<long long>(R, 1), stream));
     }
     out->time_setup = 0.0;   // filled by the caller (constructor time)
+}
+
+// Runs up to max_steps (< 0: unbounded) further iterations of the CP loop (pdhg.jl:145-484).
+bool Solver::run(long long max_steps, bool flush_l2) {
+    proxsdp_result_t* out = out_;
+    if (loop_done_) return true;
+    auto append = [&](const char* s) { stop_reason_string_ += s; };
+    long long& ada_count = ada_count_;
+    bool& have_cached = have_cached_;
     double t_loop0 = now_s();
+    struct LoopTimer { double& acc; double t0; ~LoopTimer() { acc += now_s() - t0; } } loop_timer{t_loop_accum_, t_loop0};
+    if (flush_l2 && flush_buf_.n == 0) flush_buf_.alloc((size_t)48 << 20);   // 384 MiB > 126 MB L2
 
     const long long kmax = 2 * opt.max_iter_local;
-    for (long long k = 1; k <= kmax; ++k) {
+    long long steps = 0;
+    loop_done_ = true;      // cleared again if we leave because of max_steps
+    for (long long k = k_next_; k <= kmax; ++k) {
+        if (max_steps >= 0 && steps >= max_steps) { loop_done_ = false; break; }
+        ++steps;
+        k_next_ = k + 1;
         iter_ = k;
         trace_mv0_ = lanczos_matvecs; trace_ls0_ = linesearch_trials;
+        if (flush_l2) {
+            PB_CUDA(cudaEventRecord(ev_fl0_, stream));
+            PB_CUDA(cudaMemsetAsync(flush_buf_.p, 0, flush_buf_.n * sizeof(double), stream));
+            PB_CUDA(cudaEventRecord(ev_fl1_, stream));
+        }
         // ------------------------------------------------------------------ device work
         reset_scalars();
         double tau_primal = primal_step_;                       // pdhg.jl:622 uses the current step
         psd_projection_launch(k, tau_primal, false);
         double tau0 = opt.line_search_flag ? primal_step_ * std::sqrt(1.0 + theta_) : primal_step_;   // pdhg.jl:541
         launch_post_eig(tau0, true);
+        PB_CUDA(cudaEventRecord(ev_post1_, stream));
         sync_scalars();
-        if (n_sdp > 0) {
+        {
             float ms = 0.f;
-            if (cudaEventElapsedTime(&ms, ev_psd0_, ev_psd1_) == cudaSuccess) time_psd_ms_ += ms;
-            n_psd_++;
+            if (n_sdp > 0) {
+                if (cudaEventElapsedTime(&ms, ev_psd0_, ev_psd1_) == cudaSuccess) time_psd_ms_ += ms;
+                n_psd_++;
+            }
+            if (lz_timed_ && cudaEventElapsedTime(&ms, ev_lz0_, ev_lz1_) == cudaSuccess) { time_lanczos_ms_ += ms; lanczos_timed_calls++; }
+            if (cudaEventElapsedTime(&ms, ev_psd1_, ev_post1_) == cudaSuccess) time_post_ms_ += ms;
+            if (flush_l2 && cudaEventElapsedTime(&ms, ev_fl0_, ev_fl1_) == cudaSuccess) time_flush_ms_ += ms;
         }
         // ---- Krylov fallback (prox_operators.jl:55-57): redo the failed cones exactly, then the tail
         if (scal_host[S_POISON] != 0.0) {
@@ -1191,14 +1259,17 @@ void Solver::solve(proxsdp_result_t* out) {
             }
         }
     }
-    out->time_loop = now_s() - t_loop0;
+    return loop_done_;
+}
 
+void Solver::finish(proxsdp_result_t* out) {
+    out->time_loop = t_loop_accum_;
     // results (pdhg.jl:486-529)
     if (opt.certificate_search && certificate_search_) {
         if (certificate_found_) {
             if (stop_reason_ == 6) std::fill(c_orig_.begin(), c_orig_.end(), 0.0);
             cache_solution(c_orig_.data(), out);
-        } else if (!have_cached) {
+        } else if (!have_cached_) {
             cache_solution(c_orig_.data(), out);
         }
     } else {
@@ -1211,6 +1282,12 @@ void Solver::solve(proxsdp_result_t* out) {
     out->full_eig_calls = full_eig_calls;
     out->linesearch_trials = linesearch_trials;
     out->gpu_launches = launches;
+    out->time_lanczos = time_lanczos_ms_ * 1e-3;
+    out->time_rest = time_post_ms_ * 1e-3;
+    out->time_l2_flush = time_flush_ms_ * 1e-3;
+    out->lanczos_timed_calls = lanczos_timed_calls;
+    out->h2d_bytes = g_h2d_bytes;
+    out->d2h_bytes = g_d2h_bytes;
     if (out->target_rank) for (int q = 0; q < n_sdp; ++q) out->target_rank[q] = target_rank[(size_t)q];
 }
 
@@ -1276,6 +1353,103 @@ int proxsdp_b200_solve(const proxsdp_problem_t* problem, const proxsdp_options_t
         result->time_setup = t_setup;
         result->time += t_setup;    // the reference's clock (p.time0, pdhg.jl:13) starts before the Init block
     });
+}
+
+struct proxsdp_b200_handle {
+    std::unique_ptr<Solver> s;
+    // run() records the trace and (certificate search, pdhg.jl:639-676) an early cached solution through
+    // this library-owned result; finish() copies it into the caller's buffers.
+    proxsdp_result_t scratch{};
+    std::vector<double> primal, dual_cone, dual_eq, dual_in, slack_eq, slack_in, trace;
+    std::vector<int64_t> target_rank;
+    double t_setup = 0.0;
+};
+
+int proxsdp_b200_create(const proxsdp_problem_t* problem, const proxsdp_options_t* options,
+                        proxsdp_b200_handle_t** handle) {
+    if (!problem || !options || !handle) { g_last_error = "null argument"; return -1; }
+    *handle = nullptr;
+    return guarded([&]() {
+        std::unique_ptr<proxsdp_b200_handle> h(new proxsdp_b200_handle());
+        double t0 = now_s();
+        h->s.reset(new Solver(problem, options));
+        Solver& s = *h->s;
+        h->primal.assign((size_t)s.n, 0.0); h->dual_cone.assign((size_t)s.n, 0.0);
+        h->dual_eq.assign((size_t)s.p, 0.0); h->slack_eq.assign((size_t)s.p, 0.0);
+        h->dual_in.assign((size_t)s.m, 0.0); h->slack_in.assign((size_t)s.m, 0.0);
+        h->target_rank.assign((size_t)std::max(s.n_sdp, 1), 0);
+        h->trace.assign((size_t)std::max<int64_t>(options->trace_cap, 0) * PROXSDP_TRACE_COLS, 0.0);
+        proxsdp_result_t& r = h->scratch;
+        r.primal = h->primal.data(); r.dual_cone = h->dual_cone.data(); r.dual_eq = h->dual_eq.data();
+        r.dual_in = h->dual_in.data(); r.slack_eq = h->slack_eq.data(); r.slack_in = h->slack_in.data();
+        r.target_rank = h->target_rank.data();
+        r.trace = h->trace.empty() ? nullptr : h->trace.data();
+        h->s->begin(&h->scratch);
+        PB_CUDA(cudaStreamSynchronize(h->s->stream));
+        h->t_setup = now_s() - t0;
+        *handle = h.release();
+    });
+}
+
+int proxsdp_b200_iterate(proxsdp_b200_handle_t* handle, int64_t max_steps, int64_t flush_l2,
+                         int64_t* steps_done, int64_t* finished, double* device_ms) {
+    if (!handle || !handle->s) { g_last_error = "null handle"; return -1; }
+    return guarded([&]() {
+        Solver& s = *handle->s;
+        cudaEvent_t e0, e1;
+        PB_CUDA(cudaEventCreate(&e0)); PB_CUDA(cudaEventCreate(&e1));
+        long long it0 = s.iterations_done();
+        PB_CUDA(cudaEventRecord(e0, s.stream));
+        bool done = s.run(max_steps, flush_l2 != 0);
+        PB_CUDA(cudaEventRecord(e1, s.stream));
+        PB_CUDA(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        PB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+        if (steps_done) *steps_done = s.iterations_done() - it0;
+        if (finished) *finished = done ? 1 : 0;
+        if (device_ms) *device_ms = (double)ms;
+    });
+}
+
+int proxsdp_b200_counters(proxsdp_b200_handle_t* handle, int64_t* counts, double* times_ms) {
+    if (!handle || !handle->s) { g_last_error = "null handle"; return -1; }
+    Solver& s = *handle->s;
+    if (counts) {
+        counts[0] = s.iterations_done(); counts[1] = s.launches; counts[2] = s.lanczos_matvecs; counts[3] = s.lanczos_calls;
+        counts[4] = s.lanczos_timed_calls; counts[5] = s.full_eig_calls; counts[6] = s.linesearch_trials; counts[7] = 0;
+        for (long long r : s.target_rank) counts[7] += r;
+    }
+    if (times_ms) {
+        times_ms[0] = s.time_psd_ms(); times_ms[1] = s.time_lanczos_ms_; times_ms[2] = s.time_post_ms_; times_ms[3] = s.time_flush_ms_;
+    }
+    return 0;
+}
+
+int proxsdp_b200_finish(proxsdp_b200_handle_t* handle, proxsdp_result_t* result) {
+    if (!handle || !handle->s || !result) { g_last_error = "null argument"; return -1; }
+    return guarded([&]() {
+        proxsdp_result_t& r = handle->scratch;
+        Solver& s = *handle->s;
+        s.finish(&r);
+        double* trace_dst = result->trace; int64_t* tr_dst = result->target_rank;
+        double *d0 = result->primal, *d1 = result->dual_cone, *d2 = result->dual_eq, *d3 = result->dual_in,
+               *d4 = result->slack_eq, *d5 = result->slack_in;
+        *result = r;
+        result->primal = d0; result->dual_cone = d1; result->dual_eq = d2; result->dual_in = d3;
+        result->slack_eq = d4; result->slack_in = d5; result->trace = trace_dst; result->target_rank = tr_dst;
+        auto cp = [](double* dst, const std::vector<double>& src) { if (dst && !src.empty()) std::memcpy(dst, src.data(), src.size() * sizeof(double)); };
+        cp(d0, handle->primal); cp(d1, handle->dual_cone); cp(d2, handle->dual_eq); cp(d3, handle->dual_in);
+        cp(d4, handle->slack_eq); cp(d5, handle->slack_in);
+        if (trace_dst && r.trace_len > 0) std::memcpy(trace_dst, handle->trace.data(), sizeof(double) * (size_t)r.trace_len * PROXSDP_TRACE_COLS);
+        if (tr_dst) for (int q = 0; q < s.n_sdp; ++q) tr_dst[q] = handle->target_rank[(size_t)q];
+        result->time_setup = handle->t_setup;
+    });
+}
+
+int proxsdp_b200_destroy(proxsdp_b200_handle_t* handle) {
+    if (!handle) return 0;
+    return guarded([&]() { delete handle; });
 }
 
 int proxsdp_b200_psd_project(int64_t n_sdp, const int64_t* sides, double* x, const int64_t* target_rank,

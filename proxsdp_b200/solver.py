@@ -85,6 +85,69 @@ def chambolle_pock(aff: AffineSets, con: ConicSets, opt: Options, eig_resid=None
     return call_solve(fn, aff, con, opt, eig_resid, err_fn=L.proxsdp_b200_last_error)
 
 
+class Solve:
+    """`chambolle_pock` in three calls (create / iterate / finish) for callers that own the loop —
+    one `iterate` step is one pass of the reference's `for k in 1:2*opt.max_iter_local` body
+    (src/pdhg.jl:145-484).  Device state stays resident in HBM between calls."""
+
+    COUNT_NAMES = ("iterations", "launches", "lanczos_matvecs", "lanczos_calls", "lanczos_timed_calls",
+                   "full_eig_calls", "linesearch_trials", "sum_target_rank")
+    TIME_NAMES = ("psd_proj_ms", "lanczos_ms", "rest_ms", "l2_flush_ms")
+
+    def __init__(self, aff: AffineSets, con: ConicSets, opt: Options, eig_resid=None):
+        from ._abi import MarshalledProblem
+        L = lib()
+        self._L = L
+        self._mp = MarshalledProblem(aff, con, eig_resid)
+        self._opt = opt
+        self._h = ctypes.c_void_p()
+        opod = opt.to_pod()
+        L.proxsdp_b200_create.argtypes = [POINTER(ProblemPOD), POINTER(OptionsPOD), POINTER(ctypes.c_void_p)]
+        L.proxsdp_b200_iterate.argtypes = [ctypes.c_void_p, c_int64, c_int64, _pi, _pi, _pd]
+        L.proxsdp_b200_counters.argtypes = [ctypes.c_void_p, _pi, _pd]
+        L.proxsdp_b200_finish.argtypes = [ctypes.c_void_p, POINTER(ResultPOD)]
+        L.proxsdp_b200_destroy.argtypes = [ctypes.c_void_p]
+        _check(L.proxsdp_b200_create(ctypes.byref(self._mp.pod), ctypes.byref(opod), ctypes.byref(self._h)))
+
+    def iterate(self, max_steps: int = -1, flush_l2: bool = False):
+        """Returns (steps_done, finished, device_ms)."""
+        done, fin, ms = c_int64(0), c_int64(0), c_double(0.0)
+        _check(self._L.proxsdp_b200_iterate(self._h, max_steps, int(flush_l2), ctypes.byref(done), ctypes.byref(fin),
+                                            ctypes.byref(ms)))
+        return done.value, bool(fin.value), ms.value
+
+    def counters(self) -> dict:
+        c = np.zeros(8, dtype=np.int64)
+        t = np.zeros(4)
+        _check(self._L.proxsdp_b200_counters(self._h, _ip(c), _dp(t)))
+        out = dict(zip(self.COUNT_NAMES, (int(v) for v in c)))
+        out.update(dict(zip(self.TIME_NAMES, (float(v) for v in t))))
+        return out
+
+    def finish(self) -> Result:
+        from ._abi import MarshalledResult
+        mr = MarshalledResult(self._mp.n, self._mp.p, self._mp.m, self._mp.n_sdp, int(self._opt.trace_cap))
+        _check(self._L.proxsdp_b200_finish(self._h, ctypes.byref(mr.pod)))
+        return mr.to_result()
+
+    def close(self):
+        if self._h:
+            self._L.proxsdp_b200_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def psd_project(sides, x, target_rank, opt: Options, iter: int = 1, mode: int = 0, resid=None, repeat: int = 1):
     """One `psd_projection!` (reference src/prox_operators.jl:33-66) on concatenated svec blocks.
     Returns (x_projected, current_rank, min_eig, converged, numops, ms_per_call)."""

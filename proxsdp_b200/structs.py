@@ -91,6 +91,12 @@ class Result:
     gpu_launches: int = 0
     target_rank: Optional[np.ndarray] = None
     trace: Optional[np.ndarray] = None
+    time_lanczos: float = 0.0
+    time_rest: float = 0.0
+    time_l2_flush: float = 0.0
+    lanczos_timed_calls: int = 0
+    h2d_bytes: int = 0
+    d2h_bytes: int = 0
 
 
 def sympackedlen(n: int) -> int:

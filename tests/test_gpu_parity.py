@@ -252,13 +252,17 @@ def test_solve_krylov_sdplib(gpu, oracle_mod, golden_dir, name, optimum):
     assert abs(rg.iter - ro.iter) <= 0.25 * ro.iter
 
 
-def test_solve_gpp500_long_row(gpu, golden_dir):
-    """gpp500-1 has one constraint row with 125 250 non-zeros (SpMV long-row path)."""
+def test_solve_gpp500_long_row(gpu, oracle_mod, golden_dir):
+    """gpp500-1 has one constraint row with 125 250 non-zeros (SpMV long-row path): the first
+    iterations (before truncated-projection trajectories can separate) match the oracle to 1e-6."""
     aff, con = load_problem(f"{golden_dir}/sdplib_gpp500-1.npz")
-    rg = gpu.chambolle_pock(aff, con, Options(max_iter=400, trace_cap=400))
-    assert rg.iter == 400 and np.all(np.isfinite(rg.trace))
-    # equality feasibility of the long row is what the long-row kernel feeds
-    assert rg.trace[-1, 4] < rg.trace[5, 4]
+    opt = Options(max_iter=60, trace_cap=60)
+    rg = gpu.chambolle_pock(aff, con, opt)
+    ro = oracle_mod.chambolle_pock(aff, con, opt)
+    assert rg.iter == ro.iter == 60 and np.all(np.isfinite(rg.trace))
+    assert np.abs(rg.trace[:, 1:9] - ro.trace[:, 1:9]).max() <= 1e-6 * max(1.0, np.abs(ro.trace[:, 1:9]).max())
+    assert list(rg.trace[:, 12]) == list(ro.trace[:, 12])
+    assert np.abs(rg.slack_eq - ro.slack_eq).max() <= 1e-6 * max(1.0, np.abs(ro.slack_eq).max())
 
 
 def test_solve_mixed_soc_psd(gpu, oracle_mod):
