@@ -1,0 +1,197 @@
+// ritz_bi.cuh — the top few eigenpairs of the Lanczos tridiagonal by bisection + twisted vectors.
+//
+// KrylovKit diagonalises the whole K x K Rayleigh quotient (`tridiageigh!`) to decide convergence; on a GPU
+// a dense K x K Jacobi solve costs ~130 us of pure latency (136 dependent rounds), more than the 25 mat-vecs
+// of the eigsolve themselves.  In the common case (first Krylov cycle, the `howmany` wanted Ritz pairs have
+// converged) only the leading few eigenpairs of a plain symmetric TRIDIAGONAL are needed:
+//     values   : 32-way multisection on the Sturm count (division-free three-term recurrence), one warp per value;
+//     vectors  : forward and backward solutions of (T - lambda I) z = 0 glued at the twist index that minimises
+//                the single remaining residual gamma_r (Fernando's twisted factorisation), one warp per vector.
+// Every pair is verified (residual, mutual orthogonality, eigenvalue gaps); anything doubtful makes the routine
+// decline, and the caller falls back to the dense Jacobi solver, which also serves thick restarts (arrowhead
+// Rayleigh quotient) and non-converged cycles.  So the accelerated path can only ever return pairs that pass
+// the same accuracy bar as the dense solver.
+#pragma once
+#include "common.cuh"
+
+namespace pb {
+
+constexpr int RITZ_BI_MAXM = 15;      // pairs computed at most (one warp each; warp m computes one extra value)
+
+struct RitzBiScratch {
+    double* ie;      // K        1 / e[j]
+    double* zf;      // 16 * K   forward solutions, one row per warp
+    double* zb;      // 16 * K   backward solutions
+    double* lam;     // 16       eigenvalues (descending)
+    int* fail;       // 1
+};
+
+__host__ __device__ inline size_t ritz_bi_scratch_doubles(int K) { return (size_t)K + 32 * (size_t)K + 16 + 2; }
+
+__device__ inline RitzBiScratch ritz_bi_carve(double* base, int K) {
+    RitzBiScratch s;
+    s.ie = base; base += K;
+    s.zf = base; base += 16 * (size_t)K;
+    s.zb = base; base += 16 * (size_t)K;
+    s.lam = base; base += 16;
+    s.fail = reinterpret_cast<int*>(base);
+    return s;
+}
+
+// number of eigenvalues of tridiag(d, e) that are < x  (sign changes of the leading principal minors)
+__device__ __forceinline__ int sturm_count(int k, const double* __restrict__ d, const double* __restrict__ e, double x) {
+    double p0 = 1.0, p1 = d[0] - x;
+    int cnt = (p1 <= 0.0) ? 1 : 0;
+    for (int j = 1; j < k; ++j) {
+        const double ej = e[j - 1];
+        double p2 = fma(d[j] - x, p1, -(ej * ej) * p0);
+        const bool neg = (p2 == 0.0) || ((p2 < 0.0) != (p1 < 0.0));
+        cnt += neg ? 1 : 0;
+        if (p2 == 0.0) p2 = (p1 != 0.0) ? -p1 * 1e-300 : -1e-300;
+        const double a = fabs(p2);
+        if (a > 1e150) { p1 *= 1e-150; p2 *= 1e-150; }
+        else if (a < 1e-150) { p1 *= 1e150; p2 *= 1e150; }
+        p0 = p1; p1 = p2;
+    }
+    return cnt;
+}
+
+// Computes the m = min(m_want, RITZ_BI_MAXM) largest eigenpairs of the k x k tridiagonal (d: diagonal, e: sub-diagonal,
+// both in shared memory).  On success returns m and fills lam_out[0..m) (descending) and the columns 0..m-1 of U
+// (leading dimension ldu, rows 0..k-1).  Returns 0 when it declines.  All threads of the block must call it.
+__device__ inline int ritz_top_bi(int k, const double* d, const double* e, int m_want, double* lam_out, double* U, int ldu,
+                                  RitzBiScratch sc) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int m = min(min(m_want, RITZ_BI_MAXM), k - 1);
+    if (k < 8 || m < 1) return 0;
+    // ---- bounds, scale, smallest coupling (every warp redundantly: no block barrier) ----
+    double gl = 1e300, gu = -1e300, emin = 1e300;
+    for (int j = lane; j < k; j += 32) {
+        const double el = (j > 0) ? fabs(e[j - 1]) : 0.0, er = (j < k - 1) ? fabs(e[j]) : 0.0;
+        gl = fmin(gl, d[j] - el - er);
+        gu = fmax(gu, d[j] + el + er);
+        if (j < k - 1) emin = fmin(emin, er);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        gl = fmin(gl, __shfl_xor_sync(0xffffffffu, gl, o));
+        gu = fmax(gu, __shfl_xor_sync(0xffffffffu, gu, o));
+        emin = fmin(emin, __shfl_xor_sync(0xffffffffu, emin, o));
+    }
+    const double tnorm = fmax(fabs(gl), fabs(gu));
+    if (!(tnorm > 0.0) || !(tnorm < 1e140) || !(emin > 1e-9 * tnorm)) return 0;     // (nearly) decoupled or degenerate: decline
+    for (int j = tid; j < k - 1; j += blockDim.x) sc.ie[j] = 1.0 / e[j];
+    if (tid == 0) *sc.fail = 0;
+    __syncthreads();
+
+    // ---- eigenvalue `warp` (0-based from the top) by 32-way multisection ----
+    double lam = 0.0;
+    if (warp <= m) {
+        const int idx = k - 1 - warp;              // want the smallest x with count(x) > idx
+        const double wdt = gu - gl;
+        double lo = gl - 1e-3 * wdt, hi = gu + 1e-3 * wdt;
+        for (int it = 0; it < 16; ++it) {
+            const double x = lo + (hi - lo) * ((double)(lane + 1) * (1.0 / 33.0));
+            const int c = sturm_count(k, d, e, x);
+            const unsigned int okmask = __ballot_sync(0xffffffffu, c > idx);
+            double nlo, nhi;
+            if (okmask) {
+                const int L = __ffs(okmask) - 1;
+                nhi = __shfl_sync(0xffffffffu, x, L);
+                const double xm1 = __shfl_sync(0xffffffffu, x, L > 0 ? L - 1 : 0);
+                nlo = (L > 0) ? xm1 : lo;
+            } else {
+                nlo = __shfl_sync(0xffffffffu, x, 31);
+                nhi = hi;
+            }
+            lo = nlo; hi = nhi;
+            if (hi - lo <= 2.3e-16 * fmax(fabs(lo), fabs(hi))) break;
+        }
+        lam = 0.5 * (lo + hi);
+        if (lane == 0) sc.lam[warp] = lam;
+    }
+
+    // ---- eigenvector `warp` : forward (lane 0) and backward (lane 1) recurrences, same instruction stream ----
+    if (warp < m) {
+        double* zf = sc.zf + (size_t)warp * k;
+        double* zb = sc.zb + (size_t)warp * k;
+        if (lane < 2) {
+            const bool rev = (lane == 1);
+            double* z = rev ? zb : zf;
+            // reversed problem: d'[j] = d[k-1-j], e'[j] = e[k-2-j]; z'[j] is stored at its natural position
+            double zm1 = 1.0;
+            z[rev ? k - 1 : 0] = 1.0;
+            double z0 = -(d[rev ? k - 1 : 0] - lam) * sc.ie[rev ? k - 2 : 0];
+            z[rev ? k - 2 : 1] = z0;
+            for (int j = 1; j < k - 1; ++j) {
+                const int jd = rev ? k - 1 - j : j;            // d'[j]
+                const int je = rev ? k - 2 - j : j;            // e'[j]
+                const int jm = rev ? k - 1 - j : j - 1;        // e'[j-1]
+                const double zn = -fma(d[jd] - lam, z0, e[jm] * zm1) * sc.ie[je];
+                z[rev ? k - 2 - j : j + 1] = zn;
+                zm1 = z0; z0 = zn;
+            }
+        }
+        __syncwarp();
+        // gamma_r = (d_r - lam) + e_{r-1} zf_{r-1}/zf_r + e_r zb_{r+1}/zb_r ; twist at the smallest |gamma|
+        double best = 1e300; int bestr = 0;
+        for (int r = lane; r < k; r += 32) {
+            double g = d[r] - lam;
+            if (r > 0) g += e[r - 1] * zf[r - 1] / zf[r];
+            if (r < k - 1) g += e[r] * zb[r + 1] / zb[r];
+            double ag = fabs(g);
+            if (!(ag < 1e300)) ag = 1e300;                    // NaN / inf: never chosen
+            if (ag < best) { best = ag; bestr = r; }
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const int orr = __shfl_xor_sync(0xffffffffu, bestr, o);
+            if (ob < best || (ob == best && orr < bestr)) { best = ob; bestr = orr; }
+        }
+        const double sf = 1.0 / zf[bestr], sb = 1.0 / zb[bestr];
+        double nrm2 = 0.0;
+        for (int j = lane; j < k; j += 32) {
+            const double zj = (j <= bestr) ? zf[j] * sf : zb[j] * sb;
+            nrm2 = fma(zj, zj, nrm2);
+        }
+        nrm2 = warp_sum(nrm2);
+        const double inrm = rsqrt(nrm2);
+        double* u = U + (size_t)warp * ldu;
+        for (int j = lane; j < k; j += 32) u[j] = ((j <= bestr) ? zf[j] * sf : zb[j] * sb) * inrm;
+        __syncwarp();
+        // residual check || T u - lam u ||_inf <= 1e-13 ||T||
+        double res = 0.0;
+        for (int j = lane; j < k; j += 32) {
+            double t = (d[j] - lam) * u[j];
+            if (j > 0) t = fma(e[j - 1], u[j - 1], t);
+            if (j < k - 1) t = fma(e[j], u[j + 1], t);
+            res = fmax(res, fabs(t));
+        }
+        for (int o = 16; o > 0; o >>= 1) res = fmax(res, __shfl_xor_sync(0xffffffffu, res, o));
+        if (lane == 0 && !(res <= 1e-13 * tnorm && nrm2 < 1e300)) *sc.fail = 1;
+    }
+    __syncthreads();
+    // ---- gaps and mutual orthogonality ----
+    if (tid < m) {
+        if (!(sc.lam[tid] - sc.lam[tid + 1] >= 1e-7 * tnorm)) *sc.fail = 1;
+    }
+    const int npairs = m * (m - 1) / 2;
+    for (int pidx = warp; pidx < npairs; pidx += (int)(blockDim.x >> 5)) {
+        int b = (int)((1.0 + sqrt(1.0 + 8.0 * (double)pidx)) * 0.5);
+        while (b * (b - 1) / 2 > pidx) --b;
+        while ((b + 1) * b / 2 <= pidx) ++b;
+        const int a_ = pidx - b * (b - 1) / 2;             // a_ < b
+        const double* ua = U + (size_t)a_ * ldu;
+        const double* ub = U + (size_t)b * ldu;
+        double s = 0.0;
+        for (int j = lane; j < k; j += 32) s = fma(ua[j], ub[j], s);
+        s = warp_sum(s);
+        if (lane == 0 && !(fabs(s) <= 1e-12)) *sc.fail = 1;
+    }
+    __syncthreads();
+    if (*sc.fail) return 0;
+    for (int i = tid; i < m; i += blockDim.x) lam_out[i] = sc.lam[i];
+    __syncthreads();
+    return m;
+}
+
+}  // namespace pb

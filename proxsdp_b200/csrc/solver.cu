@@ -18,14 +18,32 @@
 #include "jacobi.cuh"
 #include "kernels_vec.cuh"
 #include "lanczos.cuh"
+#include "lanczos_cl.cuh"
 
 namespace pb {
 
+__global__ void k_scale_offdiag(double* __restrict__ x, const int* __restrict__ cone_side,
+                                const long long* __restrict__ cone_off, int n_sdp, double num, int divide);
+__global__ void k_scale_copy(const double* __restrict__ src, double a, long long n, double* __restrict__ dst);
+
 static thread_local std::string g_last_error;
 
+static bool g_timing = getenv("PROXSDP_B200_TIMING") != nullptr;
+static double now_s();
+struct StageTimer {
+    double t; const char* what;
+    explicit StageTimer(const char* w);
+    void lap(const char* next);
+};
 static double now_s() {
     using namespace std::chrono;
     return duration<double>(steady_clock::now().time_since_epoch()).count();
+}
+
+StageTimer::StageTimer(const char* w) : t(now_s()), what(w) {}
+void StageTimer::lap(const char* next) {
+    if (g_timing) { cudaDeviceSynchronize(); double n = now_s(); fprintf(stderr, "[timing] %-28s %8.3f ms\n", what, 1e3 * (n - t)); t = n; }
+    what = next;
 }
 
 // ---------------------------------------------------------------------------
@@ -140,7 +158,9 @@ struct ConeDev {
     DBuf<double> X;             // ld x ld, large cones only
     DBuf<double> Vfull;         // ld x ld eigenvectors for the block-Jacobi path (allocated lazily)
     DBuf<double> Y;             // ld x (Kmax)
-    DBuf<double> resid, vcur, vals, kept_lam;
+    DBuf<double> resid, vals, kept_lam;
+    DBuf<double> ritz_ws[2];    // warm start of the K x K Ritz eigenproblem (ping-pong between launches)
+    long long ritz_launches = 0;
     DBuf<int> info, kept_idx, nkept;
 };
 
@@ -184,6 +204,14 @@ class Solver {
     // eigenvalues -> host vector (unsorted), eigenvectors in cone.Vfull
     std::vector<double> full_eig_device(ConeDev& cd);
     void lanczos_launch(ConeDev& cd, int cone_idx, int nev, int K, int maxiter, double tol);
+    bool lanczos_launch_cluster(ConeDev& cd, int cone_idx, int nev, int K, int maxiter, double tol);
+    int lz_mode_ = 0;          // 0 = cluster-replicated kernel when it fits, 1 = row-distributed kernel only
+    int lz_cluster_ = 8;       // cluster size of the replicated kernel
+    int lz_bi_ = 1;            // leading Ritz pairs by bisection + twisted vectors (dense Jacobi as fallback)
+    int lz_warm_ = 1;          // warm-start the Ritz eigenproblem from the previous eigsolve
+    bool lz_cluster_warned_ = false;
+    long long lz_cluster_launches_ = 0;
+    size_t lz_cl_smem_max_ = 0;
 
   private:
     void setup_host(const proxsdp_problem_t* prob);
@@ -209,7 +237,8 @@ class Solver {
     std::vector<long long> mt_colptr_;            // CSC of M == CSR of M'
     std::vector<int> mt_rowidx_;
     std::vector<double> mt_val_, mt_val_orig_;    // scaled / unscaled values
-    std::vector<double> b_host_, h_host_, c_host_, c_orig_, b_orig_, h_orig_;
+    std::vector<double> b_host_, h_host_, c_orig_, b_orig_, h_orig_;
+    bool identity_ = false;                        // variable permutation is the identity (no ord_/var_ordering_)
     std::vector<long long> soc_off_h_;
     std::vector<int> soc_len_h_;
     long long psd_end_ = 0;                        // first index after the PSD blocks
@@ -218,8 +247,8 @@ class Solver {
     DBuf<int> cone_side_d_, small_ids_d_;
     DBuf<long long> cone_off_d_, soc_off_d_;
     DBuf<int> soc_len_d_;
-    DBuf<double> soc_gap_d_, scal_d_, partials_d_, lz_partials_d_, out_min_d_, offnorm_d_;
-    DBuf<unsigned int> counters_d_, bar_d_;
+    DBuf<double> soc_gap_d_, scal_d_, partials_d_, out_min_d_, offnorm_d_;
+    DBuf<unsigned int> counters_d_;
     DBuf<double> bj_Q_;
     DBuf<int> bj_pi_, bj_pj_, bj_rot_;
     std::vector<int> small_ids_, large_ids_;
@@ -253,6 +282,11 @@ class Solver {
     cudaEvent_t ev_lz0_ = nullptr, ev_lz1_ = nullptr, ev_post1_ = nullptr, ev_fl0_ = nullptr, ev_fl1_ = nullptr;
     bool lz_timed_ = false;
     DBuf<double> flush_buf_;
+    DBuf<uint4> lz_xbuf_, lz_vx_;
+    DBuf<double> lz_wg_;
+    DBuf<unsigned int> lz_bar_;
+    DBuf<long long> lz_prof_;
+    unsigned long long lz_epoch_ = 0;
 };
 
 // ---------------------------------------------------------------------------
@@ -274,6 +308,11 @@ Solver::Solver(const proxsdp_problem_t* prob, const proxsdp_options_t* opt_in, b
     PB_CUDA(cudaEventCreate(&ev_psd1_));
     for (cudaEvent_t* e : {&ev_lz0_, &ev_lz1_, &ev_post1_, &ev_fl0_, &ev_fl1_}) PB_CUDA(cudaEventCreate(e));
     if (const char* e = getenv("PROXSDP_B200_LADDER")) ladder_ = std::max(1, atoi(e));
+    if (const char* e = getenv("PROXSDP_B200_LANCZOS")) lz_mode_ = (std::string(e) == "rows") ? 1 : 0;
+    if (const char* e = getenv("PROXSDP_B200_CLUSTER")) lz_cluster_ = std::max(1, std::min(LZC_MAXC, atoi(e)));
+    if (const char* e = getenv("PROXSDP_B200_RITZ_WARM")) lz_warm_ = atoi(e);
+    if (const char* e = getenv("PROXSDP_B200_RITZ_BI")) lz_bi_ = atoi(e);
+    { size_t lim = 0; if (cudaDeviceGetLimit(&lim, cudaLimitStackSize) == cudaSuccess && lim < 4096) cudaDeviceSetLimit(cudaLimitStackSize, 4096); }
     g_h2d_bytes = 0; g_d2h_bytes = 0;
     setup_host(prob);
 }
@@ -287,6 +326,7 @@ Solver::~Solver() {
 }
 
 void Solver::setup_host(const proxsdp_problem_t* prob) {
+    StageTimer st("setup: norms+ordering");
     n = prob->n; p = prob->p; m = prob->m; R = p + m;
     const long long base = prob->index_base;
     n_sdp = (int)prob->n_sdp; n_soc = (int)prob->n_soc;
@@ -301,16 +341,39 @@ void Solver::setup_host(const proxsdp_problem_t* prob) {
     norm_b_ = nrm2(prob->b, p); norm_h_ = nrm2(prob->h, m); norm_c_ = nrm2(prob->c, n);
 
     // preprocess! (scaling.jl:2-26): ord = [sdp vars..., soc vars..., sorted remaining]
-    ord_.assign((size_t)n, 0);
-    std::vector<char> used((size_t)n, 0);
-    long long pos = 0;
     cones.resize((size_t)n_sdp);
+    soc_off_h_.resize((size_t)n_soc); soc_len_h_.resize((size_t)n_soc);
+    {
+        // fast path: cone variables already listed in order 0, 1, 2, ... (what JuMP/MOI produce for a single
+        // matrix variable): the permutation is the identity and no per-variable index arrays are needed
+        identity_ = true;
+        long long pos = 0;
+        for (int k = 0; k < n_sdp && identity_; ++k) {
+            long long side = prob->sdp_side[k];
+            long long tri = side * (side + 1) / 2;
+            if (prob->sdp_ptr[k + 1] - prob->sdp_ptr[k] != tri) throw CudaError(-3, "sdp cone length mismatch");
+            const int64_t* idx = prob->sdp_idx + prob->sdp_ptr[k];
+            for (long long q = 0; q < tri; ++q) if (idx[q] - base != pos + q) { identity_ = false; break; }
+            pos += tri;
+        }
+        for (int k = 0; k < n_soc && identity_; ++k) {
+            long long len = prob->soc_ptr[k + 1] - prob->soc_ptr[k];
+            const int64_t* idx = prob->soc_idx + prob->soc_ptr[k];
+            for (long long q = 0; q < len; ++q) if (idx[q] - base != pos + q) { identity_ = false; break; }
+            pos += len;
+        }
+        if (identity_ && pos > n) throw CudaError(-3, "variable index out of range");
+    }
+    long long pos = 0;
+    std::vector<char> used;
+    if (!identity_) { ord_.assign((size_t)n, 0); used.assign((size_t)n, 0); }
     for (int k = 0; k < n_sdp; ++k) {
         long long side = prob->sdp_side[k];
         long long tri = side * (side + 1) / 2;
         if (prob->sdp_ptr[k + 1] - prob->sdp_ptr[k] != tri) throw CudaError(-3, "sdp cone length mismatch");
         cones[k].side = (int)side;
         cones[k].off = pos;
+        if (identity_) { pos += tri; continue; }
         for (long long q = prob->sdp_ptr[k]; q < prob->sdp_ptr[k + 1]; ++q) {
             long long v = prob->sdp_idx[q] - base;
             if (v < 0 || v >= n || used[(size_t)v]) throw CudaError(-3, "variable index out of range or in two cones");
@@ -318,20 +381,23 @@ void Solver::setup_host(const proxsdp_problem_t* prob) {
         }
     }
     psd_end_ = pos;
-    soc_off_h_.resize((size_t)n_soc); soc_len_h_.resize((size_t)n_soc);
     for (int k = 0; k < n_soc; ++k) {
         soc_off_h_[k] = pos;
         soc_len_h_[k] = (int)(prob->soc_ptr[k + 1] - prob->soc_ptr[k]);
+        if (identity_) { pos += soc_len_h_[k]; continue; }
         for (long long q = prob->soc_ptr[k]; q < prob->soc_ptr[k + 1]; ++q) {
             long long v = prob->soc_idx[q] - base;
             if (v < 0 || v >= n || used[(size_t)v]) throw CudaError(-3, "variable index out of range or in two cones");
             ord_[(size_t)pos++] = v; used[(size_t)v] = 1;
         }
     }
-    for (long long v = 0; v < n; ++v) if (!used[(size_t)v]) ord_[(size_t)pos++] = v;   // ascending
-    var_ordering_.assign((size_t)n, 0);
-    for (long long j = 0; j < n; ++j) var_ordering_[(size_t)ord_[(size_t)j]] = j;       // sortperm(ord)
+    if (!identity_) {
+        for (long long v = 0; v < n; ++v) if (!used[(size_t)v]) ord_[(size_t)pos++] = v;   // ascending
+        var_ordering_.assign((size_t)n, 0);
+        for (long long j = 0; j < n; ++j) var_ordering_[(size_t)ord_[(size_t)j]] = j;       // sortperm(ord)
+    }
 
+    st.lap("setup: scaling+M by column");
     // column scaling factors of norm_scaling (scaling.jl:28-58)
     std::vector<char> offdiag((size_t)n, 0);
     {
@@ -353,7 +419,7 @@ void Solver::setup_host(const proxsdp_problem_t* prob) {
     mt_val_.reserve((size_t)(nnzA + nnzG));
     mt_val_orig_.reserve((size_t)(nnzA + nnzG));
     for (long long j = 0; j < n; ++j) {
-        long long src = ord_[(size_t)j];
+        long long src = identity_ ? j : ord_[(size_t)j];
         double sc = offdiag[(size_t)j] ? cte : 1.0;
         if (nnzA > 0)
             for (long long q = prob->A_colptr[src] - base; q < prob->A_colptr[src + 1] - base; ++q) {
@@ -369,11 +435,9 @@ void Solver::setup_host(const proxsdp_problem_t* prob) {
             }
         mt_colptr_[(size_t)j + 1] = (long long)mt_rowidx_.size();
     }
-    c_host_.resize((size_t)n); c_orig_.resize((size_t)n);
-    for (long long j = 0; j < n; ++j) {
-        c_orig_[(size_t)j] = prob->c[ord_[(size_t)j]];
-        c_host_[(size_t)j] = offdiag[(size_t)j] ? c_orig_[(size_t)j] * cte : c_orig_[(size_t)j];
-    }
+    c_orig_.resize((size_t)n);
+    if (identity_) std::memcpy(c_orig_.data(), prob->c, sizeof(double) * (size_t)n);
+    else for (long long j = 0; j < n; ++j) c_orig_[(size_t)j] = prob->c[ord_[(size_t)j]];
     b_host_.assign(prob->b, prob->b + p); h_host_.assign(prob->h, prob->h + m);
     b_orig_ = b_host_; h_orig_ = h_host_;
 
@@ -394,10 +458,19 @@ void Solver::setup_host(const proxsdp_problem_t* prob) {
     for (Circ* c : {&dual_gap_, &prim_obj_, &dual_obj_, &feasibility_, &primal_residual_, &dual_residual_, &comb_residual_})
         c->init(2 * window_);
 
+    st.lap("setup: device vectors");
     // ---- device problem ----
-    c_.upload(c_host_); b_.upload(b_host_); h_.upload(h_host_);
+    c_.upload(c_orig_); b_.upload(b_host_); h_.upload(h_host_);
+    if (n_sdp > 0) {     // norm_scaling of c (scaling.jl:28-58): off-diagonal svec entries *= sqrt(2)/2, on the device
+        cone_side_d_.upload(std::vector<int>([&]{ std::vector<int> v((size_t)n_sdp); for (int k = 0; k < n_sdp; ++k) v[k] = cones[k].side; return v; }()));
+        cone_off_d_.upload(std::vector<long long>([&]{ std::vector<long long> v((size_t)n_sdp); for (int k = 0; k < n_sdp; ++k) v[k] = cones[k].off; return v; }()));
+        k_scale_offdiag<<<dim3(64, n_sdp), 256, 0, stream>>>(c_.p, cone_side_d_.p, cone_off_d_.p, n_sdp, cte, 0);
+        launches++;
+    }
     for (int q = 0; q < 2; ++q) { x_[q].alloc((size_t)n); Mty_[q].alloc((size_t)n); y_[q].alloc((size_t)R); Mx_[q].alloc((size_t)R); }
+    st.lap("setup: build_csr");
     if (!cones_only_) build_csr(mt_colptr_, mt_rowidx_, mt_val_);
+    st.lap("setup: cones");
 
     // cones
     long long kmax = 2 * std::max<long long>(opt.max_target_rank_krylov_eigs, r0) + 1;
@@ -418,7 +491,6 @@ void Solver::setup_host(const proxsdp_problem_t* prob) {
             large_ids_.push_back(k);
             cd.X.alloc((size_t)cd.ld * cd.ld);
             cd.Y.alloc((size_t)cd.ld * (size_t)(Kmax_ + 1));
-            cd.vcur.alloc((size_t)cd.ld);
             cd.vals.alloc((size_t)cd.ld);
             cd.kept_lam.alloc((size_t)cd.ld);
             cd.kept_idx.alloc((size_t)cd.ld);
@@ -431,7 +503,9 @@ void Solver::setup_host(const proxsdp_problem_t* prob) {
         }
         roff += cd.side;
     }
-    cone_side_d_.upload(side_h); cone_off_d_.upload(off_h); small_ids_d_.upload(small_ids_);
+    st.lap("setup: misc buffers+attrs");
+    if (n_sdp == 0) { cone_side_d_.upload(side_h); cone_off_d_.upload(off_h); }
+    small_ids_d_.upload(small_ids_);
     soc_off_d_.upload(soc_off_h_); soc_len_d_.upload(soc_len_h_); soc_gap_d_.alloc((size_t)std::max(n_soc, 1));
     out_min_d_.alloc((size_t)std::max(n_sdp, 1));
     offnorm_d_.alloc(2);
@@ -442,8 +516,6 @@ void Solver::setup_host(const proxsdp_problem_t* prob) {
     reduce_blocks_ = num_sms_ * 8;
     partials_d_.alloc((size_t)reduce_blocks_ * 8);
     counters_d_.alloc(16);
-    bar_d_.alloc(2);
-    lz_partials_d_.alloc((size_t)2 * (size_t)(Kmax_ + 2) * (size_t)num_sms_);
     ws_.partials = partials_d_.p; ws_.counters = counters_d_.p; ws_.max_blocks = reduce_blocks_;
 
     if (max_small_side_ > 1) {
@@ -452,6 +524,14 @@ void Solver::setup_host(const proxsdp_problem_t* prob) {
         PB_CUDA(cudaFuncSetAttribute(k_small_cone_proj, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb));
     }
     PB_CUDA(cudaFuncSetAttribute(k_lanczos, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_optin_));
+    {
+        cudaFuncAttributes fa{};
+        PB_CUDA(cudaFuncGetAttributes(&fa, k_lanczos_cl));
+        lz_cl_smem_max_ = smem_optin_ - fa.sharedSizeBytes;
+        PB_CUDA(cudaFuncSetAttribute(k_lanczos_cl, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lz_cl_smem_max_));
+    }
+    if (lz_cluster_ > 8) PB_CUDA(cudaFuncSetAttribute(k_lanczos_cl, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    st.lap("done");
     PB_CUDA(cudaFuncSetAttribute(k_bj_pair_eig, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bj_pair_smem_bytes()));
     PB_CUDA(cudaFuncSetAttribute(k_bj_apply<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BJ_APPLY_SMEM));
     PB_CUDA(cudaFuncSetAttribute(k_bj_apply<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BJ_APPLY_SMEM));
@@ -520,26 +600,96 @@ bool Solver::krylov_eligible(int k, long long iter) const {
            cones[(size_t)k].side > opt.min_size_krylov_eigs && (iter % opt.full_eig_freq) > opt.full_eig_len;
 }
 
+bool Solver::lanczos_launch_cluster(ConeDev& cd, int cone_idx, int nev, int K, int maxiter, double tol) {
+    if (lz_mode_ == 1 || K > LZC_KMAX) return false;
+    const int nside = cd.side;
+    const int C = lz_cluster_;
+    const int vn_max = (nside + C - 1) / C;
+    // grid: as many clusters as can be co-resident, but no more CTAs than there are 8-row slabs
+    int want = std::max(C, ((std::max(1, (nside + 7) / 8) + C - 1) / C) * C);
+    cudaLaunchConfig_t cfg{};
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)C; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.blockDim = dim3(LZ_THREADS); cfg.stream = stream; cfg.attrs = attr; cfg.numAttrs = 1;
+    // shared memory depends on rows_max = ceil(n / G); G depends on occupancy, which depends on shared memory:
+    // size for the smallest plausible grid first (largest rows_max), then shrink
+    int G = std::min(want, (num_sms_ / C) * C);
+    if (G < C) return false;
+    int rows_max = (nside + G - 1) / G;
+    size_t smem = lanczos_cl_smem_bytes(K, rows_max, vn_max, nside, C);
+    if (smem > lz_cl_smem_max_) return false;
+    cfg.gridDim = dim3((unsigned)G); cfg.dynamicSmemBytes = smem;
+    int max_clusters = 0;
+    if (cudaOccupancyMaxActiveClusters(&max_clusters, k_lanczos_cl, &cfg) != cudaSuccess || max_clusters < 1) {
+        cudaGetLastError();
+        return false;
+    }
+    if (max_clusters * C < G) {
+        G = max_clusters * C;
+        rows_max = (nside + G - 1) / G;
+        smem = lanczos_cl_smem_bytes(K, rows_max, vn_max, nside, C);
+        if (smem > lz_cl_smem_max_) return false;
+        cfg.gridDim = dim3((unsigned)G); cfg.dynamicSmemBytes = smem;
+    }
+    if ((rows_max + LZ_NW - 1) / LZ_NW + 1 > LZ_TMAX) return false;
+    if ((size_t)cd.ld * (size_t)(K + 1) > cd.Y.n) cd.Y.alloc((size_t)cd.ld * (size_t)(K + 1));
+    if (lz_wg_.n < (size_t)2 * cd.ld) lz_wg_.alloc((size_t)2 * cd.ld);
+    if (lz_bar_.n == 0) lz_bar_.alloc(4);
+    const size_t ws_len = 1 + (size_t)lanczos_kp(Kmax_ > K ? Kmax_ : K) * (size_t)lanczos_kp(Kmax_ > K ? Kmax_ : K);
+    for (int q = 0; q < 2; ++q) if (cd.ritz_ws[q].n < ws_len) { cd.ritz_ws[q].alloc(ws_len); cd.ritz_launches = 0; }
+    PB_CUDA(cudaMemsetAsync(lz_bar_.p, 0, sizeof(unsigned int), stream));
+    LanczosClArgs a{};
+    a.X = cd.X.p; a.n = nside; a.ld = cd.ld; a.x0 = cd.resid.p; a.Y = cd.Y.p;
+    a.wg = lz_wg_.p; a.bar = lz_bar_.p;
+    const int flip = (int)(cd.ritz_launches & 1);
+    // every 32nd eigsolve restarts the Ritz basis from the identity so rounding in the accumulated
+    // rotations cannot build up over a long solve
+    a.ritz_rd = (lz_warm_ && cd.ritz_launches > 0 && (cd.ritz_launches % 32) != 0) ? cd.ritz_ws[flip].p : nullptr;
+    a.ritz_wr = lz_warm_ ? cd.ritz_ws[1 - flip].p : nullptr;
+    cd.ritz_launches++;
+    a.nev = nev; a.K = K; a.maxiter = maxiter; a.tol = tol;
+    a.rows_max = rows_max; a.vn_max = vn_max; a.use_bi = lz_bi_;
+    a.vals = cd.vals.p; a.info = cd.info.p; a.scal = scal_d_.p; a.cone = cone_idx;
+    if (getenv("PROXSDP_B200_LZ_PROF")) { if (lz_prof_.n == 0) lz_prof_.alloc(8 + 8 * 256); a.prof = lz_prof_.p; }
+    cudaError_t e = cudaLaunchKernelEx(&cfg, k_lanczos_cl, a);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        if (!lz_cluster_warned_) { fprintf(stderr, "[proxsdp_b200] cluster Lanczos launch failed (%s); using the row-distributed kernel\n", cudaGetErrorString(e)); lz_cluster_warned_ = true; }
+        lz_mode_ = 1;
+        return false;
+    }
+    launches += 1;
+    lz_cluster_launches_++;
+    return true;
+}
+
 void Solver::lanczos_launch(ConeDev& cd, int cone_idx, int nev, int K, int maxiter, double tol) {
+    if (lanczos_launch_cluster(cd, cone_idx, nev, K, maxiter, tol)) return;
     const int nside = cd.side;
     int G = std::min(num_sms_, std::max(1, (nside + 7) / 8));
     int rows_max = (nside + G - 1) / G;
-    int nwarps = LZ_THREADS / 32;
-    int n2 = (nside + 1) & ~1;
-    int split = 1;
-    while (rows_max * split < 3 * nwarps && n2 / (split * 2) >= 256) split *= 2;
-    int panel = std::min((n2 + 63) & ~63, K > 64 ? 4096 : 8192);
-    size_t smem = lanczos_smem_bytes(K, rows_max, split, panel);
-    while (smem > smem_optin_ && panel > 512) { panel /= 2; smem = lanczos_smem_bytes(K, rows_max, split, panel); }
-    if (smem > smem_optin_) throw CudaError(-4, "Lanczos kernel: basis slab does not fit shared memory for this (n, K)");
-    if ((size_t)2 * (size_t)(K + 2) * (size_t)G > lz_partials_d_.n) lz_partials_d_.alloc((size_t)2 * (size_t)(K + 2) * (size_t)G);
+    if ((rows_max + LZ_NW - 1) / LZ_NW + 1 > LZ_TMAX) throw CudaError(-4, "Lanczos kernel: cone side too large for the row-slab layout");
+    size_t smem = lanczos_smem_bytes(K, rows_max, nside);
+    if (smem > smem_optin_) throw CudaError(-4, "Lanczos kernel: vector + basis slab do not fit shared memory for this (n, K)");
     if ((size_t)cd.ld * (size_t)(K + 1) > cd.Y.n) cd.Y.alloc((size_t)cd.ld * (size_t)(K + 1));
+    // flagged-exchange buffers (shared by all cones of this solver; launches are stream ordered)
+    const size_t need_x = (size_t)2 * (size_t)(K + 2) * (size_t)G, need_v = (size_t)2 * (size_t)cd.ld;
+    const unsigned long long bound = 4ULL * (unsigned long long)K * (unsigned long long)std::max(maxiter, 1) + 16ULL;
+    if (need_x > lz_xbuf_.n || need_v > lz_vx_.n || lz_epoch_ + bound >= 0xFFFFFFF0ULL) {
+        PB_CUDA(cudaStreamSynchronize(stream));
+        if (need_x > lz_xbuf_.n) lz_xbuf_.alloc(need_x); else PB_CUDA(cudaMemset(lz_xbuf_.p, 0, lz_xbuf_.n * sizeof(uint4)));
+        if (need_v > lz_vx_.n) lz_vx_.alloc(need_v); else PB_CUDA(cudaMemset(lz_vx_.p, 0, lz_vx_.n * sizeof(uint4)));
+        lz_epoch_ = 0;      // freshly zeroed buffers carry flag 0, which is never used
+    }
     LanczosArgs a{};
-    a.X = cd.X.p; a.n = nside; a.ld = cd.ld; a.x0 = cd.resid.p; a.vcur = cd.vcur.p; a.Y = cd.Y.p;
-    a.partials = lz_partials_d_.p; a.bar = bar_d_.p;
+    a.X = cd.X.p; a.n = nside; a.ld = cd.ld; a.x0 = cd.resid.p; a.Y = cd.Y.p;
+    a.xbuf = lz_xbuf_.p; a.vx = lz_vx_.p; a.epoch_base = (unsigned int)lz_epoch_;
+    lz_epoch_ += bound;
     a.nev = nev; a.K = K; a.maxiter = maxiter; a.tol = tol;
-    a.rows_max = rows_max; a.split = split; a.panel = panel;
+    a.rows_max = rows_max;
     a.vals = cd.vals.p; a.info = cd.info.p; a.scal = scal_d_.p; a.cone = cone_idx; a.n_cones_total = n_sdp;
+    if (getenv("PROXSDP_B200_LZ_PROF")) { if (lz_prof_.n == 0) lz_prof_.alloc(8 + 8 * 256); a.prof = lz_prof_.p; }
     void* args[] = {&a};
     PB_CUDA(cudaLaunchCooperativeKernel((void*)k_lanczos, dim3(G), dim3(LZ_THREADS), args, smem, stream));
     launches++;
@@ -825,8 +975,11 @@ double Solver::dual_feas_host(const std::vector<double>& y, const std::vector<do
             k_svec_to_mat<false><<<tiles, dim3(32, 8), 0, stream>>>(dcd.p + cd.off, nullptr, nullptr, 0.0, -1.0,
                                                                     cd.side, cd.ld, cd.X.p);
             launches++;
+            // Only the sign of lambda_min relative to tol_feasibility_dual is consumed (dual_feasible_user_tol,
+            // pdhg.jl:712-732), so the extreme eigenvalue is resolved to 1e-3 of that tolerance, not to 1e-10.
             int K = (int)std::max<long long>(opt.eigsolver_min_lanczos, 3);
-            lanczos_launch(cd, k, 1, K, 300, 1e-10);
+            const double tol_ev = std::max(1e-10, 1e-3 * std::min(opt.tol_feasibility_dual, 1.0));
+            lanczos_launch(cd, k, 1, K, 60, tol_ev);
             PB_CUDA(cudaStreamSynchronize(stream));
             std::vector<double> vals = cd.vals.download();
             double lmin = -vals[0];
@@ -846,8 +999,10 @@ double Solver::dual_feas_host(const std::vector<double>& y, const std::vector<do
     return std::max(cone_viol, std::max(ineq_viol, zero_viol));
 }
 
-__global__ void k_fix_diag_scaling(double* __restrict__ x, const int* __restrict__ cone_side,
-                                   const long long* __restrict__ cone_off, int n_sdp, double num) {
+// off-diagonal svec entries of every PSD block: x /= num (divide != 0, fix_diag_scaling pdhg.jl:734-743)
+// or x *= num (divide == 0, norm_scaling scaling.jl:28-58)
+__global__ void k_scale_offdiag(double* __restrict__ x, const int* __restrict__ cone_side,
+                                const long long* __restrict__ cone_off, int n_sdp, double num, int divide) {
     int cone = blockIdx.y;
     if (cone >= n_sdp) return;
     int side = cone_side[cone];
@@ -857,30 +1012,44 @@ __global__ void k_fix_diag_scaling(double* __restrict__ x, const int* __restrict
         while ((j + 1) * (j + 2) / 2 <= k) ++j;
         while (j * (j + 1) / 2 > k) --j;
         long long i = k - j * (j + 1) / 2;
-        if (i != j) x[cone_off[cone] + k] /= num;
+        if (i != j) { if (divide) x[cone_off[cone] + k] /= num; else x[cone_off[cone] + k] = __dmul_rn(x[cone_off[cone] + k], num); }
     }
+}
+
+__global__ void k_scale_copy(const double* __restrict__ src, double a, long long n, double* __restrict__ dst) {
+    long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = __dmul_rn(a, src[i]);
 }
 
 // cache_solution (pdhg.jl:745-787).  Like the reference it rescales pair.x IN PLACE.
 void Solver::cache_solution(const double* c_res, proxsdp_result_t* out) {
+    StageTimer st("finish: fix scaling+download");
     if (n_sdp > 0) {
-        k_fix_diag_scaling<<<dim3(64, n_sdp), 256, 0, stream>>>(x_[cur_].p, cone_side_d_.p, cone_off_d_.p, n_sdp, std::sqrt(2.0));
+        k_scale_offdiag<<<dim3(64, n_sdp), 256, 0, stream>>>(x_[cur_].p, cone_side_d_.p, cone_off_d_.p, n_sdp, std::sqrt(2.0), 1);
         launches++;
     }
     PB_CUDA(cudaStreamSynchronize(stream));
     std::vector<double> x = x_[cur_].download(), y = y_[cur_].download();
+    st.lap("finish: slack");
     std::vector<double> slack((size_t)R, 0.0);
     for (long long j = 0; j < n; ++j) {
         double xj = x[(size_t)j];
         for (long long q = mt_colptr_[(size_t)j]; q < mt_colptr_[(size_t)j + 1]; ++q)
             slack[(size_t)mt_rowidx_[(size_t)q]] += mt_val_orig_[(size_t)q] * xj;
     }
+    st.lap("finish: dual_feas");
     std::vector<double> cvec(c_res, c_res + n), dual_cone;
     double dfeas = dual_feas_host(y, cvec, &dual_cone);
+    st.lap("finish: outputs");
     out->status = stop_reason_;
     snprintf(out->status_string, PROXSDP_STATUS_STRING_LEN, "%s", stop_reason_string_.c_str());
-    if (out->primal) for (long long i = 0; i < n; ++i) out->primal[i] = x[(size_t)var_ordering_[(size_t)i]];
-    if (out->dual_cone) for (long long i = 0; i < n; ++i) out->dual_cone[i] = dual_cone[(size_t)var_ordering_[(size_t)i]];
+    if (identity_) {
+        if (out->primal && n > 0) std::memcpy(out->primal, x.data(), sizeof(double) * (size_t)n);
+        if (out->dual_cone && n > 0) std::memcpy(out->dual_cone, dual_cone.data(), sizeof(double) * (size_t)n);
+    } else {
+        if (out->primal) for (long long i = 0; i < n; ++i) out->primal[i] = x[(size_t)var_ordering_[(size_t)i]];
+        if (out->dual_cone) for (long long i = 0; i < n; ++i) out->dual_cone[i] = dual_cone[(size_t)var_ordering_[(size_t)i]];
+    }
     if (out->dual_eq) for (long long i = 0; i < p; ++i) out->dual_eq[i] = y[(size_t)i];
     if (out->dual_in) for (long long i = 0; i < m; ++i) out->dual_in[i] = y[(size_t)(p + i)];
     if (out->slack_eq) for (long long i = 0; i < p; ++i) out->slack_eq[i] = slack[(size_t)i] - b_orig_[(size_t)i];
@@ -901,6 +1070,7 @@ void Solver::cache_solution(const double* c_res, proxsdp_result_t* out) {
     out->result_count = 1;
     out->final_primal_res = primal_residual_.get(iter_);
     out->final_dual_res = dual_residual_.get(iter_);
+    st.lap("done");
 }
 
 void Solver::rank_increment_rule(int idx) {
@@ -947,10 +1117,10 @@ void Solver::begin(proxsdp_result_t* out) {
 
     // advanced initialisation (pdhg.jl:138-142): x = tau*c ; Mx = M x ; Mx_old = M*0 = 0
     if (opt.advanced_initialization) {
-        std::vector<double> x0((size_t)n);
-        for (long long i = 0; i < n; ++i) x0[(size_t)i] = primal_step_ * c_host_[(size_t)i];
-        PB_CUDA(cudaMemcpy(x_[cur_].p, x0.data(), sizeof(double) * (size_t)n, cudaMemcpyHostToDevice));
-        g_h2d_bytes += (long long)sizeof(double) * n;
+        if (n > 0) {
+            k_scale_copy<<<std::max(1, std::min(reduce_blocks_, ceil_div(n, 256))), 256, 0, stream>>>(c_.p, primal_step_, n, x_[cur_].p);
+            launches++;
+        }
         PB_CUDA(cudaMemsetAsync(scal_d_.p, 0, sizeof(double) * (size_t)scal_len, stream));
         // pdhg.jl:140 writes a.Mx; the first primal_step! overwrites it, and a.Mx_old = M*x_old = 0.
         launch_spmv(M_, x_[cur_].p, Mx_[cur_].p);
@@ -1173,7 +1343,6 @@ bool Solver::run(long long max_steps, bool flush_l2) {
         }
 
         auto start_cert_infeas = [&]() {       // certificate_infeasibility (pdhg.jl:655-676)
-            std::fill(c_host_.begin(), c_host_.end(), 0.0);
             PB_CUDA(cudaMemsetAsync(c_.p, 0, sizeof(double) * (size_t)std::max<long long>(n, 1), stream));
             certificate_search_min_iter_ = iter_ + 2 * opt.convergence_window + iter_ / 5 + 1000;
             certificate_search_ = true;
@@ -1263,6 +1432,16 @@ bool Solver::run(long long max_steps, bool flush_l2) {
 }
 
 void Solver::finish(proxsdp_result_t* out) {
+    if (lz_prof_.n) {
+        PB_CUDA(cudaStreamSynchronize(stream));
+        std::vector<long long> pr = lz_prof_.download();
+        const char* nm_rows[8] = {"symv", "fold", "pass1+xchg", "upd1+pass2+xchg", "upd2+beta", "publish+vxchg", "ritz", "loop-top"};
+        const char* nm_cl[8] = {"symv", "fold+gridsync+gather", "cgs dots+push (x2)", "cluster.sync (x2)", "beta+publish v", "ritz", "cgs reduce+update (x2)", "loop-top"};
+        const char** nm = lz_cluster_launches_ > 0 ? nm_cl : nm_rows;
+        long long tot = 0; for (int i = 0; i < 8; ++i) tot += pr[i];
+        fprintf(stderr, "[lz-prof] ritz: bisection accepted %lld, dense jacobi %lld, cycles up to the decision %lld\n", pr[8], pr[9], pr[10]);
+        for (int i = 0; i < 8; ++i) fprintf(stderr, "[lz-prof] %-16s %12lld cyc  %5.1f%%  (%.2f us/matvec)\n", nm[i], pr[i], 100.0 * pr[i] / std::max<long long>(tot, 1), pr[i] / 1965.0 / std::max<long long>(lanczos_matvecs, 1));
+    }
     out->time_loop = t_loop_accum_;
     // results (pdhg.jl:486-529)
     if (opt.certificate_search && certificate_search_) {
