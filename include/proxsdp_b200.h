@@ -91,6 +91,19 @@ int proxsdp_b200_lanczos(int64_t n, const double* A, const double* x0, int64_t h
  * w: n eigenvalues ascending; Z: n x n eigenvectors (may be NULL). */
 int proxsdp_b200_eigh(int64_t n, const double* A, double* w, double* Z);
 
+/* Multi-GPU: one process per GPU.  The communicator wraps NCCL: rank 0 obtains a
+ * 128-byte id, the host language broadcasts it (torch.distributed / MPI.jl), every rank calls comm_create.
+ * proxsdp_b200_solve_sharded is proxsdp_b200_solve on this rank's blocks with all whole-problem scalars
+ * combined across ranks: one all-gather of the 19-double iteration record per iteration plus one of the two
+ * line-search norms per trial; no vector ever crosses NVLink.  Results are this rank's pieces. */
+typedef struct proxsdp_b200_comm proxsdp_b200_comm_t;
+int proxsdp_b200_comm_unique_id(char id[128]);
+int proxsdp_b200_comm_create(const char id[128], int64_t rank, int64_t nranks, int64_t device_id,
+                             proxsdp_b200_comm_t** comm);
+int proxsdp_b200_comm_destroy(proxsdp_b200_comm_t* comm);
+int proxsdp_b200_solve_sharded(const proxsdp_problem_t* local_problem, const proxsdp_options_t* options,
+                               const proxsdp_shard_t* shard, proxsdp_result_t* local_result);
+
 /* Library / device information. */
 int proxsdp_b200_device_count(void);
 const char* proxsdp_b200_last_error(void);
@@ -99,6 +112,7 @@ const char* proxsdp_b200_version(void);
 int64_t proxsdp_b200_sizeof_problem(void);
 int64_t proxsdp_b200_sizeof_options(void);
 int64_t proxsdp_b200_sizeof_result(void);
+int64_t proxsdp_b200_sizeof_shard(void);
 
 #ifdef __cplusplus
 }

@@ -217,6 +217,22 @@ typedef struct proxsdp_result {
     int64_t d2h_bytes;           /* device->host bytes copied during this solve                           */
 } proxsdp_result_t;
 
+/* ---- sharded solves (independent blocks of a stacked problem, one block set per GPU) --------------
+ * The reference is single-process; this is the B200 extension of SURVEY.md section 8(e).  Each rank passes
+ * the sub-problem made of its blocks (variables, cones and rows that are coupled only among themselves:
+ * proxsdp_b200/sharding.py builds them) plus this descriptor.  Everything that the reference computes over
+ * the WHOLE problem — ||b||, ||c||, ||h||, ||M||_F, sqrt(N), sqrt(R), the line-search norms, the residual /
+ * feasibility maxima, the objective dot products, the convergence flags — is combined across ranks, so all
+ * ranks walk through exactly the iterations of the un-sharded solve and stop together. */
+typedef void (*proxsdp_reduce_fn)(double* vals, int64_t count, int64_t op /* 0 = sum, 1 = max */, void* ctx);
+typedef struct proxsdp_shard {
+    int64_t rank, nranks;
+    int64_t global_n, global_p, global_m;   /* sizes of the whole problem */
+    void*   comm;                           /* proxsdp_b200_comm_t* (product); NULL for the oracle       */
+    proxsdp_reduce_fn reduce;               /* oracle only (test infrastructure): host all-reduce callback */
+    void*   reduce_ctx;
+} proxsdp_shard_t;
+
 #ifdef __cplusplus
 }
 #endif

@@ -129,3 +129,27 @@ def num_threads() -> int:
 
 def set_num_threads(nt: int) -> None:
     lib().proxsdp_oracle_set_num_threads(nt)
+
+
+def chambolle_pock_sharded(aff_loc, con_loc, opt: Options, info, reduce_fn):
+    """Oracle counterpart of `proxsdp_b200_solve_sharded`: this rank's blocks, whole-problem scalars combined by
+    `reduce_fn(vals: np.ndarray, op: int)` (op 0 = sum, 1 = max; in place).  Test infrastructure for the
+    world_size > 1 host logic (gloo)."""
+    from proxsdp_b200._abi import MarshalledProblem, MarshalledResult, ProblemPOD, ResultPOD
+    from proxsdp_b200.sharding import REDUCE_FN, ShardPOD
+
+    def _cb(ptr, count, op, _ctx):
+        arr = np.ctypeslib.as_array(ptr, shape=(int(count),))
+        reduce_fn(arr, int(op))
+
+    cb = REDUCE_FN(_cb)
+    shard = ShardPOD(info.rank, info.world, info.global_n, info.global_p, info.global_m, None, cb, None)
+    mp = MarshalledProblem(aff_loc, con_loc)
+    mr = MarshalledResult(mp.n, mp.p, mp.m, mp.n_sdp, int(opt.trace_cap))
+    opod = opt.to_pod()
+    fn = lib().proxsdp_oracle_solve_sharded
+    fn.argtypes = [POINTER(ProblemPOD), POINTER(OptionsPOD), POINTER(ShardPOD), POINTER(ResultPOD)]
+    fn.restype = ctypes.c_int
+    rc = fn(ctypes.byref(mp.pod), ctypes.byref(opod), ctypes.byref(shard), ctypes.byref(mr.pod))
+    assert rc == 0, rc
+    return mr.to_result()

@@ -258,7 +258,16 @@ typedef struct {
     /* stats */
     double time_psd; int64_t n_psd, lanczos_matvecs, lanczos_calls, full_eig_calls, linesearch_trials;
     int64_t trace_mv0, trace_ls0;
+    /* sharded runs (test infrastructure for the multi-GPU host logic): whole-problem scalars are combined
+       across ranks through the host callback of proxsdp_shard_t */
+    const proxsdp_shard_t* shard;
+    int64_t global_n, global_R;
+    int global_has_soc;
 } state_t;
+
+static void red(const state_t* s, double* vals, int64_t count, int64_t op) {
+    if (s->shard && s->shard->nranks > 1 && s->shard->reduce) s->shard->reduce(vals, count, op, s->shard->reduce_ctx);
+}
 
 typedef proxsdp_options_t opts_t;
 
@@ -434,6 +443,11 @@ static void linesearch(state_t* s, const opts_t* opt) {
         for (int64_t i = 0; i < R; ++i) s->y_temp[i] -= s->y_old[i];
         double y_norm = vnorm2(R, s->y_temp);
         double Mty_norm = vnorm2(s->n, s->Mty);
+        if (s->shard) {
+            double v[2] = {y_norm * y_norm, Mty_norm * Mty_norm};
+            red(s, v, 2, 0);
+            y_norm = sqrt(v[0]); Mty_norm = sqrt(v[1]);
+        }
         if (sqrt(s->beta) * s->primal_step * Mty_norm <= opt->delta * y_norm) {
             break;
         } else {
@@ -471,19 +485,23 @@ static void compute_residual(state_t* s) {
     #pragma omp parallel for schedule(static) if (n > PAR_MIN)
     for (int64_t i = 0; i < n; ++i) s->x_old[i] -= s->Mty_old[i];
     mx1 = vnorminf(n, s->Mty_old);
+    double nx = vnorminf(n, s->x_old);
+    if (s->shard) { double v[2] = {mx1, nx}; red(s, v, 2, 1); mx1 = v[0]; nx = v[1]; }
     if (s->norm_b > mx1) mx1 = s->norm_b;
     if (s->norm_h > mx1) mx1 = s->norm_h;
     if (1.0 > mx1) mx1 = 1.0;
-    double pr = sqrt((double)n) * vnorminf(n, s->x_old) / mx1;
+    double pr = sqrt((double)(s->shard ? s->global_n : n)) * nx / mx1;
     circ_set(&s->primal_residual, s->iter, pr);
 
     for (int64_t i = 0; i < R; ++i) s->Mx_old[i] = s->y_old[i] - s->dual_step * s->Mx_old[i];
     for (int64_t i = 0; i < R; ++i) s->y_old[i] = s->y[i] - s->dual_step * s->Mx[i];
     for (int64_t i = 0; i < R; ++i) s->y_old[i] -= s->Mx_old[i];
     double mx2 = vnorminf(R, s->Mx_old);
+    double ny = vnorminf(R, s->y_old);
+    if (s->shard) { double v[2] = {mx2, ny}; red(s, v, 2, 1); mx2 = v[0]; ny = v[1]; }
     if (s->norm_c > mx2) mx2 = s->norm_c;
     if (1.0 > mx2) mx2 = 1.0;
-    double dr = sqrt((double)R) * vnorminf(R, s->y_old) / mx2;
+    double dr = sqrt((double)(s->shard ? s->global_R : R)) * ny / mx2;
     circ_set(&s->dual_residual, s->iter, dr);
     circ_set(&s->comb_residual, s->iter, pr > dr ? pr : dr);
 
@@ -495,22 +513,24 @@ static void compute_residual(state_t* s) {
 
 /* compute_gap! (residuals.jl:2-35) */
 static void compute_gap(state_t* s) {
-    if (s->p > 0) {
-        double f = 0.0;
-        for (int64_t i = 0; i < s->p; ++i) { double t = fabs(s->Mx[i] - s->b[i]); if (t > f) f = t; }
-        s->equa_feasibility = f / (1.0 + s->norm_b);
-    }
-    if (s->m > 0) {
-        double f = 0.0;
-        for (int64_t i = 0; i < s->m; ++i) { double t = s->Mx[s->p + i] - s->h[i]; if (t > f) f = t; }
-        s->ineq_feasibility = f / (1.0 + s->norm_h);
-    }
+    /* sharded: a rank may hold no equality (inequality) rows while the whole problem does */
+    double fe = 0.0, fi = 0.0;
+    for (int64_t i = 0; i < s->p; ++i) { double t = fabs(s->Mx[i] - s->b[i]); if (t > fe) fe = t; }
+    for (int64_t i = 0; i < s->m; ++i) { double t = s->Mx[s->p + i] - s->h[i]; if (t > fi) fi = t; }
+    int64_t gp = s->p, gm = s->m;
+    if (s->shard) { double v[2] = {fe, fi}; red(s, v, 2, 1); fe = v[0]; fi = v[1]; gp = s->shard->global_p; gm = s->shard->global_m; }
+    if (gp > 0) s->equa_feasibility = fe / (1.0 + s->norm_b);
+    if (gm > 0) s->ineq_feasibility = fi / (1.0 + s->norm_h);
     double feas = s->equa_feasibility > s->ineq_feasibility ? s->equa_feasibility : s->ineq_feasibility;
     circ_set(&s->feasibility, s->iter, feas);
     double po = vdot(s->n, s->c, s->x);
+    double by = 0.0, hy = 0.0;
+    if (s->p > 0) by = vdot(s->p, s->b, s->y);
+    if (s->m > 0) hy = vdot(s->m, s->h, s->y + s->p);
+    if (s->shard) { double v[3] = {po, by, hy}; red(s, v, 3, 0); po = v[0]; by = v[1]; hy = v[2]; }
     double dobj = 0.0;
-    if (s->p > 0) dobj -= vdot(s->p, s->b, s->y);
-    if (s->m > 0) dobj -= vdot(s->m, s->h, s->y + s->p);
+    if (gp > 0) dobj -= by;
+    if (gm > 0) dobj -= hy;
     circ_set(&s->prim_obj, s->iter, po);
     circ_set(&s->dual_obj, s->iter, dobj);
     circ_set(&s->dual_gap, s->iter, fabs(po - dobj) / (1.0 + fabs(po) + fabs(dobj)));
@@ -518,21 +538,24 @@ static void compute_gap(state_t* s) {
 
 /* soc_convergence (residuals.jl:73-86) */
 static int soc_convergence(const state_t* s, const opts_t* opt) {
+    int ok = 1;
     for (int64_t k = 0; k < s->n_soc; ++k) {
         const double* t = s->x + s->soc_off[k];
-        if (vnorm2(s->soc_len[k] - 1, t + 1) - t[0] >= opt->tol_soc) return 0;
+        if (vnorm2(s->soc_len[k] - 1, t + 1) - t[0] >= opt->tol_soc) { ok = 0; break; }
     }
-    return 1;
+    if (s->shard) { double f = ok ? 0.0 : 1.0; red(s, &f, 1, 1); ok = (f == 0.0); }
+    return ok;
 }
 /* convergedrank (residuals.jl:88-101) */
 static int convergedrank(const state_t* s, const opts_t* opt) {
+    int ok = 1;
     for (int64_t k = 0; k < s->n_sdp; ++k) {
         if (!(s->sdp_side[k] < opt->min_size_krylov_eigs ||
               s->target_rank[k] > opt->max_target_rank_krylov_eigs ||
-              s->min_eig[k] < opt->tol_psd))
-            return 0;
+              s->min_eig[k] < opt->tol_psd)) { ok = 0; break; }
     }
-    return 1;
+    if (s->shard) { double f = ok ? 0.0 : 1.0; red(s, &f, 1, 1); ok = (f == 0.0); }
+    return ok;
 }
 
 /* fix_diag_scaling (pdhg.jl:734-743) */
@@ -607,6 +630,7 @@ static double dual_feas_y(state_t* s, const double* y, const double* c) {
     get_duals(s, y, c, dc);
     double r = dual_feas_from(s, y + s->p, dc);
     free(dc);
+    red(s, &r, 1, 1);
     return r;
 }
 
@@ -622,6 +646,7 @@ static void cache_solution(state_t* s, const opts_t* opt, const double* c, proxs
     if (m > 0) { csc_mul(&s->G_orig, s->x, slack_in); for (int64_t i = 0; i < m; ++i) slack_in[i] -= s->h_orig[i]; }
     get_duals(s, s->y, c, dual_cone);
     double dfeas = dual_feas_from(s, s->y + p, dual_cone);
+    red(s, &dfeas, 1, 1);
 
     out->status = s->stop_reason;
     snprintf(out->status_string, PROXSDP_STATUS_STRING_LEN, "%s", s->stop_reason_string);
@@ -640,6 +665,7 @@ static void cache_solution(state_t* s, const opts_t* opt, const double* c, proxs
     out->iter = s->iter;
     int64_t fr = 0;
     for (int64_t k = 0; k < s->n_sdp; ++k) fr += s->current_rank[k];
+    { double f = (double)fr; red(s, &f, 1, 0); fr = (int64_t)f; }
     out->final_rank = fr;
     out->primal_feasible_user_tol = circ_get(&s->feasibility, s->iter) <= opt->tol_feasibility;
     out->dual_feasible_user_tol = dfeas <= opt->tol_feasibility_dual;
@@ -714,7 +740,18 @@ static void record_trace(state_t* s, proxsdp_result_t* out, int64_t cap) {
 /* ------------------------------------------------------------------------- */
 /* chambolle_pock (pdhg.jl:1-530)                                            */
 /* ------------------------------------------------------------------------- */
+static int oracle_solve_impl(const proxsdp_problem_t* prob, const proxsdp_options_t* opt_in, const proxsdp_shard_t* shard,
+                             proxsdp_result_t* out);
 int proxsdp_oracle_solve(const proxsdp_problem_t* prob, const proxsdp_options_t* opt_in, proxsdp_result_t* out) {
+    return oracle_solve_impl(prob, opt_in, NULL, out);
+}
+/* the same solve on this rank's blocks of a stacked problem; whole-problem scalars go through shard->reduce */
+int proxsdp_oracle_solve_sharded(const proxsdp_problem_t* prob, const proxsdp_options_t* opt_in, const proxsdp_shard_t* shard,
+                                 proxsdp_result_t* out) {
+    return oracle_solve_impl(prob, opt_in, (shard && shard->nranks > 1) ? shard : NULL, out);
+}
+static int oracle_solve_impl(const proxsdp_problem_t* prob, const proxsdp_options_t* opt_in, const proxsdp_shard_t* shard,
+                             proxsdp_result_t* out) {
     opts_t optv = *opt_in;          /* the reference mutates opt (pdhg.jl:33-41,673-674) */
     opts_t* opt = &optv;
     state_t S;
@@ -723,6 +760,8 @@ int proxsdp_oracle_solve(const proxsdp_problem_t* prob, const proxsdp_options_t*
     int64_t n = prob->n, p = prob->p, m = prob->m, base = prob->index_base;
     s->n = n; s->p = p; s->m = m; s->R = p + m;
     int64_t R = s->R;
+    s->shard = shard;
+    if (shard) { s->global_n = shard->global_n; s->global_R = shard->global_p + shard->global_m; }
     if (opt->equilibration || opt->equilibration_force) return -2;   /* out of scope */
 
     /* Params (pdhg.jl:7-31) */
@@ -734,6 +773,11 @@ int proxsdp_oracle_solve(const proxsdp_problem_t* prob, const proxsdp_options_t*
     s->norm_b = vnorm2(p, prob->b);
     s->norm_h = vnorm2(m, prob->h);
     s->norm_c = vnorm2(n, prob->c);
+    if (shard) {
+        double v[3] = {s->norm_b * s->norm_b, s->norm_h * s->norm_h, s->norm_c * s->norm_c};
+        red(s, v, 3, 0);
+        s->norm_b = sqrt(v[0]); s->norm_h = sqrt(v[1]); s->norm_c = sqrt(v[2]);
+    }
     s->rank_update = 0; s->stop_reason = 0; s->update_cont = 0;
     snprintf(s->stop_reason_string, PROXSDP_STATUS_STRING_LEN, "Not optimized");
     s->n_sdp = prob->n_sdp; s->n_soc = prob->n_soc;
@@ -751,8 +795,10 @@ int proxsdp_oracle_solve(const proxsdp_problem_t* prob, const proxsdp_options_t*
     int64_t ada_count = 0;
     int have_cached = 0;               /* sol = Array{Result}(undef, 0) */
 
+    double any_cone = (nso > 0 || nsd > 0) ? 1.0 : 0.0;
+    if (shard) red(s, &any_cone, 1, 1);
     if (opt->max_iter <= 0) {
-        if (nso > 0 || nsd > 0) opt->max_iter_local = opt->max_iter_conic;
+        if (any_cone != 0.0) opt->max_iter_local = opt->max_iter_conic;
         else opt->max_iter_local = opt->max_iter_lp;
     } else {
         opt->max_iter_local = opt->max_iter;
@@ -871,6 +917,7 @@ int proxsdp_oracle_solve(const proxsdp_problem_t* prob, const proxsdp_options_t*
     s->M = csc_vstack(&s->A, &s->G);
     s->Mt = csc_transpose(&s->M);
     double spectral_norm = vnorm2(s->M.nnz, s->M.val);       /* approx_norm = true: Frobenius */
+    if (shard) { double v = spectral_norm * spectral_norm; red(s, &v, 1, 0); spectral_norm = sqrt(v); }
     if (spectral_norm < 1e-10) spectral_norm = 1.0;
     s->primal_step = 1.0 / spectral_norm;
     s->primal_step_old = s->primal_step;
@@ -971,10 +1018,13 @@ int proxsdp_oracle_solve(const proxsdp_problem_t* prob, const proxsdp_options_t*
                    s->rank_update > s->window) {
             s->update_cont += 1;
             if (s->update_cont > opt->divergence_min_update) {
+                double any_room = 0.0;
                 for (int64_t idx = 0; idx < nsd; ++idx) {
-                    if (s->target_rank[idx] < s->sdp_side[idx]) { s->rank_update = 0; s->update_cont = 0; }
+                    if (s->target_rank[idx] < s->sdp_side[idx]) any_room = 1.0;
                     rank_increment_rule(s, opt, idx);
                 }
+                if (shard) red(s, &any_room, 1, 1);
+                if (any_room != 0.0) { s->rank_update = 0; s->update_cont = 0; }
             }
         } else if (pr_k > opt->tol_primal && dr_k < opt->tol_dual && k > s->window) {
             ada_count += 1;
@@ -1005,7 +1055,9 @@ int proxsdp_oracle_solve(const proxsdp_problem_t* prob, const proxsdp_options_t*
         }
 
         /* max_iter or time limit (pdhg.jl:335-382) */
-        if (s->iter >= opt->max_iter_local || now_s() - s->time0 >= opt->time_limit) {
+        double elapsed_k = now_s() - s->time0;
+        if (shard) red(s, &elapsed_k, 1, 1);      /* all ranks must leave the loop together */
+        if (s->iter >= opt->max_iter_local || elapsed_k >= opt->time_limit) {
             if (s->iter > opt->min_iter_time_infeas &&
                 circ_max_abs_diff(&s->dual_gap) < opt->infeas_stable_gap_tol &&
                 circ_get(&s->dual_gap, k) > opt->infeas_limit_gap_tol) {
@@ -1041,7 +1093,7 @@ int proxsdp_oracle_solve(const proxsdp_problem_t* prob, const proxsdp_options_t*
                 snprintf(s->stop_reason_string, PROXSDP_STATUS_STRING_LEN,
                          "Time limit hit, limit: %g time: %g", opt->time_limit, now_s() - s->time0);
             }
-            if (s->iter >= opt->max_iter_local || now_s() - s->time0 >= opt->time_limit) break;
+            if (s->iter >= opt->max_iter_local || elapsed_k >= opt->time_limit) break;
         }
 
         if (opt->certificate_search && s->certificate_search) continue;            /* pdhg.jl:385-387 */

@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libproxsdp_b200.so")
 SOURCES = ["solver.cu"]
-HEADERS = ["common.cuh", "jacobi.cuh", "kernels_vec.cuh", "lanczos.cuh", "fulleig.cuh"]
+HEADERS = ["common.cuh", "jacobi.cuh", "kernels_vec.cuh", "lanczos.cuh", "lanczos_cl.cuh", "ritz_bi.cuh", "fulleig.cuh"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-shared",
@@ -35,7 +35,7 @@ def is_stale() -> bool:
 def build_extension(force: bool = False, verbose: bool = False) -> str:
     if not force and not is_stale():
         return LIB
-    cmd = [_nvcc()] + NVCC_FLAGS + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+    cmd = [_nvcc()] + NVCC_FLAGS + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES] + ["-ldl"]
     if verbose:
         cmd += ["-Xptxas", "-v"]
     res = subprocess.run(cmd, capture_output=True, text=True)

@@ -38,6 +38,7 @@ enum ScalarSlot {
     S_SOC_GAP,          // max over SOC cones of ||v|| - t
     S_POISON,           // != 0: a Lanczos call did not converge; the rest of the iteration was skipped
     S_NUMOPS,           // Lanczos mat-vecs performed this iteration
+    S_ELAPSED,          // host wall-clock seconds since the start of the solve (sharded runs: max over ranks decides time limits)
     S_HEADER            // per-cone records follow: current_rank, min_eig, converged (3 doubles each)
 };
 
@@ -274,7 +275,7 @@ k_spmv_mt_norm(MtArgs a, double* __restrict__ scal, ReduceWs ws) {
             double tau = scal[S_TAU];
             double lhs = mul_rn(mul_rn(sqrt(a.beta), tau), sqrt(s));
             double rhs = mul_rn(a.delta, sqrt(scal[S_YNORM2]));
-            if (!a.do_test || lhs <= rhs) {
+            if (a.do_test != 2 && (!a.do_test || lhs <= rhs)) {      // do_test == 2: sharded run, k_ls_decide decides
                 scal[S_LS_ACCEPTED] = 1.0;
                 scal[S_LS_TRIAL] = (double)a.trial;
             }
@@ -389,9 +390,46 @@ k_residual_dual(int p, int m, double beta, int use_beta, double sigma_fixed,
 }
 
 // reset the per-iteration scalar record (keeps nothing from the previous iteration)
-__global__ void k_scal_reset(double* __restrict__ scal, int n) {
+__global__ void k_scal_reset(double* __restrict__ scal, int n, double soc_gap_init, double elapsed) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) scal[i] = 0.0;
+    if (i < n) scal[i] = (i == S_SOC_GAP) ? soc_gap_init : (i == S_ELAPSED ? elapsed : 0.0);
+}
+
+// ---------------------------------------------------------------------------
+// sharded runs: combine the per-rank iteration records (gathered in rank order) in place.
+// sums: objective dot products, mat-vec count; maxima (NaN-propagating for the residual norms): the rest.
+// The line-search slots are already identical on every rank (k_ls_decide).
+// ---------------------------------------------------------------------------
+__global__ void k_fold_header(const double* __restrict__ gathered, int nranks, double* __restrict__ scal) {
+    int slot = threadIdx.x;
+    if (slot >= S_HEADER) return;
+    double v = gathered[slot];
+    for (int r = 1; r < nranks; ++r) {
+        double o = gathered[(size_t)r * S_HEADER + slot];
+        switch (slot) {
+            case S_PRIM_OBJ: case S_BY: case S_HY: case S_NUMOPS: v += o; break;
+            case S_RES_P_NUM: case S_RES_P_DEN: case S_RES_D_NUM: case S_RES_D_DEN: v = nanmax(v, o); break;
+            case S_EQ_MAX: case S_IN_MAX: case S_SOC_GAP: case S_POISON: case S_ELAPSED: v = fmax(v, o); break;
+            default: break;     // line-search slots: rank 0's copy (identical everywhere)
+        }
+    }
+    scal[slot] = v;
+}
+
+// sharded line search: sums of the two squared norms over ranks (rank order), then the accept test of
+// pdhg.jl:566 exactly as k_spmv_mt_norm evaluates it in the single-GPU case.  gathered: [nranks][2].
+__global__ void k_ls_decide(const double* __restrict__ gathered, int nranks, double* __restrict__ scal,
+                            double beta, double delta, int trial) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    if (scal[S_LS_ACCEPTED] != 0.0) return;
+    double yn = 0.0, mn = 0.0;
+    for (int r = 0; r < nranks; ++r) { yn += gathered[2 * r]; mn += gathered[2 * r + 1]; }
+    scal[S_YNORM2] = yn; scal[S_MTYNORM2] = mn;
+    scal[S_LS_EVALS] = (double)(trial + 1);
+    double tau = scal[S_TAU];
+    double lhs = mul_rn(mul_rn(sqrt(beta), tau), sqrt(mn));
+    double rhs = mul_rn(delta, sqrt(yn));
+    if (lhs <= rhs) { scal[S_LS_ACCEPTED] = 1.0; scal[S_LS_TRIAL] = (double)trial; }
 }
 
 // max over SOC cones of the stored gaps -> scal[S_SOC_GAP]  (single small block)

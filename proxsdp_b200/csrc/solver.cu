@@ -12,6 +12,9 @@
 #include <numeric>
 #include <vector>
 
+#include <dlfcn.h>
+#include <nccl.h>
+
 #include "../../include/proxsdp_b200.h"
 #include "common.cuh"
 #include "fulleig.cuh"
@@ -27,6 +30,39 @@ __global__ void k_scale_offdiag(double* __restrict__ x, const int* __restrict__ 
 __global__ void k_scale_copy(const double* __restrict__ src, double a, long long n, double* __restrict__ dst);
 
 static thread_local std::string g_last_error;
+
+// ---------------------------------------------------------------------------
+// NCCL, bound at run time (dlopen) so that the library loads on machines without it; only the
+// sharded (multi-GPU) entry points need it.
+// ---------------------------------------------------------------------------
+struct NcclApi {
+    void* handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+static NcclApi& nccl_api() {
+    static NcclApi api;
+    if (api.handle) return api;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* nm : names) { api.handle = dlopen(nm, RTLD_NOW | RTLD_GLOBAL); if (api.handle) break; }
+    if (!api.handle) throw CudaError(-6, "NCCL not found (dlopen libnccl.so.2 failed): multi-GPU entry points are unavailable");
+    auto sym = [&](const char* n) { void* f = dlsym(api.handle, n); if (!f) throw CudaError(-6, std::string("NCCL symbol missing: ") + n); return f; };
+    api.GetUniqueId = reinterpret_cast<decltype(api.GetUniqueId)>(sym("ncclGetUniqueId"));
+    api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(sym("ncclCommInitRank"));
+    api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(sym("ncclCommDestroy"));
+    api.AllGather = reinterpret_cast<decltype(api.AllGather)>(sym("ncclAllGather"));
+    api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(sym("ncclGetErrorString"));
+    return api;
+}
+#define PB_NCCL(expr)                                                                              \
+    do {                                                                                           \
+        ncclResult_t _r = (expr);                                                                  \
+        if (_r != ncclSuccess) throw pb::CudaError(-7, std::string(#expr " failed: ") + nccl_api().GetErrorString(_r)); \
+    } while (0)
+
 
 static bool g_timing = getenv("PROXSDP_B200_TIMING") != nullptr;
 static double now_s();
@@ -148,6 +184,13 @@ static void eig_resid_default(long long n, long long seed, long long init, doubl
     }
 }
 
+}  // namespace pb
+struct proxsdp_b200_comm {
+    ncclComm_t comm = nullptr;
+    int rank = 0, nranks = 1, device = 0;
+};
+namespace pb {
+
 // ---------------------------------------------------------------------------
 // per-cone device state
 // ---------------------------------------------------------------------------
@@ -166,7 +209,8 @@ struct ConeDev {
 
 class Solver {
   public:
-    Solver(const proxsdp_problem_t* prob, const proxsdp_options_t* opt_in, bool cones_only = false, bool force_large = false);
+    Solver(const proxsdp_problem_t* prob, const proxsdp_options_t* opt_in, bool cones_only = false, bool force_large = false,
+           const proxsdp_shard_t* shard = nullptr);
     ~Solver();
     void solve(proxsdp_result_t* out);
     // stepwise form of the same loop (bench / step-level seam): begin -> run(max_steps)* -> finish
@@ -274,6 +318,14 @@ class Solver {
     long long n_psd_ = 0;
     int ladder_ = 4;
     long long trace_mv0_ = 0, trace_ls0_ = 0;
+    // sharded solves: whole-problem scalars are combined across ranks
+    proxsdp_b200_comm* comm_ = nullptr;
+    int nranks_ = 1, rank_ = 0;
+    long long global_n_ = -1, global_R_ = -1, global_p_ = -1, global_m_ = -1;
+    bool global_has_soc_ = false;
+    DBuf<double> gather_d_, red_d_;
+    void host_reduce(double* vals, int count, int op);          // op 0 = sum, 1 = max (rank-ordered, deterministic)
+    bool sharded() const { return nranks_ > 1; }
     // loop-carried state of chambolle_pock's main loop
     long long ada_count_ = 0, k_next_ = 1;
     bool have_cached_ = false, loop_done_ = false;
@@ -292,8 +344,18 @@ class Solver {
 // ---------------------------------------------------------------------------
 // construction / setup  (pdhg.jl:7-142)
 // ---------------------------------------------------------------------------
-Solver::Solver(const proxsdp_problem_t* prob, const proxsdp_options_t* opt_in, bool cones_only, bool force_large)
+Solver::Solver(const proxsdp_problem_t* prob, const proxsdp_options_t* opt_in, bool cones_only, bool force_large,
+               const proxsdp_shard_t* shard)
     : opt(*opt_in), force_large_(force_large), cones_only_(cones_only) {
+    if (shard && shard->nranks > 1) {
+        if (!shard->comm) throw CudaError(-1, "sharded solve needs a communicator");
+        comm_ = static_cast<proxsdp_b200_comm*>(shard->comm);
+        nranks_ = comm_->nranks; rank_ = comm_->rank;
+        if (nranks_ != shard->nranks || rank_ != shard->rank) throw CudaError(-1, "shard descriptor does not match the communicator");
+        global_n_ = shard->global_n; global_R_ = shard->global_p + shard->global_m;
+        global_p_ = shard->global_p; global_m_ = shard->global_m;
+        opt.device_id = comm_->device;
+    }
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) throw CudaError(-5, "no CUDA device available");
     dev_ = (int)opt.device_id;
@@ -339,6 +401,7 @@ void Solver::setup_host(const proxsdp_problem_t* prob) {
     // norms before any permutation / scaling (pdhg.jl:14-16)
     auto nrm2 = [](const double* v, long long len) { double s = 0; for (long long i = 0; i < len; ++i) s += v[i] * v[i]; return std::sqrt(s); };
     norm_b_ = nrm2(prob->b, p); norm_h_ = nrm2(prob->h, m); norm_c_ = nrm2(prob->c, n);
+    // (sharded runs combine these with the other ranks once the stream exists: see finish_setup_sharded)
 
     // preprocess! (scaling.jl:2-26): ord = [sdp vars..., soc vars..., sorted remaining]
     cones.resize((size_t)n_sdp);
@@ -444,6 +507,17 @@ void Solver::setup_host(const proxsdp_problem_t* prob) {
     // step size: 1 / ||M||_F (pdhg.jl:121-133)
     double fro = 0.0;
     for (double v : mt_val_) fro += v * v;
+    double any_cone = (n_soc > 0 || n_sdp > 0) ? 1.0 : 0.0, any_soc = n_soc > 0 ? 1.0 : 0.0;
+    if (sharded()) {
+        // whole-problem norms: sqrt of the rank-ordered sum of the per-rank sums of squares
+        double sums[4] = {norm_b_ * norm_b_, norm_h_ * norm_h_, norm_c_ * norm_c_, fro};
+        host_reduce(sums, 4, 0);
+        norm_b_ = std::sqrt(sums[0]); norm_h_ = std::sqrt(sums[1]); norm_c_ = std::sqrt(sums[2]); fro = sums[3];
+        double flags[2] = {any_cone, any_soc};
+        host_reduce(flags, 2, 1);
+        any_cone = flags[0]; any_soc = flags[1];
+    }
+    global_has_soc_ = any_soc != 0.0;
     fro = std::sqrt(fro);
     if (fro < 1e-10) fro = 1.0;
     primal_step_ = 1.0 / fro; primal_step_old_ = primal_step_; dual_step_ = primal_step_;
@@ -453,7 +527,7 @@ void Solver::setup_host(const proxsdp_problem_t* prob) {
     beta_ = opt.initial_beta;
     long long r0 = opt.initial_target_rank > 0 ? opt.initial_target_rank : 2;
     target_rank.assign((size_t)n_sdp, r0); current_rank.assign((size_t)n_sdp, r0); min_eig.assign((size_t)n_sdp, 0.0);
-    if (opt.max_iter <= 0) opt.max_iter_local = (n_soc > 0 || n_sdp > 0) ? opt.max_iter_conic : opt.max_iter_lp;
+    if (opt.max_iter <= 0) opt.max_iter_local = (any_cone != 0.0) ? opt.max_iter_conic : opt.max_iter_lp;
     else opt.max_iter_local = opt.max_iter;
     for (Circ* c : {&dual_gap_, &prim_obj_, &dual_obj_, &feasibility_, &primal_residual_, &dual_residual_, &comb_residual_})
         c->init(2 * window_);
@@ -845,10 +919,17 @@ void Solver::launch_dual_trial(int trial, double tau0) {
     MtArgs t{};
     t.N = (int)n; t.rowptr = Mt_.rowptr.p; t.colidx = Mt_.colidx.p; t.val = Mt_.val.p;
     t.y_new = y_[1 - cur_].p; t.Mty = Mty_[cur_].p; t.Mty_new = Mty_[1 - cur_].p;
-    t.beta = beta_; t.delta = opt.delta; t.trial = trial; t.do_test = opt.line_search_flag ? 1 : 0;
+    t.beta = beta_; t.delta = opt.delta; t.trial = trial;
+    t.do_test = opt.line_search_flag ? (sharded() ? 2 : 1) : 0;
     int blocks2 = std::max(1, std::min(reduce_blocks_, ceil_div(n, 256)));
     k_spmv_mt_norm<<<blocks2, 256, 0, stream>>>(t, scal_d_.p, ws_);
     launches += 2;
+    if (sharded() && opt.line_search_flag) {
+        if (red_d_.n < (size_t)nranks_ * 16) red_d_.alloc((size_t)nranks_ * 16);
+        PB_NCCL(nccl_api().AllGather(scal_d_.p + S_YNORM2, red_d_.p, 2, ncclDouble, comm_->comm, stream));
+        k_ls_decide<<<1, 32, 0, stream>>>(red_d_.p, nranks_, scal_d_.p, beta_, opt.delta, trial);
+        launches++;
+    }
 }
 
 // everything after the eigen-solves: SOC projection, Mx, dual step / linesearch ladder, residuals
@@ -872,7 +953,7 @@ void Solver::launch_post_eig(double tau0, bool first_pass) {
         launches += 2;
     }
     launch_spmv(M_, xn, Mx_[1 - cur_].p);
-    int ntr = opt.line_search_flag ? ladder_ : 1;
+    int ntr = opt.line_search_flag ? (sharded() ? 1 : ladder_) : 1;
     for (int t = 0; t < ntr; ++t) launch_dual_trial(t, tau0);
     int blocksN = std::max(1, std::min(reduce_blocks_, ceil_div(n, 512)));
     k_residual_primal<<<blocksN, 256, 0, stream>>>(n, xn, x_[cur_].p, Mty_[1 - cur_].p, Mty_[cur_].p, c_.p, scal_d_.p, ws_);
@@ -891,7 +972,8 @@ void Solver::launch_soc_only() {
 }
 
 void Solver::reset_scalars() {
-    k_scal_reset<<<ceil_div(scal_len, 256), 256, 0, stream>>>(scal_d_.p, scal_len);
+    const double soc_init = (sharded() && n_soc == 0) ? -1.0e300 : 0.0;
+    k_scal_reset<<<ceil_div(scal_len, 256), 256, 0, stream>>>(scal_d_.p, scal_len, soc_init, time0_ > 0 ? now_s() - time0_ : 0.0);
     launches++;
 }
 
@@ -899,6 +981,7 @@ void Solver::reset_scalars() {
 // redone with the full eigendecomposition; the others only need their (skipped) reconstruction.
 void Solver::fallback_projection(long long iter) {
     PB_CUDA(cudaMemsetAsync(scal_d_.p + S_POISON, 0, sizeof(double), stream));
+    if (sharded()) PB_CUDA(cudaMemsetAsync(scal_d_.p + S_LS_ACCEPTED, 0, sizeof(double) * (S_LS_EVALS + 1), stream));   // other ranks ran their trials on partial sums
     for (int kk : large_ids_) {
         if (!krylov_eligible(kk, iter)) continue;
         if (scal_host[S_HEADER + 3 * kk + 2] == 0.0) {
@@ -914,11 +997,38 @@ void Solver::fallback_projection(long long iter) {
 }
 
 void Solver::sync_scalars() {
+    if (sharded()) {
+        if (gather_d_.n < (size_t)nranks_ * S_HEADER) gather_d_.alloc((size_t)nranks_ * S_HEADER);
+        PB_NCCL(nccl_api().AllGather(scal_d_.p, gather_d_.p, S_HEADER, ncclDouble, comm_->comm, stream));
+        k_fold_header<<<1, 32, 0, stream>>>(gather_d_.p, nranks_, scal_d_.p);
+        launches++;
+    }
     PB_CUDA(cudaMemcpyAsync(scal_host, scal_d_.p, sizeof(double) * (size_t)scal_len, cudaMemcpyDeviceToHost, stream));
     g_d2h_bytes += (long long)sizeof(double) * scal_len;
     PB_CUDA(cudaStreamSynchronize(stream));
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) throw CudaError(-100 - (int)e, std::string("kernel launch failed: ") + cudaGetErrorString(e));
+}
+
+// host-level all-reduce of a few doubles (setup norms, rare convergence flags): all-gather + rank-ordered fold
+void Solver::host_reduce(double* vals, int count, int op) {
+    if (!sharded()) return;
+    if (count > 16) throw CudaError(-1, "host_reduce: too many values");
+    if (red_d_.n < (size_t)(nranks_ + 1) * 16) red_d_.alloc((size_t)(nranks_ + 1) * 16);
+    double* send = red_d_.p + (size_t)nranks_ * 16;
+    PB_CUDA(cudaMemcpyAsync(send, vals, sizeof(double) * (size_t)count, cudaMemcpyHostToDevice, stream));
+    PB_NCCL(nccl_api().AllGather(send, red_d_.p, (size_t)count, ncclDouble, comm_->comm, stream));
+    std::vector<double> all((size_t)nranks_ * (size_t)count);
+    PB_CUDA(cudaMemcpyAsync(all.data(), red_d_.p, sizeof(double) * all.size(), cudaMemcpyDeviceToHost, stream));
+    PB_CUDA(cudaStreamSynchronize(stream));
+    for (int i = 0; i < count; ++i) {
+        double v = all[(size_t)i];
+        for (int r = 1; r < nranks_; ++r) {
+            double o = all[(size_t)r * count + i];
+            v = (op == 0) ? v + o : jl_max(v, o);
+        }
+        vals[i] = v;
+    }
 }
 
 // ---------------------------------------------------------------------------
@@ -1040,6 +1150,7 @@ void Solver::cache_solution(const double* c_res, proxsdp_result_t* out) {
     st.lap("finish: dual_feas");
     std::vector<double> cvec(c_res, c_res + n), dual_cone;
     double dfeas = dual_feas_host(y, cvec, &dual_cone);
+    host_reduce(&dfeas, 1, 1);
     st.lap("finish: outputs");
     out->status = stop_reason_;
     snprintf(out->status_string, PROXSDP_STATUS_STRING_LEN, "%s", stop_reason_string_.c_str());
@@ -1063,6 +1174,7 @@ void Solver::cache_solution(const double* c_res, proxsdp_result_t* out) {
     out->iter = iter_;
     long long fr = 0;
     for (long long r : current_rank) fr += r;
+    if (sharded()) { double f = (double)fr; host_reduce(&f, 1, 0); fr = (long long)f; }
     out->final_rank = fr;
     out->primal_feasible_user_tol = feasibility_.get(iter_) <= opt.tol_feasibility;
     out->dual_feasible_user_tol = dfeas <= opt.tol_feasibility_dual;
@@ -1183,7 +1295,7 @@ bool Solver::run(long long max_steps, bool flush_l2) {
         // ---- linesearch beyond the speculative ladder (pdhg.jl:543-571)
         long long evals = (long long)scal_host[S_LS_EVALS];
         if (opt.line_search_flag && scal_host[S_LS_ACCEPTED] == 0.0) {
-            long long t = ladder_;
+            long long t = sharded() ? 1 : ladder_;
             while (scal_host[S_LS_ACCEPTED] == 0.0 && t < opt.max_linsearch_steps) {
                 launch_dual_trial((int)t, tau0);
                 sync_scalars();
@@ -1223,23 +1335,24 @@ bool Solver::run(long long max_steps, bool flush_l2) {
             current_rank[(size_t)q] = (long long)scal_host[S_HEADER + 3 * q + 0];
             min_eig[(size_t)q] = scal_host[S_HEADER + 3 * q + 1];
         }
-        soc_gap_max_ = n_soc > 0 ? scal_host[S_SOC_GAP] : -1.0;
+        soc_gap_max_ = (n_soc > 0 || global_has_soc_) ? scal_host[S_SOC_GAP] : -1.0;
         // compute_residual! (residuals.jl:37-71)
         {
             double den = jl_max(jl_max(scal_host[S_RES_P_DEN], norm_b_), jl_max(norm_h_, 1.0));
-            double pr = std::sqrt((double)n) * scal_host[S_RES_P_NUM] / den;
+            double pr = std::sqrt((double)(sharded() ? global_n_ : n)) * scal_host[S_RES_P_NUM] / den;
             double den2 = jl_max(jl_max(scal_host[S_RES_D_DEN], norm_c_), 1.0);
-            double dr = std::sqrt((double)R) * scal_host[S_RES_D_NUM] / den2;
+            double dr = std::sqrt((double)(sharded() ? global_R_ : R)) * scal_host[S_RES_D_NUM] / den2;
             primal_residual_.set(k, pr); dual_residual_.set(k, dr); comb_residual_.set(k, jl_max(pr, dr));
         }
         // compute_gap! (residuals.jl:2-35)
         {
-            if (p > 0) equa_feasibility_ = scal_host[S_EQ_MAX] / (1.0 + norm_b_);
-            if (m > 0) ineq_feasibility_ = scal_host[S_IN_MAX] / (1.0 + norm_h_);
+            const long long gp = sharded() ? global_p_ : p, gm = sharded() ? global_m_ : m;
+            if (gp > 0) equa_feasibility_ = scal_host[S_EQ_MAX] / (1.0 + norm_b_);
+            if (gm > 0) ineq_feasibility_ = scal_host[S_IN_MAX] / (1.0 + norm_h_);
             feasibility_.set(k, std::max(equa_feasibility_, ineq_feasibility_));
             double po = scal_host[S_PRIM_OBJ], dobj = 0.0;
-            if (p > 0) dobj -= scal_host[S_BY];
-            if (m > 0) dobj -= scal_host[S_HY];
+            if (gp > 0) dobj -= scal_host[S_BY];
+            if (gm > 0) dobj -= scal_host[S_HY];
             prim_obj_.set(k, po); dual_obj_.set(k, dobj);
             dual_gap_.set(k, std::fabs(po - dobj) / (1.0 + std::fabs(po) + std::fabs(dobj)));
         }
@@ -1251,6 +1364,7 @@ bool Solver::run(long long max_steps, bool flush_l2) {
             for (long long i = 0; i < n; ++i) cc[(size_t)i] = f * c_orig_[(size_t)i];
             std::vector<double> y = y_[cur_].download();
             dual_feasibility_ = dual_feas_host(y, cc, nullptr);
+            host_reduce(&dual_feasibility_, 1, 1);
             dual_feasibility_check_ = true;
         } else {
             dual_feasibility_check_ = false;
@@ -1265,6 +1379,7 @@ bool Solver::run(long long max_steps, bool flush_l2) {
                     std::vector<double> cc((size_t)n, 0.0);
                     std::vector<double> y = y_[cur_].download();
                     dual_feasibility_ = dual_feas_host(y, cc, nullptr);
+                    host_reduce(&dual_feasibility_, 1, 1);
                     dual_feasibility_check_ = true;
                     if (dual_feasibility_ < opt.tol_feasibility_dual) {
                         certificate_found_ = true;
@@ -1299,7 +1414,8 @@ bool Solver::run(long long max_steps, bool flush_l2) {
             for (int q = 0; q < n_sdp; ++q)
                 if (!(cones[(size_t)q].side < opt.min_size_krylov_eigs || target_rank[(size_t)q] > opt.max_target_rank_krylov_eigs ||
                       min_eig[(size_t)q] < opt.tol_psd)) { conv_rank = false; break; }
-            bool conv_soc = !(n_soc > 0 && soc_gap_max_ >= opt.tol_soc);      // residuals.jl:73-86
+            bool conv_soc = !((n_soc > 0 || global_has_soc_) && soc_gap_max_ >= opt.tol_soc);      // residuals.jl:73-86
+            if (sharded()) { double f = conv_rank ? 0.0 : 1.0; host_reduce(&f, 1, 1); conv_rank = (f == 0.0); }
             if (conv_rank && conv_soc && iter_ > opt.min_iter) {
                 if (!certificate_search_) {
                     stop_reason_ = 1;
@@ -1319,10 +1435,13 @@ bool Solver::run(long long max_steps, bool flush_l2) {
         } else if (k > window_ && comb_residual_.get(k - window_) < comb_residual_.get(k) && rank_update_ > window_) {
             update_cont_ += 1;
             if (update_cont_ > opt.divergence_min_update) {
+                bool any_room = false;
                 for (int q = 0; q < n_sdp; ++q) {
-                    if (target_rank[(size_t)q] < cones[(size_t)q].side) { rank_update_ = 0; update_cont_ = 0; }
+                    if (target_rank[(size_t)q] < cones[(size_t)q].side) any_room = true;
                     rank_increment_rule(q);
                 }
+                if (sharded()) { double f = any_room ? 1.0 : 0.0; host_reduce(&f, 1, 1); any_room = (f != 0.0); }
+                if (any_room) { rank_update_ = 0; update_cont_ = 0; }     // the counters are whole-problem state
             }
         } else if (pr_k > opt.tol_primal && dr_k < opt.tol_dual && k > window_) {
             ada_count += 1;
@@ -1363,7 +1482,8 @@ bool Solver::run(long long max_steps, bool flush_l2) {
         };
 
         // max_iter or time limit (pdhg.jl:335-382)
-        if (iter_ >= opt.max_iter_local || now_s() - time0_ >= opt.time_limit) {
+        const double elapsed_k = sharded() ? scal_host[S_ELAPSED] : now_s() - time0_;      // sharded: max over ranks, so all ranks stop together
+        if (iter_ >= opt.max_iter_local || elapsed_k >= opt.time_limit) {
             if (iter_ > opt.min_iter_time_infeas && dual_gap_.max_abs_diff() < opt.infeas_stable_gap_tol &&
                 dual_gap_.get(k) > opt.infeas_limit_gap_tol) {
                 if (feasibility_.get(iter_) <= opt.tol_feasibility / 100) {
@@ -1388,7 +1508,7 @@ bool Solver::run(long long max_steps, bool flush_l2) {
                 snprintf(buf, sizeof(buf), "Time limit hit, limit: %g time: %g", opt.time_limit, now_s() - time0_);
                 stop_reason_string_ = buf;
             }
-            if (iter_ >= opt.max_iter_local || now_s() - time0_ >= opt.time_limit) break;
+            if (iter_ >= opt.max_iter_local || elapsed_k >= opt.time_limit) break;
         }
 
         if (opt.certificate_search && certificate_search_) continue;          // pdhg.jl:385-387
@@ -1531,6 +1651,55 @@ int proxsdp_b200_solve(const proxsdp_problem_t* problem, const proxsdp_options_t
         s.solve(result);
         result->time_setup = t_setup;
         result->time += t_setup;    // the reference's clock (p.time0, pdhg.jl:13) starts before the Init block
+    });
+}
+
+int proxsdp_b200_comm_unique_id(char id[128]) {
+    if (!id) { g_last_error = "null argument"; return -1; }
+    return guarded([&]() {
+        static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is expected to be 128 bytes");
+        ncclUniqueId uid;
+        PB_NCCL(nccl_api().GetUniqueId(&uid));
+        std::memcpy(id, &uid, 128);
+    });
+}
+
+int proxsdp_b200_comm_create(const char id[128], int64_t rank, int64_t nranks, int64_t device_id,
+                             proxsdp_b200_comm_t** comm) {
+    if (!id || !comm || nranks < 1 || rank < 0 || rank >= nranks) { g_last_error = "invalid argument"; return -1; }
+    *comm = nullptr;
+    return guarded([&]() {
+        int ndev = 0;
+        if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) throw CudaError(-5, "no CUDA device available");
+        if (device_id < 0 || device_id >= ndev) throw CudaError(-1, "device_id out of range");
+        PB_CUDA(cudaSetDevice((int)device_id));
+        std::unique_ptr<proxsdp_b200_comm> c(new proxsdp_b200_comm());
+        c->rank = (int)rank; c->nranks = (int)nranks; c->device = (int)device_id;
+        ncclUniqueId uid;
+        std::memcpy(&uid, id, 128);
+        PB_NCCL(nccl_api().CommInitRank(&c->comm, (int)nranks, uid, (int)rank));
+        *comm = c.release();
+    });
+}
+
+int proxsdp_b200_comm_destroy(proxsdp_b200_comm_t* comm) {
+    if (!comm) return 0;
+    return guarded([&]() {
+        if (comm->comm) nccl_api().CommDestroy(comm->comm);
+        delete comm;
+    });
+}
+
+int proxsdp_b200_solve_sharded(const proxsdp_problem_t* problem, const proxsdp_options_t* options,
+                               const proxsdp_shard_t* shard, proxsdp_result_t* result) {
+    if (!problem || !options || !shard || !result) { g_last_error = "null argument"; return -1; }
+    return guarded([&]() {
+        double t0 = now_s();
+        Solver s(problem, options, false, false, shard);
+        double t_setup = now_s() - t0;
+        s.solve(result);
+        result->time_setup = t_setup;
+        result->time += t_setup;
     });
 }
 
@@ -1777,5 +1946,6 @@ const char* proxsdp_b200_version(void) { return "proxsdp_b200 0.1.0 (sm_100a)"; 
 int64_t proxsdp_b200_sizeof_problem(void) { return (int64_t)sizeof(proxsdp_problem_t); }
 int64_t proxsdp_b200_sizeof_options(void) { return (int64_t)sizeof(proxsdp_options_t); }
 int64_t proxsdp_b200_sizeof_result(void) { return (int64_t)sizeof(proxsdp_result_t); }
+int64_t proxsdp_b200_sizeof_shard(void) { return (int64_t)sizeof(proxsdp_shard_t); }
 
 }  // extern "C"
