@@ -237,6 +237,21 @@ k_dual_trial(DualArgs a, double* __restrict__ scal, ReduceWs ws) {
     }
 }
 
+// long rows of M' (a variable that appears in thousands of constraints, e.g. the anchor block of the
+// sensor-localisation SDP): one block per row, same gating as the line-search trial it belongs to
+__global__ void k_spmv_mt_long(const int* __restrict__ long_rows, const int* __restrict__ rowptr,
+                               const int* __restrict__ colidx, const double* __restrict__ val,
+                               const double* __restrict__ y, double* __restrict__ out, const double* __restrict__ scal) {
+    __shared__ double red[40];
+    if (scal[S_POISON] != 0.0 || scal[S_LS_ACCEPTED] != 0.0) return;
+    int row = long_rows[blockIdx.x];
+    int b = rowptr[row], e = rowptr[row + 1];
+    double s = 0.0;
+    for (int k = b + threadIdx.x; k < e; k += blockDim.x) s += val[k] * y[colidx[k]];
+    s = block_sum(s, red);
+    if (threadIdx.x == 0) out[row] = s;
+}
+
 // ---------------------------------------------------------------------------
 // K13+K17: Mty_new = M' y_new (CSR of M' == CSC of M, one thread per row of M'),
 // fused with ||Mty_new - Mty||^2 and the accept test
@@ -245,6 +260,7 @@ k_dual_trial(DualArgs a, double* __restrict__ scal, ReduceWs ws) {
 // ---------------------------------------------------------------------------
 struct MtArgs {
     int N; const int* rowptr; const int* colidx; const double* val;
+    int long_threshold;      // rows of M' longer than this were computed by k_spmv_mt_long into Mty_new already
     const double* y_new; const double* Mty; double* Mty_new;
     double beta, delta; int trial, do_test;
 };
@@ -258,8 +274,12 @@ k_spmv_mt_norm(MtArgs a, double* __restrict__ scal, ReduceWs ws) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.N; i += gridDim.x * blockDim.x) {
         int b = a.rowptr[i], e = a.rowptr[i + 1];
         double s = 0.0;
-        for (int k = b; k < e; ++k) s += a.val[k] * a.y_new[a.colidx[k]];
-        a.Mty_new[i] = s;
+        if (e - b > a.long_threshold) {
+            s = a.Mty_new[i];
+        } else {
+            for (int k = b; k < e; ++k) s += a.val[k] * a.y_new[a.colidx[k]];
+            a.Mty_new[i] = s;
+        }
         double d = sub_rn(s, a.Mty[i]);
         acc += d * d;
     }

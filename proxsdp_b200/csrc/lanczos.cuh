@@ -45,6 +45,7 @@ struct LanczosArgs {
     double* scal;        // iteration scalar record (S_POISON, S_NUMOPS, per-cone slots)
     int cone;            // cone index for the per-cone slots
     int n_cones_total;
+    int jac_inplace;     // 1: the three K x K Jacobi matrices do not fit shared memory -> two-matrix in-place solver
     long long* prof;     // optional (debug): per-phase clock64 totals of CTA 0, 8 slots
 };
 
@@ -125,14 +126,14 @@ __host__ __device__ inline int lanczos_rlp(int rows_max) { return rows_max | 1; 
 __host__ __device__ inline int lanczos_kp(int K) { return (K + 2) | 1; }
 __host__ __device__ inline int lanczos_cpr(int n) { return (n + 63) / 64; }
 
-__host__ __device__ inline size_t lanczos_smem_bytes(int K, int rows_max, int n) {
+__host__ __device__ inline size_t lanczos_smem_bytes(int K, int rows_max, int n, int jac_inplace = 0) {
     size_t RLp = (size_t)lanczos_rlp(rows_max), Kp = (size_t)lanczos_kp(K);
     size_t d = (size_t)lanczos_cpr(n) * 64 + 2 * (size_t)(K + 1) * RLp + RLp + (size_t)LZ_NW * LZ_TMAX + (size_t)(K + 2) +
-               5 * (size_t)K + 3 * Kp * Kp;
+               5 * (size_t)K + (jac_inplace ? 2 : 3) * Kp * Kp;
     return d * sizeof(double) + sizeof(int) * (size_t)(((K + 2 + 3) & ~3) + 32) + jacobi_scratch_bytes((int)Kp) + 64;
 }
 
-__device__ inline LanczosSmem lanczos_carve(unsigned char* base, int K, int rows_max, int n) {
+__device__ inline LanczosSmem lanczos_carve(unsigned char* base, int K, int rows_max, int n, int jac_inplace) {
     LanczosSmem s;
     size_t RLp = (size_t)lanczos_rlp(rows_max), Kp = (size_t)lanczos_kp(K);
     double* d = reinterpret_cast<double*>(base);
@@ -148,7 +149,7 @@ __device__ inline LanczosSmem lanczos_carve(unsigned char* base, int K, int rows
     s.D = d; d += K;
     s.f = d; d += K;
     s.JA = d; d += Kp * Kp;
-    s.JB = d; d += Kp * Kp;
+    s.JB = d; if (!jac_inplace) d += Kp * Kp;      // in-place Jacobi (huge K): JB is not used
     s.JU = d; d += Kp * Kp;
     s.order = reinterpret_cast<int*>(d);
     s.wgs = s.order + ((K + 2 + 3) & ~3);
@@ -166,7 +167,7 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) k_lanczos(LanczosArgs a) {
     const int RLp = lanczos_rlp(a.rows_max);
     const int cpr = lanczos_cpr(n);            // 64-double chunks per row
     const int Kp2 = K + 2;
-    LanczosSmem sm = lanczos_carve(smem_raw, K, a.rows_max, n);
+    LanczosSmem sm = lanczos_carve(smem_raw, K, a.rows_max, n, a.jac_inplace);
     JacobiScratch js = jacobi_carve(sm.jscratch, lanczos_kp(K));
     double* slab = sm.slabA;       // current basis slab: slab[q * RLp + r]
     double* slab_alt = sm.slabB;
@@ -436,7 +437,9 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) k_lanczos(LanczosArgs a) {
                 sm.JA[r + c * lda] = v;
             }
             __syncthreads();
-            const double* Jd = jacobi_eigh_smem_fast(m, sm.JA, sm.JB, lda, sm.JU, lda, js);
+            const double* Jd = sm.JA;
+            if (a.jac_inplace) jacobi_eigh_smem(m, sm.JA, lda, sm.JU, lda, js);
+            else Jd = jacobi_eigh_smem_fast(m, sm.JA, sm.JB, lda, sm.JU, lda, js);
             __syncthreads();
             rank_sort_desc(k, Jd, lda, sm.order);
             __syncthreads();

@@ -281,14 +281,17 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) k_lanczos_cl(LanczosClArgs a) {
             const int hw = tid >> 4, hl = tid & 15;
             for (int qb = 0; qb <= j + 1; qb += LZ_THREADS / 16) {
                 const int q = qb + hw;
-                double s0 = 0.0, s1 = 0.0;
+                double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
                 if (q <= j + 1) {
                     const double* vq = (q <= j) ? Vs + (size_t)q * VNp : sm.wv;
                     int t = hl;
-                    for (; t + 16 < vn; t += 32) { s0 = fma(vq[t], sm.wv[t], s0); s1 = fma(vq[t + 16], sm.wv[t + 16], s1); }
-                    if (t < vn) s0 = fma(vq[t], sm.wv[t], s0);
+                    for (; t + 48 < vn; t += 64) {          // four independent chains: FP64 FMA latency is the bound here
+                        s0 = fma(vq[t], sm.wv[t], s0); s1 = fma(vq[t + 16], sm.wv[t + 16], s1);
+                        s2 = fma(vq[t + 32], sm.wv[t + 32], s2); s3 = fma(vq[t + 48], sm.wv[t + 48], s3);
+                    }
+                    for (; t < vn; t += 16) s0 = fma(vq[t], sm.wv[t], s0);
                 }
-                double s = s0 + s1;
+                double s = (s0 + s1) + (s2 + s3);
                 s += __shfl_xor_sync(0xffffffffu, s, 8);
                 s += __shfl_xor_sync(0xffffffffu, s, 4);
                 s += __shfl_xor_sync(0xffffffffu, s, 2);
@@ -304,7 +307,12 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) k_lanczos_cl(LanczosClArgs a) {
                 double s = 0.0;
                 if (q <= j + 1) {
                     const double* hp = sm.hpart + (size_t)pass * C * Kp2 + q;
-                    for (int c = 0; c < C; ++c) s += hp[(size_t)c * Kp2];
+                    if (C == 8) {        // fixed pairwise tree (3 dependent adds instead of 8)
+                        s = ((hp[0] + hp[(size_t)Kp2]) + (hp[(size_t)2 * Kp2] + hp[(size_t)3 * Kp2])) +
+                            ((hp[(size_t)4 * Kp2] + hp[(size_t)5 * Kp2]) + (hp[(size_t)6 * Kp2] + hp[(size_t)7 * Kp2]));
+                    } else {
+                        for (int c = 0; c < C; ++c) s += hp[(size_t)c * Kp2];
+                    }
                     sm.hred[q] = s;
                 }
                 double sq = (q <= j) ? s * s : 0.0;
@@ -322,16 +330,18 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) k_lanczos_cl(LanczosClArgs a) {
             // w <- w - V h on my rows (two threads per row when there are enough threads)
             if (2 * vn <= LZ_THREADS) {
                 const int t = tid >> 1, sub = tid & 1;
-                double s0 = 0.0, s1 = 0.0;
+                double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
                 if (t < vn) {
                     int q = sub;
-                    for (; q + 2 <= j; q += 4) {
+                    for (; q + 6 <= j; q += 8) {
                         s0 = fma(sm.hred[q], Vs[(size_t)q * VNp + t], s0);
                         s1 = fma(sm.hred[q + 2], Vs[(size_t)(q + 2) * VNp + t], s1);
+                        s2 = fma(sm.hred[q + 4], Vs[(size_t)(q + 4) * VNp + t], s2);
+                        s3 = fma(sm.hred[q + 6], Vs[(size_t)(q + 6) * VNp + t], s3);
                     }
-                    if (q <= j) s0 = fma(sm.hred[q], Vs[(size_t)q * VNp + t], s0);
+                    for (; q <= j; q += 2) s0 = fma(sm.hred[q], Vs[(size_t)q * VNp + t], s0);
                 }
-                double sacc = s0 + s1;
+                double sacc = (s0 + s1) + (s2 + s3);
                 sacc += __shfl_xor_sync(0xffffffffu, sacc, 1);
                 if (t < vn && sub == 0) sm.wv[t] -= sacc;
             } else {

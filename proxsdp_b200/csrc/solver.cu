@@ -621,6 +621,11 @@ void Solver::build_csr(const std::vector<long long>& colptr, const std::vector<i
         for (long long j = 0; j <= n; ++j) rp[(size_t)j] = (int)colptr[(size_t)j];
         Mt_.nrows = (int)n; Mt_.ncols = (int)R; Mt_.nnz = (int)nnz;
         Mt_.rowptr.upload(rp); Mt_.colidx.upload(rowidx); Mt_.val.upload(val);
+        Mt_.long_threshold = 256;      // one thread per row below this, one block per row above
+        std::vector<int> longs_t;
+        for (long long j = 0; j < n; ++j) if (rp[(size_t)j + 1] - rp[(size_t)j] > Mt_.long_threshold) longs_t.push_back((int)j);
+        Mt_.n_long = (int)longs_t.size();
+        Mt_.long_rows.upload(longs_t);
     }
     // M_: transpose by counting sort (keeps increasing column order inside a row)
     std::vector<int> rp((size_t)R + 1, 0), ci((size_t)nnz);
@@ -744,7 +749,9 @@ void Solver::lanczos_launch(ConeDev& cd, int cone_idx, int nev, int K, int maxit
     int G = std::min(num_sms_, std::max(1, (nside + 7) / 8));
     int rows_max = (nside + G - 1) / G;
     if ((rows_max + LZ_NW - 1) / LZ_NW + 1 > LZ_TMAX) throw CudaError(-4, "Lanczos kernel: cone side too large for the row-slab layout");
-    size_t smem = lanczos_smem_bytes(K, rows_max, nside);
+    int jac_inplace = 0;
+    size_t smem = lanczos_smem_bytes(K, rows_max, nside, 0);
+    if (smem > smem_optin_) { jac_inplace = 1; smem = lanczos_smem_bytes(K, rows_max, nside, 1); }
     if (smem > smem_optin_) throw CudaError(-4, "Lanczos kernel: vector + basis slab do not fit shared memory for this (n, K)");
     if ((size_t)cd.ld * (size_t)(K + 1) > cd.Y.n) cd.Y.alloc((size_t)cd.ld * (size_t)(K + 1));
     // flagged-exchange buffers (shared by all cones of this solver; launches are stream ordered)
@@ -761,7 +768,7 @@ void Solver::lanczos_launch(ConeDev& cd, int cone_idx, int nev, int K, int maxit
     a.xbuf = lz_xbuf_.p; a.vx = lz_vx_.p; a.epoch_base = (unsigned int)lz_epoch_;
     lz_epoch_ += bound;
     a.nev = nev; a.K = K; a.maxiter = maxiter; a.tol = tol;
-    a.rows_max = rows_max;
+    a.rows_max = rows_max; a.jac_inplace = jac_inplace;
     a.vals = cd.vals.p; a.info = cd.info.p; a.scal = scal_d_.p; a.cone = cone_idx; a.n_cones_total = n_sdp;
     if (getenv("PROXSDP_B200_LZ_PROF")) { if (lz_prof_.n == 0) lz_prof_.alloc(8 + 8 * 256); a.prof = lz_prof_.p; }
     void* args[] = {&a};
@@ -917,7 +924,12 @@ void Solver::launch_dual_trial(int trial, double tau0) {
     int blocks = std::max(1, std::min(reduce_blocks_, ceil_div(R, 256)));
     k_dual_trial<<<blocks, 256, 0, stream>>>(d, scal_d_.p, ws_);
     MtArgs t{};
-    t.N = (int)n; t.rowptr = Mt_.rowptr.p; t.colidx = Mt_.colidx.p; t.val = Mt_.val.p;
+    t.N = (int)n; t.rowptr = Mt_.rowptr.p; t.colidx = Mt_.colidx.p; t.val = Mt_.val.p; t.long_threshold = Mt_.long_threshold;
+    if (Mt_.n_long > 0) {
+        k_spmv_mt_long<<<Mt_.n_long, 512, 0, stream>>>(Mt_.long_rows.p, Mt_.rowptr.p, Mt_.colidx.p, Mt_.val.p, y_[1 - cur_].p,
+                                                       Mty_[1 - cur_].p, scal_d_.p);
+        launches++;
+    }
     t.y_new = y_[1 - cur_].p; t.Mty = Mty_[cur_].p; t.Mty_new = Mty_[1 - cur_].p;
     t.beta = beta_; t.delta = opt.delta; t.trial = trial;
     t.do_test = opt.line_search_flag ? (sharded() ? 2 : 1) : 0;
