@@ -131,7 +131,7 @@ def config_dict(n_gpus: int, flush: bool, extra=None):
                        "(N = 2 001 000 svec variables), 2000 equality rows diag(X) = 1, FP64, default Options",
         "step": "one PDHG iteration (iterations 1..K from the reference's cold start)",
         "parallelism": "single cone: replicas only" if n_gpus > 1 else "1 GPU",
-        "l2": ("flushed before every iteration (384 MiB memset on the solver's stream, inside the timed region)"
+        "l2": ("flushed before every iteration (192 MiB memset > 126 MB L2, on the solver's stream, inside the timed region)"
                if flush else "not flushed: every iteration consumes the previous iteration's outputs"),
     }
     if extra:
@@ -150,6 +150,12 @@ def run_reference(args):
     from proxsdp_b200 import Options
     oracle.build()
     aff, con = build_workload()
+    # all host cores this process may use (torchrun exports OMP_NUM_THREADS=1, which would cripple the CPU arm)
+    try:
+        ncores = len(os.sched_getaffinity(0))
+    except Exception:
+        ncores = os.cpu_count() or 1
+    oracle.set_num_threads(ncores)
     cores = oracle.num_threads()
     budget_s = float(args.cpu_budget)
     if args.warmup > 0:
@@ -295,6 +301,10 @@ def run_b200(args):
     if world == 1 and not args.no_cpu_baseline:
         from oracle import oracle
         oracle.build()
+        try:
+            oracle.set_num_threads(len(os.sched_getaffinity(0)))
+        except Exception:
+            pass
         cores = oracle.num_threads()
         budget = float(args.cpu_budget)
         oracle.chambolle_pock(aff, con, Options(max_iter=3))

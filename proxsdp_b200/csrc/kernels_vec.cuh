@@ -261,6 +261,7 @@ __global__ void k_spmv_mt_long(const int* __restrict__ long_rows, const int* __r
 struct MtArgs {
     int N; const int* rowptr; const int* colidx; const double* val;
     int long_threshold;      // rows of M' longer than this were computed by k_spmv_mt_long into Mty_new already
+    const int* nz_rows; int n_nz;   // non-empty rows of M' (DCSR): Mty is identically zero on all other rows, so only these are walked
     const double* y_new; const double* Mty; double* Mty_new;
     double beta, delta; int trial, do_test;
 };
@@ -271,7 +272,8 @@ k_spmv_mt_norm(MtArgs a, double* __restrict__ scal, ReduceWs ws) {
     __shared__ int s_last;
     if (scal[S_POISON] != 0.0 || scal[S_LS_ACCEPTED] != 0.0) return;
     double acc = 0.0;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.N; i += gridDim.x * blockDim.x) {
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < a.n_nz; q += gridDim.x * blockDim.x) {
+        const int i = a.nz_rows[q];
         int b = a.rowptr[i], e = a.rowptr[i + 1];
         double s = 0.0;
         if (e - b > a.long_threshold) {
@@ -318,14 +320,34 @@ k_residual_primal(long long N, const double* __restrict__ x, const double* __res
     const double tau = scal[S_TAU];
     double num = 0.0, den = 0.0, obj = 0.0;
     long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += stride) {
-        double xo = x_old[i], xn = x[i];
-        double pold = sub_rn(xo, mul_rn(tau, Mty_old[i]));
-        double pnew = sub_rn(xn, mul_rn(tau, Mty[i]));
+    // 128-bit loads, two independent pairs per thread per trip: ten 16-byte loads in flight per thread
+    const long long npair = N >> 1;
+    const double2* x2 = reinterpret_cast<const double2*>(x);
+    const double2* xo2 = reinterpret_cast<const double2*>(x_old);
+    const double2* m2 = reinterpret_cast<const double2*>(Mty);
+    const double2* mo2 = reinterpret_cast<const double2*>(Mty_old);
+    const double2* c2 = reinterpret_cast<const double2*>(c);
+    double obj1 = 0.0;
+    auto one = [&](double xn, double xo, double mt, double mo, double cc, double& ob) {
+        double pold = sub_rn(xo, mul_rn(tau, mo));
+        double pnew = sub_rn(xn, mul_rn(tau, mt));
         num = nanmax(num, fabs(sub_rn(pnew, pold)));
         den = nanmax(den, fabs(pold));
-        obj += c[i] * xn;
+        ob = fma(cc, xn, ob);
+    };
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + stride < npair; i += 2 * stride) {
+        const double2 a0 = x2[i], b0 = xo2[i], d0 = m2[i], e0 = mo2[i], f0 = c2[i];
+        const double2 a1 = x2[i + stride], b1 = xo2[i + stride], d1 = m2[i + stride], e1 = mo2[i + stride], f1 = c2[i + stride];
+        one(a0.x, b0.x, d0.x, e0.x, f0.x, obj); one(a0.y, b0.y, d0.y, e0.y, f0.y, obj1);
+        one(a1.x, b1.x, d1.x, e1.x, f1.x, obj); one(a1.y, b1.y, d1.y, e1.y, f1.y, obj1);
     }
+    for (; i < npair; i += stride) {
+        const double2 a0 = x2[i], b0 = xo2[i], d0 = m2[i], e0 = mo2[i], f0 = c2[i];
+        one(a0.x, b0.x, d0.x, e0.x, f0.x, obj); one(a0.y, b0.y, d0.y, e0.y, f0.y, obj1);
+    }
+    if ((N & 1) && blockIdx.x == 0 && threadIdx.x == 0) one(x[N - 1], x_old[N - 1], Mty[N - 1], Mty_old[N - 1], c[N - 1], obj);
+    obj += obj1;
     num = block_nanmax(num, red);
     den = block_nanmax(den, red);
     obj = block_sum(obj, red);

@@ -129,7 +129,8 @@ struct DBuf {
 
 struct CsrDev {
     int nrows = 0, ncols = 0, nnz = 0, group = 1, n_long = 0, long_threshold = 1 << 30;
-    DBuf<int> rowptr, colidx, long_rows;
+    DBuf<int> rowptr, colidx, long_rows, nz_rows;
+    int n_nz = 0;
     DBuf<double> val;
 };
 
@@ -626,6 +627,10 @@ void Solver::build_csr(const std::vector<long long>& colptr, const std::vector<i
         for (long long j = 0; j < n; ++j) if (rp[(size_t)j + 1] - rp[(size_t)j] > Mt_.long_threshold) longs_t.push_back((int)j);
         Mt_.n_long = (int)longs_t.size();
         Mt_.long_rows.upload(longs_t);
+        std::vector<int> nzr;
+        for (long long j = 0; j < n; ++j) if (rp[(size_t)j + 1] > rp[(size_t)j]) nzr.push_back((int)j);
+        Mt_.n_nz = (int)nzr.size();
+        Mt_.nz_rows.upload(nzr);
     }
     // M_: transpose by counting sort (keeps increasing column order inside a row)
     std::vector<int> rp((size_t)R + 1, 0), ci((size_t)nnz);
@@ -925,6 +930,7 @@ void Solver::launch_dual_trial(int trial, double tau0) {
     k_dual_trial<<<blocks, 256, 0, stream>>>(d, scal_d_.p, ws_);
     MtArgs t{};
     t.N = (int)n; t.rowptr = Mt_.rowptr.p; t.colidx = Mt_.colidx.p; t.val = Mt_.val.p; t.long_threshold = Mt_.long_threshold;
+    t.nz_rows = Mt_.nz_rows.p; t.n_nz = Mt_.n_nz;
     if (Mt_.n_long > 0) {
         k_spmv_mt_long<<<Mt_.n_long, 512, 0, stream>>>(Mt_.long_rows.p, Mt_.rowptr.p, Mt_.colidx.p, Mt_.val.p, y_[1 - cur_].p,
                                                        Mty_[1 - cur_].p, scal_d_.p);
@@ -933,7 +939,7 @@ void Solver::launch_dual_trial(int trial, double tau0) {
     t.y_new = y_[1 - cur_].p; t.Mty = Mty_[cur_].p; t.Mty_new = Mty_[1 - cur_].p;
     t.beta = beta_; t.delta = opt.delta; t.trial = trial;
     t.do_test = opt.line_search_flag ? (sharded() ? 2 : 1) : 0;
-    int blocks2 = std::max(1, std::min(reduce_blocks_, ceil_div(n, 256)));
+    int blocks2 = std::max(1, std::min(reduce_blocks_, ceil_div(Mt_.n_nz, 256)));
     k_spmv_mt_norm<<<blocks2, 256, 0, stream>>>(t, scal_d_.p, ws_);
     launches += 2;
     if (sharded() && opt.line_search_flag) {
@@ -1262,7 +1268,7 @@ bool Solver::run(long long max_steps, bool flush_l2) {
     bool& have_cached = have_cached_;
     double t_loop0 = now_s();
     struct LoopTimer { double& acc; double t0; ~LoopTimer() { acc += now_s() - t0; } } loop_timer{t_loop_accum_, t_loop0};
-    if (flush_l2 && flush_buf_.n == 0) flush_buf_.alloc((size_t)48 << 20);   // 384 MiB > 126 MB L2
+    if (flush_l2 && flush_buf_.n == 0) flush_buf_.alloc((size_t)24 << 20);   // 192 MiB > 126 MB L2
 
     const long long kmax = 2 * opt.max_iter_local;
     long long steps = 0;
