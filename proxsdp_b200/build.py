@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libproxsdp_b200.so")
 SOURCES = ["solver.cu"]
-HEADERS = ["common.cuh", "jacobi.cuh", "kernels_vec.cuh", "lanczos.cuh", "lanczos_cl.cuh", "ritz_bi.cuh", "fulleig.cuh"]
+HEADERS = ["common.cuh", "jacobi.cuh", "kernels_vec.cuh", "lanczos.cuh", "lanczos_cl.cuh", "lanczos_cl3.cuh", "ritz_bi.cuh", "fulleig.cuh"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-shared",

@@ -22,6 +22,7 @@
 #include "kernels_vec.cuh"
 #include "lanczos.cuh"
 #include "lanczos_cl.cuh"
+#include "lanczos_cl3.cuh"
 
 namespace pb {
 
@@ -250,6 +251,11 @@ class Solver {
     std::vector<double> full_eig_device(ConeDev& cd);
     void lanczos_launch(ConeDev& cd, int cone_idx, int nev, int K, int maxiter, double tol);
     bool lanczos_launch_cluster(ConeDev& cd, int cone_idx, int nev, int K, int maxiter, double tol);
+    bool lanczos_launch_cluster3(ConeDev& cd, int cone_idx, int nev, int K, int maxiter, double tol);
+    int lz_kernel_ = 3;        // 3 = third-generation cluster kernel (lanczos_cl3.cuh), 2 = second generation (lanczos_cl.cuh)
+    int lz_xres_ = 1;          // keep as much of X as fits in the spare shared memory (cl3 only)
+    size_t lz_cl3_smem_max_ = 0;
+    unsigned int lz_epoch3_ = 0;
     int lz_mode_ = 0;          // 0 = cluster-replicated kernel when it fits, 1 = row-distributed kernel only
     int lz_cluster_ = 8;       // cluster size of the replicated kernel
     int lz_bi_ = 1;            // leading Ritz pairs by bisection + twisted vectors (dense Jacobi as fallback)
@@ -337,7 +343,8 @@ class Solver {
     DBuf<double> flush_buf_;
     DBuf<uint4> lz_xbuf_, lz_vx_;
     DBuf<double> lz_wg_;
-    DBuf<unsigned int> lz_bar_;
+    DBuf<unsigned int> lz_bar_, lz_flags_;
+    DBuf<double> lz_apart_;
     DBuf<long long> lz_prof_;
     unsigned long long lz_epoch_ = 0;
 };
@@ -374,6 +381,8 @@ Solver::Solver(const proxsdp_problem_t* prob, const proxsdp_options_t* opt_in, b
     if (const char* e = getenv("PROXSDP_B200_LANCZOS")) lz_mode_ = (std::string(e) == "rows") ? 1 : 0;
     if (const char* e = getenv("PROXSDP_B200_CLUSTER")) lz_cluster_ = std::max(1, std::min(LZC_MAXC, atoi(e)));
     if (const char* e = getenv("PROXSDP_B200_RITZ_WARM")) lz_warm_ = atoi(e);
+    if (const char* e = getenv("PROXSDP_B200_LZ_KERNEL")) lz_kernel_ = atoi(e);
+    if (const char* e = getenv("PROXSDP_B200_LZ_XRES")) lz_xres_ = atoi(e);
     if (const char* e = getenv("PROXSDP_B200_RITZ_BI")) lz_bi_ = atoi(e);
     { size_t lim = 0; if (cudaDeviceGetLimit(&lim, cudaLimitStackSize) == cudaSuccess && lim < 4096) cudaDeviceSetLimit(cudaLimitStackSize, 4096); }
     g_h2d_bytes = 0; g_d2h_bytes = 0;
@@ -605,7 +614,16 @@ void Solver::setup_host(const proxsdp_problem_t* prob) {
         lz_cl_smem_max_ = smem_optin_ - fa.sharedSizeBytes;
         PB_CUDA(cudaFuncSetAttribute(k_lanczos_cl, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lz_cl_smem_max_));
     }
-    if (lz_cluster_ > 8) PB_CUDA(cudaFuncSetAttribute(k_lanczos_cl, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    {
+        cudaFuncAttributes fa{};
+        PB_CUDA(cudaFuncGetAttributes(&fa, k_lanczos_cl3));
+        lz_cl3_smem_max_ = smem_optin_ - fa.sharedSizeBytes;
+        PB_CUDA(cudaFuncSetAttribute(k_lanczos_cl3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lz_cl3_smem_max_));
+    }
+    if (lz_cluster_ > 8) {
+        PB_CUDA(cudaFuncSetAttribute(k_lanczos_cl, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        PB_CUDA(cudaFuncSetAttribute(k_lanczos_cl3, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    }
     st.lap("done");
     PB_CUDA(cudaFuncSetAttribute(k_bj_pair_eig, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bj_pair_smem_bytes()));
     PB_CUDA(cudaFuncSetAttribute(k_bj_apply<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BJ_APPLY_SMEM));
@@ -748,7 +766,83 @@ bool Solver::lanczos_launch_cluster(ConeDev& cd, int cone_idx, int nev, int K, i
     return true;
 }
 
+// third-generation cluster kernel (lanczos_cl3.cuh): flag-array grid exchange, fused alpha + one Gram-Schmidt
+// pass, X partly resident in shared memory.  Returns false when the configuration does not fit; the caller then
+// tries the second-generation kernel.
+bool Solver::lanczos_launch_cluster3(ConeDev& cd, int cone_idx, int nev, int K, int maxiter, double tol) {
+    if (lz_mode_ == 1 || lz_kernel_ != 3 || K > LZC_KMAX) return false;
+    const int nside = cd.side;
+    const int C = lz_cluster_;
+    const int vn_max = (nside + C - 1) / C;
+    int want = std::max(C, ((std::max(1, (nside + 7) / 8) + C - 1) / C) * C);
+    cudaLaunchConfig_t cfg{};
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)C; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.blockDim = dim3(LZ_THREADS); cfg.stream = stream; cfg.attrs = attr; cfg.numAttrs = 1;
+    int G = std::min(std::min(want, (num_sms_ / C) * C), (LZ3_GMAX / C) * C);
+    if (G < C) return false;
+    int rows_max = (nside + G - 1) / G;
+    size_t smem = lanczos_cl3_smem_bytes(K, rows_max, vn_max, nside, C, 0);
+    if (smem > lz_cl3_smem_max_) return false;
+    cfg.gridDim = dim3((unsigned)G); cfg.dynamicSmemBytes = smem;
+    int max_clusters = 0;
+    if (cudaOccupancyMaxActiveClusters(&max_clusters, k_lanczos_cl3, &cfg) != cudaSuccess || max_clusters < 1) {
+        cudaGetLastError();
+        return false;
+    }
+    if (max_clusters * C < G) {
+        G = max_clusters * C;
+        rows_max = (nside + G - 1) / G;
+        smem = lanczos_cl3_smem_bytes(K, rows_max, vn_max, nside, C, 0);
+        if (smem > lz_cl3_smem_max_) return false;
+    }
+    if ((rows_max + LZ_NW - 1) / LZ_NW + 1 > LZ_TMAX) return false;
+    // spare shared memory keeps X chunks on chip: the same share for every warp, at most what a warp owns
+    int xres = 0;
+    if (lz_xres_) {
+        const long long per_warp_need = ((long long)rows_max * lanczos_cpr(nside) + LZ_NW - 1) / LZ_NW + 1;
+        const long long per_warp_fit = (long long)((lz_cl3_smem_max_ - smem) / ((size_t)LZ_NW * 64 * sizeof(double)));
+        xres = (int)std::max<long long>(0, std::min(per_warp_need, per_warp_fit));
+        smem = lanczos_cl3_smem_bytes(K, rows_max, vn_max, nside, C, xres);
+    }
+    cfg.gridDim = dim3((unsigned)G); cfg.dynamicSmemBytes = smem;
+    if ((size_t)cd.ld * (size_t)(K + 1) > cd.Y.n) cd.Y.alloc((size_t)cd.ld * (size_t)(K + 1));
+    if (lz_wg_.n < (size_t)2 * cd.ld) lz_wg_.alloc((size_t)2 * cd.ld);
+    if (lz_flags_.n == 0) { lz_flags_.alloc(LZ3_GMAX); lz_apart_.alloc(2 * LZ3_GMAX); lz_epoch3_ = 0; }
+    const unsigned int bound = (unsigned int)K * (unsigned int)(std::max(maxiter, 1) + 1) + 16u;
+    if (lz_epoch3_ > 0x40000000u) {          // keep stale flags of unused grid slots well inside the signed window
+        PB_CUDA(cudaMemsetAsync(lz_flags_.p, 0, sizeof(unsigned int) * LZ3_GMAX, stream));
+        lz_epoch3_ = 0;
+    }
+    const size_t ws_len = 1 + (size_t)lanczos_kp(Kmax_ > K ? Kmax_ : K) * (size_t)lanczos_kp(Kmax_ > K ? Kmax_ : K);
+    for (int q = 0; q < 2; ++q) if (cd.ritz_ws[q].n < ws_len) { cd.ritz_ws[q].alloc(ws_len); cd.ritz_launches = 0; }
+    LanczosCl3Args a{};
+    a.X = cd.X.p; a.n = nside; a.ld = cd.ld; a.x0 = cd.resid.p; a.Y = cd.Y.p;
+    a.wg = lz_wg_.p; a.apart = lz_apart_.p; a.flags = lz_flags_.p; a.epoch_base = lz_epoch3_;
+    const int flip = (int)(cd.ritz_launches & 1);
+    a.ritz_rd = (lz_warm_ && cd.ritz_launches > 0 && (cd.ritz_launches % 32) != 0) ? cd.ritz_ws[flip].p : nullptr;
+    a.ritz_wr = lz_warm_ ? cd.ritz_ws[1 - flip].p : nullptr;
+    a.nev = nev; a.K = K; a.maxiter = maxiter; a.tol = tol;
+    a.rows_max = rows_max; a.vn_max = vn_max; a.xres_chunks = xres; a.use_bi = lz_bi_;
+    a.vals = cd.vals.p; a.info = cd.info.p; a.scal = scal_d_.p; a.cone = cone_idx;
+    if (getenv("PROXSDP_B200_LZ_PROF")) { if (lz_prof_.n == 0) lz_prof_.alloc(8 + 8 * 256); a.prof = lz_prof_.p; }
+    cudaError_t e = cudaLaunchKernelEx(&cfg, k_lanczos_cl3, a);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        if (!lz_cluster_warned_) { fprintf(stderr, "[proxsdp_b200] cl3 Lanczos launch failed (%s); using the second-generation kernel\n", cudaGetErrorString(e)); lz_cluster_warned_ = true; }
+        lz_kernel_ = 2;
+        return false;
+    }
+    cd.ritz_launches++;
+    lz_epoch3_ += bound;
+    launches += 1;
+    lz_cluster_launches_++;
+    return true;
+}
+
 void Solver::lanczos_launch(ConeDev& cd, int cone_idx, int nev, int K, int maxiter, double tol) {
+    if (lanczos_launch_cluster3(cd, cone_idx, nev, K, maxiter, tol)) return;
     if (lanczos_launch_cluster(cd, cone_idx, nev, K, maxiter, tol)) return;
     const int nside = cd.side;
     int G = std::min(num_sms_, std::max(1, (nside + 7) / 8));
@@ -1574,7 +1668,7 @@ void Solver::finish(proxsdp_result_t* out) {
         PB_CUDA(cudaStreamSynchronize(stream));
         std::vector<long long> pr = lz_prof_.download();
         const char* nm_rows[8] = {"symv", "fold", "pass1+xchg", "upd1+pass2+xchg", "upd2+beta", "publish+vxchg", "ritz", "loop-top"};
-        const char* nm_cl[8] = {"symv", "fold+gridsync+gather", "cgs dots+push (x2)", "cluster.sync (x2)", "beta+publish v", "ritz", "cgs reduce+update (x2)", "loop-top"};
+        const char* nm_cl[8] = {"symv", "fold+gridxchg+gather(+local)", "gs dots+push", "cluster.sync", "beta+publish v", "ritz", "gs reduce+update", "loop-top"};
         const char** nm = lz_cluster_launches_ > 0 ? nm_cl : nm_rows;
         long long tot = 0; for (int i = 0; i < 8; ++i) tot += pr[i];
         fprintf(stderr, "[lz-prof] ritz: bisection accepted %lld, dense jacobi %lld, cycles up to the decision %lld\n", pr[8], pr[9], pr[10]);

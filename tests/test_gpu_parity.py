@@ -309,8 +309,10 @@ def test_c2_fullsize_properties(gpu, oracle_mod):
 
 # ------------------------------------------------------------------ kernel variants / step-wise API
 def test_lanczos_kernel_variants_agree(gpu, oracle_mod, monkeypatch):
-    """The cluster-replicated kernel (default), the row-distributed kernel and the two Ritz solvers (bisection +
-    twisted vectors vs dense Jacobi) implement the same eigsolve: identical counts, values to 1e-10."""
+    """The third-generation cluster kernel (default: flag-array exchange, fused alpha + one Gram-Schmidt pass,
+    X resident in shared memory), the second-generation cluster kernel (CGS2, counter barrier), the
+    row-distributed kernel and the two Ritz solvers (bisection + twisted vectors vs dense Jacobi) implement the
+    same eigsolve: identical counts, values to 1e-10."""
     n, nev, K = 700, 5, 25
     A = _lowrank_plus_noise(n, 9, 77)
     x0 = oracle_mod.eig_resid(n)
@@ -318,8 +320,11 @@ def test_lanczos_kernel_variants_agree(gpu, oracle_mod, monkeypatch):
     outs = {}
     for tag, env in (("cluster+bi", {}), ("cluster+jacobi", {"PROXSDP_B200_RITZ_BI": "0"}),
                      ("cluster cold jacobi", {"PROXSDP_B200_RITZ_BI": "0", "PROXSDP_B200_RITZ_WARM": "0"}),
-                     ("rows", {"PROXSDP_B200_LANCZOS": "rows"}), ("cluster4", {"PROXSDP_B200_CLUSTER": "4"})):
-        for k_ in ("PROXSDP_B200_RITZ_BI", "PROXSDP_B200_RITZ_WARM", "PROXSDP_B200_LANCZOS", "PROXSDP_B200_CLUSTER"):
+                     ("rows", {"PROXSDP_B200_LANCZOS": "rows"}), ("cluster4", {"PROXSDP_B200_CLUSTER": "4"}),
+                     ("gen3 no xres", {"PROXSDP_B200_LZ_XRES": "0"}), ("gen2", {"PROXSDP_B200_LZ_KERNEL": "2"}),
+                     ("gen2 cluster4", {"PROXSDP_B200_LZ_KERNEL": "2", "PROXSDP_B200_CLUSTER": "4"})):
+        for k_ in ("PROXSDP_B200_RITZ_BI", "PROXSDP_B200_RITZ_WARM", "PROXSDP_B200_LANCZOS", "PROXSDP_B200_CLUSTER",
+                   "PROXSDP_B200_LZ_KERNEL", "PROXSDP_B200_LZ_XRES"):
             monkeypatch.delenv(k_, raising=False)
         for k_, v_ in env.items():
             monkeypatch.setenv(k_, v_)
