@@ -60,8 +60,10 @@ __device__ __forceinline__ int sturm_count(int k, const double* __restrict__ d, 
 // both in shared memory).  On success returns m and fills lam_out[0..m) (descending) and the columns 0..m-1 of U
 // (leading dimension ldu, rows 0..k-1).  Returns 0 when it declines.  All threads of the block must call it.
 __device__ inline int ritz_top_bi(int k, const double* d, const double* e, int m_want, double* lam_out, double* U, int ldu,
-                                  RitzBiScratch sc) {
+                                  RitzBiScratch sc, long long* prof = nullptr) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    long long tp = prof ? clock64() : 0;
+#define RITZ_TICK(slot) do { if (prof && tid == 0) { long long tn = clock64(); prof[slot] += tn - tp; tp = tn; } } while (0)
     const int m = min(min(m_want, RITZ_BI_MAXM), k - 1);
     if (k < 8 || m < 1) return 0;
     // ---- bounds, scale, smallest coupling (every warp redundantly: no block barrier) ----
@@ -82,6 +84,7 @@ __device__ inline int ritz_top_bi(int k, const double* d, const double* e, int m
     for (int j = tid; j < k - 1; j += blockDim.x) sc.ie[j] = 1.0 / e[j];
     if (tid == 0) *sc.fail = 0;
     __syncthreads();
+    RITZ_TICK(11);
 
     // ---- eigenvalue `warp` (0-based from the top) by 32-way multisection ----
     double lam = 0.0;
@@ -109,6 +112,7 @@ __device__ inline int ritz_top_bi(int k, const double* d, const double* e, int m
         lam = 0.5 * (lo + hi);
         if (lane == 0) sc.lam[warp] = lam;
     }
+    RITZ_TICK(12);
 
     // ---- eigenvector `warp` : forward (lane 0) and backward (lane 1) recurrences, same instruction stream ----
     if (warp < m) {
@@ -170,6 +174,7 @@ __device__ inline int ritz_top_bi(int k, const double* d, const double* e, int m
         if (lane == 0 && !(res <= 1e-13 * tnorm && nrm2 < 1e300)) *sc.fail = 1;
     }
     __syncthreads();
+    RITZ_TICK(13);
     // ---- gaps and mutual orthogonality ----
     if (tid < m) {
         if (!(sc.lam[tid] - sc.lam[tid + 1] >= 1e-7 * tnorm)) *sc.fail = 1;
@@ -188,6 +193,7 @@ __device__ inline int ritz_top_bi(int k, const double* d, const double* e, int m
         if (lane == 0 && !(fabs(s) <= 1e-12)) *sc.fail = 1;
     }
     __syncthreads();
+    RITZ_TICK(14);
     if (*sc.fail) return 0;
     for (int i = tid; i < m; i += blockDim.x) lam_out[i] = sc.lam[i];
     __syncthreads();

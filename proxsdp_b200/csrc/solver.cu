@@ -253,9 +253,9 @@ class Solver {
     bool lanczos_launch_cluster(ConeDev& cd, int cone_idx, int nev, int K, int maxiter, double tol);
     bool lanczos_launch_cluster3(ConeDev& cd, int cone_idx, int nev, int K, int maxiter, double tol);
     int lz_kernel_ = 3;        // 3 = third-generation cluster kernel (lanczos_cl3.cuh), 2 = second generation (lanczos_cl.cuh)
-    int lz_xres_ = 1;          // keep as much of X as fits in the spare shared memory (cl3 only)
+    int lz_xres_ = 1;          // keep as many slab rows of X as fit in the spare shared memory (cl3, strip symv)
+    int lz_bar_mode_ = 0;      // cl3 grid exchange: 0 one counter, 2 group counters + global counter
     size_t lz_cl3_smem_max_ = 0;
-    unsigned int lz_epoch3_ = 0;
     int lz_mode_ = 0;          // 0 = cluster-replicated kernel when it fits, 1 = row-distributed kernel only
     int lz_cluster_ = 8;       // cluster size of the replicated kernel
     int lz_bi_ = 1;            // leading Ritz pairs by bisection + twisted vectors (dense Jacobi as fallback)
@@ -343,7 +343,7 @@ class Solver {
     DBuf<double> flush_buf_;
     DBuf<uint4> lz_xbuf_, lz_vx_;
     DBuf<double> lz_wg_;
-    DBuf<unsigned int> lz_bar_, lz_flags_;
+    DBuf<unsigned int> lz_bar_;
     DBuf<double> lz_apart_;
     DBuf<long long> lz_prof_;
     unsigned long long lz_epoch_ = 0;
@@ -383,6 +383,7 @@ Solver::Solver(const proxsdp_problem_t* prob, const proxsdp_options_t* opt_in, b
     if (const char* e = getenv("PROXSDP_B200_RITZ_WARM")) lz_warm_ = atoi(e);
     if (const char* e = getenv("PROXSDP_B200_LZ_KERNEL")) lz_kernel_ = atoi(e);
     if (const char* e = getenv("PROXSDP_B200_LZ_XRES")) lz_xres_ = atoi(e);
+    if (const char* e = getenv("PROXSDP_B200_LZ_BAR")) lz_bar_mode_ = std::max(0, std::min(2, atoi(e)));
     if (const char* e = getenv("PROXSDP_B200_RITZ_BI")) lz_bi_ = atoi(e);
     { size_t lim = 0; if (cudaDeviceGetLimit(&lim, cudaLimitStackSize) == cudaSuccess && lim < 4096) cudaDeviceSetLimit(cudaLimitStackSize, 4096); }
     g_h2d_bytes = 0; g_d2h_bytes = 0;
@@ -766,14 +767,19 @@ bool Solver::lanczos_launch_cluster(ConeDev& cd, int cone_idx, int nev, int K, i
     return true;
 }
 
-// third-generation cluster kernel (lanczos_cl3.cuh): flag-array grid exchange, fused alpha + one Gram-Schmidt
-// pass, X partly resident in shared memory.  Returns false when the configuration does not fit; the caller then
+// third-generation cluster kernel (lanczos_cl3.cuh): fused alpha + one Gram-Schmidt pass, strip symv with X partly
+// resident in shared memory, spill-free step.  Returns false when the configuration does not fit; the caller then
 // tries the second-generation kernel.
 bool Solver::lanczos_launch_cluster3(ConeDev& cd, int cone_idx, int nev, int K, int maxiter, double tol) {
     if (lz_mode_ == 1 || lz_kernel_ != 3 || K > LZC_KMAX) return false;
     const int nside = cd.side;
     const int C = lz_cluster_;
     const int vn_max = (nside + C - 1) / C;
+    const int cpr = lanczos_cpr(nside);
+    int cpw = (cpr + LZ_NW - 1) / LZ_NW;
+    if (cpw == 7) cpw = 8;
+    if (cpw > 8) return false;                 // side > 8192: the strip symv has no instantiation that wide
+    if ((vn_max + LZ_NW - 1) / LZ_NW > 64) return false;      // the gather keeps two rows per lane in registers
     int want = std::max(C, ((std::max(1, (nside + 7) / 8) + C - 1) / C) * C);
     cudaLaunchConfig_t cfg{};
     cudaLaunchAttribute attr[1];
@@ -783,7 +789,8 @@ bool Solver::lanczos_launch_cluster3(ConeDev& cd, int cone_idx, int nev, int K, 
     int G = std::min(std::min(want, (num_sms_ / C) * C), (LZ3_GMAX / C) * C);
     if (G < C) return false;
     int rows_max = (nside + G - 1) / G;
-    size_t smem = lanczos_cl3_smem_bytes(K, rows_max, vn_max, nside, C, 0);
+    Lz3Layout L = lanczos_cl3_layout(K, rows_max, vn_max, nside, C, 0);
+    size_t smem = (size_t)L.total * sizeof(double);
     if (smem > lz_cl3_smem_max_) return false;
     cfg.gridDim = dim3((unsigned)G); cfg.dynamicSmemBytes = smem;
     int max_clusters = 0;
@@ -794,38 +801,39 @@ bool Solver::lanczos_launch_cluster3(ConeDev& cd, int cone_idx, int nev, int K, 
     if (max_clusters * C < G) {
         G = max_clusters * C;
         rows_max = (nside + G - 1) / G;
-        smem = lanczos_cl3_smem_bytes(K, rows_max, vn_max, nside, C, 0);
+        L = lanczos_cl3_layout(K, rows_max, vn_max, nside, C, 0);
+        smem = (size_t)L.total * sizeof(double);
         if (smem > lz_cl3_smem_max_) return false;
     }
-    if ((rows_max + LZ_NW - 1) / LZ_NW + 1 > LZ_TMAX) return false;
-    // spare shared memory keeps X chunks on chip: the same share for every warp, at most what a warp owns
+    // spare shared memory keeps the first xres rows of the slab on chip
     int xres = 0;
     if (lz_xres_) {
-        const long long per_warp_need = ((long long)rows_max * lanczos_cpr(nside) + LZ_NW - 1) / LZ_NW + 1;
-        const long long per_warp_fit = (long long)((lz_cl3_smem_max_ - smem) / ((size_t)LZ_NW * 64 * sizeof(double)));
-        xres = (int)std::max<long long>(0, std::min(per_warp_need, per_warp_fit));
-        smem = lanczos_cl3_smem_bytes(K, rows_max, vn_max, nside, C, xres);
+        const long long fit = (long long)((lz_cl3_smem_max_ - smem) / ((size_t)cpr * 64 * sizeof(double)));
+        xres = (int)std::max<long long>(0, std::min<long long>(rows_max, fit));
+        if (lz_xres_ > 1) xres = std::min(xres, lz_xres_ - 1);       // PROXSDP_B200_LZ_XRES = rows + 1: cap for experiments
+        L = lanczos_cl3_layout(K, rows_max, vn_max, nside, C, xres);
+        smem = (size_t)L.total * sizeof(double);
     }
     cfg.gridDim = dim3((unsigned)G); cfg.dynamicSmemBytes = smem;
     if ((size_t)cd.ld * (size_t)(K + 1) > cd.Y.n) cd.Y.alloc((size_t)cd.ld * (size_t)(K + 1));
     if (lz_wg_.n < (size_t)2 * cd.ld) lz_wg_.alloc((size_t)2 * cd.ld);
-    if (lz_flags_.n == 0) { lz_flags_.alloc(LZ3_GMAX); lz_apart_.alloc(2 * LZ3_GMAX); lz_epoch3_ = 0; }
-    const unsigned int bound = (unsigned int)K * (unsigned int)(std::max(maxiter, 1) + 1) + 16u;
-    if (lz_epoch3_ > 0x40000000u) {          // keep stale flags of unused grid slots well inside the signed window
-        PB_CUDA(cudaMemsetAsync(lz_flags_.p, 0, sizeof(unsigned int) * LZ3_GMAX, stream));
-        lz_epoch3_ = 0;
-    }
+    if (lz_apart_.n == 0) lz_apart_.alloc(2 * LZ3_GMAX);
+    if (lz_bar_.n < (size_t)(1 + LZ3_GMAX / 2) * 32) lz_bar_.alloc((size_t)(1 + LZ3_GMAX / 2) * 32);
+    PB_CUDA(cudaMemsetAsync(lz_bar_.p, 0, sizeof(unsigned int) * 32 * (size_t)(1 + (lz_bar_mode_ == 2 ? G / C : 0)), stream));
     const size_t ws_len = 1 + (size_t)lanczos_kp(Kmax_ > K ? Kmax_ : K) * (size_t)lanczos_kp(Kmax_ > K ? Kmax_ : K);
     for (int q = 0; q < 2; ++q) if (cd.ritz_ws[q].n < ws_len) { cd.ritz_ws[q].alloc(ws_len); cd.ritz_launches = 0; }
     LanczosCl3Args a{};
     a.X = cd.X.p; a.n = nside; a.ld = cd.ld; a.x0 = cd.resid.p; a.Y = cd.Y.p;
-    a.wg = lz_wg_.p; a.apart = lz_apart_.p; a.flags = lz_flags_.p; a.epoch_base = lz_epoch3_;
+    a.wg = lz_wg_.p; a.apart = lz_apart_.p; a.bar = lz_bar_.p; a.bar_mode = lz_bar_mode_ == 2 ? 2 : 0;
+    a.cpw = cpw; a.xres_rows = xres;
     const int flip = (int)(cd.ritz_launches & 1);
     a.ritz_rd = (lz_warm_ && cd.ritz_launches > 0 && (cd.ritz_launches % 32) != 0) ? cd.ritz_ws[flip].p : nullptr;
     a.ritz_wr = lz_warm_ ? cd.ritz_ws[1 - flip].p : nullptr;
     a.nev = nev; a.K = K; a.maxiter = maxiter; a.tol = tol;
-    a.rows_max = rows_max; a.vn_max = vn_max; a.xres_chunks = xres; a.use_bi = lz_bi_;
+    a.vn_max = vn_max; a.use_bi = lz_bi_;
+    a.rbase = nside / G; a.rrem = nside % G; a.vbase = nside / C; a.vrem = nside % C;
     a.vals = cd.vals.p; a.info = cd.info.p; a.scal = scal_d_.p; a.cone = cone_idx;
+    a.L = L;
     if (getenv("PROXSDP_B200_LZ_PROF")) { if (lz_prof_.n == 0) lz_prof_.alloc(8 + 8 * 256); a.prof = lz_prof_.p; }
     cudaError_t e = cudaLaunchKernelEx(&cfg, k_lanczos_cl3, a);
     if (e != cudaSuccess) {
@@ -835,7 +843,6 @@ bool Solver::lanczos_launch_cluster3(ConeDev& cd, int cone_idx, int nev, int K, 
         return false;
     }
     cd.ritz_launches++;
-    lz_epoch3_ += bound;
     launches += 1;
     lz_cluster_launches_++;
     return true;
@@ -1672,7 +1679,19 @@ void Solver::finish(proxsdp_result_t* out) {
         const char** nm = lz_cluster_launches_ > 0 ? nm_cl : nm_rows;
         long long tot = 0; for (int i = 0; i < 8; ++i) tot += pr[i];
         fprintf(stderr, "[lz-prof] ritz: bisection accepted %lld, dense jacobi %lld, cycles up to the decision %lld\n", pr[8], pr[9], pr[10]);
-        for (int i = 0; i < 8; ++i) fprintf(stderr, "[lz-prof] %-16s %12lld cyc  %5.1f%%  (%.2f us/matvec)\n", nm[i], pr[i], 100.0 * pr[i] / std::max<long long>(tot, 1), pr[i] / 1965.0 / std::max<long long>(lanczos_matvecs, 1));
+        fprintf(stderr, "[lz-prof] ritz_top_bi cycles: setup %lld, multisection %lld, vectors %lld, checks %lld\n", pr[11], pr[12], pr[13], pr[14]);
+        const double mv = (double)std::max<long long>(lanczos_matvecs, 1);
+        for (int i = 0; i < 8; ++i) fprintf(stderr, "[lz-prof] %-30s %12lld cyc  %5.1f%%  (%.2f us/matvec)\n", nm[i], pr[i], 100.0 * pr[i] / std::max<long long>(tot, 1), pr[i] / 1965.0 / mv);
+        if (lz_kernel_ == 3 && lz_cluster_launches_ > 0) {
+            fprintf(stderr, "[lz-prof] us/matvec per profiled CTA (0, C-1, G/2, G-1):\n");
+            const char* nm2[10] = {"symv", "fold..post-barrier sync", " fold+publish", " arrive+wait", "gather+alpha+local", "gs dots+push", "cluster.sync 1", "reduce+update+publish", "cluster.sync 2", "ritz"};
+            const int sl[10] = {0, 17, 15, 16, 1, 2, 3, 6, 4, 5};
+            for (int q = 0; q < 10; ++q) {
+                fprintf(stderr, "[lz-prof]   %-24s", nm2[q]);
+                for (int r = 0; r < 4; ++r) fprintf(stderr, " %6.2f", pr[(size_t)32 * r + sl[q]] / 1965.0 / mv);
+                fprintf(stderr, "\n");
+            }
+        }
     }
     out->time_loop = t_loop_accum_;
     // results (pdhg.jl:486-529)
