@@ -18,16 +18,21 @@
 //     generation kept ~25 shared-memory pointers live (50 registers) and spilled loop state, which showed up as
 //     ~1.7 us of "fold" per step.  Here the shared-memory layout travels as integer offsets in the kernel
 //     parameters (constant bank) and addresses are rebuilt where they are used.
-//  3. Strip symv with X partly on chip.  The second-generation symv gave every warp a run of 64-double chunks
-//     of the slab: ragged row tails made up to 13 dependent L2 round trips per mat-vec and the v operand was
-//     re-read from shared memory for every row.  Here warp w owns a column strip of CPW chunks for ALL rows of
-//     the slab: its piece of v sits in registers, the loads of a batch of RB rows are issued back to back,
-//     the per-row partial sums of the 32 lanes are combined by a transposing butterfly (16 shuffles per 16
-//     rows), and the first xres_rows rows of the slab are kept in the shared memory left over by the basis
-//     replica, filled by the first mat-vec of the launch.
-//  4. Grid exchange: relaxed polling + one acquire fence (an acquire load per poll costs a CCTL.IVALL each);
-//     bar_mode 2 adds a two-level counter (group of C CTAs, then global) against the serialisation of 120
-//     atomics on one address.
+//  3. Strip symv without shuffles.  The second-generation symv gave every warp a run of 64-double chunks of the
+//     slab: ragged row tails made up to 13 dependent L2 round trips per mat-vec, the v operand was re-read from
+//     shared memory for every row, and every row cost a 5-step shuffle tree (~110 cycles per 64-bit step).  Here
+//     warp w owns a column strip of CPW chunks for ALL rows of the slab: its piece of v sits in registers, the
+//     loads of a batch of RB rows are issued back to back, every lane parks its per-row partial sums in shared
+//     memory ([row][thread], conflict-free) and after one block barrier half-warp h adds up the 512 partials of
+//     row h in four chains and stores the finished w entry straight to global memory — the separate "fold" phase
+//     and all shuffles are gone.  alpha's partial is row number rl of the same table.  (Keeping half of the slab
+//     resident in shared memory was tried and measured: no gain, the symv is not L2-bandwidth-bound at n = 2000.)
+//  4. No grid barrier.  A counter barrier costs release fence (~500 cycles with stores in flight) + atomic + poll
+//     + acquire fence, ~0.9 us on top of the slowest CTA, and then the data still has to be fetched.  Here the w
+//     entries and the alpha partials travel as flagged 16-byte words (two 8-byte halves {lo32, tag}, {hi32, tag}:
+//     a reader that sees the tag in both halves has the value — the "LL" exchange of lanczos.cuh): the lanes that
+//     need a value poll that value, no fence on either side.  Completing the alpha all-gather (every CTA needs
+//     every CTA's partial) is what orders a step after the previous one, so two buffers suffice.
 #pragma once
 #include <cooperative_groups.h>
 
@@ -44,10 +49,8 @@ constexpr int LZ3_GMAX = 256;    // largest grid the partial-alpha rows / group 
 
 // shared-memory layout, in doubles from the start of dynamic shared memory (host-computed, read from the constant bank)
 struct Lz3Layout {
-    int xs;      // xres_rows * cpr * 64   resident rows of my X slab (laid out like X)
-    int rls;     // row stride of wrow (odd, > rows_max)
-    int wrow;    // LZ_NW * rls            strip partials of the slab symv, [strip][row]
-    int walpha;  // LZ_NW                  per-warp partial of alpha = v_j[slab] . (X v_j)[slab]
+    int part;    // (round_rows + 1) * LZ_THREADS   per-thread partial sums of the slab symv, [row][thread]; last row: alpha
+    int red2;    // 32 * 16                half-warp partials of the row reduction
     int dpart;   // LZ_NW * (K+2)          per-warp partial Gram-Schmidt dots
     int vbuf;    // cpr * 64               newest Lanczos vector (written by the cluster peers)
     int Vs;      // (K+1) * VNp            basis rows owned by this CTA
@@ -64,15 +67,13 @@ struct Lz3Layout {
 
 __host__ __device__ inline int lanczos_cl3_rls(int rows_max) { return (rows_max + 1) | 1; }
 
-__host__ inline Lz3Layout lanczos_cl3_layout(int K, int rows_max, int vn_max, int n, int C, int xres_rows) {
+__host__ inline Lz3Layout lanczos_cl3_layout(int K, int round_rows, int vn_max, int n, int C) {
     Lz3Layout L{};
     const int Kp = lanczos_kp(K), VNp = lanczos_cl_vnp(vn_max), cpr = lanczos_cpr(n);
     int d = 0;
     auto take = [&](int cnt) { int o = d; d += (cnt + 1) & ~1; return o; };     // keep everything 16-byte aligned
-    L.xs = take(xres_rows * cpr * 64);
-    L.rls = lanczos_cl3_rls(rows_max);
-    L.wrow = take(L.rls * LZ_NW);
-    L.walpha = take(LZ_NW);
+    L.part = take((round_rows + 1) * LZ_THREADS);
+    L.red2 = take(32 * 16);
     L.dpart = take(LZ_NW * (K + 2));
     L.vbuf = take(cpr * 64);
     L.Vs = take((K + 1) * VNp);
@@ -92,12 +93,10 @@ struct LanczosCl3Args {
     const double* X; int n, ld;
     const double* x0;
     double* Y;                 // out: Ritz vectors, ld x K
-    double* wg;                // [2][ld] gathered mat-vec result (global)
-    double* apart;             // [2][LZ3_GMAX] per-CTA partial alpha = v_j[slab] . w[slab]
-    unsigned int* bar;         // [(1 + LZ3_GMAX / 2) * 32] counters, one per 128-byte line, zeroed per launch
-    int bar_mode;              // 0: one counter ; 2: group counters + global counter
-    int cpw;                   // 64-double chunks per symv strip (1..8), strips = ceil(cpr / cpw) <= LZ_NW
-    int xres_rows;             // slab rows kept in shared memory
+    uint4* wg;                 // [2][ld] mat-vec result, flagged ("LL") words: data and ready-signal in one 16-byte store
+    uint4* apart;              // [2][LZ3_GMAX] per-CTA partial alpha = v_j[slab] . w[slab], flagged words
+    unsigned int epoch_base;   // the g-th exchange of this launch is tagged epoch_base + g (unique over launches: no memset)
+    int round_rows;            // slab rows whose partial sums fit the shared-memory table at once (<= 31)
     const double* ritz_rd;     // optional warm start of the Ritz eigenproblem (see LanczosClArgs)
     double* ritz_wr;
     int nev, K, maxiter;
@@ -111,51 +110,27 @@ struct LanczosCl3Args {
     Lz3Layout L;
 };
 
-// sums NP per-lane values over the 32 lanes of a warp with a transposing butterfly: after the call the lanes
-// whose low (5 - log2 NP) bits are zero hold the warp total of value number `sel` (returned per lane).
-template <int NP>
-__device__ __forceinline__ double warp_multi_sum(double (&a)[NP], int lane, int& sel) {
-    int o = 16, row = 0;
-#pragma unroll
-    for (int cnt = NP; cnt > 1; cnt >>= 1) {
-        const bool up = (lane & o) != 0;
-#pragma unroll
-        for (int i = 0; i < cnt / 2; ++i) {
-            const double send = up ? a[i] : a[i + cnt / 2];
-            const double keep = up ? a[i + cnt / 2] : a[i];
-            a[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
-        }
-        if (up) row += cnt / 2;
-        o >>= 1;
-    }
-    double s = a[0];
-#pragma unroll
-    for (int oo = 32 / NP / 2; oo > 0; oo >>= 1) s += __shfl_xor_sync(0xffffffffu, s, oo);
-    sel = row;
-    return s;
-}
-
 // One batch of the strip symv: RB rows x CPW chunks of X (16 bytes per lane each) against the warp's piece of v.
-// SRC 0: X from global ; 1: from global, copy kept in shared memory ; 2: from shared memory.  A full batch
-// (nrows == RB, nch == CPW) is branch-free: all loads are issued back to back, then the FMAs.
-template <int CPW, int RB, int NP, int SRC>
-__device__ __forceinline__ void strip_batch(const double* __restrict__ gp, const size_t gstride, double* sp, const int sstride,
-                                            const int nrows, const int nch, const double2 (&vr)[CPW], double (&acc)[NP]) {
+// A full batch is branch-free (all loads issued back to back, then the FMAs); a batch short of rows takes one uniform
+// branch per row; only a ragged last strip (nch < CPW) pays a predicate per load.
+template <int CPW, int RB>
+__device__ __forceinline__ void strip_batch(const double* __restrict__ gp, const size_t gstride, const int nrows, const int nch,
+                                            const double2 (&vr)[CPW], double (&acc)[RB]) {
     double2 x[RB][CPW];
-    if (nrows == RB && nch == CPW) {
+    if (nch == CPW && nrows == RB) {
 #pragma unroll
         for (int i = 0; i < RB; ++i) {
 #pragma unroll
-            for (int c = 0; c < CPW; ++c) {
-                if (SRC == 2) x[i][c] = *reinterpret_cast<const double2*>(sp + i * sstride + c * 64);
-                else x[i][c] = ld_stream_d2(reinterpret_cast<const double2*>(gp + i * gstride + c * 64));
-            }
+            for (int c = 0; c < CPW; ++c) x[i][c] = ld_stream_d2(reinterpret_cast<const double2*>(gp + i * gstride + c * 64));
         }
-        if (SRC == 1) {
+    } else if (nch == CPW) {
 #pragma unroll
-            for (int i = 0; i < RB; ++i) {
+        for (int i = 0; i < RB; ++i) {
 #pragma unroll
-                for (int c = 0; c < CPW; ++c) *reinterpret_cast<double2*>(sp + i * sstride + c * 64) = x[i][c];
+            for (int c = 0; c < CPW; ++c) x[i][c] = make_double2(0.0, 0.0);
+            if (i < nrows) {
+#pragma unroll
+                for (int c = 0; c < CPW; ++c) x[i][c] = ld_stream_d2(reinterpret_cast<const double2*>(gp + i * gstride + c * 64));
             }
         }
     } else {
@@ -164,84 +139,210 @@ __device__ __forceinline__ void strip_batch(const double* __restrict__ gp, const
 #pragma unroll
             for (int c = 0; c < CPW; ++c) {
                 x[i][c] = make_double2(0.0, 0.0);
-                if (i < nrows && c < nch) {
-                    if (SRC == 2) x[i][c] = *reinterpret_cast<const double2*>(sp + i * sstride + c * 64);
-                    else x[i][c] = ld_stream_d2(reinterpret_cast<const double2*>(gp + i * gstride + c * 64));
-                    if (SRC == 1) *reinterpret_cast<double2*>(sp + i * sstride + c * 64) = x[i][c];
-                }
+                if (i < nrows && c < nch) x[i][c] = ld_stream_d2(reinterpret_cast<const double2*>(gp + i * gstride + c * 64));
             }
         }
     }
 #pragma unroll
-    for (int i = 0; i < NP; ++i) {
+    for (int i = 0; i < RB; ++i) {
         double t = 0.0;
-        if (i < RB) {
 #pragma unroll
-            for (int c = 0; c < CPW; ++c) { t = fma(x[i][c].x, vr[c].x, t); t = fma(x[i][c].y, vr[c].y, t); }
-        }
+        for (int c = 0; c < CPW; ++c) { t = fma(x[i][c].x, vr[c].x, t); t = fma(x[i][c].y, vr[c].y, t); }
         acc[i] = t;
     }
 }
 
-// strip symv: warp (strip s, row group rg) owns the columns of CPW chunks for the rows rg, rg + nrg, ... of the slab;
-// the per-row partial dot products go to wrow[s * RLs + row].  The first xres_rows rows of the slab live in shared
-// memory (xs, laid out like X: row * cpr chunks) once the first mat-vec of the launch has put them there.
-// The warp's share of alpha = v[slab] . (X v)[slab] rides the last butterfly in the spare slot NP - 1 (RB < NP) and
-// lands in walpha[warp]: no extra shuffle.
+// sum of cnt doubles at p[l], p[l + 16], ... (l = lane within the half-warp), four chains
+__device__ __forceinline__ double strided16_sum(const double* p, const int l, const int cnt) {
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    int i = l;
+    for (; i + 48 < cnt; i += 64) { s0 += p[i]; s1 += p[i + 16]; s2 += p[i + 32]; s3 += p[i + 48]; }
+    for (; i < cnt; i += 16) s0 += p[i];
+    return (s0 + s1) + (s2 + s3);
+}
+
+// Slab symv w[r0 : r0 + rl] = X[r0 : r0 + rl, :] v plus this CTA's share of alpha = v[slab] . w[slab], written straight
+// to global memory (wg_slab[row], *alpha_out).  Warp (strip s, row group rg) owns the columns of CPW chunks for the
+// rows rg, rg + nrg, ... ; the slab is walked in rounds of round_rows rows (one round at n = 2000): every thread parks
+// its per-row partial sums in part[row][thread], one block barrier, half-warp h reduces row h and publishes it as a
+// flagged word.  All threads of the block must call it.
 template <int CPW, int RB>
-__device__ __forceinline__ void symv_strips(const double* __restrict__ X, const int ld, const int r0, const int rl, const int cpr,
-                                            const double* vbuf, double* xs, const int xres_rows, const bool first, double* wrow,
-                                            const int RLs, double* walpha, const int warp, const int lane) {
-    constexpr int NP = RB < 2 ? 2 : RB < 4 ? 4 : RB < 8 ? 8 : 16;
-    static_assert(RB < NP, "one butterfly slot must stay free for alpha");
+__device__ __forceinline__ void symv_slab(const double* __restrict__ X, const int ld, const int r0, const int rl, const int cpr,
+                                          const double* vbuf, double* part, double* red2, const int round_rows,
+                                          uint4* wg_slab, uint4* alpha_out, const unsigned int tag) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int NS = (cpr + CPW - 1) / CPW;
     const int nrg = LZ_NW / NS;
     const int s = warp % NS, rg = warp / NS;
-    const int n_my = (warp < NS * nrg && rl > rg) ? (rl - rg + nrg - 1) / nrg : 0;      // my rows: rg + i * nrg, i < n_my
-    if (n_my == 0) { if (lane == 0) walpha[warp] = 0.0; return; }
+    const bool active = warp < NS * nrg;
     const int nch = min(CPW, cpr - s * CPW);
     double2 vr[CPW];
 #pragma unroll
-    for (int c = 0; c < CPW; ++c) vr[c] = (c < nch) ? *reinterpret_cast<const double2*>(vbuf + (s * CPW + c) * 64 + 2 * lane) : make_double2(0.0, 0.0);
-    const int n_res = min(n_my, (xres_rows > rg) ? (xres_rows - rg + nrg - 1) / nrg : 0);   // the first n_res of my rows are resident
-    const double* gp = X + (size_t)(r0 + rg) * ld + (size_t)s * CPW * 64 + 2 * lane;
-    double* sp = xs + (rg * cpr + s * CPW) * 64 + 2 * lane;
+    for (int c = 0; c < CPW; ++c) vr[c] = (active && c < nch) ? *reinterpret_cast<const double2*>(vbuf + (s * CPW + c) * 64 + 2 * lane) : make_double2(0.0, 0.0);
+    const double* gcol = X + (size_t)r0 * ld + (size_t)s * CPW * 64 + 2 * lane;
     const size_t gstride = (size_t)nrg * ld;
-    const int sstride = nrg * cpr * 64;
     double pa = 0.0;
-    for (int ib = 0; ib < n_my; ) {
-        double acc[NP];
-        int nrows;
-        if (ib < n_res) {
-            nrows = min(RB, n_res - ib);
-            if (first) strip_batch<CPW, RB, NP, 1>(gp + ib * gstride, gstride, sp + ib * sstride, sstride, nrows, nch, vr, acc);
-            else strip_batch<CPW, RB, NP, 2>(gp + ib * gstride, gstride, sp + ib * sstride, sstride, nrows, nch, vr, acc);
-        } else {
-            nrows = min(RB, n_my - ib);
-            strip_batch<CPW, RB, NP, 0>(gp + ib * gstride, gstride, sp, sstride, nrows, nch, vr, acc);
-        }
-        // alpha share of this batch: sum_i acc[i] * v[row_i] (three chains), kept per lane until the last batch
-        {
-            double p0 = 0.0, p1 = 0.0, p2 = 0.0;
+    for (int rbeg = 0; rbeg < rl; rbeg += round_rows) {
+        const int rend = min(rl, rbeg + round_rows);
+        if (active) {
+            int row = rbeg + ((rg - rbeg) % nrg + nrg) % nrg;        // my first row of this round: row = rg (mod nrg)
+            for (; row < rend; row += RB * nrg) {
+                const int nrows = min(RB, (rend - row + nrg - 1) / nrg);
+                double acc[RB];
+                strip_batch<CPW, RB>(gcol + (size_t)row * ld, gstride, nrows, nch, vr, acc);
+                double p0 = 0.0, p1 = 0.0, p2 = 0.0;
 #pragma unroll
-            for (int i = 0; i < RB; ++i) {
-                const double vi = (i < nrows) ? vbuf[r0 + rg + (ib + i) * nrg] : 0.0;
-                if (i % 3 == 0) p0 = fma(acc[i], vi, p0); else if (i % 3 == 1) p1 = fma(acc[i], vi, p1); else p2 = fma(acc[i], vi, p2);
+                for (int i = 0; i < RB; ++i) {
+                    if (i < nrows) {
+                        const int ri = row + i * nrg;
+                        part[(ri - rbeg) * LZ_THREADS + tid] = acc[i];
+                        const double vi = vbuf[r0 + ri];
+                        if (i % 3 == 0) p0 = fma(acc[i], vi, p0); else if (i % 3 == 1) p1 = fma(acc[i], vi, p1); else p2 = fma(acc[i], vi, p2);
+                    }
+                }
+                pa += (p0 + p1) + p2;
             }
-            pa += (p0 + p1) + p2;
         }
-        const bool last = (ib + nrows >= n_my);
-        if (last) acc[NP - 1] = pa;
-        int sel;
-        const double tot = warp_multi_sum<NP>(acc, lane, sel);
-        if ((lane & (32 / NP - 1)) == 0) {
-            if (sel < nrows) wrow[s * RLs + rg + (ib + sel) * nrg] = tot;
-            else if (last && sel == NP - 1) walpha[warp] = tot;
+        const bool last_round = (rend == rl);
+        if (last_round) part[(rend - rbeg) * LZ_THREADS + tid] = pa;      // alpha: one more row of the table
+        __syncthreads();
+        {
+            const int h = tid >> 4, l = tid & 15;
+            const int nred = (rend - rbeg) + (last_round ? 1 : 0);
+            if (h < nred) {
+                const bool is_alpha = (h == rend - rbeg);
+                const int row = rbeg + h;
+                // a row gets partials only from the NS warps of its row group; alpha from every thread
+                const int base = is_alpha ? 0 : 32 * NS * (row % nrg);
+                const int cnt = is_alpha ? LZ_THREADS : 32 * NS;
+                red2[h * 16 + l] = strided16_sum(part + h * LZ_THREADS + base, l, cnt);
+            }
+            __syncwarp();
+            if (h < nred && l == 0) {
+                const double* q = red2 + h * 16;
+                const double sres = ((q[0] + q[4]) + (q[8] + q[12])) + ((q[1] + q[5]) + (q[9] + q[13])) +
+                                    (((q[2] + q[6]) + (q[10] + q[14])) + ((q[3] + q[7]) + (q[11] + q[15])));
+                if (h == rend - rbeg) ll_store(alpha_out, sres, tag); else ll_store(wg_slab + rbeg + h, sres, tag);
+            }
         }
-        ib += nrows;
+        if (!last_round) __syncthreads();          // the table is rewritten by the next round
     }
 }
 
+// Ritz analysis + thick restart, out of line: it runs once or twice per launch, and keeping its ~100 KB of code
+// out of the per-step loop keeps the loop inside the instruction cache.  State in/out through st[] (shared memory):
+//   st[0] k, st[2] arrow, st[3] howmany, st[4] numiter, st[5] first_analysis, st[6] converged, st[7] finished.
+// All threads of the CTA call it; every CTA of the grid computes the same result from bitwise identical data.
+__device__ __noinline__ void lz3_ritz(const LanczosCl3Args& a, double* sbase, int* st, const double beta, const int vn, const int cta,
+                                      long long* prof) {
+#define SMD(field) (sbase + a.L.field)
+    const int tid = threadIdx.x;
+    const int K = a.K, VNp = lanczos_cl_vnp(a.vn_max);
+    int k = st[0], arrow = st[2], howmany = st[3], numiter = st[4];
+    const bool first_analysis = st[5] != 0;
+    int converged = 0, finished = 0;
+    __syncthreads();                              // everybody has read the state before thread 0 rewrites it
+    const int lda = lanczos_kp(K);
+    const int m = (k + 1) & ~1;
+    long long t_in = prof ? clock64() : 0;
+    // ---- fast path: leading pairs of the plain tridiagonal by bisection + twisted vectors ----
+    bool done_bi = false;
+    if (a.use_bi && arrow < 0 && 2 * (size_t)lda * lda >= ritz_bi_scratch_doubles(K)) {
+        RitzBiScratch bs = ritz_bi_carve(SMD(JA), K);          // JA and JB are contiguous and unused here
+        const int mb = ritz_top_bi(k, SMD(Hd), SMD(He), howmany + 4, SMD(D), SMD(JU), lda, bs, prof);
+        if (mb > 0) {
+            int* order = reinterpret_cast<int*>(SMD(order));
+            for (int i = tid; i < mb; i += LZ_THREADS) { order[i] = i; SMD(f)[i] = beta * SMD(JU)[(k - 1) + i * lda]; }
+            __syncthreads();
+            int cv = 0;
+            while (cv < mb && fabs(SMD(f)[cv]) <= a.tol) cv++;
+            if (cv >= howmany && cv < mb) { converged = cv; finished = 1; done_bi = true; }
+            __syncthreads();
+        }
+    }
+    if (prof && tid == 0) { prof[8 + (done_bi ? 0 : 1)] += 1; prof[10] += clock64() - t_in; }
+    bool first_out = first_analysis;
+    if (!done_bi) {
+        {
+            double* JA = SMD(JA);
+            for (int idx = tid; idx < m * m; idx += LZ_THREADS) {
+                int r = idx % m, c = idx / m;
+                double v = 0.0;
+                if (r < k && c < k) {
+                    if (r == c) v = SMD(Hd)[r];
+                    else {
+                        int lo = min(r, c), hi = max(r, c);
+                        if (hi == arrow && lo < arrow) v = SMD(Harr)[lo];
+                        else if (hi == lo + 1 && !(lo < arrow && hi <= arrow)) v = SMD(He)[lo];
+                    }
+                }
+                JA[r + c * lda] = v;
+            }
+            for (int idx = tid; idx < lda * lda; idx += LZ_THREADS) SMD(JB)[idx] = 0.0;
+        }
+        __syncthreads();
+        JacobiScratch js = jacobi_carve(SMD(jscratch), lda);
+        const double* Jd;
+        const bool warm = first_analysis && a.ritz_rd && (int)a.ritz_rd[0] == k && k == K;
+        if (warm) Jd = jacobi_eigh_smem_warm(m, k, SMD(JA), SMD(JB), lda, SMD(JU), lda, a.ritz_rd + 1, js);
+        else Jd = jacobi_eigh_smem_fast(m, SMD(JA), SMD(JB), lda, SMD(JU), lda, js);
+        __syncthreads();
+        if (first_analysis && a.ritz_wr && cta == 0) {
+            for (int idx = tid; idx < lda * lda; idx += LZ_THREADS) a.ritz_wr[1 + idx] = SMD(JU)[idx];
+            if (tid == 0) a.ritz_wr[0] = (k == K) ? (double)k : -1.0;
+        }
+        first_out = false;
+        int* order = reinterpret_cast<int*>(SMD(order));
+        rank_sort_desc(k, Jd, lda, order);
+        __syncthreads();
+        for (int i = tid; i < k; i += LZ_THREADS) {
+            int o = order[i];
+            SMD(D)[i] = Jd[o + o * lda];
+            SMD(f)[i] = beta * SMD(JU)[(k - 1) + o * lda];
+        }
+        __syncthreads();
+        converged = 0;
+        while (converged < k && fabs(SMD(f)[converged]) <= a.tol) converged++;
+        if (converged >= howmany) {
+            finished = 1;
+        } else if (k == K) {
+            if (numiter == a.maxiter) {
+                finished = 1;
+            } else {
+                // ---- thick restart: V[:, 0:keep] <- V U[:, order[0:keep]], in place row by row ----
+                const int keep = (3 * K + 2 * converged) / 5;
+                double* Vs = SMD(Vs);
+                for (int t = tid; t < vn; t += LZ_THREADS) {
+                    double row[LZC_KMAX];
+                    for (int i = 0; i < K; ++i) row[i] = Vs[i * VNp + t];
+                    for (int q = 0; q < keep; ++q) {
+                        const double* u = SMD(JU) + order[q] * lda;
+                        double s = 0.0;
+                        for (int i = 0; i < K; ++i) s = fma(row[i], u[i], s);
+                        Vs[q * VNp + t] = s;
+                    }
+                    Vs[keep * VNp + t] = Vs[K * VNp + t];
+                }
+                __syncthreads();
+                for (int i = tid; i < K; i += LZ_THREADS) {
+                    double d = (i < keep) ? SMD(D)[i] : 0.0;
+                    double fa = (i < keep) ? SMD(f)[i] : 0.0;
+                    SMD(Hd)[i] = d; SMD(Harr)[i] = fa; SMD(He)[i] = 0.0;
+                }
+                arrow = keep;
+                k = keep;                       // the caller's k++ makes it keep + 1
+                numiter++;
+            }
+        }
+    }
+    if (tid == 0) {
+        st[0] = k; st[2] = arrow; st[3] = howmany; st[4] = numiter; st[5] = first_out ? 1 : 0; st[6] = converged; st[7] = finished;
+    }
+    __syncthreads();
+#undef SMD
+}
+
+template <int CPW, int RB>
 __global__ void __launch_bounds__(LZ_THREADS, 1) k_lanczos_cl3(const __grid_constant__ LanczosCl3Args a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cg::cluster_group cluster = cg::this_cluster();
@@ -259,7 +360,6 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) k_lanczos_cl3(const __grid_cons
     const int VNp = lanczos_cl_vnp(a.vn_max);
     const int cpr = lanczos_cpr(n);
     const int Kp2 = K + 2;
-    const int RLs = a.L.rls;
     // shared-memory arrays: rebuilt from the constant-bank offsets at the point of use (no long-lived pointers)
     double* const sbase = reinterpret_cast<double*>(smem_raw);
 #define SMD(field) (sbase + a.L.field)
@@ -281,6 +381,7 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) k_lanczos_cl3(const __grid_cons
     const int prow = (cta == 0) ? 0 : (cta == C - 1) ? 1 : (cta == G / 2) ? 2 : (cta == G - 1) ? 3 : -1;
     const bool profiling = (a.prof != nullptr) && prow >= 0;
     if (tid < 32) s_prof[tid] = 0;
+    if (tid == 0) s_ok = 1;
     // (the running clock sits in s_prof[31], not in a register that would have to live across the symv)
 #define tprev s_prof[31]
 #define LZ3_TICK(slot) do { if (profiling && tid == 0) { long long tn = clock64(); s_prof[slot] += tn - tprev; tprev = tn; } } while (0)
@@ -306,95 +407,61 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) k_lanczos_cl3(const __grid_cons
             s_state[0] = k; s_state[1] = (int)gsync; s_state[2] = arrow; s_state[3] = howmany; s_state[4] = numiter;
             s_state[5] = first_analysis ? 1 : 0; s_beta = beta;
         }
-        // ================= symv on my slab of rows: strip partials of X[r0:r1, :] v_j =================
-        {
-            const bool first = (gsync == 0);
-            switch (a.cpw) {
-#define LZ3_SYMV(CPW, RB) symv_strips<CPW, RB>(a.X, a.ld, r0, rl, cpr, SMD(vbuf), SMD(xs), a.xres_rows, first, SMD(wrow), RLs, SMD(walpha), warp, lane)
-                case 1: LZ3_SYMV(1, 15); break;
-                case 2: LZ3_SYMV(2, 9); break;
-                case 3: LZ3_SYMV(3, 6); break;
-                case 4: LZ3_SYMV(4, 3); break;
-                case 5: LZ3_SYMV(5, 3); break;
-                case 6: LZ3_SYMV(6, 3); break;
-                default: LZ3_SYMV(8, 2); break;
-#undef LZ3_SYMV
-            }
-        }
-        __syncthreads();
+        // ================= symv on my slab of rows: w slab and my share of alpha straight to global =================
+        // (gsync still counts the exchanges done so far: this step's buffers have parity (gsync + 1) & 1)
+        symv_slab<CPW, RB>(a.X, a.ld, r0, rl, cpr, SMD(vbuf), SMD(part), SMD(red2), a.round_rows,
+                           a.wg + (size_t)((gsync + 1) & 1) * a.ld + r0, a.apart + (size_t)((gsync + 1) & 1) * LZ3_GMAX + cta,
+                           a.epoch_base + gsync + 1);
+        // (no block barrier here: the state words were written a whole step ago)
         k = s_state[0]; gsync = (unsigned int)s_state[1]; arrow = s_state[2]; howmany = s_state[3]; numiter = s_state[4];
         first_analysis = s_state[5] != 0; beta = s_beta;
         const int j = k - 1;
         LZ3_TICK(0);
-        // ======== fold the strip partials, publish my w slab + partial alpha, grid exchange (warp 0) ========
-        // Every dependent step of a single warp costs 25-110 cycles on B200 (DFMA 23, LDS ~35, one 64-bit shuffle
+        ++gsync;
+        // ======== gather + local three-term step + partial Gram-Schmidt dots, warp by warp ========
+        // Every dependent step of a single warp costs 25-110 cycles on B200 (DFMA 23, LDS ~35-70, one 64-bit shuffle
         // step ~110: scripts/lat_bench.cu), so the phases below are laid out for short chains: conflict-free
         // shared-memory columns and serial adds in 4 chains instead of shuffle trees.
-        ++gsync;
-        if (warp == 0) {
-            double* wgp = a.wg + (size_t)(gsync & 1) * a.ld + r0;
-            for (int r = lane; r <= rl; r += 32) {           // lane r: row r of my slab; lane rl: my share of alpha
-                const double* wr = (r < rl) ? SMD(wrow) + r : SMD(walpha);
-                const int stride = (r < rl) ? RLs : 1;
-                const int cnt = (r < rl) ? (cpr + a.cpw - 1) / a.cpw : LZ_NW;
-                double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-                int q = 0;
-                for (; q + 3 < cnt; q += 4) { s0 += wr[q * stride]; s1 += wr[(q + 1) * stride]; s2 += wr[(q + 2) * stride]; s3 += wr[(q + 3) * stride]; }
-                for (; q < cnt; ++q) s0 += wr[q * stride];
-                const double sres = (s0 + s1) + (s2 + s3);
-                if (r < rl) __stcg(wgp + r, sres);
-                else __stcg(a.apart + (size_t)(gsync & 1) * LZ3_GMAX + cta, sres);
-            }
-            __syncwarp();
-            long long t0 = 0;
-            if (profiling && lane == 0) { t0 = clock64(); s_prof[15] += t0 - tprev; }      // fold + publish
-            if (lane == 0) {
-                int ok = 1;
-                unsigned int target;
-                if (a.bar_mode == 2) {
-                    // group counter first; the last arriver of the group bumps the global counter
-                    unsigned int old;
-                    asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(old) : "l"(a.bar + (size_t)(1 + cta / C) * 32) : "memory");
-                    if (old + 1 == gsync * (unsigned int)C) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(a.bar) : "memory");
-                    target = gsync * (unsigned int)(G / C);
-                } else {
-                    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(a.bar) : "memory");
-                    target = gsync * (unsigned int)G;
-                }
-                unsigned int v;
-                const long long tw = clock64();
-                do {
-                    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(a.bar) : "memory");
-                    if (v >= target) break;
-                    if (clock64() - tw > 4000000000LL) { ok = 0; break; }   // ~2 s: give up instead of hanging the GPU
-                } while (true);
-                asm volatile("fence.acq_rel.gpu;" ::: "memory");
-                s_ok = ok;
-                if (profiling) s_prof[16] += clock64() - t0;      // arrive + wait
-            }
-        }
-        __syncthreads();
-        if (!s_ok) { failed = 1; break; }
-        LZ3_TICK(17);
-        // ======== gather + local three-term step + partial Gram-Schmidt dots, warp by warp ========
-        // Warp w owns the basis rows [w RW, (w+1) RW) of this CTA for the whole phase, so no block barrier is needed
-        // between gathering w, the local step and the dots; the only block-wide value is alpha, which warp LZ_NW-1
-        // sums from the per-CTA partials.  alpha is only needed to about 1e-7: the Gram-Schmidt pass removes
-        // whatever is left along v_j exactly (alpha_j = alpha~ + h_j), so its shuffle tree runs in FP32 (35 instead
-        // of 110 cycles per step).
+        // Warp w owns the basis rows [w RW, (w+1) RW) of this CTA for the whole phase: its lanes poll the flagged w
+        // entries of exactly those rows, so no block barrier is needed between the exchange, the local step and the
+        // dots; the only block-wide value is alpha, which warp LZ_NW-1 sums from the per-CTA partials.  alpha is only
+        // needed to about 1e-7: the Gram-Schmidt pass removes whatever is left along v_j exactly (alpha_j = alpha~ +
+        // h_j), so its shuffle tree runs in FP32 (35 instead of 110 cycles per step).
         const int RW = (a.vn_max + LZ_NW - 1) / LZ_NW;
         const int t_lo = min(vn, warp * RW), t_hi = min(vn, (warp + 1) * RW);
         {
-            const double* wgp = a.wg + (size_t)(gsync & 1) * a.ld + v0;
+            const unsigned int tag = a.epoch_base + gsync;
+            const uint4* wgp = a.wg + (size_t)(gsync & 1) * a.ld + v0;
             const double* Vs = SMD(Vs);
             double* wv = SMD(wv);
             double wreg[2];                                  // RW <= 64 rows per warp is checked on the host
+            {
+                uint4 rr[2];
+                bool have[2];
 #pragma unroll
-            for (int u = 0; u < 2; ++u) { const int t = t_lo + lane + 32 * u; wreg[u] = (t < t_hi) ? __ldcg(wgp + t) : 0.0; }
+                for (int u = 0; u < 2; ++u) have[u] = !(t_lo + lane + 32 * u < t_hi);
+                const long long tw = clock64();
+                while (true) {
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) {
+                        if (!have[u]) { rr[u] = ll_peek(wgp + t_lo + lane + 32 * u); have[u] = (rr[u].y == tag && rr[u].w == tag); }
+                    }
+                    if (__all_sync(0xffffffffu, have[0] && have[1])) break;
+                    if (clock64() - tw > 4000000000LL) { s_ok = 0; break; }      // ~2 s: a peer died; give up instead of hanging
+                }
+#pragma unroll
+                for (int u = 0; u < 2; ++u) wreg[u] = (t_lo + lane + 32 * u < t_hi) ? ll_value(rr[u]) : 0.0;
+            }
             if (warp == LZ_NW - 1) {
-                const double* app = a.apart + (size_t)(gsync & 1) * LZ3_GMAX;
+                const uint4* app = a.apart + (size_t)(gsync & 1) * LZ3_GMAX;
                 double sd = 0.0;
-                for (int c = lane; c < G; c += 32) sd += __ldcg(app + c);
+                const long long tw = clock64();
+                for (int c = lane; c < G; c += 32) {
+                    uint4 r;
+                    do { r = ll_peek(app + c); } while (!(r.y == tag && r.w == tag) && clock64() - tw <= 4000000000LL);
+                    if (!(r.y == tag && r.w == tag)) s_ok = 0;
+                    sd += ll_value(r);
+                }
                 float sf = (float)sd;
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) sf += __shfl_xor_sync(0xffffffffu, sf, o);
@@ -412,6 +479,7 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) k_lanczos_cl3(const __grid_cons
                 for (int u = 0; u < 2; ++u) { const int t = t_lo + lane + 32 * u; if (t < t_hi) wreg[u] = fma(-bprev, Vs[(j - 1) * VNp + t], wreg[u]); }
             }
             __syncthreads();
+            if (!s_ok) { failed = 1; break; }
             const double alpha0 = SMD(hred)[K + 1];
 #pragma unroll
             for (int u = 0; u < 2; ++u) { const int t = t_lo + lane + 32 * u; if (t < t_hi) wv[t] = fma(-alpha0, Vs[j * VNp + t], wreg[u]); }
@@ -513,9 +581,11 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) k_lanczos_cl3(const __grid_cons
         }
         // ||w_new||^2 = ||w||^2 - ||h||^2 ; v_{j+1} = w / beta: keep my rows, push them into every peer's staging buffer
         {
+            // 1/beta by rsqrt (one MUFU + two Newton steps) instead of sqrt followed by a division: both sit on the
+            // critical path of every thread; beta itself is beta2 * (1/beta), good to an ulp
             const double beta2 = fmax(wn2 - hn2, 0.0);
-            beta = sqrt(beta2);
-            const double ib = (beta > 0.0) ? 1.0 / beta : 0.0;
+            const double ib = (beta2 > 0.0) ? rsqrt(beta2) : 0.0;
+            beta = beta2 * ib;
             if (tid == 0) { SMD(Hd)[j] = alpha; SMD(He)[j] = beta; }
             if (2 * vn <= LZ_THREADS) {
                 // the thread pair of row t shares the pushes: sub 0 -> peers 0, 2, ..., sub 1 -> peers 1, 3, ...
@@ -540,102 +610,17 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) k_lanczos_cl3(const __grid_cons
         cluster.sync();
         LZ3_TICK(4);
 
-        // ================= Ritz analysis (redundant in every CTA) =================
+        // ================= Ritz analysis (redundant in every CTA; out of line) =================
         if (beta <= a.tol && k < howmany) howmany = k;
         if (k == K || beta <= a.tol) {
-            const int lda = lanczos_kp(K);
-            const int m = (k + 1) & ~1;
-            // ---- fast path: leading pairs of the plain tridiagonal by bisection + twisted vectors ----
-            bool done_bi = false;
-            if (a.use_bi && arrow < 0 && 2 * (size_t)lda * lda >= ritz_bi_scratch_doubles(K)) {
-                RitzBiScratch bs = ritz_bi_carve(SMD(JA), K);          // JA and JB are contiguous and unused here
-                const int mb = ritz_top_bi(k, SMD(Hd), SMD(He), howmany + 4, SMD(D), SMD(JU), lda, bs, profiling ? s_prof : nullptr);
-                if (mb > 0) {
-                    int* order = reinterpret_cast<int*>(SMD(order));
-                    for (int i = tid; i < mb; i += LZ_THREADS) { order[i] = i; SMD(f)[i] = beta * SMD(JU)[(k - 1) + i * lda]; }
-                    __syncthreads();
-                    int cv = 0;
-                    while (cv < mb && fabs(SMD(f)[cv]) <= a.tol) cv++;
-                    if (cv >= howmany && cv < mb) { converged = cv; finished = 1; done_bi = true; }
-                    __syncthreads();
-                }
-            }
-            if (profiling && tid == 0) { s_prof[8 + (done_bi ? 0 : 1)] += 1; s_prof[10] += clock64() - tprev; }
-            if (done_bi) { LZ3_TICK(5); continue; }
-            {
-                double* JA = SMD(JA);
-                for (int idx = tid; idx < m * m; idx += LZ_THREADS) {
-                    int r = idx % m, c = idx / m;
-                    double v = 0.0;
-                    if (r < k && c < k) {
-                        if (r == c) v = SMD(Hd)[r];
-                        else {
-                            int lo = min(r, c), hi = max(r, c);
-                            if (hi == arrow && lo < arrow) v = SMD(Harr)[lo];
-                            else if (hi == lo + 1 && !(lo < arrow && hi <= arrow)) v = SMD(He)[lo];
-                        }
-                    }
-                    JA[r + c * lda] = v;
-                }
-                for (int idx = tid; idx < lda * lda; idx += LZ_THREADS) SMD(JB)[idx] = 0.0;
+            if (tid == 0) {
+                s_state[0] = k; s_state[2] = arrow; s_state[3] = howmany; s_state[4] = numiter; s_state[5] = first_analysis ? 1 : 0;
             }
             __syncthreads();
-            JacobiScratch js = jacobi_carve(SMD(jscratch), lda);
-            const double* Jd;
-            const bool warm = first_analysis && a.ritz_rd && (int)a.ritz_rd[0] == k && k == K;
-            if (warm) Jd = jacobi_eigh_smem_warm(m, k, SMD(JA), SMD(JB), lda, SMD(JU), lda, a.ritz_rd + 1, js);
-            else Jd = jacobi_eigh_smem_fast(m, SMD(JA), SMD(JB), lda, SMD(JU), lda, js);
-            __syncthreads();
-            if (first_analysis && a.ritz_wr && cta == 0) {
-                for (int idx = tid; idx < lda * lda; idx += LZ_THREADS) a.ritz_wr[1 + idx] = SMD(JU)[idx];
-                if (tid == 0) a.ritz_wr[0] = (k == K) ? (double)k : -1.0;
-            }
-            first_analysis = false;
-            int* order = reinterpret_cast<int*>(SMD(order));
-            rank_sort_desc(k, Jd, lda, order);
-            __syncthreads();
-            for (int i = tid; i < k; i += LZ_THREADS) {
-                int o = order[i];
-                SMD(D)[i] = Jd[o + o * lda];
-                SMD(f)[i] = beta * SMD(JU)[(k - 1) + o * lda];
-            }
-            __syncthreads();
-            converged = 0;
-            while (converged < k && fabs(SMD(f)[converged]) <= a.tol) converged++;
-            if (converged >= howmany) {
-                finished = 1;
-            } else if (k == K) {
-                if (numiter == a.maxiter) {
-                    finished = 1;
-                } else {
-                    // ---- thick restart: V[:, 0:keep] <- V U[:, order[0:keep]], in place row by row ----
-                    const int keep = (3 * K + 2 * converged) / 5;
-                    double* Vs = SMD(Vs);
-                    for (int t = tid; t < vn; t += LZ_THREADS) {
-                        double row[LZC_KMAX];
-                        for (int i = 0; i < K; ++i) row[i] = Vs[i * VNp + t];
-                        for (int q = 0; q < keep; ++q) {
-                            const double* u = SMD(JU) + order[q] * lda;
-                            double s = 0.0;
-                            for (int i = 0; i < K; ++i) s = fma(row[i], u[i], s);
-                            Vs[q * VNp + t] = s;
-                        }
-                        Vs[keep * VNp + t] = Vs[K * VNp + t];
-                    }
-                    __syncthreads();
-                    for (int i = tid; i < K; i += LZ_THREADS) {
-                        double d = (i < keep) ? SMD(D)[i] : 0.0;
-                        double fa = (i < keep) ? SMD(f)[i] : 0.0;
-                        SMD(Hd)[i] = d; SMD(Harr)[i] = fa; SMD(He)[i] = 0.0;
-                    }
-                    __syncthreads();
-                    arrow = keep;
-                    k = keep + 1;
-                    numiter++;
-                    LZ3_TICK(5);
-                    continue;
-                }
-            }
+            lz3_ritz(a, sbase, s_state, beta, vn, cta, profiling ? s_prof : nullptr);
+            k = s_state[0]; arrow = s_state[2]; howmany = s_state[3]; numiter = s_state[4]; first_analysis = s_state[5] != 0;
+            converged = s_state[6]; finished = s_state[7];
+            __syncthreads();                    // the state words are rewritten at the top of the next step
         }
         LZ3_TICK(5);
         if (!finished) k++;

@@ -65,6 +65,20 @@ static NcclApi& nccl_api() {
     } while (0)
 
 
+// the strip width (64-double chunks per warp) selects the kernel instance: cpw = ceil(ceil(n / 64) / 16)
+static const void* lanczos_cl3_kernel(int cpw) {
+    switch (cpw) {
+        case 1: return (const void*)k_lanczos_cl3<1, 15>;
+        case 2: return (const void*)k_lanczos_cl3<2, 9>;
+        case 3: return (const void*)k_lanczos_cl3<3, 6>;
+        case 4: return (const void*)k_lanczos_cl3<4, 3>;
+        case 5: return (const void*)k_lanczos_cl3<5, 3>;
+        case 6: return (const void*)k_lanczos_cl3<6, 3>;
+        case 8: return (const void*)k_lanczos_cl3<8, 2>;
+        default: return nullptr;
+    }
+}
+
 static bool g_timing = getenv("PROXSDP_B200_TIMING") != nullptr;
 static double now_s();
 struct StageTimer {
@@ -254,7 +268,6 @@ class Solver {
     bool lanczos_launch_cluster3(ConeDev& cd, int cone_idx, int nev, int K, int maxiter, double tol);
     int lz_kernel_ = 3;        // 3 = third-generation cluster kernel (lanczos_cl3.cuh), 2 = second generation (lanczos_cl.cuh)
     int lz_xres_ = 1;          // keep as many slab rows of X as fit in the spare shared memory (cl3, strip symv)
-    int lz_bar_mode_ = 0;      // cl3 grid exchange: 0 one counter, 2 group counters + global counter
     size_t lz_cl3_smem_max_ = 0;
     int lz_mode_ = 0;          // 0 = cluster-replicated kernel when it fits, 1 = row-distributed kernel only
     int lz_cluster_ = 8;       // cluster size of the replicated kernel
@@ -344,7 +357,8 @@ class Solver {
     DBuf<uint4> lz_xbuf_, lz_vx_;
     DBuf<double> lz_wg_;
     DBuf<unsigned int> lz_bar_;
-    DBuf<double> lz_apart_;
+    DBuf<uint4> lz3_wg_, lz3_apart_;
+    unsigned long long lz3_epoch_ = 0;
     DBuf<long long> lz_prof_;
     unsigned long long lz_epoch_ = 0;
 };
@@ -383,7 +397,6 @@ Solver::Solver(const proxsdp_problem_t* prob, const proxsdp_options_t* opt_in, b
     if (const char* e = getenv("PROXSDP_B200_RITZ_WARM")) lz_warm_ = atoi(e);
     if (const char* e = getenv("PROXSDP_B200_LZ_KERNEL")) lz_kernel_ = atoi(e);
     if (const char* e = getenv("PROXSDP_B200_LZ_XRES")) lz_xres_ = atoi(e);
-    if (const char* e = getenv("PROXSDP_B200_LZ_BAR")) lz_bar_mode_ = std::max(0, std::min(2, atoi(e)));
     if (const char* e = getenv("PROXSDP_B200_RITZ_BI")) lz_bi_ = atoi(e);
     { size_t lim = 0; if (cudaDeviceGetLimit(&lim, cudaLimitStackSize) == cudaSuccess && lim < 4096) cudaDeviceSetLimit(cudaLimitStackSize, 4096); }
     g_h2d_bytes = 0; g_d2h_bytes = 0;
@@ -615,16 +628,21 @@ void Solver::setup_host(const proxsdp_problem_t* prob) {
         lz_cl_smem_max_ = smem_optin_ - fa.sharedSizeBytes;
         PB_CUDA(cudaFuncSetAttribute(k_lanczos_cl, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lz_cl_smem_max_));
     }
-    {
+    lz_cl3_smem_max_ = smem_optin_;
+    for (int cpw = 1; cpw <= 8; ++cpw) {
+        const void* fn = lanczos_cl3_kernel(cpw);
+        if (!fn) continue;
         cudaFuncAttributes fa{};
-        PB_CUDA(cudaFuncGetAttributes(&fa, k_lanczos_cl3));
-        lz_cl3_smem_max_ = smem_optin_ - fa.sharedSizeBytes;
-        PB_CUDA(cudaFuncSetAttribute(k_lanczos_cl3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lz_cl3_smem_max_));
+        PB_CUDA(cudaFuncGetAttributes(&fa, fn));
+        lz_cl3_smem_max_ = std::min(lz_cl3_smem_max_, smem_optin_ - fa.sharedSizeBytes);
     }
-    if (lz_cluster_ > 8) {
-        PB_CUDA(cudaFuncSetAttribute(k_lanczos_cl, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-        PB_CUDA(cudaFuncSetAttribute(k_lanczos_cl3, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    for (int cpw = 1; cpw <= 8; ++cpw) {
+        const void* fn = lanczos_cl3_kernel(cpw);
+        if (!fn) continue;
+        PB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lz_cl3_smem_max_));
+        if (lz_cluster_ > 8) PB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     }
+    if (lz_cluster_ > 8) PB_CUDA(cudaFuncSetAttribute(k_lanczos_cl, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     st.lap("done");
     PB_CUDA(cudaFuncSetAttribute(k_bj_pair_eig, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bj_pair_smem_bytes()));
     PB_CUDA(cudaFuncSetAttribute(k_bj_apply<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BJ_APPLY_SMEM));
@@ -789,43 +807,51 @@ bool Solver::lanczos_launch_cluster3(ConeDev& cd, int cone_idx, int nev, int K, 
     int G = std::min(std::min(want, (num_sms_ / C) * C), (LZ3_GMAX / C) * C);
     if (G < C) return false;
     int rows_max = (nside + G - 1) / G;
-    Lz3Layout L = lanczos_cl3_layout(K, rows_max, vn_max, nside, C, 0);
-    size_t smem = (size_t)L.total * sizeof(double);
-    if (smem > lz_cl3_smem_max_) return false;
+    // the partial-sum table of the symv takes what the basis replica leaves: at least one row + alpha must fit
+    auto fit_rounds = [&](int rmax, Lz3Layout& Lout, size_t& bytes) -> int {
+        Lz3Layout L1 = lanczos_cl3_layout(K, 1, vn_max, nside, C);
+        if ((size_t)L1.total * sizeof(double) > lz_cl3_smem_max_) return 0;
+        const long long spare_rows = (long long)((lz_cl3_smem_max_ - (size_t)L1.total * sizeof(double)) / ((size_t)LZ_THREADS * sizeof(double)));
+        int rr = (int)std::min<long long>(std::min(rmax, 31), 1 + spare_rows);
+        if (lz_xres_ > 1) rr = std::min(rr, lz_xres_ - 1);        // PROXSDP_B200_LZ_XRES = rows + 1: cap for experiments
+        Lout = lanczos_cl3_layout(K, rr, vn_max, nside, C);
+        bytes = (size_t)Lout.total * sizeof(double);
+        return rr;
+    };
+    Lz3Layout L{};
+    size_t smem = 0;
+    int round_rows = fit_rounds(rows_max, L, smem);
+    if (round_rows < 1) return false;
     cfg.gridDim = dim3((unsigned)G); cfg.dynamicSmemBytes = smem;
+    const void* kfn = lanczos_cl3_kernel(cpw);
     int max_clusters = 0;
-    if (cudaOccupancyMaxActiveClusters(&max_clusters, k_lanczos_cl3, &cfg) != cudaSuccess || max_clusters < 1) {
+    if (cudaOccupancyMaxActiveClusters(&max_clusters, kfn, &cfg) != cudaSuccess || max_clusters < 1) {
         cudaGetLastError();
         return false;
     }
     if (max_clusters * C < G) {
         G = max_clusters * C;
         rows_max = (nside + G - 1) / G;
-        L = lanczos_cl3_layout(K, rows_max, vn_max, nside, C, 0);
-        smem = (size_t)L.total * sizeof(double);
-        if (smem > lz_cl3_smem_max_) return false;
-    }
-    // spare shared memory keeps the first xres rows of the slab on chip
-    int xres = 0;
-    if (lz_xres_) {
-        const long long fit = (long long)((lz_cl3_smem_max_ - smem) / ((size_t)cpr * 64 * sizeof(double)));
-        xres = (int)std::max<long long>(0, std::min<long long>(rows_max, fit));
-        if (lz_xres_ > 1) xres = std::min(xres, lz_xres_ - 1);       // PROXSDP_B200_LZ_XRES = rows + 1: cap for experiments
-        L = lanczos_cl3_layout(K, rows_max, vn_max, nside, C, xres);
-        smem = (size_t)L.total * sizeof(double);
+        round_rows = fit_rounds(rows_max, L, smem);
+        if (round_rows < 1) return false;
     }
     cfg.gridDim = dim3((unsigned)G); cfg.dynamicSmemBytes = smem;
     if ((size_t)cd.ld * (size_t)(K + 1) > cd.Y.n) cd.Y.alloc((size_t)cd.ld * (size_t)(K + 1));
-    if (lz_wg_.n < (size_t)2 * cd.ld) lz_wg_.alloc((size_t)2 * cd.ld);
-    if (lz_apart_.n == 0) lz_apart_.alloc(2 * LZ3_GMAX);
-    if (lz_bar_.n < (size_t)(1 + LZ3_GMAX / 2) * 32) lz_bar_.alloc((size_t)(1 + LZ3_GMAX / 2) * 32);
-    PB_CUDA(cudaMemsetAsync(lz_bar_.p, 0, sizeof(unsigned int) * 32 * (size_t)(1 + (lz_bar_mode_ == 2 ? G / C : 0)), stream));
+    // flagged-exchange buffers (shared by all cones of this solver; launches are stream ordered); tags are unique over
+    // launches, freshly zeroed buffers carry tag 0, which is never used
+    const unsigned long long bound = (unsigned long long)K * (unsigned long long)(std::max(maxiter, 1) + 1) + 16ULL;
+    if (lz3_wg_.n < (size_t)2 * cd.ld || lz3_apart_.n == 0 || lz3_epoch_ + bound >= 0xFFFFFFF0ULL) {
+        PB_CUDA(cudaStreamSynchronize(stream));
+        if (lz3_wg_.n < (size_t)2 * cd.ld) lz3_wg_.alloc((size_t)2 * cd.ld); else PB_CUDA(cudaMemset(lz3_wg_.p, 0, lz3_wg_.n * sizeof(uint4)));
+        if (lz3_apart_.n == 0) lz3_apart_.alloc(2 * LZ3_GMAX); else PB_CUDA(cudaMemset(lz3_apart_.p, 0, lz3_apart_.n * sizeof(uint4)));
+        lz3_epoch_ = 0;
+    }
     const size_t ws_len = 1 + (size_t)lanczos_kp(Kmax_ > K ? Kmax_ : K) * (size_t)lanczos_kp(Kmax_ > K ? Kmax_ : K);
     for (int q = 0; q < 2; ++q) if (cd.ritz_ws[q].n < ws_len) { cd.ritz_ws[q].alloc(ws_len); cd.ritz_launches = 0; }
     LanczosCl3Args a{};
     a.X = cd.X.p; a.n = nside; a.ld = cd.ld; a.x0 = cd.resid.p; a.Y = cd.Y.p;
-    a.wg = lz_wg_.p; a.apart = lz_apart_.p; a.bar = lz_bar_.p; a.bar_mode = lz_bar_mode_ == 2 ? 2 : 0;
-    a.cpw = cpw; a.xres_rows = xres;
+    a.wg = lz3_wg_.p; a.apart = lz3_apart_.p; a.epoch_base = (unsigned int)lz3_epoch_;
+    a.round_rows = round_rows;
     const int flip = (int)(cd.ritz_launches & 1);
     a.ritz_rd = (lz_warm_ && cd.ritz_launches > 0 && (cd.ritz_launches % 32) != 0) ? cd.ritz_ws[flip].p : nullptr;
     a.ritz_wr = lz_warm_ ? cd.ritz_ws[1 - flip].p : nullptr;
@@ -835,7 +861,8 @@ bool Solver::lanczos_launch_cluster3(ConeDev& cd, int cone_idx, int nev, int K, 
     a.vals = cd.vals.p; a.info = cd.info.p; a.scal = scal_d_.p; a.cone = cone_idx;
     a.L = L;
     if (getenv("PROXSDP_B200_LZ_PROF")) { if (lz_prof_.n == 0) lz_prof_.alloc(8 + 8 * 256); a.prof = lz_prof_.p; }
-    cudaError_t e = cudaLaunchKernelEx(&cfg, k_lanczos_cl3, a);
+    void* kargs[] = {&a};
+    cudaError_t e = cudaLaunchKernelExC(&cfg, kfn, kargs);
     if (e != cudaSuccess) {
         cudaGetLastError();
         if (!lz_cluster_warned_) { fprintf(stderr, "[proxsdp_b200] cl3 Lanczos launch failed (%s); using the second-generation kernel\n", cudaGetErrorString(e)); lz_cluster_warned_ = true; }
@@ -843,6 +870,7 @@ bool Solver::lanczos_launch_cluster3(ConeDev& cd, int cone_idx, int nev, int K, 
         return false;
     }
     cd.ritz_launches++;
+    lz3_epoch_ += bound;
     launches += 1;
     lz_cluster_launches_++;
     return true;
@@ -1684,8 +1712,8 @@ void Solver::finish(proxsdp_result_t* out) {
         for (int i = 0; i < 8; ++i) fprintf(stderr, "[lz-prof] %-30s %12lld cyc  %5.1f%%  (%.2f us/matvec)\n", nm[i], pr[i], 100.0 * pr[i] / std::max<long long>(tot, 1), pr[i] / 1965.0 / mv);
         if (lz_kernel_ == 3 && lz_cluster_launches_ > 0) {
             fprintf(stderr, "[lz-prof] us/matvec per profiled CTA (0, C-1, G/2, G-1):\n");
-            const char* nm2[10] = {"symv", "fold..post-barrier sync", " fold+publish", " arrive+wait", "gather+alpha+local", "gs dots+push", "cluster.sync 1", "reduce+update+publish", "cluster.sync 2", "ritz"};
-            const int sl[10] = {0, 17, 15, 16, 1, 2, 3, 6, 4, 5};
+            const char* nm2[10] = {"symv+reduce+publish", "exchange+alpha+local", "gs dots+push", "cluster.sync 1", "reduce+update+publish", "cluster.sync 2", "ritz", "loop-top", "-", "-"};
+            const int sl[10] = {0, 1, 2, 3, 6, 4, 5, 7, 15, 16};
             for (int q = 0; q < 10; ++q) {
                 fprintf(stderr, "[lz-prof]   %-24s", nm2[q]);
                 for (int r = 0; r < 4; ++r) fprintf(stderr, " %6.2f", pr[(size_t)32 * r + sl[q]] / 1965.0 / mv);
