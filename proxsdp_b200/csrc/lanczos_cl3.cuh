@@ -169,8 +169,9 @@ __device__ __forceinline__ double strided16_sum(const double* p, const int l, co
 template <int CPW, int RB>
 __device__ __forceinline__ void symv_slab(const double* __restrict__ X, const int ld, const int r0, const int rl, const int cpr,
                                           const double* vbuf, double* part, double* red2, const int round_rows,
-                                          uint4* wg_slab, uint4* alpha_out, const unsigned int tag) {
+                                          uint4* wg_slab, uint4* alpha_out, const unsigned int tag, long long* prof) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    long long tp = (prof && tid == 0) ? clock64() : 0;
     const int NS = (cpr + CPW - 1) / CPW;
     const int nrg = LZ_NW / NS;
     const int s = warp % NS, rg = warp / NS;
@@ -205,7 +206,9 @@ __device__ __forceinline__ void symv_slab(const double* __restrict__ X, const in
         }
         const bool last_round = (rend == rl);
         if (last_round) part[(rend - rbeg) * LZ_THREADS + tid] = pa;      // alpha: one more row of the table
+        if (prof && tid == 0) { const long long tn = clock64(); prof[15] += tn - tp; tp = tn; }      // warp 0: loads + FMAs + parking
         __syncthreads();
+        if (prof && tid == 0) { const long long tn = clock64(); prof[16] += tn - tp; tp = tn; }      // waiting for the slowest warp
         {
             const int h = tid >> 4, l = tid & 15;
             const int nred = (rend - rbeg) + (last_round ? 1 : 0);
@@ -225,6 +228,7 @@ __device__ __forceinline__ void symv_slab(const double* __restrict__ X, const in
                 if (h == rend - rbeg) ll_store(alpha_out, sres, tag); else ll_store(wg_slab + rbeg + h, sres, tag);
             }
         }
+        if (prof && tid == 0) { const long long tn = clock64(); prof[17] += tn - tp; tp = tn; }      // row reduction + publish
         if (!last_round) __syncthreads();          // the table is rewritten by the next round
     }
 }
@@ -411,7 +415,7 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) k_lanczos_cl3(const __grid_cons
         // (gsync still counts the exchanges done so far: this step's buffers have parity (gsync + 1) & 1)
         symv_slab<CPW, RB>(a.X, a.ld, r0, rl, cpr, SMD(vbuf), SMD(part), SMD(red2), a.round_rows,
                            a.wg + (size_t)((gsync + 1) & 1) * a.ld + r0, a.apart + (size_t)((gsync + 1) & 1) * LZ3_GMAX + cta,
-                           a.epoch_base + gsync + 1);
+                           a.epoch_base + gsync + 1, profiling ? s_prof : nullptr);
         // (no block barrier here: the state words were written a whole step ago)
         k = s_state[0]; gsync = (unsigned int)s_state[1]; arrow = s_state[2]; howmany = s_state[3]; numiter = s_state[4];
         first_analysis = s_state[5] != 0; beta = s_beta;
@@ -454,13 +458,26 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) k_lanczos_cl3(const __grid_cons
             }
             if (warp == LZ_NW - 1) {
                 const uint4* app = a.apart + (size_t)(gsync & 1) * LZ3_GMAX;
+                // four partials per lane polled concurrently (one L2 round trip when they are there), 128 CTAs per sweep
                 double sd = 0.0;
                 const long long tw = clock64();
-                for (int c = lane; c < G; c += 32) {
-                    uint4 r;
-                    do { r = ll_peek(app + c); } while (!(r.y == tag && r.w == tag) && clock64() - tw <= 4000000000LL);
-                    if (!(r.y == tag && r.w == tag)) s_ok = 0;
-                    sd += ll_value(r);
+                for (int cb = 0; cb < G; cb += 128) {
+                    uint4 pr[4];
+                    bool got[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) got[u] = !(cb + lane + 32 * u < G);
+                    while (true) {
+                        bool all = true;
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            if (!got[u]) { pr[u] = ll_peek(app + cb + lane + 32 * u); got[u] = (pr[u].y == tag && pr[u].w == tag); }
+                            all = all && got[u];
+                        }
+                        if (__all_sync(0xffffffffu, all)) break;
+                        if (clock64() - tw > 4000000000LL) { s_ok = 0; break; }
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) if (cb + lane + 32 * u < G) sd += ll_value(pr[u]);
                 }
                 float sf = (float)sd;
 #pragma unroll

@@ -20,17 +20,19 @@ constexpr int RITZ_BI_MAXM = 15;      // pairs computed at most (one warp each; 
 
 struct RitzBiScratch {
     double* ie;      // K        1 / e[j]
+    double* e2s;     // K        (e[j] / ||T||)^2
     double* zf;      // 16 * K   forward solutions, one row per warp
     double* zb;      // 16 * K   backward solutions
     double* lam;     // 16       eigenvalues (descending)
     int* fail;       // 1
 };
 
-__host__ __device__ inline size_t ritz_bi_scratch_doubles(int K) { return (size_t)K + 32 * (size_t)K + 16 + 2; }
+__host__ __device__ inline size_t ritz_bi_scratch_doubles(int K) { return 2 * (size_t)K + 32 * (size_t)K + 16 + 2; }
 
 __device__ inline RitzBiScratch ritz_bi_carve(double* base, int K) {
     RitzBiScratch s;
     s.ie = base; base += K;
+    s.e2s = base; base += K;
     s.zf = base; base += 16 * (size_t)K;
     s.zb = base; base += 16 * (size_t)K;
     s.lam = base; base += 16;
@@ -38,20 +40,39 @@ __device__ inline RitzBiScratch ritz_bi_carve(double* base, int K) {
     return s;
 }
 
-// number of eigenvalues of tridiag(d, e) that are < x  (sign changes of the leading principal minors)
-__device__ __forceinline__ int sturm_count(int k, const double* __restrict__ d, const double* __restrict__ e, double x) {
-    double p0 = 1.0, p1 = d[0] - x;
+// number of eigenvalues of tridiag(d, e) that are < x  (sign changes of the leading principal minors).
+// The minors are those of (T - x I) / ||T||: entries of size <= 2, so the products cannot overflow between two
+// rescaling checks (every 8 steps), and the recurrence p_j = dx_j p_{j-1} - e2_{j-1} p_{j-2} has ONE fused
+// multiply-add on its dependent chain: e2_{j-1} p_{j-2} is formed a step early.  FP64 FMA latency is 23 cycles on
+// B200, a count is ~30 cycles per row; scripts/sturm_check.py checks this arithmetic against LAPACK.
+__device__ __forceinline__ int sturm_count(int k, const double* __restrict__ d, const double* __restrict__ e2s, double x, double inv_t) {
+    double p0 = 1.0, p1 = (d[0] - x) * inv_t;
     int cnt = (p1 <= 0.0) ? 1 : 0;
-    for (int j = 1; j < k; ++j) {
-        const double ej = e[j - 1];
-        double p2 = fma(d[j] - x, p1, -(ej * ej) * p0);
-        const bool neg = (p2 == 0.0) || ((p2 < 0.0) != (p1 < 0.0));
-        cnt += neg ? 1 : 0;
-        if (p2 == 0.0) p2 = (p1 != 0.0) ? -p1 * 1e-300 : -1e-300;
-        const double a = fabs(p2);
-        if (a > 1e150) { p1 *= 1e-150; p2 *= 1e-150; }
-        else if (a < 1e-150) { p1 *= 1e150; p2 *= 1e150; }
-        p0 = p1; p1 = p2;
+    double t0 = (k > 1) ? e2s[0] * p0 : 0.0;
+    // blocks of 8 rows: the 16 shared-memory loads and the 8 shifted diagonals of a block are formed before its
+    // chain starts, so the chain itself is one FMA (+ the zero rescue) per row
+    for (int jb = 1; jb < k; jb += 8) {
+        double dx[8], ee[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int j = jb + u;
+            dx[u] = (j < k) ? (d[j] - x) * inv_t : 0.0;
+            ee[u] = (j < k - 1) ? e2s[j] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            if (jb + u < k) {
+                double p2 = fma(dx[u], p1, -t0);
+                const bool neg = (p2 == 0.0) || ((p2 < 0.0) != (p1 < 0.0));
+                cnt += neg ? 1 : 0;
+                if (p2 == 0.0) p2 = (p1 != 0.0) ? -p1 * 1e-300 : -1e-300;
+                t0 = ee[u] * p1;
+                p0 = p1; p1 = p2;
+            }
+        }
+        const double a = fabs(p1);
+        if (a > 1e100) { p0 *= 1e-100; p1 *= 1e-100; t0 *= 1e-100; }
+        else if (a < 1e-100) { p0 *= 1e100; p1 *= 1e100; t0 *= 1e100; }
     }
     return cnt;
 }
@@ -81,7 +102,8 @@ __device__ inline int ritz_top_bi(int k, const double* d, const double* e, int m
     }
     const double tnorm = fmax(fabs(gl), fabs(gu));
     if (!(tnorm > 0.0) || !(tnorm < 1e140) || !(emin > 1e-9 * tnorm)) return 0;     // (nearly) decoupled or degenerate: decline
-    for (int j = tid; j < k - 1; j += blockDim.x) sc.ie[j] = 1.0 / e[j];
+    const double inv_t = 1.0 / tnorm;
+    for (int j = tid; j < k - 1; j += blockDim.x) { sc.ie[j] = 1.0 / e[j]; const double es = e[j] * inv_t; sc.e2s[j] = es * es; }
     if (tid == 0) *sc.fail = 0;
     __syncthreads();
     RITZ_TICK(11);
@@ -94,7 +116,7 @@ __device__ inline int ritz_top_bi(int k, const double* d, const double* e, int m
         double lo = gl - 1e-3 * wdt, hi = gu + 1e-3 * wdt;
         for (int it = 0; it < 16; ++it) {
             const double x = lo + (hi - lo) * ((double)(lane + 1) * (1.0 / 33.0));
-            const int c = sturm_count(k, d, e, x);
+            const int c = sturm_count(k, d, sc.e2s, x, inv_t);
             const unsigned int okmask = __ballot_sync(0xffffffffu, c > idx);
             double nlo, nhi;
             if (okmask) {
@@ -107,7 +129,9 @@ __device__ inline int ritz_top_bi(int k, const double* d, const double* e, int m
                 nhi = hi;
             }
             lo = nlo; hi = nhi;
-            if (hi - lo <= 2.3e-16 * fmax(fabs(lo), fabs(hi))) break;
+            // a tridiagonal defines its eigenvalues to eps ||T|| only: stop there instead of chasing relative accuracy
+            // on eigenvalues that are small next to ||T|| (5 more rounds for nothing; every pair is verified below)
+            if (hi - lo <= fmax(2.3e-16 * fmax(fabs(lo), fabs(hi)), 2.3e-16 * tnorm)) break;
         }
         lam = 0.5 * (lo + hi);
         if (lane == 0) sc.lam[warp] = lam;

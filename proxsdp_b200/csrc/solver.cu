@@ -1712,10 +1712,10 @@ void Solver::finish(proxsdp_result_t* out) {
         for (int i = 0; i < 8; ++i) fprintf(stderr, "[lz-prof] %-30s %12lld cyc  %5.1f%%  (%.2f us/matvec)\n", nm[i], pr[i], 100.0 * pr[i] / std::max<long long>(tot, 1), pr[i] / 1965.0 / mv);
         if (lz_kernel_ == 3 && lz_cluster_launches_ > 0) {
             fprintf(stderr, "[lz-prof] us/matvec per profiled CTA (0, C-1, G/2, G-1):\n");
-            const char* nm2[10] = {"symv+reduce+publish", "exchange+alpha+local", "gs dots+push", "cluster.sync 1", "reduce+update+publish", "cluster.sync 2", "ritz", "loop-top", "-", "-"};
-            const int sl[10] = {0, 1, 2, 3, 6, 4, 5, 7, 15, 16};
+            const char* nm2[10] = {"symv+reduce+publish", "exchange+alpha+local", "gs dots+push", "cluster.sync 1", "reduce+update+publish", "cluster.sync 2", "ritz", " symv: warp 0 loads+FMA+park", " symv: wait for slowest warp", " symv: row reduce+publish"};
+            const int sl[10] = {0, 1, 2, 3, 6, 4, 5, 15, 16, 17};
             for (int q = 0; q < 10; ++q) {
-                fprintf(stderr, "[lz-prof]   %-24s", nm2[q]);
+                fprintf(stderr, "[lz-prof]   %-32s", nm2[q]);
                 for (int r = 0; r < 4; ++r) fprintf(stderr, " %6.2f", pr[(size_t)32 * r + sl[q]] / 1965.0 / mv);
                 fprintf(stderr, "\n");
             }

@@ -18,6 +18,6 @@ if [ "${SKIP_NCU:-0}" != "1" ]; then
 echo "== ncu launch list"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_$TAG.csv python bench.py --steps 30 --warmup 3 --no-cpu-baseline --no-flush-l2 > gpurun_out/ncu_launch_$TAG.log 2>&1
 echo "== ncu full (lanczos)"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_lanczos_cl -s 20 -c 1 -o gpurun_out/prof_lanczos_$TAG -f python bench.py --steps 30 --warmup 3 --no-cpu-baseline --no-flush-l2 > gpurun_out/ncu_full_$TAG.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_lanczos_cl3 -s 20 -c 1 -o gpurun_out/prof_lanczos_$TAG -f python bench.py --steps 30 --warmup 3 --no-cpu-baseline --no-flush-l2 > gpurun_out/ncu_full_$TAG.log 2>&1
 ls -la gpurun_out
 fi
