@@ -237,6 +237,9 @@ def run_b200(args):
     flush_ms = c1["l2_flush_ms"] - c0["l2_flush_ms"]
 
     # ---- end to end through the reference-facing call, host buffers in / host buffers out
+    # (one untimed call of W iterations first, like the W warm-up steps of the device-timed arm: the first call after
+    #  a solver has been torn down pays for the allocator re-mapping device memory)
+    solver.chambolle_pock(aff, con, Options(device_id=local_rank, max_iter=max(W, 3)))
     barrier()
     t0 = time.perf_counter()
     r2 = solver.chambolle_pock(aff, con, Options(device_id=local_rank, max_iter=K))
@@ -282,6 +285,7 @@ def run_b200(args):
             "value": e2e_value, "unit": UNIT,
             "h2d_bytes_per_step": r2.h2d_bytes / max(r2.iter, 1), "d2h_bytes_per_step": r2.d2h_bytes / max(r2.iter, 1),
             "steps": int(r2.iter), "wall_s": e2e_wall, "setup_s": r2.time_setup, "loop_s": r2.time_loop,
+            "warmup_calls": 1,
         },
         "gpu_launches": int(launches),
         "roofline": roofline,

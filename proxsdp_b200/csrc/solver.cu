@@ -103,6 +103,44 @@ void StageTimer::lap(const char* next) {
 // host<->device traffic of the current solve (reported as h2d/d2h bytes by the bench)
 static thread_local long long g_h2d_bytes = 0, g_d2h_bytes = 0;
 
+// Device memory comes from the device's default stream-ordered pool (cudaMallocAsync on the legacy stream) with
+// the release threshold lifted, so the ~40 buffers of a solve are carved out of memory the process already holds:
+// a cold cudaMalloc costs 0.1-3 ms each and made the end-to-end time of one chambolle_pock call swing between
+// 0.24 and 0.42 s (measured, profiles/r1h).  PROXSDP_B200_MALLOC=sync restores plain cudaMalloc / cudaFree.
+static bool pb_pool_enabled() {
+    static int state = -1;
+    if (state < 0) {
+        const char* e = getenv("PROXSDP_B200_MALLOC");
+        state = (e && std::string(e) == "sync") ? 0 : 1;
+    }
+    return state == 1;
+}
+static void pb_pool_prepare(int device) {
+    static thread_local int prepared_for = -1;
+    if (!pb_pool_enabled() || prepared_for == device) return;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        unsigned long long keep = ~0ULL;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    } else {
+        cudaGetLastError();
+    }
+    prepared_for = device;
+}
+static cudaError_t pb_malloc(void** p, size_t bytes) {
+    if (pb_pool_enabled()) {
+        cudaError_t e = cudaMallocAsync(p, bytes, 0);
+        if (e == cudaSuccess) return e;
+        cudaGetLastError();
+    }
+    return cudaMalloc(p, bytes);
+}
+static void pb_free(void* p) {
+    if (!p) return;
+    if (pb_pool_enabled()) { if (cudaFreeAsync(p, 0) == cudaSuccess) return; cudaGetLastError(); }
+    cudaFree(p);
+}
+
 template <class T>
 struct DBuf {
     T* p = nullptr;
@@ -112,15 +150,15 @@ struct DBuf {
     DBuf& operator=(const DBuf&) = delete;
     DBuf(DBuf&& o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
     DBuf& operator=(DBuf&& o) noexcept {
-        if (this != &o) { if (p) cudaFree(p); p = o.p; n = o.n; o.p = nullptr; o.n = 0; }
+        if (this != &o) { if (p) pb_free(p); p = o.p; n = o.n; o.p = nullptr; o.n = 0; }
         return *this;
     }
-    ~DBuf() { if (p) cudaFree(p); }
+    ~DBuf() { if (p) pb_free(p); }
     void alloc(size_t count) {
-        if (p) { cudaFree(p); p = nullptr; }
+        if (p) { pb_free(p); p = nullptr; }
         n = count;
         size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
-        cudaError_t e = cudaMalloc(&p, bytes);
+        cudaError_t e = pb_malloc(reinterpret_cast<void**>(&p), bytes);
         if (e != cudaSuccess) throw CudaError(-4, std::string("cudaMalloc failed: ") + cudaGetErrorString(e));
         PB_CUDA(cudaMemset(p, 0, bytes));
     }
@@ -383,6 +421,7 @@ Solver::Solver(const proxsdp_problem_t* prob, const proxsdp_options_t* opt_in, b
     dev_ = (int)opt.device_id;
     if (dev_ < 0 || dev_ >= ndev) throw CudaError(-1, "device_id out of range");
     PB_CUDA(cudaSetDevice(dev_));
+    pb_pool_prepare(dev_);
     cudaDeviceProp prop;
     PB_CUDA(cudaGetDeviceProperties(&prop, dev_));
     num_sms_ = prop.multiProcessorCount;
