@@ -110,6 +110,41 @@ struct LanczosCl3Args {
     Lz3Layout L;
 };
 
+// ---------------------------------------------------------------------------
+// Cluster exchange without fences: st.async delivers an 8-byte value into a peer's shared memory and credits the
+// peer's mbarrier with the bytes; the consumer arms the phase with the byte count it expects and waits on the
+// phase parity.  A cluster barrier costs MEMBAR.ALL.GPU + barrier + L1 invalidate on every thread (~12 % of the
+// kernel's stall samples in profiles/r1h); here only the data travels.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ unsigned int smem_u32(const void* p) { return (unsigned int)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ unsigned int mapa_u32(unsigned int addr, int cta_rank) {
+    unsigned int r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(cta_rank));
+    return r;
+}
+__device__ __forceinline__ void st_async_f64(unsigned int remote_addr, double v, unsigned int remote_mbar) {
+    asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];" ::"r"(remote_addr), "l"(__double_as_longlong(v)),
+                 "r"(remote_mbar)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned int bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// all threads call it; returns false after ~2 s (a peer died)
+__device__ __forceinline__ bool mbar_wait(unsigned long long* bar, unsigned int parity) {
+    const unsigned int a = smem_u32(bar);
+    unsigned int done = 0;
+    const long long t0 = clock64();
+    while (true) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(a), "r"(parity) : "memory");
+        if (done) return true;
+        if (clock64() - t0 > 4000000000LL) return false;
+    }
+}
+
 // One batch of the strip symv: RB rows x CPW chunks of X (16 bytes per lane each) against the warp's piece of v.
 // A full batch is branch-free (all loads issued back to back, then the FMAs); a batch short of rows takes one uniform
 // branch per row; only a ragged last strip (nch < CPW) pays a predicate per load.
@@ -380,8 +415,11 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) k_lanczos_cl3(const __grid_cons
     // read-modify-write per tick would stall warp 0, the warp on the critical path) and are flushed at the end
     __shared__ long long s_prof[32];
     __shared__ int s_ok;
-    __shared__ int s_state[8];
+    __shared__ int s_state[10];
     __shared__ double s_beta;
+    __shared__ __align__(8) unsigned long long s_mbar[2];      // [0] Gram-Schmidt dots exchange, [1] publication of v_{j+1}
+    unsigned int ph_dots = 0;                                  // dots exchanges completed so far (parity = phase & 1); the
+                                                               // publication phase is the step number: parity (gsync - 1) & 1
     const int prow = (cta == 0) ? 0 : (cta == C - 1) ? 1 : (cta == G / 2) ? 2 : (cta == G - 1) ? 3 : -1;
     const bool profiling = (a.prof != nullptr) && prow >= 0;
     if (tid < 32) s_prof[tid] = 0;
@@ -399,7 +437,12 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) k_lanczos_cl3(const __grid_cons
         for (int t = tid; t < vn; t += LZ_THREADS) SMD(Vs)[t] = a.x0[v0 + t] * inv_beta0;
         for (int c = tid; c < cpr * 64; c += LZ_THREADS) SMD(vbuf)[c] = (c < n) ? a.x0[c] * inv_beta0 : 0.0;
     }
-    cluster.sync();       // everybody's shared memory is initialised before any peer writes into it
+    if (tid == 0) {
+        mbar_init(&s_mbar[0], 1);
+        mbar_init(&s_mbar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    cluster.sync();       // everybody's shared memory and barriers are initialised before any peer writes into them
     if (profiling && tid == 0) tprev = clock64();
 
     while (!finished) {
@@ -409,7 +452,7 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) k_lanczos_cl3(const __grid_cons
         // spill re-read after a fence is an L2 round trip because the fence invalidates L1.
         if (tid == 0) {
             s_state[0] = k; s_state[1] = (int)gsync; s_state[2] = arrow; s_state[3] = howmany; s_state[4] = numiter;
-            s_state[5] = first_analysis ? 1 : 0; s_beta = beta;
+            s_state[5] = first_analysis ? 1 : 0; s_state[8] = (int)ph_dots; s_beta = beta;
         }
         // ================= symv on my slab of rows: w slab and my share of alpha straight to global =================
         // (gsync still counts the exchanges done so far: this step's buffers have parity (gsync + 1) & 1)
@@ -418,7 +461,7 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) k_lanczos_cl3(const __grid_cons
                            a.epoch_base + gsync + 1, profiling ? s_prof : nullptr);
         // (no block barrier here: the state words were written a whole step ago)
         k = s_state[0]; gsync = (unsigned int)s_state[1]; arrow = s_state[2]; howmany = s_state[3]; numiter = s_state[4];
-        first_analysis = s_state[5] != 0; beta = s_beta;
+        first_analysis = s_state[5] != 0; ph_dots = (unsigned int)s_state[8]; beta = s_beta;
         const int j = k - 1;
         LZ3_TICK(0);
         ++gsync;
@@ -535,10 +578,13 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) k_lanczos_cl3(const __grid_cons
 #pragma unroll
                 for (int w = 0; w < LZ_NW; w += 4) { s0 += dp[w * Kp2]; s1 += dp[(w + 1) * Kp2]; s2 += dp[(w + 2) * Kp2]; s3 += dp[(w + 3) * Kp2]; }
                 const double sres = (s0 + s1) + (s2 + s3);
-                for (int c = 0; c < C; ++c) cluster.map_shared_rank(SMD(hpart), c)[pass * C * Kp2 + crank * Kp2 + q] = sres;
+                const unsigned int dst = smem_u32(SMD(hpart) + pass * C * Kp2 + crank * Kp2 + q), mb = smem_u32(&s_mbar[0]);
+                for (int c = 0; c < C; ++c) st_async_f64(mapa_u32(dst, c), sres, mapa_u32(mb, c));
             }
+            if (tid == 0) mbar_expect_tx(&s_mbar[0], (unsigned int)(C * (j + 2) * 8));      // j + 2 dots from each of the C peers (me included)
             LZ3_TICK(2);
-            cluster.sync();
+            if (!mbar_wait(&s_mbar[0], ph_dots & 1)) s_ok = 0;
+            ++ph_dots;
             LZ3_TICK(3);
             // h[q] = sum over the C peers in rank order (fixed tree)
             for (int q = tid; q <= j + 1; q += LZ_THREADS) {
@@ -612,19 +658,22 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) k_lanczos_cl3(const __grid_cons
                 if (t < vn) {
                     const double v = wnew * ib;
                     if (sub == 0) SMD(Vs)[k * VNp + t] = v;
-                    for (int c = sub; c < C; c += 2) cluster.map_shared_rank(SMD(vbuf), c)[v0 + t] = v;
+                    const unsigned int dst = smem_u32(SMD(vbuf) + v0 + t), mb = smem_u32(&s_mbar[1]);
+                    for (int c = sub; c < C; c += 2) st_async_f64(mapa_u32(dst, c), v, mapa_u32(mb, c));
                 }
             } else {
                 __syncthreads();
                 for (int t = tid; t < vn; t += LZ_THREADS) {
                     const double v = SMD(wv)[t] * ib;
                     SMD(Vs)[k * VNp + t] = v;
-                    for (int c = 0; c < C; ++c) cluster.map_shared_rank(SMD(vbuf), c)[v0 + t] = v;
+                    const unsigned int dst = smem_u32(SMD(vbuf) + v0 + t), mb = smem_u32(&s_mbar[1]);
+                    for (int c = 0; c < C; ++c) st_async_f64(mapa_u32(dst, c), v, mapa_u32(mb, c));
                 }
             }
         }
+        if (tid == 0) mbar_expect_tx(&s_mbar[1], (unsigned int)(n * 8));      // every row of v_{j+1}, from whichever peer owns it
         LZ3_TICK(6);
-        cluster.sync();
+        if (!mbar_wait(&s_mbar[1], (gsync + 1) & 1)) s_ok = 0;
         LZ3_TICK(4);
 
         // ================= Ritz analysis (redundant in every CTA; out of line) =================
