@@ -146,35 +146,28 @@ __device__ __forceinline__ bool mbar_wait(unsigned long long* bar, unsigned int 
 }
 
 // One batch of the strip symv: RB rows x CPW chunks of X (16 bytes per lane each) against the warp's piece of v.
-// A full batch is branch-free (all loads issued back to back, then the FMAs); a batch short of rows takes one uniform
-// branch per row; only a ragged last strip (nch < CPW) pays a predicate per load.
+// Branch-free when the strip is full (nch == CPW): all loads are issued back to back, then the FMAs; a batch short
+// of rows simply re-reads its last valid row (the caller ignores those sums).  Only a ragged last strip pays a
+// predicate per load.
 template <int CPW, int RB>
 __device__ __forceinline__ void strip_batch(const double* __restrict__ gp, const size_t gstride, const int nrows, const int nch,
                                             const double2 (&vr)[CPW], double (&acc)[RB]) {
     double2 x[RB][CPW];
-    if (nch == CPW && nrows == RB) {
+    if (nch == CPW) {
 #pragma unroll
         for (int i = 0; i < RB; ++i) {
+            const double* rp = gp + (size_t)min(i, nrows - 1) * gstride;
 #pragma unroll
-            for (int c = 0; c < CPW; ++c) x[i][c] = ld_stream_d2(reinterpret_cast<const double2*>(gp + i * gstride + c * 64));
-        }
-    } else if (nch == CPW) {
-#pragma unroll
-        for (int i = 0; i < RB; ++i) {
-#pragma unroll
-            for (int c = 0; c < CPW; ++c) x[i][c] = make_double2(0.0, 0.0);
-            if (i < nrows) {
-#pragma unroll
-                for (int c = 0; c < CPW; ++c) x[i][c] = ld_stream_d2(reinterpret_cast<const double2*>(gp + i * gstride + c * 64));
-            }
+            for (int c = 0; c < CPW; ++c) x[i][c] = ld_stream_d2(reinterpret_cast<const double2*>(rp + c * 64));
         }
     } else {
 #pragma unroll
         for (int i = 0; i < RB; ++i) {
+            const double* rp = gp + (size_t)min(i, nrows - 1) * gstride;
 #pragma unroll
             for (int c = 0; c < CPW; ++c) {
                 x[i][c] = make_double2(0.0, 0.0);
-                if (i < nrows && c < nch) x[i][c] = ld_stream_d2(reinterpret_cast<const double2*>(gp + i * gstride + c * 64));
+                if (c < nch) x[i][c] = ld_stream_d2(reinterpret_cast<const double2*>(rp + c * 64));
             }
         }
     }
@@ -189,11 +182,14 @@ __device__ __forceinline__ void strip_batch(const double* __restrict__ gp, const
 
 // sum of cnt doubles at p[l], p[l + 16], ... (l = lane within the half-warp), four chains
 __device__ __forceinline__ double strided16_sum(const double* p, const int l, const int cnt) {
-    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0, s4 = 0.0, s5 = 0.0, s6 = 0.0, s7 = 0.0;      // eight chains: 4 adds deep for 512 partials
     int i = l;
-    for (; i + 48 < cnt; i += 64) { s0 += p[i]; s1 += p[i + 16]; s2 += p[i + 32]; s3 += p[i + 48]; }
+    for (; i + 112 < cnt; i += 128) {
+        s0 += p[i]; s1 += p[i + 16]; s2 += p[i + 32]; s3 += p[i + 48];
+        s4 += p[i + 64]; s5 += p[i + 80]; s6 += p[i + 96]; s7 += p[i + 112];
+    }
     for (; i < cnt; i += 16) s0 += p[i];
-    return (s0 + s1) + (s2 + s3);
+    return ((s0 + s1) + (s2 + s3)) + ((s4 + s5) + (s6 + s7));
 }
 
 // Slab symv w[r0 : r0 + rl] = X[r0 : r0 + rl, :] v plus this CTA's share of alpha = v[slab] . w[slab], written straight
