@@ -240,14 +240,23 @@ def run_b200(args):
     # (one untimed call of W iterations first, like the W warm-up steps of the device-timed arm: the first call after
     #  a solver has been torn down pays for the allocator re-mapping device memory)
     solver.chambolle_pock(aff, con, Options(device_id=local_rank, max_iter=max(W, 3)))
-    barrier()
-    t0 = time.perf_counter()
-    r2 = solver.chambolle_pock(aff, con, Options(device_id=local_rank, max_iter=K))
-    e2e_wall = time.perf_counter() - t0
-    te = torch.tensor([e2e_wall], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_wall = float(te[0])
+    # three timed calls, the median is reported (all three walls are in the JSON line): one call is ~0.25 s and a
+    # single shot swings by 30 % with the state the driver's allocator happens to be in
+    e2e_walls = []
+    e2e_runs = []
+    for _ in range(3):
+        barrier()
+        t0 = time.perf_counter()
+        r2_ = solver.chambolle_pock(aff, con, Options(device_id=local_rank, max_iter=K))
+        w_ = time.perf_counter() - t0
+        te = torch.tensor([w_], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e_walls.append(float(te[0]))
+        e2e_runs.append(r2_)
+    order = sorted(range(3), key=lambda i: e2e_walls[i])
+    r2 = e2e_runs[order[1]]
+    e2e_wall = e2e_walls[order[1]]
     e2e_value = world * r2.iter / e2e_wall
 
     if rank != 0:
@@ -285,7 +294,7 @@ def run_b200(args):
             "value": e2e_value, "unit": UNIT,
             "h2d_bytes_per_step": r2.h2d_bytes / max(r2.iter, 1), "d2h_bytes_per_step": r2.d2h_bytes / max(r2.iter, 1),
             "steps": int(r2.iter), "wall_s": e2e_wall, "setup_s": r2.time_setup, "loop_s": r2.time_loop,
-            "warmup_calls": 1,
+            "warmup_calls": 1, "timed_calls_wall_s": e2e_walls, "reported": "median of the timed calls",
         },
         "gpu_launches": int(launches),
         "roofline": roofline,
