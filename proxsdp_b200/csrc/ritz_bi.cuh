@@ -47,32 +47,33 @@ __device__ inline RitzBiScratch ritz_bi_carve(double* base, int K) {
 // B200, a count is ~30 cycles per row; scripts/sturm_check.py checks this arithmetic against LAPACK.
 __device__ __forceinline__ int sturm_count(int k, const double* __restrict__ d, const double* __restrict__ e2s, double x, double inv_t) {
     double p0 = 1.0, p1 = (d[0] - x) * inv_t;
-    int cnt = (p1 <= 0.0) ? 1 : 0;
+    bool s1 = (p1 <= 0.0);                 // sign of the minor, an exact zero counting as a change of sign
+    int cnt = s1 ? 1 : 0;
     double t0 = (k > 1) ? e2s[0] * p0 : 0.0;
     // blocks of 8 rows: the 16 shared-memory loads and the 8 shifted diagonals of a block are formed before its
-    // chain starts, so the chain itself is one FMA (+ the zero rescue) per row
+    // chain starts; the chain itself is ONE FMA per row — the sign bookkeeping (a zero minor takes the sign opposite
+    // to its predecessor, and the next minor -e^2 p_{j-1} then agrees with it) runs beside it on predicates
     for (int jb = 1; jb < k; jb += 8) {
         double dx[8], ee[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
             const int j = jb + u;
-            dx[u] = (j < k) ? (d[j] - x) * inv_t : 0.0;
+            dx[u] = (j < k) ? (d[j] - x) * inv_t : 1.0;          // rows past the end: p stays put (dx = 1, e2 = 0)
             ee[u] = (j < k - 1) ? e2s[j] : 0.0;
         }
+        const int nb = min(8, k - jb);
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
-            if (jb + u < k) {
-                double p2 = fma(dx[u], p1, -t0);
-                const bool neg = (p2 == 0.0) || ((p2 < 0.0) != (p1 < 0.0));
-                cnt += neg ? 1 : 0;
-                if (p2 == 0.0) p2 = (p1 != 0.0) ? -p1 * 1e-300 : -1e-300;
-                t0 = ee[u] * p1;
-                p0 = p1; p1 = p2;
-            }
+            const double p2 = fma(dx[u], p1, -t0);
+            const bool s2 = (p2 == 0.0) ? !s1 : (p2 < 0.0);
+            cnt += (u < nb && s2 != s1) ? 1 : 0;
+            if (u < nb) s1 = s2;
+            t0 = ee[u] * p1;
+            p0 = p1; p1 = p2;
         }
         const double a = fabs(p1);
         if (a > 1e100) { p0 *= 1e-100; p1 *= 1e-100; t0 *= 1e-100; }
-        else if (a < 1e-100) { p0 *= 1e100; p1 *= 1e100; t0 *= 1e100; }
+        else if (a < 1e-100 && a > 0.0) { p0 *= 1e100; p1 *= 1e100; t0 *= 1e100; }
     }
     return cnt;
 }

@@ -7,45 +7,27 @@ import numpy as np
 def sturm_count(d, e2s, x, inv_t):
     k = len(d)
     p0, p1 = 1.0, (d[0] - x) * inv_t
-    cnt = 1 if p1 <= 0.0 else 0
+    s1 = p1 <= 0.0
+    cnt = 1 if s1 else 0
     t0 = e2s[0] * p0 if k > 1 else 0.0
     for jb in range(1, k, 8):
-        for j in range(jb, min(jb + 8, k)):
-            dx = (d[j] - x) * inv_t
+        nb = min(8, k - jb)
+        for u in range(8):
+            j = jb + u
+            dx = (d[j] - x) * inv_t if j < k else 1.0
+            ee = e2s[j] if j < k - 1 else 0.0
             p2 = dx * p1 - t0            # fma on the device; rounding differences do not matter for the count
-            neg = (p2 == 0.0) or ((p2 < 0.0) != (p1 < 0.0))
-            cnt += 1 if neg else 0
-            if p2 == 0.0:
-                p2 = -p1 * 1e-300 if p1 != 0.0 else -1e-300
-            t0 = e2s[j] * p1 if j < k - 1 else 0.0
+            s2 = (not s1) if p2 == 0.0 else (p2 < 0.0)
+            if u < nb:
+                cnt += 1 if s2 != s1 else 0
+                s1 = s2
+            t0 = ee * p1
             p0, p1 = p1, p2
         a = abs(p1)
         if a > 1e100:
             p0 *= 1e-100; p1 *= 1e-100; t0 *= 1e-100
-        elif a < 1e-100:
+        elif 0.0 < a < 1e-100:
             p0 *= 1e100; p1 *= 1e100; t0 *= 1e100
-    return cnt
-
-
-def sturm_count_v1(d, e, x):
-    """the first-generation device recurrence (unscaled, rescaling every step): reference for the convention at
-    exact zeros of the minors, where both disagree with LAPACK by one in the same way"""
-    k = len(d)
-    p0, p1 = 1.0, d[0] - x
-    cnt = 1 if p1 <= 0.0 else 0
-    for j in range(1, k):
-        ej = e[j - 1]
-        p2 = (d[j] - x) * p1 - (ej * ej) * p0
-        neg = (p2 == 0.0) or ((p2 < 0.0) != (p1 < 0.0))
-        cnt += 1 if neg else 0
-        if p2 == 0.0:
-            p2 = -p1 * 1e-300 if p1 != 0.0 else -1e-300
-        a = abs(p2)
-        if a > 1e150:
-            p1 *= 1e-150; p2 *= 1e-150
-        elif a < 1e-150:
-            p1 *= 1e150; p2 *= 1e150
-        p0, p1 = p1, p2
     return cnt
 
 
@@ -69,11 +51,8 @@ def main():
         tn = max(np.abs(d).max() + 2 * np.abs(e).max(), 1e-300)
         inv_t = 1.0 / tn
         e2s = (e * inv_t) ** 2
-        xs = np.concatenate([rng.uniform(w[0] - 0.1 * tn, w[-1] + 0.1 * tn, 40), 0.5 * (w[1:] + w[:-1])])
-        for x in d:                               # exact zeros of a minor: same convention as the first generation
-            total += 1
-            if sturm_count(d, e2s, x, inv_t) != sturm_count_v1(d, e, x):
-                bad += 1
+        # random points, mid-gaps, and the diagonal entries themselves (x = d[0] makes the first minor exactly zero)
+        xs = np.concatenate([rng.uniform(w[0] - 0.1 * tn, w[-1] + 0.1 * tn, 40), 0.5 * (w[1:] + w[:-1]), d])
         for x in xs:
             gap = np.abs(w - x).min()
             if gap < 1e-10 * tn:
