@@ -18,7 +18,15 @@ namespace pb {
 
 constexpr int SMALL_CONE_MAX = 100;   // = default min_size_krylov_eigs: such cones never take the Krylov path
 
-__host__ __device__ inline size_t small_cone_smem_bytes(int n) {
+// fast = 1: three matrices of the even-padded side m (double-buffered Jacobi, jacobi_sweeps_fast); fast = 0: two
+// matrices, in-place three-pass Jacobi (sides 94 .. 100 do not fit three matrices in 227 KB)
+__host__ __device__ inline int small_cone_m(int n) { return (n + 1) & ~1; }
+__host__ __device__ inline size_t small_cone_smem_bytes(int n, int fast = 0) {
+    if (fast) {
+        const int m = small_cone_m(n), lda = m | 1;
+        return sizeof(double) * (3 * (size_t)m * lda + 2 * (size_t)n) + sizeof(int) * (size_t)((n + 2 + 3) & ~3) +
+               jacobi_scratch_bytes(m) + 64;
+    }
     int lda = n | 1;
     return sizeof(double) * (2 * (size_t)n * lda + 2 * (size_t)n) + sizeof(int) * (size_t)((n + 2 + 3) & ~3) +
            jacobi_scratch_bytes(n) + 64;
@@ -37,9 +45,18 @@ struct SmallConeArgs {
     int mode;
     double scale;
     double* out_min;
+    int fast;                    // 1: double-buffered Jacobi on three shared-memory matrices (see small_cone_smem_bytes)
+    // warm start (fast path, mode 0): the eigenvector basis of each cone's previous projection, m x (m | 1) doubles per
+    // cone at warm + blockIdx.x * warm_stride.  Consecutive PDHG iterates have nearly the same eigenvectors, so
+    // W' A W is nearly diagonal and 2-3 sweeps replace ~9; Jacobi converges from any orthogonal start, only the
+    // rounding path differs.  warm_read = 0 on the first projection of a solve and every 32nd one (so that rounding
+    // in the accumulated rotations cannot build up).
+    double* warm;
+    long long warm_stride;
+    int warm_read;
 };
 
-__global__ void __launch_bounds__(256) k_small_cone_proj(SmallConeArgs a) {
+__global__ void __launch_bounds__(512) k_small_cone_proj(SmallConeArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int cone = a.cone_ids[blockIdx.x];
     const int n = a.cone_side[cone];
@@ -64,14 +81,20 @@ __global__ void __launch_bounds__(256) k_small_cone_proj(SmallConeArgs a) {
         }
         return;
     }
+    // fast path: side padded to the even m with a zero row/column (an exactly decoupled zero eigenvalue that no
+    // rotation ever touches); ld is the leading dimension of every matrix of this cone from here on
+    const int m = a.fast ? small_cone_m(n) : n;
+    const int ld = a.fast ? (m | 1) : lda;
     double* A = reinterpret_cast<double*>(smem_raw);
-    double* V = A + (size_t)n * lda;
-    double* lam = V + (size_t)n * lda;     // n
+    double* V = A + (size_t)m * ld;
+    double* A1 = V + (size_t)m * ld;                       // fast path only
+    double* lam = a.fast ? A1 + (size_t)m * ld : A1;       // n
     double* lamp = lam + n;                // n: positive eigenvalues (compacted)
     int* pos = reinterpret_cast<int*>(lamp + n);   // n + 2
-    JacobiScratch js = jacobi_carve(reinterpret_cast<void*>(pos + ((n + 2 + 3) & ~3)), n);
+    JacobiScratch js = jacobi_carve(reinterpret_cast<void*>(pos + ((n + 2 + 3) & ~3)), m);
 
     // svec -> full symmetric matrix (fused primal update)
+    if (m > n) for (int i = tid; i < m; i += nt) { A[i + n * ld] = 0.0; A[n + i * ld] = 0.0; }
     for (int k = tid; k < tri; k += nt) {
         int j = (int)((sqrt(8.0 * (double)k + 1.0) - 1.0) * 0.5);
         while ((j + 1) * (j + 2) / 2 <= k) ++j;
@@ -81,15 +104,23 @@ __global__ void __launch_bounds__(256) k_small_cone_proj(SmallConeArgs a) {
         if (a.mode == 0) u = sub_rn(a.x[off + k], mul_rn(a.tau, add_rn(a.Mty[off + k], a.c[off + k])));
         else u = a.x[off + k] * a.scale;
         double v = (i != j) ? u / sqrt2 : u;
-        A[i + j * lda] = v;
-        A[j + i * lda] = v;
+        A[i + j * ld] = v;
+        A[j + i * ld] = v;
     }
     __syncthreads();
-    jacobi_eigh_smem(n, A, lda, V, lda, js);
+    if (a.fast) {                                                       // eigenvalues on the diagonal of the returned buffer
+        double* W = (a.mode == 0 && a.warm) ? a.warm + (size_t)blockIdx.x * (size_t)a.warm_stride : nullptr;
+        if (W && a.warm_read) A = jacobi_eigh_smem_warm(m, m, A, A1, ld, V, ld, W, js);
+        else A = jacobi_eigh_smem_fast(m, A, A1, ld, V, ld, js);
+        __syncthreads();
+        if (W) for (int idx = tid; idx < m * ld; idx += nt) W[idx] = V[idx];
+    } else {
+        jacobi_eigh_smem(n, A, ld, V, ld, js);
+    }
     __syncthreads();
     if (a.mode == 1) {
         double mn = 1.0e300;
-        for (int i = tid; i < n; i += nt) mn = fmin(mn, A[i + i * lda]);
+        for (int i = tid; i < n; i += nt) mn = fmin(mn, A[i + i * ld]);
         mn = -block_max_id(-mn, js.red, -1.0e300);
         if (tid == 0) a.out_min[cone] = mn;
         return;
@@ -98,7 +129,7 @@ __global__ void __launch_bounds__(256) k_small_cone_proj(SmallConeArgs a) {
     if (tid == 0) {
         int np = 0, rk = 0;
         for (int i = 0; i < n; ++i) {
-            double l = A[i + i * lda];
+            double l = A[i + i * ld];
             if (l > 0.0) { pos[np] = i; lamp[np] = l; np++; if (l > a.tol_psd) rk++; }
         }
         pos[n] = np;
@@ -117,7 +148,7 @@ __global__ void __launch_bounds__(256) k_small_cone_proj(SmallConeArgs a) {
         double s = 0.0;
         for (int q = 0; q < np; ++q) {
             int col = pos[q];
-            s = fma(lamp[q] * V[i + col * lda], V[j + col * lda], s);
+            s = fma(lamp[q] * V[i + col * ld], V[j + col * ld], s);
         }
         a.x_out[off + k] = (i != j) ? s * sqrt2 : s;
     }

@@ -304,6 +304,10 @@ class Solver {
     void lanczos_launch(ConeDev& cd, int cone_idx, int nev, int K, int maxiter, double tol);
     bool lanczos_launch_cluster(ConeDev& cd, int cone_idx, int nev, int K, int maxiter, double tol);
     bool lanczos_launch_cluster3(ConeDev& cd, int cone_idx, int nev, int K, int maxiter, double tol);
+    int small_fast_ = 0;       // small cones: double-buffered Jacobi when three matrices fit shared memory
+    int small_warm_ = 1;       // small cones: warm-start the Jacobi sweeps from the previous projection's eigenvectors
+    long long small_warm_calls_ = 0;
+    DBuf<double> small_warm_d_;
     int lz_kernel_ = 3;        // 3 = third-generation cluster kernel (lanczos_cl3.cuh), 2 = second generation (lanczos_cl.cuh)
     int lz_xres_ = 1;          // keep as many slab rows of X as fit in the spare shared memory (cl3, strip symv)
     size_t lz_cl3_smem_max_ = 0;
@@ -656,7 +660,10 @@ void Solver::setup_host(const proxsdp_problem_t* prob) {
     ws_.partials = partials_d_.p; ws_.counters = counters_d_.p; ws_.max_blocks = reduce_blocks_;
 
     if (max_small_side_ > 1) {
-        size_t sb = small_cone_smem_bytes(max_small_side_);
+        small_fast_ = small_cone_smem_bytes(max_small_side_, 1) <= smem_optin_ ? 1 : 0;
+        if (const char* e = getenv("PROXSDP_B200_SMALL_FAST")) small_fast_ = (atoi(e) != 0 && small_fast_) ? 1 : 0;
+        if (const char* e = getenv("PROXSDP_B200_SMALL_WARM")) small_warm_ = atoi(e) != 0 ? 1 : 0;
+        size_t sb = small_cone_smem_bytes(max_small_side_, small_fast_);
         if (sb > smem_optin_) throw CudaError(-4, "small-cone kernel needs more shared memory than the device offers");
         PB_CUDA(cudaFuncSetAttribute(k_small_cone_proj, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb));
     }
@@ -1055,8 +1062,17 @@ void Solver::psd_projection_launch(long long iter, double tau, bool force_full) 
         a.cone_ids = small_ids_d_.p; a.cone_side = cone_side_d_.p; a.cone_off = cone_off_d_.p;
         a.x = x; a.Mty = Mty; a.c = c_.p; a.tau = tau; a.tol_psd = opt.tol_psd; a.x_out = xn; a.scal = scal_d_.p;
         a.mode = 0; a.scale = 1.0; a.out_min = out_min_d_.p;
-        size_t sb = max_small_side_ > 1 ? small_cone_smem_bytes(max_small_side_) : 0;
-        k_small_cone_proj<<<(int)small_ids_.size(), 256, sb, stream>>>(a);
+        size_t sb = max_small_side_ > 1 ? small_cone_smem_bytes(max_small_side_, small_fast_) : 0;
+        a.fast = small_fast_;
+        if (small_fast_ && small_warm_ && max_small_side_ > 1) {
+            const int mm = small_cone_m(max_small_side_);
+            const size_t stride = (size_t)mm * (size_t)(mm | 1);
+            if (small_warm_d_.n < stride * small_ids_.size()) { small_warm_d_.alloc(stride * small_ids_.size()); small_warm_calls_ = 0; }
+            a.warm = small_warm_d_.p; a.warm_stride = (long long)stride;
+            a.warm_read = (small_warm_calls_ > 0 && (small_warm_calls_ % 32) != 0) ? 1 : 0;
+            small_warm_calls_++;
+        }
+        k_small_cone_proj<<<(int)small_ids_.size(), small_fast_ ? 512 : 256, sb, stream>>>(a);
         launches++;
         full_eig_calls += (long long)small_ids_.size();
     }
@@ -1256,8 +1272,9 @@ double Solver::dual_feas_host(const std::vector<double>& y, const std::vector<do
             a.cone_ids = small_ids_d_.p; a.cone_side = cone_side_d_.p; a.cone_off = cone_off_d_.p;
             a.x = dcd.p; a.Mty = dcd.p; a.c = dcd.p; a.tau = 0.0; a.tol_psd = opt.tol_psd; a.x_out = nullptr;
             a.scal = scal_d_.p; a.mode = 1; a.scale = 1.0; a.out_min = out_min_d_.p;
-            size_t sb = max_small_side_ > 1 ? small_cone_smem_bytes(max_small_side_) : 0;
-            k_small_cone_proj<<<(int)small_ids_.size(), 256, sb, stream>>>(a);
+            size_t sb = max_small_side_ > 1 ? small_cone_smem_bytes(max_small_side_, small_fast_) : 0;
+            a.fast = small_fast_;
+            k_small_cone_proj<<<(int)small_ids_.size(), small_fast_ ? 512 : 256, sb, stream>>>(a);
             launches++;
             PB_CUDA(cudaStreamSynchronize(stream));
             std::vector<double> mins = out_min_d_.download();
