@@ -867,7 +867,10 @@ bool Solver::lanczos_launch_cluster3(ConeDev& cd, int cone_idx, int nev, int K, 
     Lz3Layout L{};
     size_t smem = 0;
     int round_rows = fit_rounds(rows_max, L, smem);
-    if (round_rows < 1) return false;
+    // more than two rounds per mat-vec (side >~ 4500 at K = 25: the basis replica leaves no room for the partial-sum
+    // table) cost more block barriers than the strip symv saves: measured 62.7 vs 51.5 us per mat-vec at side 5000
+    // (scripts/lz_large.py), so those cones go to the second-generation kernel
+    if (round_rows < 1 || (lz_xres_ <= 1 && 2 * round_rows < rows_max)) return false;
     cfg.gridDim = dim3((unsigned)G); cfg.dynamicSmemBytes = smem;
     const void* kfn = lanczos_cl3_kernel(cpw);
     int max_clusters = 0;
@@ -879,7 +882,7 @@ bool Solver::lanczos_launch_cluster3(ConeDev& cd, int cone_idx, int nev, int K, 
         G = max_clusters * C;
         rows_max = (nside + G - 1) / G;
         round_rows = fit_rounds(rows_max, L, smem);
-        if (round_rows < 1) return false;
+        if (round_rows < 1 || (lz_xres_ <= 1 && 2 * round_rows < rows_max)) return false;
     }
     cfg.gridDim = dim3((unsigned)G); cfg.dynamicSmemBytes = smem;
     if ((size_t)cd.ld * (size_t)(K + 1) > cd.Y.n) cd.Y.alloc((size_t)cd.ld * (size_t)(K + 1));
@@ -915,6 +918,9 @@ bool Solver::lanczos_launch_cluster3(ConeDev& cd, int cone_idx, int nev, int K, 
         lz_kernel_ = 2;
         return false;
     }
+    if (getenv("PROXSDP_B200_DEBUG") && cd.ritz_launches == 0)
+        fprintf(stderr, "[lanczos] cl3 kernel: side %d, K %d, grid %d x %d, strip width %d chunks, %d symv rows per round (of %d), %zu KB shared memory\n",
+                nside, K, G / C, C, cpw, round_rows, rows_max, smem >> 10);
     cd.ritz_launches++;
     lz3_epoch_ += bound;
     launches += 1;

@@ -14,6 +14,8 @@ kill $SMI
 if [ "${SKIP_TESTS:-0}" != "1" ]; then
 echo "== pytest gpu"; python -m pytest tests -m gpu -q 2>&1 | tail -30 > gpurun_out/pytest_gpu_$TAG.log; tail -15 gpurun_out/pytest_gpu_$TAG.log
 fi
+echo "== lanczos on matrices larger than L2"; timeout 600 python scripts/lz_large.py 2>&1 | tee gpurun_out/lz_large_$TAG.jsonl | cut -c1-200
+echo "== lanczos per-phase profile"; timeout 120 python scripts/lz_prof.py > gpurun_out/lz_prof_$TAG.txt 2>&1
 if [ "${SKIP_NCU:-0}" != "1" ]; then
 echo "== ncu launch list"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_$TAG.csv python bench.py --steps 30 --warmup 3 --no-cpu-baseline --no-flush-l2 > gpurun_out/ncu_launch_$TAG.log 2>&1
