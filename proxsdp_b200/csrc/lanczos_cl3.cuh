@@ -106,6 +106,8 @@ struct LanczosCl3Args {
     int vbase, vrem;           // basis rows of cluster rank c, same formula with C
     double* vals; int* info; double* scal; int cone;
     int use_bi;
+    double stop_above;         // finish as soon as the largest Ritz value exceeds this (it is a lower bound of lambda_max);
+                               // 1e300 = never: used by cone_feas, which only needs to know whether lambda_min < -tol
     long long* prof;
     Lz3Layout L;
 };
@@ -292,6 +294,7 @@ __device__ __noinline__ void lz3_ritz(const LanczosCl3Args& a, double* sbase, in
             int cv = 0;
             while (cv < mb && fabs(SMD(f)[cv]) <= a.tol) cv++;
             if (cv >= howmany && cv < mb) { converged = cv; finished = 1; done_bi = true; }
+            else if (SMD(D)[0] > a.stop_above) { converged = max(cv, 1); finished = 1; done_bi = true; }      // bound certified
             __syncthreads();
         }
     }
@@ -339,6 +342,9 @@ __device__ __noinline__ void lz3_ritz(const LanczosCl3Args& a, double* sbase, in
         converged = 0;
         while (converged < k && fabs(SMD(f)[converged]) <= a.tol) converged++;
         if (converged >= howmany) {
+            finished = 1;
+        } else if (SMD(D)[0] > a.stop_above) {      // the largest Ritz value never exceeds lambda_max: bound certified
+            converged = max(converged, 1);
             finished = 1;
         } else if (k == K) {
             if (numiter == a.maxiter) {

@@ -304,6 +304,7 @@ class Solver {
     void lanczos_launch(ConeDev& cd, int cone_idx, int nev, int K, int maxiter, double tol);
     bool lanczos_launch_cluster(ConeDev& cd, int cone_idx, int nev, int K, int maxiter, double tol);
     bool lanczos_launch_cluster3(ConeDev& cd, int cone_idx, int nev, int K, int maxiter, double tol);
+    double lz_stop_above_ = 1e300;   // cl3 kernel: early exit once the top Ritz value exceeds this (cone_feas only)
     int small_fast_ = 0;       // small cones: double-buffered Jacobi when three matrices fit shared memory
     int small_warm_ = 1;       // small cones: warm-start the Jacobi sweeps from the previous projection's eigenvectors
     long long small_warm_calls_ = 0;
@@ -905,7 +906,7 @@ bool Solver::lanczos_launch_cluster3(ConeDev& cd, int cone_idx, int nev, int K, 
     a.ritz_rd = (lz_warm_ && cd.ritz_launches > 0 && (cd.ritz_launches % 32) != 0) ? cd.ritz_ws[flip].p : nullptr;
     a.ritz_wr = lz_warm_ ? cd.ritz_ws[1 - flip].p : nullptr;
     a.nev = nev; a.K = K; a.maxiter = maxiter; a.tol = tol;
-    a.vn_max = vn_max; a.use_bi = lz_bi_;
+    a.vn_max = vn_max; a.use_bi = lz_bi_; a.stop_above = lz_stop_above_;
     a.rbase = nside / G; a.rrem = nside % G; a.vbase = nside / C; a.vrem = nside % C;
     a.vals = cd.vals.p; a.info = cd.info.p; a.scal = scal_d_.p; a.cone = cone_idx;
     a.L = L;
@@ -1298,7 +1299,11 @@ double Solver::dual_feas_host(const std::vector<double>& y, const std::vector<do
             // pdhg.jl:712-732), so the extreme eigenvalue is resolved to 1e-3 of that tolerance, not to 1e-10.
             int K = (int)std::max<long long>(opt.eigsolver_min_lanczos, 3);
             const double tol_ev = std::max(1e-10, 1e-3 * std::min(opt.tol_feasibility_dual, 1.0));
+            // ... and a Ritz value of -Z above the tolerance already proves the violation (Ritz values are lower bounds
+            // of lambda_max), so the eigsolve may stop there instead of converging an interior-looking extreme pair
+            lz_stop_above_ = opt.tol_feasibility_dual;
             lanczos_launch(cd, k, 1, K, 60, tol_ev);
+            lz_stop_above_ = 1e300;
             PB_CUDA(cudaStreamSynchronize(stream));
             std::vector<double> vals = cd.vals.download();
             double lmin = -vals[0];
