@@ -103,15 +103,16 @@ void StageTimer::lap(const char* next) {
 // host<->device traffic of the current solve (reported as h2d/d2h bytes by the bench)
 static thread_local long long g_h2d_bytes = 0, g_d2h_bytes = 0;
 
-// Device memory comes from the device's default stream-ordered pool (cudaMallocAsync on the legacy stream) with
-// the release threshold lifted, so the ~40 buffers of a solve are carved out of memory the process already holds:
-// a cold cudaMalloc costs 0.1-3 ms each and made the end-to-end time of one chambolle_pock call swing between
-// 0.24 and 0.42 s (measured, profiles/r1h).  PROXSDP_B200_MALLOC=sync restores plain cudaMalloc / cudaFree.
+// Device memory: plain cudaMalloc / cudaFree by default.  PROXSDP_B200_MALLOC=pool switches to the device's default
+// stream-ordered pool (cudaMallocAsync on the legacy stream, release threshold lifted).  Measured on B200
+// (bench.py e2e, three back-to-back chambolle_pock calls): cudaMalloc 0.229 / 0.231 / 0.231 s, pool 0.232 / 0.257 /
+// 0.354 s — frees of one solve are still pending when the next solve allocates, so the pool keeps growing; the
+// one-off cost of the very first call is what the warm-up call of bench.py absorbs.
 static bool pb_pool_enabled() {
     static int state = -1;
     if (state < 0) {
         const char* e = getenv("PROXSDP_B200_MALLOC");
-        state = (e && std::string(e) == "sync") ? 0 : 1;
+        state = (e && std::string(e) == "pool") ? 1 : 0;
     }
     return state == 1;
 }
@@ -675,19 +676,30 @@ void Solver::setup_host(const proxsdp_problem_t* prob) {
         lz_cl_smem_max_ = smem_optin_ - fa.sharedSizeBytes;
         PB_CUDA(cudaFuncSetAttribute(k_lanczos_cl, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lz_cl_smem_max_));
     }
-    lz_cl3_smem_max_ = smem_optin_;
-    for (int cpw = 1; cpw <= 8; ++cpw) {
-        const void* fn = lanczos_cl3_kernel(cpw);
-        if (!fn) continue;
-        cudaFuncAttributes fa{};
-        PB_CUDA(cudaFuncGetAttributes(&fa, fn));
-        lz_cl3_smem_max_ = std::min(lz_cl3_smem_max_, smem_optin_ - fa.sharedSizeBytes);
-    }
-    for (int cpw = 1; cpw <= 8; ++cpw) {
-        const void* fn = lanczos_cl3_kernel(cpw);
-        if (!fn) continue;
-        PB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lz_cl3_smem_max_));
-        if (lz_cluster_ > 8) PB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    // the seven instances of the cl3 kernel have the same static shared memory; their attributes are set once per
+    // process and device (7 x get + set cost ~10 ms per solver construction otherwise)
+    {
+        static thread_local int attr_dev = -1;
+        static thread_local size_t attr_smem_max = 0;
+        static thread_local bool attr_nonportable = false;
+        if (attr_dev != dev_ || (lz_cluster_ > 8 && !attr_nonportable)) {
+            size_t mx = smem_optin_;
+            for (int cpw = 1; cpw <= 8; ++cpw) {
+                const void* fn = lanczos_cl3_kernel(cpw);
+                if (!fn) continue;
+                cudaFuncAttributes fa{};
+                PB_CUDA(cudaFuncGetAttributes(&fa, fn));
+                mx = std::min(mx, smem_optin_ - fa.sharedSizeBytes);
+            }
+            for (int cpw = 1; cpw <= 8; ++cpw) {
+                const void* fn = lanczos_cl3_kernel(cpw);
+                if (!fn) continue;
+                PB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mx));
+                if (lz_cluster_ > 8) PB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+            }
+            attr_dev = dev_; attr_smem_max = mx; attr_nonportable = lz_cluster_ > 8;
+        }
+        lz_cl3_smem_max_ = attr_smem_max;
     }
     if (lz_cluster_ > 8) PB_CUDA(cudaFuncSetAttribute(k_lanczos_cl, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     st.lap("done");
