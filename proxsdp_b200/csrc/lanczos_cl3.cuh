@@ -45,7 +45,7 @@
 
 namespace pb {
 
-constexpr int LZ3_GMAX = 256;    // largest grid the partial-alpha rows / group counters are sized for
+constexpr int LZ3_GMAX = 256;    // largest grid the per-CTA alpha partials are sized for
 
 // shared-memory layout, in doubles from the start of dynamic shared memory (host-computed, read from the constant bank)
 struct Lz3Layout {
@@ -64,8 +64,6 @@ struct Lz3Layout {
     int jscratch;
     int total;   // doubles
 };
-
-__host__ __device__ inline int lanczos_cl3_rls(int rows_max) { return (rows_max + 1) | 1; }
 
 __host__ inline Lz3Layout lanczos_cl3_layout(int K, int round_rows, int vn_max, int n, int C) {
     Lz3Layout L{};

@@ -311,7 +311,7 @@ class Solver {
     long long small_warm_calls_ = 0;
     DBuf<double> small_warm_d_;
     int lz_kernel_ = 3;        // 3 = third-generation cluster kernel (lanczos_cl3.cuh), 2 = second generation (lanczos_cl.cuh)
-    int lz_xres_ = 1;          // keep as many slab rows of X as fit in the spare shared memory (cl3, strip symv)
+    int lz_xres_ = 1;          // > 1: cap the cl3 symv partial-sum table at lz_xres_ - 1 rows per round (experiments / tests)
     size_t lz_cl3_smem_max_ = 0;
     int lz_mode_ = 0;          // 0 = cluster-replicated kernel when it fits, 1 = row-distributed kernel only
     int lz_cluster_ = 8;       // cluster size of the replicated kernel
