@@ -3,7 +3,7 @@
 // Same contract as k_lanczos_cl (lanczos_cl.cuh): KrylovKit.eigsolve(A, resid, nev, :LR, Lanczos(orth, K,
 // maxiter, tol)) as called from reference src/eigsolver.jl:802-812.  The basis still lives as one replica
 // per thread-block cluster in distributed shared memory.  What changed, each item measured on B200
-// (profiles/r1g_*):
+// (profiles/r1h_* ... r1k_*, scripts/lat_bench.cu, scripts/symv_bench.cu):
 //
 //  1. One re-orthogonalisation exchange per step instead of two.  KrylovKit's recurrence is the local
 //     three-term step (w -= alpha v_j + beta_{j-1} v_{j-1}) followed by two Gram-Schmidt passes.  The local
@@ -11,7 +11,9 @@
 //     exchange performs anyway.  After the local step the components of w along the basis are O(eps ||X||)
 //     (or the known arrow row right after a thick restart), so ONE classical Gram-Schmidt pass over the whole
 //     basis restores orthogonality to machine precision; a second pass runs only when the first one removed a
-//     visible part of w (||h||^2 > 1e-4 ||w||^2: breakdown / invariant subspace).  scripts/lz_variant_check.py
+//     visible part of w (DGKS criterion, ||h||^2 > ||w||^2 / 4: breakdown / invariant subspace).  alpha for the
+//     local step is only needed to ~1e-7 (the pass removes the rest along v_j exactly), so its sum over the CTAs
+//     runs through an FP32 shuffle tree.  scripts/lz_variant_check.py
 //     shows identical mat-vec counts, converged counts and 1e-15 orthogonality versus the two-pass schemes.
 //  2. No register spills on the per-step path.  Every acquire at gpu/cluster scope makes ptxas emit CCTL.IVALL
 //     (L1 invalidate), so a spilled value re-read after a barrier costs a full L2 round trip; the second
@@ -24,15 +26,17 @@
 //     warp w owns a column strip of CPW chunks for ALL rows of the slab: its piece of v sits in registers, the
 //     loads of a batch of RB rows are issued back to back, every lane parks its per-row partial sums in shared
 //     memory ([row][thread], conflict-free) and after one block barrier half-warp h adds up the 512 partials of
-//     row h in four chains and stores the finished w entry straight to global memory — the separate "fold" phase
+//     row h in eight chains and stores the finished w entry straight to global memory — the separate "fold" phase
 //     and all shuffles are gone.  alpha's partial is row number rl of the same table.  (Keeping half of the slab
-//     resident in shared memory was tried and measured: no gain, the symv is not L2-bandwidth-bound at n = 2000.)
+//     resident in shared memory was tried and measured: no gain at n = 2000.)
 //  4. No grid barrier.  A counter barrier costs release fence (~500 cycles with stores in flight) + atomic + poll
 //     + acquire fence, ~0.9 us on top of the slowest CTA, and then the data still has to be fetched.  Here the w
 //     entries and the alpha partials travel as flagged 16-byte words (two 8-byte halves {lo32, tag}, {hi32, tag}:
 //     a reader that sees the tag in both halves has the value — the "LL" exchange of lanczos.cuh): the lanes that
 //     need a value poll that value, no fence on either side.  Completing the alpha all-gather (every CTA needs
 //     every CTA's partial) is what orders a step after the previous one, so two buffers suffice.
+//  5. No cluster barrier either: the Gram-Schmidt dots and the new Lanczos vector are delivered into the peers'
+//     shared memory with st.async ... mbarrier::complete_tx and consumed behind an mbarrier phase (helpers below).
 #pragma once
 #include <cooperative_groups.h>
 
