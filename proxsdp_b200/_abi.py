@@ -81,12 +81,19 @@ class MarshalledProblem:
 
     def __init__(self, aff: AffineSets, con: ConicSets, eig_resid=None):
         n, p, m = int(aff.n), int(aff.p), int(aff.m)
-        A = sp.csc_matrix(aff.A, shape=(p, n)) if p > 0 else sp.csc_matrix((0, n))
-        G = sp.csc_matrix(aff.G, shape=(m, n)) if m > 0 else sp.csc_matrix((0, n))
-        A.sort_indices()
-        G.sort_indices()
-        A.sum_duplicates()
-        G.sum_duplicates()
+        def canonical_csc(M, rows):
+            # one scan (has_canonical_format) instead of three; a private copy is made only when duplicates have to be
+            # summed / indices sorted, so the caller's matrix is never modified
+            if rows == 0:
+                return sp.csc_matrix((0, n))
+            M = M if (sp.isspmatrix_csc(M) and M.shape == (rows, n)) else sp.csc_matrix(M, shape=(rows, n))
+            if not M.has_canonical_format:
+                M = M.copy()
+                M.sum_duplicates()
+            return M
+
+        A = canonical_csc(aff.A, p)
+        G = canonical_csc(aff.G, m)
         self.bufs = dict(
             A_colptr=_i64(A.indptr), A_rowval=_i64(A.indices), A_nzval=_f64(A.data),
             G_colptr=_i64(G.indptr), G_rowval=_i64(G.indices), G_nzval=_f64(G.data),
