@@ -644,7 +644,11 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) k_lanczos_cl3(const __grid_cons
                 }
             }
             if (hn2 <= 0.25 * wn2) break;      // DGKS: the pass shrank w by less than 1/sqrt(2)... (margin 2x): one pass is enough
-            __syncthreads();                   // second pass (breakdown only): its dots read the updated wv of every warp
+            // second pass (breakdown only).  Its dots read the updated wv of every warp (block barrier), and they travel
+            // through the SAME mbarrier as the first pass: a peer that is already in its second pass must not credit
+            // bytes to my barrier while my first-pass phase is still open (I may be waiting for a third CTA), hence a
+            // cluster barrier on this rare path — every CTA of the cluster has closed phase one before anyone sends.
+            cluster.sync();
         }
         // ||w_new||^2 = ||w||^2 - ||h||^2 ; v_{j+1} = w / beta: keep my rows, push them into every peer's staging buffer
         {
