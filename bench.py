@@ -124,19 +124,20 @@ def build_workload():
     return maxcut_er_problem(2000, 0.01, 0)
 
 
-def config_dict(n_gpus: int, flush: bool, extra=None):
-    cfg = {
+def config_dict(n_gpus: int, flush: bool = True):
+    """Identical in both arms (the driver compares the two lines' configs key by key)."""
+    return {
         "workload": WORKLOAD,
         "description": "Max-Cut SDP, Erdos-Renyi G(2000, 0.01), unit weights: one PSD cone of side 2000 "
                        "(N = 2 001 000 svec variables), 2000 equality rows diag(X) = 1, FP64, default Options",
         "step": "one PDHG iteration (iterations 1..K from the reference's cold start)",
-        "parallelism": "single cone: replicas only" if n_gpus > 1 else "1 GPU",
-        "l2": ("flushed before every iteration (192 MiB memset > 126 MB L2, on the solver's stream, inside the timed region)"
-               if flush else "not flushed: every iteration consumes the previous iteration's outputs"),
+        "parallelism": ("1 GPU (CUDA arm) / all host cores, OpenMP (reference arm)" if n_gpus == 1 else
+                        f"{n_gpus} GPUs: a single cone does not shard, every rank solves an independent replica "
+                        "(CUDA arm) / rank 0 on all host cores (reference arm)"),
+        "l2": ("CUDA arm: flushed before every iteration (192 MiB memset > 126 MB L2, on the solver's stream, inside the "
+               "timed region); reference arm: n/a (CPU)" if flush else
+               "CUDA arm: not flushed (every iteration consumes the previous iteration's outputs); reference arm: n/a (CPU)"),
     }
-    if extra:
-        cfg.update(extra)
-    return cfg
 
 
 # ---------------------------------------------------------------------------------------------
@@ -167,7 +168,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": its,
         "warmup": min(args.warmup, 10), "ms_per_step": 1e3 * r.time_loop / its, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": config_dict(1, False, {"parallelism": "CPU, OpenMP over host cores", "l2": "n/a (CPU)"}),
+        "config": config_dict(args.gpus, not args.no_flush_l2),
         "cpu_baseline": {
             "value": value, "unit": UNIT, "cores": cores, "kind": "port",
             "sample": f"iterations 1..{its} of the workload (requested {args.steps}, wall budget {budget_s:.0f} s), "
@@ -239,7 +240,11 @@ def run_b200(args):
     # ---- end to end through the reference-facing call, host buffers in / host buffers out
     # (one untimed call of W iterations first, like the W warm-up steps of the device-timed arm: the first call after
     #  a solver has been torn down pays for the allocator re-mapping device memory)
-    solver.chambolle_pock(aff, con, Options(device_id=local_rank, max_iter=max(W, 3)))
+    # The caller's problem sits in page-locked host memory in the reference's own types (SparseMatrixCSC{Float64,Int64},
+    # Vector{Float64}, Vector{Int}): every call uploads it from there (h2d_bytes_per_step counts those bytes) and
+    # downloads primal / dual_cone / duals / slacks into page-locked result vectors (d2h_bytes_per_step).
+    aff_p, con_p = solver.pin_problem(aff, con)
+    solver.chambolle_pock(aff_p, con_p, Options(device_id=local_rank, max_iter=max(W, 3)))
     # five timed calls, the median is reported (all walls are in the JSON line): one call is ~0.23 s and a single
     # shot swings by 30 % with the state of the host (allocator, page cache, other tenants of the box)
     e2e_walls = []
@@ -247,7 +252,7 @@ def run_b200(args):
     for _ in range(5):
         barrier()
         t0 = time.perf_counter()
-        r2_ = solver.chambolle_pock(aff, con, Options(device_id=local_rank, max_iter=K))
+        r2_ = solver.chambolle_pock(aff_p, con_p, Options(device_id=local_rank, max_iter=K))
         w_ = time.perf_counter() - t0
         te = torch.tensor([w_], dtype=torch.float64, device="cuda")
         if world > 1:
@@ -288,7 +293,8 @@ def run_b200(args):
         "metric": METRIC, "value": world * steps_done / (dev_ms_max * 1e-3), "unit": UNIT, "n_gpus": world,
         "steps": steps_done, "warmup": max(W, 3), "ms_per_step": dev_ms_max / max(steps_done, 1),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": config_dict(world, flush, {"l2_flush_ms_per_step": flush_ms / max(steps_done, 1)}),
+        "config": config_dict(world, flush),
+        "l2_flush_ms_per_step": flush_ms / max(steps_done, 1),
         "clocks": clocks,
         "e2e": {
             "value": e2e_value, "unit": UNIT,

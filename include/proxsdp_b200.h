@@ -104,6 +104,15 @@ int proxsdp_b200_comm_destroy(proxsdp_b200_comm_t* comm);
 int proxsdp_b200_solve_sharded(const proxsdp_problem_t* local_problem, const proxsdp_options_t* options,
                                const proxsdp_shard_t* shard, proxsdp_result_t* local_result);
 
+/* Page-locked host memory from the library's per-process cache (cudaMallocHost blocks that are kept and re-used).
+ * Optional: any host pointer is accepted by every entry point; vectors that live in this memory (a shim would put
+ * `Result.primal` / `Result.dual_cone` and `AffineSets.c` there) cross PCIe without a staging copy.  The library
+ * itself also draws its device buffers from a per-process cache so that back-to-back solves do not pay
+ * cudaMalloc / cudaFree; proxsdp_b200_trim_caches() returns everything that is cached and unused to the driver. */
+void* proxsdp_b200_host_alloc(int64_t bytes);
+int proxsdp_b200_host_free(void* ptr);
+int proxsdp_b200_trim_caches(void);
+
 /* Library / device information. */
 int proxsdp_b200_device_count(void);
 const char* proxsdp_b200_last_error(void);

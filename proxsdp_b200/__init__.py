@@ -8,7 +8,7 @@ The arithmetic lives in the CUDA library `libproxsdp_b200.so` (csrc/), reached t
 C ABI declared in include/proxsdp_b200.h.
 """
 from .options import Options
-from .structs import AffineSets, ConicSets, Result, SDPSet, SOCSet, ivec, ivech, sympackeddim, sympackedlen
+from .structs import AffineSets, ConicSets, Result, SDPSet, SOCSet, SparseMatrixCSC, ivec, ivech, sympackeddim, sympackedlen
 from .model import MAX_SENSE, MIN_SENSE, Optimizer
 
 __all__ = [

@@ -13,7 +13,7 @@ import numpy as np
 import scipy.sparse as sp
 
 from .options import Options, OptionsPOD
-from .structs import AffineSets, ConicSets, Result
+from .structs import AffineSets, ConicSets, Result, SparseMatrixCSC
 
 STATUS_STRING_LEN = 256
 TRACE_COLS = 14
@@ -68,6 +68,15 @@ def _i64(a) -> np.ndarray:
     return np.ascontiguousarray(np.asarray(a, dtype=np.int64).ravel())
 
 
+def _concat(arrs):
+    """np.concatenate without the copy when there is nothing to join."""
+    if len(arrs) == 0:
+        return np.zeros(0, dtype=np.int64)
+    if len(arrs) == 1:
+        return arrs[0]
+    return np.concatenate(arrs)
+
+
 def _ptr_d(a: np.ndarray):
     return a.ctypes.data_as(_pd) if a.size else ctypes.cast(None, _pd)
 
@@ -81,22 +90,25 @@ class MarshalledProblem:
 
     def __init__(self, aff: AffineSets, con: ConicSets, eig_resid=None):
         n, p, m = int(aff.n), int(aff.p), int(aff.m)
-        def canonical_csc(M, rows):
-            # one scan (has_canonical_format) instead of three; a private copy is made only when duplicates have to be
-            # summed / indices sorted, so the caller's matrix is never modified
+        def csc_arrays(M, rows):
+            """(colptr, rowval, nzval) as int64 / int64 / float64 without a copy when the matrix already is a
+            SparseMatrixCSC; scipy matrices are canonicalised (sorted rows, duplicates summed — on a private copy)
+            and widened."""
             if rows == 0:
-                return sp.csc_matrix((0, n))
+                return np.zeros(n + 1, dtype=np.int64), np.zeros(0, dtype=np.int64), np.zeros(0)
+            if isinstance(M, SparseMatrixCSC):
+                assert M.shape == (rows, n), (M.shape, rows, n)
+                return M.colptr, M.rowval, M.nzval
             M = M if (sp.isspmatrix_csc(M) and M.shape == (rows, n)) else sp.csc_matrix(M, shape=(rows, n))
             if not M.has_canonical_format:
                 M = M.copy()
                 M.sum_duplicates()
-            return M
+            return _i64(M.indptr), _i64(M.indices), _f64(M.data)
 
-        A = canonical_csc(aff.A, p)
-        G = canonical_csc(aff.G, m)
+        Acp, Arv, Anz = csc_arrays(aff.A, p)
+        Gcp, Grv, Gnz = csc_arrays(aff.G, m)
         self.bufs = dict(
-            A_colptr=_i64(A.indptr), A_rowval=_i64(A.indices), A_nzval=_f64(A.data),
-            G_colptr=_i64(G.indptr), G_rowval=_i64(G.indices), G_nzval=_f64(G.data),
+            A_colptr=Acp, A_rowval=Arv, A_nzval=Anz, G_colptr=Gcp, G_rowval=Grv, G_nzval=Gnz,
             b=_f64(aff.b), h=_f64(aff.h), c=_f64(aff.c),
         )
         sides = [int(s.sq_side) for s in con.sdpcone]
@@ -109,9 +121,9 @@ class MarshalledProblem:
             soc_ptr[k + 1] = soc_ptr[k] + len(s.idx)
         self.bufs.update(
             sdp_side=_i64(sides), sdp_ptr=sdp_ptr,
-            sdp_idx=_i64(np.concatenate([s.vec_i for s in con.sdpcone]) if sides else []),
+            sdp_idx=_i64(_concat([s.vec_i for s in con.sdpcone])),
             soc_ptr=soc_ptr,
-            soc_idx=_i64(np.concatenate([s.idx for s in con.socone]) if con.socone else []),
+            soc_idx=_i64(_concat([s.idx for s in con.socone])),
         )
         if eig_resid is not None:
             self.bufs["eig_resid"] = _f64(eig_resid)
@@ -130,9 +142,11 @@ class MarshalledProblem:
 
 
 class MarshalledResult:
-    def __init__(self, n: int, p: int, m: int, n_sdp: int, trace_cap: int = 0):
-        self.primal = np.zeros(n)
-        self.dual_cone = np.zeros(n)
+    def __init__(self, n: int, p: int, m: int, n_sdp: int, trace_cap: int = 0, empty=None):
+        # `empty(count)`: allocator of the two n-long outputs (the product binding passes page-locked memory so that
+        # the device->host copies need no staging and no first-touch page faults)
+        self.primal = np.zeros(n) if empty is None else empty(n)
+        self.dual_cone = np.zeros(n) if empty is None else empty(n)
         self.dual_eq = np.zeros(p)
         self.dual_in = np.zeros(m)
         self.slack_eq = np.zeros(p)
@@ -177,10 +191,10 @@ class MarshalledResult:
         )
 
 
-def call_solve(fn, aff: AffineSets, con: ConicSets, opt: Options, eig_resid=None, err_fn=None) -> Result:
+def call_solve(fn, aff: AffineSets, con: ConicSets, opt: Options, eig_resid=None, err_fn=None, empty=None) -> Result:
     """Invoke a `int solve(const proxsdp_problem_t*, const proxsdp_options_t*, proxsdp_result_t*)`."""
     mp = MarshalledProblem(aff, con, eig_resid)
-    mr = MarshalledResult(mp.n, mp.p, mp.m, mp.n_sdp, int(opt.trace_cap))
+    mr = MarshalledResult(mp.n, mp.p, mp.m, mp.n_sdp, int(opt.trace_cap), empty=empty)
     opod = opt.to_pod()
     rc = fn(ctypes.byref(mp.pod), ctypes.byref(opod), ctypes.byref(mr.pod))
     if rc != 0:

@@ -132,4 +132,17 @@ __device__ __forceinline__ bool last_block_arrive(unsigned int* counter, int* s_
 
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+// Is position pos (working order: [PSD svec blocks | SOC blocks | free]) an off-diagonal entry of a PSD block?
+// svec order inside a block: k = j (j + 1) / 2 + i, i <= j (reference src/scaling.jl:28-58, prox_operators.jl:1-16).
+__device__ __forceinline__ bool offdiag_position(long long pos, long long psd_end, const long long* __restrict__ cone_off, int n_sdp) {
+    if (pos >= psd_end) return false;
+    int lo = 0, hi = n_sdp - 1;               // last cone with off <= pos
+    while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (cone_off[mid] <= pos) lo = mid; else hi = mid - 1; }
+    const long long k = pos - cone_off[lo];
+    long long j = (long long)((sqrt(8.0 * (double)k + 1.0) - 1.0) * 0.5);
+    while ((j + 1) * (j + 2) / 2 <= k) ++j;
+    while (j * (j + 1) / 2 > k) --j;
+    return k != j * (j + 1) / 2 + j;
+}
+
 }  // namespace pb

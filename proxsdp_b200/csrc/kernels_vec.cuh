@@ -239,17 +239,19 @@ k_dual_trial(DualArgs a, double* __restrict__ scal, ReduceWs ws) {
 
 // long rows of M' (a variable that appears in thousands of constraints, e.g. the anchor block of the
 // sensor-localisation SDP): one block per row, same gating as the line-search trial it belongs to
-__global__ void k_spmv_mt_long(const int* __restrict__ long_rows, const int* __restrict__ rowptr,
+// (M' is stored as DCSR: compact row q is variable nz_rows[q], entries rowptr[q] .. rowptr[q + 1]; long_rows holds
+//  compact indices)
+__global__ void k_spmv_mt_long(const int* __restrict__ long_rows, const int* __restrict__ nz_rows, const int* __restrict__ rowptr,
                                const int* __restrict__ colidx, const double* __restrict__ val,
                                const double* __restrict__ y, double* __restrict__ out, const double* __restrict__ scal) {
     __shared__ double red[40];
-    if (scal[S_POISON] != 0.0 || scal[S_LS_ACCEPTED] != 0.0) return;
-    int row = long_rows[blockIdx.x];
-    int b = rowptr[row], e = rowptr[row + 1];
+    if (scal && (scal[S_POISON] != 0.0 || scal[S_LS_ACCEPTED] != 0.0)) return;
+    const int q = long_rows[blockIdx.x];
+    int b = rowptr[q], e = rowptr[q + 1];
     double s = 0.0;
     for (int k = b + threadIdx.x; k < e; k += blockDim.x) s += val[k] * y[colidx[k]];
     s = block_sum(s, red);
-    if (threadIdx.x == 0) out[row] = s;
+    if (threadIdx.x == 0) out[nz_rows[q]] = s;
 }
 
 // ---------------------------------------------------------------------------
@@ -259,7 +261,7 @@ __global__ void k_spmv_mt_long(const int* __restrict__ long_rows, const int* __r
 // evaluated by the last block.
 // ---------------------------------------------------------------------------
 struct MtArgs {
-    int N; const int* rowptr; const int* colidx; const double* val;
+    int N; const int* rowptr; const int* colidx; const double* val;   // DCSR: rowptr is compact (n_nz + 1 entries)
     int long_threshold;      // rows of M' longer than this were computed by k_spmv_mt_long into Mty_new already
     const int* nz_rows; int n_nz;   // non-empty rows of M' (DCSR): Mty is identically zero on all other rows, so only these are walked
     const double* y_new; const double* Mty; double* Mty_new;
@@ -274,7 +276,7 @@ k_spmv_mt_norm(MtArgs a, double* __restrict__ scal, ReduceWs ws) {
     double acc = 0.0;
     for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < a.n_nz; q += gridDim.x * blockDim.x) {
         const int i = a.nz_rows[q];
-        int b = a.rowptr[i], e = a.rowptr[i + 1];
+        int b = a.rowptr[q], e = a.rowptr[q + 1];
         double s = 0.0;
         if (e - b > a.long_threshold) {
             s = a.Mty_new[i];
@@ -302,6 +304,178 @@ k_spmv_mt_norm(MtArgs a, double* __restrict__ scal, ReduceWs ws) {
                 scal[S_LS_TRIAL] = (double)a.trial;
             }
         }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// K13-K17, whole speculative ladder in two launches (single-GPU runs).
+//
+// The line search (pdhg.jl:543-571) tries tau_t = tau0 decay^t, t = 0, 1, ...; trial t is accepted when
+// sqrt(beta) tau_t ||M'(y_t - y)|| <= delta ||y_t - y||.  Mean number of trials on Max-Cut: 2.2, so the first T <= 4
+// trials are evaluated side by side:
+//   k_ls_ladder  computes, for every trial of the ladder, ||y_t - y||^2 and ||M'y_t - M'y||^2 WITHOUT writing any
+//                vector: y_t is an elementwise function of (y, Mx, Mx_old, b, h), so the M' product recomputes the few
+//                entries of y_t it needs (M' is walked through its non-empty rows, DCSR).  The last block applies the
+//                accept test to trial 0, 1, ... in order and records the first accepted one.
+//   k_ls_apply   writes y_new and Mty_new for the recorded trial (or for the last one when none was accepted: the
+//                reference keeps the last trial's vectors when its loop runs out, and the host carries on with
+//                further single trials otherwise).
+// Rows of M' longer than the threshold are summed by one CTA each (k_ls_long_rows) before k_ls_ladder.
+// ---------------------------------------------------------------------------
+constexpr int LS_MAXT = 4;
+
+struct LadderArgs {
+    const double* y; const double* Mx; const double* Mx_old; const double* b; const double* h;
+    int p, m;
+    double tau0, decay, tau_old, beta, sigma_fixed, delta;
+    int use_theta;           // 1: line search (theta from the trial step); 0: fixed-step dual_step! (pdhg.jl:584-609)
+    int ntrials;             // T: trials evaluated by this launch (1 .. LS_MAXT)
+    int do_test;             // 0: accept trial 0 unconditionally (fixed step)
+    // M' in DCSR
+    const int* nz_rows; const int* nz_ptr; const int* colidx; const double* val; int n_nz;
+    int long_threshold; const int* long_rows; int n_long;
+    double* long_sums;       // [n_long][LS_MAXT]
+    const double* Mty;       // current M'y
+    double* y_new; double* Mty_new;
+};
+
+struct TrialCoef { double tau, sigma, w1, w2; };
+
+__device__ __forceinline__ TrialCoef ls_trial_coef(const LadderArgs& a, int trial) {
+    TrialCoef c;
+    c.tau = a.tau0;
+    for (int t = 0; t < trial; ++t) c.tau = mul_rn(c.tau, a.decay);      // sequential products, as pdhg.jl:569 does
+    if (a.use_theta) {
+        const double theta = c.tau / a.tau_old;
+        c.sigma = mul_rn(a.beta, c.tau);
+        c.w1 = add_rn(1.0, theta);
+        c.w2 = theta;
+    } else {
+        c.sigma = a.sigma_fixed; c.w1 = 2.0; c.w2 = 1.0;
+    }
+    return c;
+}
+// y_new[i] of one trial (pdhg.jl:544-553 with box_projection!, prox_operators.jl:160-170)
+__device__ __forceinline__ double ls_y_new(const LadderArgs& a, const TrialCoef& c, int i, double yi, double mx, double mxo) {
+    const double yh = add_rn(yi, mul_rn(c.sigma, sub_rn(mul_rn(c.w1, mx), mul_rn(c.w2, mxo))));
+    const double proj = (i < a.p) ? a.b[i] : fmin(yh / c.sigma, a.h[i - a.p]);
+    return sub_rn(yh, mul_rn(c.sigma, proj));
+}
+
+// one CTA per long row of M': long_sums[row][t] = sum_k val[k] y_t[col[k]] for every trial of the ladder
+__global__ void __launch_bounds__(512) k_ls_long_rows(LadderArgs a, const double* __restrict__ scal, int trial0) {
+    __shared__ double red[40];
+    if (scal[S_POISON] != 0.0) return;
+    const int q = a.long_rows[blockIdx.x];
+    const int kb = a.nz_ptr[q], ke = a.nz_ptr[q + 1];
+    TrialCoef c[LS_MAXT];
+#pragma unroll
+    for (int t = 0; t < LS_MAXT; ++t) c[t] = ls_trial_coef(a, trial0 + min(t, a.ntrials - 1));
+    double s[LS_MAXT] = {0.0, 0.0, 0.0, 0.0};
+    for (int k = kb + threadIdx.x; k < ke; k += blockDim.x) {
+        const int col = a.colidx[k];
+        const double v = a.val[k], yi = a.y[col], mx = a.Mx[col], mxo = a.Mx_old[col];
+#pragma unroll
+        for (int t = 0; t < LS_MAXT; ++t) if (t < a.ntrials) s[t] = fma(v, ls_y_new(a, c[t], col, yi, mx, mxo), s[t]);
+    }
+#pragma unroll
+    for (int t = 0; t < LS_MAXT; ++t) {
+        const double r = block_sum(s[t], red);
+        if (threadIdx.x == 0) a.long_sums[(size_t)blockIdx.x * LS_MAXT + t] = r;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_ls_ladder(LadderArgs a, double* __restrict__ scal, ReduceWs ws, int trial0) {
+    __shared__ double red[40];
+    __shared__ int s_last;
+    if (scal[S_POISON] != 0.0 || scal[S_LS_ACCEPTED] != 0.0) return;
+    TrialCoef c[LS_MAXT];
+#pragma unroll
+    for (int t = 0; t < LS_MAXT; ++t) c[t] = ls_trial_coef(a, trial0 + min(t, a.ntrials - 1));
+    double yn[LS_MAXT] = {0.0, 0.0, 0.0, 0.0}, mn[LS_MAXT] = {0.0, 0.0, 0.0, 0.0};
+    const int R = a.p + a.m;
+    const int stride = gridDim.x * blockDim.x, t0 = blockIdx.x * blockDim.x + threadIdx.x;
+    for (int i = t0; i < R; i += stride) {
+        const double yi = a.y[i], mx = a.Mx[i], mxo = a.Mx_old[i];
+#pragma unroll
+        for (int t = 0; t < LS_MAXT; ++t)
+            if (t < a.ntrials) { const double d = sub_rn(ls_y_new(a, c[t], i, yi, mx, mxo), yi); yn[t] += d * d; }
+    }
+    for (int q = t0; q < a.n_nz; q += stride) {
+        const int kb = a.nz_ptr[q], ke = a.nz_ptr[q + 1];
+        double s[LS_MAXT] = {0.0, 0.0, 0.0, 0.0};
+        if (ke - kb > a.long_threshold) {
+            // compact index of this row among the long rows: long_rows is ascending
+            int lo = 0, hi = a.n_long - 1;
+            while (lo < hi) { const int mid = (lo + hi) >> 1; if (a.long_rows[mid] < q) lo = mid + 1; else hi = mid; }
+#pragma unroll
+            for (int t = 0; t < LS_MAXT; ++t) s[t] = a.long_sums[(size_t)lo * LS_MAXT + t];
+        } else {
+            for (int k = kb; k < ke; ++k) {
+                const int col = a.colidx[k];
+                const double v = a.val[k], yi = a.y[col], mx = a.Mx[col], mxo = a.Mx_old[col];
+#pragma unroll
+                for (int t = 0; t < LS_MAXT; ++t) if (t < a.ntrials) s[t] += v * ls_y_new(a, c[t], col, yi, mx, mxo);
+            }
+        }
+        const double old = a.Mty[a.nz_rows[q]];
+#pragma unroll
+        for (int t = 0; t < LS_MAXT; ++t) if (t < a.ntrials) { const double d = sub_rn(s[t], old); mn[t] += d * d; }
+    }
+    const int nb = gridDim.x;
+#pragma unroll
+    for (int t = 0; t < LS_MAXT; ++t) {
+        const double u = block_sum(yn[t], red), w = block_sum(mn[t], red);
+        if (threadIdx.x == 0) { ws.partials[(2 * t) * nb + blockIdx.x] = u; ws.partials[(2 * t + 1) * nb + blockIdx.x] = w; }
+    }
+    if (last_block_arrive(ws.counters + 0, &s_last)) {
+        double tot[2 * LS_MAXT];
+#pragma unroll
+        for (int t = 0; t < 2 * LS_MAXT; ++t) {
+            double v = 0.0;
+            for (int b = threadIdx.x; b < nb; b += blockDim.x) v += __ldcg(ws.partials + t * nb + b);
+            tot[t] = block_sum(v, red);
+        }
+        if (threadIdx.x == 0) {
+            int chosen = -1;
+            for (int t = 0; t < a.ntrials && chosen < 0; ++t) {
+                const double lhs = mul_rn(mul_rn(sqrt(a.beta), c[t].tau), sqrt(tot[2 * t + 1]));
+                const double rhs = mul_rn(a.delta, sqrt(tot[2 * t]));
+                if (!a.do_test || lhs <= rhs) chosen = t;
+            }
+            const int last = chosen >= 0 ? chosen : a.ntrials - 1;
+            scal[S_YNORM2] = tot[2 * last]; scal[S_MTYNORM2] = tot[2 * last + 1];
+            scal[S_TAU] = c[last].tau;
+            scal[S_LS_EVALS] = (double)(trial0 + last + 1);
+            scal[S_LS_TRIAL] = (double)(trial0 + last);
+            if (chosen >= 0) scal[S_LS_ACCEPTED] = 1.0;
+        }
+    }
+}
+
+// writes y_new / Mty_new of trial scal[S_LS_TRIAL] (set by k_ls_ladder of the same ladder)
+__global__ void __launch_bounds__(256) k_ls_apply(LadderArgs a, const double* __restrict__ scal, int trial0) {
+    if (scal[S_POISON] != 0.0) return;
+    const int trial = (int)scal[S_LS_TRIAL];
+    if (trial < trial0 || trial >= trial0 + a.ntrials) return;      // an earlier ladder was accepted
+    const TrialCoef c = ls_trial_coef(a, trial);
+    const int R = a.p + a.m;
+    const int stride = gridDim.x * blockDim.x, t0 = blockIdx.x * blockDim.x + threadIdx.x;
+    for (int i = t0; i < R; i += stride) a.y_new[i] = ls_y_new(a, c, i, a.y[i], a.Mx[i], a.Mx_old[i]);
+    for (int q = t0; q < a.n_nz; q += stride) {
+        const int kb = a.nz_ptr[q], ke = a.nz_ptr[q + 1];
+        double s = 0.0;
+        if (ke - kb > a.long_threshold) {
+            int lo = 0, hi = a.n_long - 1;
+            while (lo < hi) { const int mid = (lo + hi) >> 1; if (a.long_rows[mid] < q) lo = mid + 1; else hi = mid; }
+            s = a.long_sums[(size_t)lo * LS_MAXT + (trial - trial0)];
+        } else {
+            for (int k = kb; k < ke; ++k) {
+                const int col = a.colidx[k];
+                s += a.val[k] * ls_y_new(a, c, col, a.y[col], a.Mx[col], a.Mx_old[col]);
+            }
+        }
+        a.Mty_new[a.nz_rows[q]] = s;
     }
 }
 
@@ -435,6 +609,24 @@ k_residual_dual(int p, int m, double beta, int use_beta, double sigma_fixed,
 __global__ void k_scal_reset(double* __restrict__ scal, int n, double soc_gap_init, double elapsed) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) scal[i] = (i == S_SOC_GAP) ? soc_gap_init : (i == S_ELAPSED ? elapsed : 0.0);
+}
+
+// End of an iteration on a single GPU: hand the scalar record to the host through mapped page-locked memory (the host
+// spins on the sequence word: no cudaMemcpy, no stream synchronisation) and clear it for the next iteration.
+__global__ void k_publish_record(double* __restrict__ scal, int n, int reset_mode, double* __restrict__ host_rec,
+                                 volatile unsigned long long* __restrict__ host_seq, unsigned long long seq) {
+    // reset_mode 0: publish only (the host is in the middle of an iteration: more trials / a fallback follow);
+    // 1 / 2: the iteration is complete unless the record says otherwise (poisoned eigsolve; 1: line search without an
+    // accepted trial) — exactly the conditions under which the host keeps working on this record
+    __shared__ int s_reset;
+    if (threadIdx.x == 0)
+        s_reset = reset_mode != 0 && scal[S_POISON] == 0.0 && (reset_mode == 2 || scal[S_LS_ACCEPTED] != 0.0);
+    __syncthreads();
+    const bool reset = s_reset != 0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) { host_rec[i] = scal[i]; if (reset && i < S_HEADER) scal[i] = 0.0; }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) { *host_seq = seq; __threadfence_system(); }
 }
 
 // ---------------------------------------------------------------------------

@@ -110,6 +110,9 @@ struct LanczosCl3Args {
     int use_bi;
     double stop_above;         // finish as soon as the largest Ritz value exceeds this (it is a lower bound of lambda_max);
                                // 1e300 = never: used by cone_feas, which only needs to know whether lambda_min < -tol
+    int strict;                // 1: KrylovKit's arithmetic to the letter — alpha of the local step summed in FP64 and two
+                               // Gram-Schmidt passes on every step (PROXSDP_B200_LZ_STRICT=1); 0: FP32 tree for the provisional
+                               // alpha and a second pass only when the DGKS test asks for it (same counts)
     long long* prof;
     Lz3Layout L;
 };
@@ -526,10 +529,15 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) k_lanczos_cl3(const __grid_cons
 #pragma unroll
                     for (int u = 0; u < 4; ++u) if (cb + lane + 32 * u < G) sd += ll_value(pr[u]);
                 }
-                float sf = (float)sd;
+                if (a.strict) {
+                    sd = warp_sum(sd);
+                    if (lane == 0) SMD(hred)[K + 1] = sd;
+                } else {
+                    float sf = (float)sd;
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) sf += __shfl_xor_sync(0xffffffffu, sf, o);
-                if (lane == 0) SMD(hred)[K + 1] = (double)sf;
+                    for (int o = 16; o > 0; o >>= 1) sf += __shfl_xor_sync(0xffffffffu, sf, o);
+                    if (lane == 0) SMD(hred)[K + 1] = (double)sf;
+                }
             }
             if (j == arrow) {
 #pragma unroll
@@ -609,7 +617,7 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) k_lanczos_cl3(const __grid_cons
             {
                 const double* Vs = SMD(Vs);
                 const double* hred = SMD(hred);
-                if (2 * vn <= LZ_THREADS) {
+                if (2 * a.vn_max <= LZ_THREADS) {      // cluster-uniform choice: every CTA sums ||h||^2 in the same order
                     const int t = min(tid >> 1, vn - 1), sub = tid & 1;
                     double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0, g0 = 0.0, g1 = 0.0, g2 = 0.0, g3 = 0.0;
                     int q = sub;
@@ -643,7 +651,7 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) k_lanczos_cl3(const __grid_cons
                     }
                 }
             }
-            if (hn2 <= 0.25 * wn2) break;      // DGKS: the pass shrank w by less than 1/sqrt(2)... (margin 2x): one pass is enough
+            if (pass == 1 || (!a.strict && hn2 <= 0.25 * wn2)) break;      // DGKS: the pass shrank w by less than 1/sqrt(2)... (margin 2x): one pass is enough
             // second pass (breakdown only).  Its dots read the updated wv of every warp (block barrier), and they travel
             // through the SAME mbarrier as the first pass: a peer that is already in its second pass must not credit
             // bytes to my barrier while my first-pass phase is still open (I may be waiting for a third CTA), hence a
@@ -658,7 +666,7 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) k_lanczos_cl3(const __grid_cons
             const double ib = (beta2 > 0.0) ? rsqrt(beta2) : 0.0;
             beta = beta2 * ib;
             if (tid == 0) { SMD(Hd)[j] = alpha; SMD(He)[j] = beta; }
-            if (2 * vn <= LZ_THREADS) {
+            if (2 * a.vn_max <= LZ_THREADS) {      // cluster-uniform choice: every CTA sums ||h||^2 in the same order
                 // the thread pair of row t shares the pushes: sub 0 -> peers 0, 2, ..., sub 1 -> peers 1, 3, ...
                 const int t = tid >> 1, sub = tid & 1;
                 double wnew = (t < vn && sub == 0) ? SMD(wv)[t] : 0.0;

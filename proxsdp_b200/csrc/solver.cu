@@ -17,17 +17,20 @@
 
 #include "../../include/proxsdp_b200.h"
 #include "common.cuh"
+#include "runtime.cuh"
 #include "fulleig.cuh"
 #include "jacobi.cuh"
 #include "kernels_vec.cuh"
+#include "kernels_result.cuh"
 #include "lanczos.cuh"
 #include "lanczos_cl.cuh"
 #include "lanczos_cl3.cuh"
 
 namespace pb {
 
-__global__ void k_scale_offdiag(double* __restrict__ x, const int* __restrict__ cone_side,
-                                const long long* __restrict__ cone_off, int n_sdp, double num, int divide);
+__global__ void k_scale_offdiag_copy(const double* __restrict__ src, long long n, long long psd_end,
+                                     const long long* __restrict__ cone_off, int n_sdp, double num, int divide,
+                                     double* __restrict__ dst);
 __global__ void k_scale_copy(const double* __restrict__ src, double a, long long n, double* __restrict__ dst);
 
 static thread_local std::string g_last_error;
@@ -96,97 +99,6 @@ void StageTimer::lap(const char* next) {
     if (g_timing) { cudaDeviceSynchronize(); double n = now_s(); fprintf(stderr, "[timing] %-28s %8.3f ms\n", what, 1e3 * (n - t)); t = n; }
     what = next;
 }
-
-// ---------------------------------------------------------------------------
-// device buffers
-// ---------------------------------------------------------------------------
-// host<->device traffic of the current solve (reported as h2d/d2h bytes by the bench)
-static thread_local long long g_h2d_bytes = 0, g_d2h_bytes = 0;
-
-// Device memory: plain cudaMalloc / cudaFree by default.  PROXSDP_B200_MALLOC=pool switches to the device's default
-// stream-ordered pool (cudaMallocAsync on the legacy stream, release threshold lifted).  Measured on B200
-// (bench.py e2e, three back-to-back chambolle_pock calls): cudaMalloc 0.229 / 0.231 / 0.231 s, pool 0.232 / 0.257 /
-// 0.354 s — frees of one solve are still pending when the next solve allocates, so the pool keeps growing; the
-// one-off cost of the very first call is what the warm-up call of bench.py absorbs.
-static bool pb_pool_enabled() {
-    static int state = -1;
-    if (state < 0) {
-        const char* e = getenv("PROXSDP_B200_MALLOC");
-        state = (e && std::string(e) == "pool") ? 1 : 0;
-    }
-    return state == 1;
-}
-static void pb_pool_prepare(int device) {
-    static thread_local int prepared_for = -1;
-    if (!pb_pool_enabled() || prepared_for == device) return;
-    cudaMemPool_t pool;
-    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
-        unsigned long long keep = ~0ULL;
-        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-    } else {
-        cudaGetLastError();
-    }
-    prepared_for = device;
-}
-static cudaError_t pb_malloc(void** p, size_t bytes) {
-    if (pb_pool_enabled()) {
-        cudaError_t e = cudaMallocAsync(p, bytes, 0);
-        if (e == cudaSuccess) return e;
-        cudaGetLastError();
-    }
-    return cudaMalloc(p, bytes);
-}
-static void pb_free(void* p) {
-    if (!p) return;
-    if (pb_pool_enabled()) { if (cudaFreeAsync(p, 0) == cudaSuccess) return; cudaGetLastError(); }
-    cudaFree(p);
-}
-
-template <class T>
-struct DBuf {
-    T* p = nullptr;
-    size_t n = 0;
-    DBuf() = default;
-    DBuf(const DBuf&) = delete;
-    DBuf& operator=(const DBuf&) = delete;
-    DBuf(DBuf&& o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
-    DBuf& operator=(DBuf&& o) noexcept {
-        if (this != &o) { if (p) pb_free(p); p = o.p; n = o.n; o.p = nullptr; o.n = 0; }
-        return *this;
-    }
-    ~DBuf() { if (p) pb_free(p); }
-    void alloc(size_t count) {
-        if (p) { pb_free(p); p = nullptr; }
-        n = count;
-        size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
-        cudaError_t e = pb_malloc(reinterpret_cast<void**>(&p), bytes);
-        if (e != cudaSuccess) throw CudaError(-4, std::string("cudaMalloc failed: ") + cudaGetErrorString(e));
-        PB_CUDA(cudaMemset(p, 0, bytes));
-    }
-    void upload(const std::vector<T>& h) {
-        alloc(h.size());
-        if (!h.empty()) PB_CUDA(cudaMemcpy(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
-        g_h2d_bytes += (long long)(h.size() * sizeof(T));
-    }
-    void upload(const T* h, size_t count) {
-        alloc(count);
-        if (count) PB_CUDA(cudaMemcpy(p, h, count * sizeof(T), cudaMemcpyHostToDevice));
-        g_h2d_bytes += (long long)(count * sizeof(T));
-    }
-    std::vector<T> download() const {
-        std::vector<T> h(n);
-        if (n) PB_CUDA(cudaMemcpy(h.data(), p, n * sizeof(T), cudaMemcpyDeviceToHost));
-        g_d2h_bytes += (long long)(n * sizeof(T));
-        return h;
-    }
-};
-
-struct CsrDev {
-    int nrows = 0, ncols = 0, nnz = 0, group = 1, n_long = 0, long_threshold = 1 << 30;
-    DBuf<int> rowptr, colidx, long_rows, nz_rows;
-    int n_nz = 0;
-    DBuf<double> val;
-};
 
 // Julia's max() propagates NaN
 static double jl_max(double a, double b) { return (a != a || b != b) ? NAN : std::max(a, b); }
@@ -278,7 +190,7 @@ class Solver {
     long long lanczos_timed_calls = 0;
     // step-level seam: one psd_projection! on x (device x_[cur_] -> x_[1-cur_]) with tau = 0
     void psd_projection_launch(long long iter, double tau, bool force_full);
-    void sync_scalars();
+    void sync_scalars(bool iteration_end = false);
     void reset_scalars();
     void fallback_projection(long long iter);
     void launch_soc_only();
@@ -311,6 +223,7 @@ class Solver {
     long long small_warm_calls_ = 0;
     DBuf<double> small_warm_d_;
     int lz_kernel_ = 3;        // 3 = third-generation cluster kernel (lanczos_cl3.cuh), 2 = second generation (lanczos_cl.cuh)
+    int lz_strict_ = 0;        // cl3 kernel: FP64 alpha + two Gram-Schmidt passes on every step (PROXSDP_B200_LZ_STRICT=1)
     int lz_xres_ = 1;          // > 1: cap the cl3 symv partial-sum table at lz_xres_ - 1 rows per round (experiments / tests)
     size_t lz_cl3_smem_max_ = 0;
     int lz_mode_ = 0;          // 0 = cluster-replicated kernel when it fits, 1 = row-distributed kernel only
@@ -323,16 +236,16 @@ class Solver {
 
   private:
     void setup_host(const proxsdp_problem_t* prob);
-    void build_csr(const std::vector<long long>& colptr, const std::vector<int>& rowidx,
-                   const std::vector<double>& val);
     void launch_spmv(const CsrDev& A, const double* x, double* y);
     void launch_full_projection_large(int k);
     void launch_reconstruct(ConeDev& cd, double* x_out);
     void launch_post_eig(double tau0, bool first_pass);
     void launch_dual_trial(int trial, double tau0);
-    void cache_solution(const double* c_res, proxsdp_result_t* out);
-    double dual_feas_host(const std::vector<double>& y, const std::vector<double>& cvec,
-                          std::vector<double>* dual_cone_out);
+    void launch_ladder(int trial0, int T, double tau0);
+    void cache_solution(double c_factor, proxsdp_result_t* out);
+    // get_duals + dual_feas (pdhg.jl:701-732) on the device: dual_cone = c_factor * c + M'y (un-scaled, off-diagonals / 2)
+    // is left in res_dc_d_ (position order); returns the dual infeasibility measure
+    double dual_feas_device(const double* y_dev, double c_factor);
     void rank_increment_rule(int idx);
     void record_trace(proxsdp_result_t* out);
     bool krylov_eligible(int k, long long iter) const;
@@ -340,18 +253,29 @@ class Solver {
     bool cones_only_ = false;
     int dev_ = 0, num_sms_ = 148;
     size_t smem_optin_ = 0;
-    // host problem data (permuted; scaled for the working copy)
-    std::vector<long long> ord_, var_ordering_;
-    std::vector<long long> mt_colptr_;            // CSC of M == CSR of M'
-    std::vector<int> mt_rowidx_;
-    std::vector<double> mt_val_, mt_val_orig_;    // scaled / unscaled values
-    std::vector<double> b_host_, h_host_, c_orig_, b_orig_, h_orig_;
-    bool identity_ = false;                        // variable permutation is the identity (no ord_/var_ordering_)
+    // host problem data: only the right-hand sides (R doubles) and the cone table stay on the host
+    std::vector<double> b_host_, h_host_;
+    bool identity_ = false;                        // variable permutation is the identity (no ord / var_ordering)
     std::vector<long long> soc_off_h_;
     std::vector<int> soc_len_h_;
     long long psd_end_ = 0;                        // first index after the PSD blocks
-    // device problem
+    long long listed_end_ = 0;                     // first index after the SOC blocks (free variables follow)
+    // device problem (built by ingest_problem, runtime.cu)
     CsrDev M_, Mt_;
+    DBuf<int> ord_d_, var_ordering_d_;             // empty when identity_
+    DBuf<double> c_orig_d_, b_orig_d_, h_orig_d_;  // un-scaled objective (position order) and right-hand sides
+    DBuf<double> res_x_d_, res_dc_d_, res_user_d_, res_slack_d_, feas_d_, scal_scratch_d_;
+    double* scal_target_ = nullptr;                // scalar record the eigen kernels write to (scal_d_ inside the loop)
+    // the iteration record reaches the host through mapped page-locked memory (scal_host) + a sequence word
+    double* scal_host_dev_ = nullptr;
+    unsigned long long* pub_seq_host_ = nullptr;
+    unsigned long long* pub_seq_dev_ = nullptr;
+    unsigned long long pub_seq_ = 0;
+    bool scal_clean_ = false;                      // the header of the device record is already zero (reset by the last publish)
+    bool spin_sync_ = true;                        // PROXSDP_B200_SYNC=memcpy: cudaMemcpyAsync + cudaStreamSynchronize instead
+    int fused_ladder_ = 1;                         // PROXSDP_B200_LADDER_FUSED=0: one launch pair per trial (first-round path)
+    DBuf<double> ls_long_sums_;
+    double* feas_host_ = nullptr;
     DBuf<int> cone_side_d_, small_ids_d_;
     DBuf<long long> cone_off_d_, soc_off_d_;
     DBuf<int> soc_len_d_;
@@ -427,7 +351,6 @@ Solver::Solver(const proxsdp_problem_t* prob, const proxsdp_options_t* opt_in, b
     dev_ = (int)opt.device_id;
     if (dev_ < 0 || dev_ >= ndev) throw CudaError(-1, "device_id out of range");
     PB_CUDA(cudaSetDevice(dev_));
-    pb_pool_prepare(dev_);
     cudaDeviceProp prop;
     PB_CUDA(cudaGetDeviceProperties(&prop, dev_));
     num_sms_ = prop.multiProcessorCount;
@@ -442,6 +365,7 @@ Solver::Solver(const proxsdp_problem_t* prob, const proxsdp_options_t* opt_in, b
     if (const char* e = getenv("PROXSDP_B200_RITZ_WARM")) lz_warm_ = atoi(e);
     if (const char* e = getenv("PROXSDP_B200_LZ_KERNEL")) lz_kernel_ = atoi(e);
     if (const char* e = getenv("PROXSDP_B200_LZ_XRES")) lz_xres_ = atoi(e);
+    if (const char* e = getenv("PROXSDP_B200_LZ_STRICT")) lz_strict_ = atoi(e) != 0 ? 1 : 0;
     if (const char* e = getenv("PROXSDP_B200_RITZ_BI")) lz_bi_ = atoi(e);
     { size_t lim = 0; if (cudaDeviceGetLimit(&lim, cudaLimitStackSize) == cudaSuccess && lim < 4096) cudaDeviceSetLimit(cudaLimitStackSize, 4096); }
     g_h2d_bytes = 0; g_d2h_bytes = 0;
@@ -449,7 +373,11 @@ Solver::Solver(const proxsdp_problem_t* prob, const proxsdp_options_t* opt_in, b
 }
 
 Solver::~Solver() {
-    if (scal_host) cudaFreeHost(scal_host);
+    // the device blocks of this solver go back to the per-process cache (runtime.cu): nothing may still be running on them
+    if (stream) cudaStreamSynchronize(stream);
+    if (scal_host) pb_host_free(scal_host);
+    if (feas_host_) pb_host_free(feas_host_);
+    if (pub_seq_host_) pb_host_free(pub_seq_host_);
     if (ev_psd0_) cudaEventDestroy(ev_psd0_);
     if (ev_psd1_) cudaEventDestroy(ev_psd1_);
     for (cudaEvent_t e : {ev_lz0_, ev_lz1_, ev_post1_, ev_fl0_, ev_fl1_}) if (e) cudaEventDestroy(e);
@@ -457,7 +385,7 @@ Solver::~Solver() {
 }
 
 void Solver::setup_host(const proxsdp_problem_t* prob) {
-    StageTimer st("setup: norms+ordering");
+    StageTimer st("setup: cone table + ingest");
     n = prob->n; p = prob->p; m = prob->m; R = p + m;
     const long long base = prob->index_base;
     n_sdp = (int)prob->n_sdp; n_soc = (int)prob->n_soc;
@@ -467,115 +395,54 @@ void Solver::setup_host(const proxsdp_problem_t* prob) {
     if (!opt.approx_norm) throw CudaError(-2, "approx_norm=false (exact spectral norm) is not supported");
     if (n >= (1LL << 31) - 64 || R >= (1LL << 31) - 64) throw CudaError(-1, "problem too large for 32-bit indices");
 
-    // norms before any permutation / scaling (pdhg.jl:14-16)
+    // norms of the right-hand sides before any scaling (pdhg.jl:14-15); ||c|| comes back from the device ingest
     auto nrm2 = [](const double* v, long long len) { double s = 0; for (long long i = 0; i < len; ++i) s += v[i] * v[i]; return std::sqrt(s); };
-    norm_b_ = nrm2(prob->b, p); norm_h_ = nrm2(prob->h, m); norm_c_ = nrm2(prob->c, n);
-    // (sharded runs combine these with the other ranks once the stream exists: see finish_setup_sharded)
+    norm_b_ = nrm2(prob->b, p); norm_h_ = nrm2(prob->h, m);
 
-    // preprocess! (scaling.jl:2-26): ord = [sdp vars..., soc vars..., sorted remaining]
+    // cone table in position order (preprocess!, scaling.jl:2-26: [PSD blocks | SOC blocks | free variables])
     cones.resize((size_t)n_sdp);
     soc_off_h_.resize((size_t)n_soc); soc_len_h_.resize((size_t)n_soc);
-    {
-        // fast path: cone variables already listed in order 0, 1, 2, ... (what JuMP/MOI produce for a single
-        // matrix variable): the permutation is the identity and no per-variable index arrays are needed
-        identity_ = true;
-        long long pos = 0;
-        for (int k = 0; k < n_sdp && identity_; ++k) {
-            long long side = prob->sdp_side[k];
-            long long tri = side * (side + 1) / 2;
-            if (prob->sdp_ptr[k + 1] - prob->sdp_ptr[k] != tri) throw CudaError(-3, "sdp cone length mismatch");
-            const int64_t* idx = prob->sdp_idx + prob->sdp_ptr[k];
-            for (long long q = 0; q < tri; ++q) if (idx[q] - base != pos + q) { identity_ = false; break; }
-            pos += tri;
-        }
-        for (int k = 0; k < n_soc && identity_; ++k) {
-            long long len = prob->soc_ptr[k + 1] - prob->soc_ptr[k];
-            const int64_t* idx = prob->soc_idx + prob->soc_ptr[k];
-            for (long long q = 0; q < len; ++q) if (idx[q] - base != pos + q) { identity_ = false; break; }
-            pos += len;
-        }
-        if (identity_ && pos > n) throw CudaError(-3, "variable index out of range");
-    }
+    std::vector<int> side_h((size_t)n_sdp);
+    std::vector<long long> off_h((size_t)n_sdp);
     long long pos = 0;
-    std::vector<char> used;
-    if (!identity_) { ord_.assign((size_t)n, 0); used.assign((size_t)n, 0); }
     for (int k = 0; k < n_sdp; ++k) {
-        long long side = prob->sdp_side[k];
-        long long tri = side * (side + 1) / 2;
-        if (prob->sdp_ptr[k + 1] - prob->sdp_ptr[k] != tri) throw CudaError(-3, "sdp cone length mismatch");
-        cones[k].side = (int)side;
-        cones[k].off = pos;
-        if (identity_) { pos += tri; continue; }
-        for (long long q = prob->sdp_ptr[k]; q < prob->sdp_ptr[k + 1]; ++q) {
-            long long v = prob->sdp_idx[q] - base;
-            if (v < 0 || v >= n || used[(size_t)v]) throw CudaError(-3, "variable index out of range or in two cones");
-            ord_[(size_t)pos++] = v; used[(size_t)v] = 1;
-        }
+        const long long side = prob->sdp_side[k], tri = side * (side + 1) / 2;
+        if (side < 1 || prob->sdp_ptr[k + 1] - prob->sdp_ptr[k] != tri || prob->sdp_ptr[k] - prob->sdp_ptr[0] != pos)
+            throw CudaError(-3, "sdp cone length mismatch");
+        cones[k].side = (int)side; cones[k].off = pos;
+        side_h[k] = (int)side; off_h[k] = pos;
+        pos += tri;
     }
     psd_end_ = pos;
     for (int k = 0; k < n_soc; ++k) {
         soc_off_h_[k] = pos;
         soc_len_h_[k] = (int)(prob->soc_ptr[k + 1] - prob->soc_ptr[k]);
-        if (identity_) { pos += soc_len_h_[k]; continue; }
-        for (long long q = prob->soc_ptr[k]; q < prob->soc_ptr[k + 1]; ++q) {
-            long long v = prob->soc_idx[q] - base;
-            if (v < 0 || v >= n || used[(size_t)v]) throw CudaError(-3, "variable index out of range or in two cones");
-            ord_[(size_t)pos++] = v; used[(size_t)v] = 1;
-        }
+        if (soc_len_h_[k] < 1 || prob->soc_ptr[k] - prob->soc_ptr[0] != pos - psd_end_) throw CudaError(-3, "soc cone length mismatch");
+        pos += soc_len_h_[k];
     }
-    if (!identity_) {
-        for (long long v = 0; v < n; ++v) if (!used[(size_t)v]) ord_[(size_t)pos++] = v;   // ascending
-        var_ordering_.assign((size_t)n, 0);
-        for (long long j = 0; j < n; ++j) var_ordering_[(size_t)ord_[(size_t)j]] = j;       // sortperm(ord)
-    }
+    listed_end_ = pos;
+    if (listed_end_ > n) throw CudaError(-3, "the cones list more variables than the problem has");
+    cone_side_d_.upload(side_h); cone_off_d_.upload(off_h);
 
-    st.lap("setup: scaling+M by column");
-    // column scaling factors of norm_scaling (scaling.jl:28-58)
-    std::vector<char> offdiag((size_t)n, 0);
-    {
-        long long cont = 0;
-        for (int k = 0; k < n_sdp; ++k) {
-            long long side = cones[k].side;
-            for (long long j = 0; j < side; ++j)
-                for (long long i = 0; i <= j; ++i) { if (i != j) offdiag[(size_t)cont] = 1; cont++; }
-        }
-    }
-    const double cte = std::sqrt(2.0) / 2.0;
-
-    // M = [A; G] with permuted columns, stored by column == CSR of M'
-    mt_colptr_.assign((size_t)n + 1, 0);
-    long long nnzA = (p > 0 && prob->A_colptr) ? prob->A_colptr[n] - base : 0;
-    long long nnzG = (m > 0 && prob->G_colptr) ? prob->G_colptr[n] - base : 0;
-    if (nnzA + nnzG >= (1LL << 31) - 64) throw CudaError(-1, "too many non-zeros for 32-bit indices");
-    mt_rowidx_.reserve((size_t)(nnzA + nnzG));
-    mt_val_.reserve((size_t)(nnzA + nnzG));
-    mt_val_orig_.reserve((size_t)(nnzA + nnzG));
-    for (long long j = 0; j < n; ++j) {
-        long long src = identity_ ? j : ord_[(size_t)j];
-        double sc = offdiag[(size_t)j] ? cte : 1.0;
-        if (nnzA > 0)
-            for (long long q = prob->A_colptr[src] - base; q < prob->A_colptr[src + 1] - base; ++q) {
-                mt_rowidx_.push_back((int)(prob->A_rowval[q] - base));
-                mt_val_orig_.push_back(prob->A_nzval[q]);
-                mt_val_.push_back(offdiag[(size_t)j] ? prob->A_nzval[q] * sc : prob->A_nzval[q]);
-            }
-        if (nnzG > 0)
-            for (long long q = prob->G_colptr[src] - base; q < prob->G_colptr[src + 1] - base; ++q) {
-                mt_rowidx_.push_back((int)(prob->G_rowval[q] - base + p));
-                mt_val_orig_.push_back(prob->G_nzval[q]);
-                mt_val_.push_back(offdiag[(size_t)j] ? prob->G_nzval[q] * sc : prob->G_nzval[q]);
-            }
-        mt_colptr_[(size_t)j + 1] = (long long)mt_rowidx_.size();
-    }
-    c_orig_.resize((size_t)n);
-    if (identity_) std::memcpy(c_orig_.data(), prob->c, sizeof(double) * (size_t)n);
-    else for (long long j = 0; j < n; ++j) c_orig_[(size_t)j] = prob->c[ord_[(size_t)j]];
+    // ---- device ingest: permutation, sqrt(2)/2 scaling, M and M', ||c||, ||M||_F (runtime.cu)
+    ConeTable ct{};
+    ct.n_sdp = n_sdp; ct.side = side_h.data(); ct.off = off_h.data(); ct.psd_end = psd_end_; ct.listed_end = listed_end_;
+    proxsdp_problem_t pr = *prob;
+    if (n_sdp > 0) pr.sdp_idx = prob->sdp_idx + prob->sdp_ptr[0];
+    if (n_soc > 0) pr.soc_idx = prob->soc_idx + prob->soc_ptr[0];
+    IngestOut ing;
+    ingest_problem(&pr, ct, cone_side_d_.p, cone_off_d_.p, !cones_only_, stream, ing);
+    launches += ing.launches;
+    identity_ = ing.identity;
+    ord_d_ = std::move(ing.ord); var_ordering_d_ = std::move(ing.var_ordering);
+    c_orig_d_ = std::move(ing.c_orig);
+    M_ = std::move(ing.M); Mt_ = std::move(ing.Mt);
+    norm_c_ = std::sqrt(ing.norm_c2);
     b_host_.assign(prob->b, prob->b + p); h_host_.assign(prob->h, prob->h + m);
-    b_orig_ = b_host_; h_orig_ = h_host_;
+    st.lap("setup: params + vectors");
 
     // step size: 1 / ||M||_F (pdhg.jl:121-133)
-    double fro = 0.0;
-    for (double v : mt_val_) fro += v * v;
+    double fro = ing.fro2;
     double any_cone = (n_soc > 0 || n_sdp > 0) ? 1.0 : 0.0, any_soc = n_soc > 0 ? 1.0 : 0.0;
     if (sharded()) {
         // whole-problem norms: sqrt of the rank-ordered sum of the per-rank sums of squares
@@ -590,6 +457,7 @@ void Solver::setup_host(const proxsdp_problem_t* prob) {
     fro = std::sqrt(fro);
     if (fro < 1e-10) fro = 1.0;
     primal_step_ = 1.0 / fro; primal_step_old_ = primal_step_; dual_step_ = primal_step_;
+    const double cte = std::sqrt(2.0) / 2.0;
 
     // ---- Params (pdhg.jl:7-31) ----
     theta_ = opt.initial_theta; adapt_level_ = opt.initial_adapt_level; window_ = opt.convergence_window;
@@ -601,31 +469,32 @@ void Solver::setup_host(const proxsdp_problem_t* prob) {
     for (Circ* c : {&dual_gap_, &prim_obj_, &dual_obj_, &feasibility_, &primal_residual_, &dual_residual_, &comb_residual_})
         c->init(2 * window_);
 
-    st.lap("setup: device vectors");
-    // ---- device problem ----
-    c_.upload(c_orig_); b_.upload(b_host_); h_.upload(h_host_);
-    if (n_sdp > 0) {     // norm_scaling of c (scaling.jl:28-58): off-diagonal svec entries *= sqrt(2)/2, on the device
-        cone_side_d_.upload(std::vector<int>([&]{ std::vector<int> v((size_t)n_sdp); for (int k = 0; k < n_sdp; ++k) v[k] = cones[k].side; return v; }()));
-        cone_off_d_.upload(std::vector<long long>([&]{ std::vector<long long> v((size_t)n_sdp); for (int k = 0; k < n_sdp; ++k) v[k] = cones[k].off; return v; }()));
-        k_scale_offdiag<<<dim3(64, n_sdp), 256, 0, stream>>>(c_.p, cone_side_d_.p, cone_off_d_.p, n_sdp, cte, 0);
+    // ---- device vectors ----
+    // working objective = c in position order with norm_scaling applied (scaling.jl:28-58: off-diagonal svec entries
+    // *= sqrt(2)/2); the un-scaled copy stays for the dual cone of the result (pdhg.jl:701-710)
+    c_.alloc_raw((size_t)n);
+    if (n > 0) {
+        k_scale_offdiag_copy<<<std::max(1, std::min(num_sms_ * 8, ceil_div(n, 256))), 256, 0, stream>>>(
+            c_orig_d_.p, n, psd_end_, cone_off_d_.p, n_sdp, cte, 0, c_.p);
         launches++;
     }
+    b_.upload(b_host_); h_.upload(h_host_);
+    b_orig_d_.upload(b_host_); h_orig_d_.upload(h_host_);
     for (int q = 0; q < 2; ++q) { x_[q].alloc((size_t)n); Mty_[q].alloc((size_t)n); y_[q].alloc((size_t)R); Mx_[q].alloc((size_t)R); }
-    st.lap("setup: build_csr");
-    if (!cones_only_) build_csr(mt_colptr_, mt_rowidx_, mt_val_);
     st.lap("setup: cones");
 
     // cones
     long long kmax = 2 * std::max<long long>(opt.max_target_rank_krylov_eigs, r0) + 1;
     kmax = std::max<long long>(kmax, opt.eigsolver_min_lanczos);
     Kmax_ = (int)kmax;
-    std::vector<int> side_h((size_t)n_sdp);
-    std::vector<long long> off_h((size_t)n_sdp);
     long long roff = 0;
     for (int k = 0; k < n_sdp; ++k) {
         ConeDev& cd = cones[k];
-        side_h[k] = cd.side; off_h[k] = cd.off;
-        cd.small = cd.side <= SMALL_CONE_MAX && !force_large_;
+        // Cones of side <= SMALL_CONE_MAX take the fused one-CTA full-eigendecomposition kernel — unless the options make
+        // them Krylov-capable (min_size_krylov_eigs below the side, prox_operators.jl:46-49): those are laid out as
+        // large cones so that the reference's truncated projection, target-rank and min_eig tracking apply to them.
+        const bool krylov_capable = !opt.full_eig_decomp && cd.side > opt.min_size_krylov_eigs && cd.side > 1;
+        cd.small = cd.side <= SMALL_CONE_MAX && !force_large_ && !krylov_capable;
         cd.ld = (cd.side + 63) & ~63;     // multiple of the block-Jacobi pivot size (no dummy blocks)
         if (cd.small) {
             small_ids_.push_back(k);
@@ -647,7 +516,6 @@ void Solver::setup_host(const proxsdp_problem_t* prob) {
         roff += cd.side;
     }
     st.lap("setup: misc buffers+attrs");
-    if (n_sdp == 0) { cone_side_d_.upload(side_h); cone_off_d_.upload(off_h); }
     small_ids_d_.upload(small_ids_);
     soc_off_d_.upload(soc_off_h_); soc_len_d_.upload(soc_len_h_); soc_gap_d_.alloc((size_t)std::max(n_soc, 1));
     out_min_d_.alloc((size_t)std::max(n_sdp, 1));
@@ -655,7 +523,20 @@ void Solver::setup_host(const proxsdp_problem_t* prob) {
 
     scal_len = S_HEADER + 3 * n_sdp;
     scal_d_.alloc((size_t)scal_len);
-    PB_CUDA(cudaMallocHost(&scal_host, sizeof(double) * (size_t)scal_len));
+    scal_host = static_cast<double*>(pb_host_alloc(sizeof(double) * (size_t)scal_len));
+    pub_seq_host_ = static_cast<unsigned long long*>(pb_host_alloc(64));
+    *pub_seq_host_ = 0;
+    if (cudaHostGetDevicePointer(reinterpret_cast<void**>(&scal_host_dev_), scal_host, 0) != cudaSuccess ||
+        cudaHostGetDevicePointer(reinterpret_cast<void**>(&pub_seq_dev_), pub_seq_host_, 0) != cudaSuccess) {
+        cudaGetLastError();
+        spin_sync_ = false;
+    }
+    if (const char* e = getenv("PROXSDP_B200_SYNC")) spin_sync_ = spin_sync_ && std::string(e) != "memcpy";
+    if (const char* e = getenv("PROXSDP_B200_LADDER_FUSED")) fused_ladder_ = atoi(e) != 0 ? 1 : 0;
+    scal_scratch_d_.alloc((size_t)scal_len);
+    scal_target_ = scal_d_.p;
+    feas_d_.alloc(8);
+    feas_host_ = static_cast<double*>(pb_host_alloc(sizeof(double) * (size_t)(8 + std::max(n_sdp, 1))));
     reduce_blocks_ = num_sms_ * 8;
     partials_d_.alloc((size_t)reduce_blocks_ * 8);
     counters_d_.alloc(16);
@@ -708,49 +589,6 @@ void Solver::setup_host(const proxsdp_problem_t* prob) {
     PB_CUDA(cudaFuncSetAttribute(k_bj_apply<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BJ_APPLY_SMEM));
 }
 
-// CSR of M (rows of M) from the by-column storage, plus device copies of both
-void Solver::build_csr(const std::vector<long long>& colptr, const std::vector<int>& rowidx,
-                       const std::vector<double>& val) {
-    const long long nnz = (long long)rowidx.size();
-    // Mt_: rows = n (columns of M)
-    {
-        std::vector<int> rp((size_t)n + 1);
-        for (long long j = 0; j <= n; ++j) rp[(size_t)j] = (int)colptr[(size_t)j];
-        Mt_.nrows = (int)n; Mt_.ncols = (int)R; Mt_.nnz = (int)nnz;
-        Mt_.rowptr.upload(rp); Mt_.colidx.upload(rowidx); Mt_.val.upload(val);
-        Mt_.long_threshold = 256;      // one thread per row below this, one block per row above
-        std::vector<int> longs_t;
-        for (long long j = 0; j < n; ++j) if (rp[(size_t)j + 1] - rp[(size_t)j] > Mt_.long_threshold) longs_t.push_back((int)j);
-        Mt_.n_long = (int)longs_t.size();
-        Mt_.long_rows.upload(longs_t);
-        std::vector<int> nzr;
-        for (long long j = 0; j < n; ++j) if (rp[(size_t)j + 1] > rp[(size_t)j]) nzr.push_back((int)j);
-        Mt_.n_nz = (int)nzr.size();
-        Mt_.nz_rows.upload(nzr);
-    }
-    // M_: transpose by counting sort (keeps increasing column order inside a row)
-    std::vector<int> rp((size_t)R + 1, 0), ci((size_t)nnz);
-    std::vector<double> vv((size_t)nnz);
-    for (long long q = 0; q < nnz; ++q) rp[(size_t)rowidx[(size_t)q] + 1]++;
-    for (long long r = 0; r < R; ++r) rp[(size_t)r + 1] += rp[(size_t)r];
-    std::vector<int> next(rp.begin(), rp.end() - 1);
-    for (long long j = 0; j < n; ++j)
-        for (long long q = colptr[(size_t)j]; q < colptr[(size_t)j + 1]; ++q) {
-            int dst = next[(size_t)rowidx[(size_t)q]]++;
-            ci[(size_t)dst] = (int)j; vv[(size_t)dst] = val[(size_t)q];
-        }
-    M_.nrows = (int)R; M_.ncols = (int)n; M_.nnz = (int)nnz;
-    M_.rowptr.upload(rp); M_.colidx.upload(ci); M_.val.upload(vv);
-    // row-length statistics -> lanes per row, long rows
-    double avg = R > 0 ? (double)nnz / (double)R : 0.0;
-    M_.group = avg <= 1.5 ? 1 : avg <= 3 ? 2 : avg <= 6 ? 4 : avg <= 12 ? 8 : avg <= 24 ? 16 : 32;
-    M_.long_threshold = 4096;
-    std::vector<int> longs;
-    for (long long r = 0; r < R; ++r) if (rp[(size_t)r + 1] - rp[(size_t)r] > M_.long_threshold) longs.push_back((int)r);
-    M_.n_long = (int)longs.size();
-    M_.long_rows.upload(longs);
-}
-
 // ---------------------------------------------------------------------------
 // launches
 // ---------------------------------------------------------------------------
@@ -783,6 +621,7 @@ bool Solver::krylov_eligible(int k, long long iter) const {
 bool Solver::lanczos_launch_cluster(ConeDev& cd, int cone_idx, int nev, int K, int maxiter, double tol) {
     if (lz_mode_ == 1 || K > LZC_KMAX) return false;
     const int nside = cd.side;
+    if (nside < 64) return false;              // tiny cones (min_size_krylov_eigs lowered by the user): one CTA suffices, row kernel
     const int C = lz_cluster_;
     const int vn_max = (nside + C - 1) / C;
     // grid: as many clusters as can be co-resident, but no more CTAs than there are 8-row slabs
@@ -830,7 +669,7 @@ bool Solver::lanczos_launch_cluster(ConeDev& cd, int cone_idx, int nev, int K, i
     cd.ritz_launches++;
     a.nev = nev; a.K = K; a.maxiter = maxiter; a.tol = tol;
     a.rows_max = rows_max; a.vn_max = vn_max; a.use_bi = lz_bi_;
-    a.vals = cd.vals.p; a.info = cd.info.p; a.scal = scal_d_.p; a.cone = cone_idx;
+    a.vals = cd.vals.p; a.info = cd.info.p; a.scal = scal_target_; a.cone = cone_idx;
     if (getenv("PROXSDP_B200_LZ_PROF")) { if (lz_prof_.n == 0) lz_prof_.alloc(8 + 8 * 256); a.prof = lz_prof_.p; }
     cudaError_t e = cudaLaunchKernelEx(&cfg, k_lanczos_cl, a);
     if (e != cudaSuccess) {
@@ -850,6 +689,7 @@ bool Solver::lanczos_launch_cluster(ConeDev& cd, int cone_idx, int nev, int K, i
 bool Solver::lanczos_launch_cluster3(ConeDev& cd, int cone_idx, int nev, int K, int maxiter, double tol) {
     if (lz_mode_ == 1 || lz_kernel_ != 3 || K > LZC_KMAX) return false;
     const int nside = cd.side;
+    if (nside < 64) return false;
     const int C = lz_cluster_;
     const int vn_max = (nside + C - 1) / C;
     const int cpr = lanczos_cpr(nside);
@@ -918,9 +758,9 @@ bool Solver::lanczos_launch_cluster3(ConeDev& cd, int cone_idx, int nev, int K, 
     a.ritz_rd = (lz_warm_ && cd.ritz_launches > 0 && (cd.ritz_launches % 32) != 0) ? cd.ritz_ws[flip].p : nullptr;
     a.ritz_wr = lz_warm_ ? cd.ritz_ws[1 - flip].p : nullptr;
     a.nev = nev; a.K = K; a.maxiter = maxiter; a.tol = tol;
-    a.vn_max = vn_max; a.use_bi = lz_bi_; a.stop_above = lz_stop_above_;
+    a.vn_max = vn_max; a.use_bi = lz_bi_; a.stop_above = lz_stop_above_; a.strict = lz_strict_;
     a.rbase = nside / G; a.rrem = nside % G; a.vbase = nside / C; a.vrem = nside % C;
-    a.vals = cd.vals.p; a.info = cd.info.p; a.scal = scal_d_.p; a.cone = cone_idx;
+    a.vals = cd.vals.p; a.info = cd.info.p; a.scal = scal_target_; a.cone = cone_idx;
     a.L = L;
     if (getenv("PROXSDP_B200_LZ_PROF")) { if (lz_prof_.n == 0) lz_prof_.alloc(8 + 8 * 256); a.prof = lz_prof_.p; }
     void* kargs[] = {&a};
@@ -968,7 +808,7 @@ void Solver::lanczos_launch(ConeDev& cd, int cone_idx, int nev, int K, int maxit
     lz_epoch_ += bound;
     a.nev = nev; a.K = K; a.maxiter = maxiter; a.tol = tol;
     a.rows_max = rows_max; a.jac_inplace = jac_inplace;
-    a.vals = cd.vals.p; a.info = cd.info.p; a.scal = scal_d_.p; a.cone = cone_idx; a.n_cones_total = n_sdp;
+    a.vals = cd.vals.p; a.info = cd.info.p; a.scal = scal_target_; a.cone = cone_idx; a.n_cones_total = n_sdp;
     if (getenv("PROXSDP_B200_LZ_PROF")) { if (lz_prof_.n == 0) lz_prof_.alloc(8 + 8 * 256); a.prof = lz_prof_.p; }
     void* args[] = {&a};
     PB_CUDA(cudaLaunchCooperativeKernel((void*)k_lanczos, dim3(G), dim3(LZ_THREADS), args, smem, stream));
@@ -1135,8 +975,8 @@ void Solver::launch_dual_trial(int trial, double tau0) {
     t.N = (int)n; t.rowptr = Mt_.rowptr.p; t.colidx = Mt_.colidx.p; t.val = Mt_.val.p; t.long_threshold = Mt_.long_threshold;
     t.nz_rows = Mt_.nz_rows.p; t.n_nz = Mt_.n_nz;
     if (Mt_.n_long > 0) {
-        k_spmv_mt_long<<<Mt_.n_long, 512, 0, stream>>>(Mt_.long_rows.p, Mt_.rowptr.p, Mt_.colidx.p, Mt_.val.p, y_[1 - cur_].p,
-                                                       Mty_[1 - cur_].p, scal_d_.p);
+        k_spmv_mt_long<<<Mt_.n_long, 512, 0, stream>>>(Mt_.long_rows.p, Mt_.nz_rows.p, Mt_.rowptr.p, Mt_.colidx.p, Mt_.val.p,
+                                                       y_[1 - cur_].p, Mty_[1 - cur_].p, scal_d_.p);
         launches++;
     }
     t.y_new = y_[1 - cur_].p; t.Mty = Mty_[cur_].p; t.Mty_new = Mty_[1 - cur_].p;
@@ -1151,6 +991,31 @@ void Solver::launch_dual_trial(int trial, double tau0) {
         k_ls_decide<<<1, 32, 0, stream>>>(red_d_.p, nranks_, scal_d_.p, beta_, opt.delta, trial);
         launches++;
     }
+}
+
+// trials [trial0, trial0 + T) of the line search in two launches (kernels_vec.cuh: k_ls_ladder / k_ls_apply)
+void Solver::launch_ladder(int trial0, int T, double tau0) {
+    LadderArgs a{};
+    a.y = y_[cur_].p; a.Mx = Mx_[1 - cur_].p; a.Mx_old = Mx_[cur_].p; a.b = b_.p; a.h = h_.p;
+    a.p = (int)p; a.m = (int)m;
+    a.tau0 = tau0; a.decay = opt.linsearch_decay; a.tau_old = primal_step_old_; a.beta = beta_;
+    a.sigma_fixed = dual_step_; a.delta = opt.delta;
+    a.use_theta = opt.line_search_flag ? 1 : 0; a.do_test = opt.line_search_flag ? 1 : 0;
+    a.ntrials = std::max(1, std::min(T, LS_MAXT));
+    a.nz_rows = Mt_.nz_rows.p; a.nz_ptr = Mt_.rowptr.p; a.colidx = Mt_.colidx.p; a.val = Mt_.val.p; a.n_nz = Mt_.n_nz;
+    a.long_threshold = Mt_.long_threshold; a.long_rows = Mt_.long_rows.p; a.n_long = Mt_.n_long;
+    if (Mt_.n_long > 0 && ls_long_sums_.n < (size_t)Mt_.n_long * LS_MAXT) ls_long_sums_.alloc((size_t)Mt_.n_long * LS_MAXT);
+    a.long_sums = ls_long_sums_.p;
+    a.Mty = Mty_[cur_].p; a.y_new = y_[1 - cur_].p; a.Mty_new = Mty_[1 - cur_].p;
+    if (Mt_.n_long > 0) {
+        k_ls_long_rows<<<Mt_.n_long, 512, 0, stream>>>(a, scal_d_.p, trial0);
+        launches++;
+    }
+    const long long work = std::max<long long>(R, Mt_.n_nz);
+    const int blocks = std::max(1, std::min(reduce_blocks_ / 2, ceil_div(work, 256)));
+    k_ls_ladder<<<blocks, 256, 0, stream>>>(a, scal_d_.p, ws_, trial0);
+    k_ls_apply<<<blocks, 256, 0, stream>>>(a, scal_d_.p, trial0);
+    launches += 2;
 }
 
 // everything after the eigen-solves: SOC projection, Mx, dual step / linesearch ladder, residuals
@@ -1174,8 +1039,9 @@ void Solver::launch_post_eig(double tau0, bool first_pass) {
         launches += 2;
     }
     launch_spmv(M_, xn, Mx_[1 - cur_].p);
-    int ntr = opt.line_search_flag ? (sharded() ? 1 : ladder_) : 1;
-    for (int t = 0; t < ntr; ++t) launch_dual_trial(t, tau0);
+    int ntr = opt.line_search_flag ? (sharded() ? 1 : (int)std::min<long long>(ladder_, std::max<long long>(opt.max_linsearch_steps, 1))) : 1;
+    if (!sharded() && fused_ladder_) launch_ladder(0, ntr, tau0);
+    else for (int t = 0; t < ntr; ++t) launch_dual_trial(t, tau0);
     int blocksN = std::max(1, std::min(reduce_blocks_, ceil_div(n, 512)));
     k_residual_primal<<<blocksN, 256, 0, stream>>>(n, xn, x_[cur_].p, Mty_[1 - cur_].p, Mty_[cur_].p, c_.p, scal_d_.p, ws_);
     int blocksR = std::max(1, std::min(reduce_blocks_, ceil_div(R, 256)));
@@ -1217,16 +1083,37 @@ void Solver::fallback_projection(long long iter) {
     }
 }
 
-void Solver::sync_scalars() {
-    if (sharded()) {
-        if (gather_d_.n < (size_t)nranks_ * S_HEADER) gather_d_.alloc((size_t)nranks_ * S_HEADER);
-        PB_NCCL(nccl_api().AllGather(scal_d_.p, gather_d_.p, S_HEADER, ncclDouble, comm_->comm, stream));
-        k_fold_header<<<1, 32, 0, stream>>>(gather_d_.p, nranks_, scal_d_.p);
+void Solver::sync_scalars(bool iteration_end) {
+    if (sharded() || !spin_sync_) {
+        if (sharded()) {
+            if (gather_d_.n < (size_t)nranks_ * S_HEADER) gather_d_.alloc((size_t)nranks_ * S_HEADER);
+            PB_NCCL(nccl_api().AllGather(scal_d_.p, gather_d_.p, S_HEADER, ncclDouble, comm_->comm, stream));
+            k_fold_header<<<1, 32, 0, stream>>>(gather_d_.p, nranks_, scal_d_.p);
+            launches++;
+        }
+        PB_CUDA(cudaMemcpyAsync(scal_host, scal_d_.p, sizeof(double) * (size_t)scal_len, cudaMemcpyDeviceToHost, stream));
+        g_d2h_bytes += (long long)sizeof(double) * scal_len;
+        PB_CUDA(cudaStreamSynchronize(stream));
+        scal_clean_ = false;
+    } else {
+        // single GPU: the last kernel of the sequence writes the record into mapped host memory and bumps a sequence
+        // word; the host spins on it (a D2H copy + stream synchronisation costs 25-40 us per iteration, this ~3)
+        ++pub_seq_;
+        const int mode = iteration_end ? (opt.line_search_flag ? 1 : 2) : 0;
+        k_publish_record<<<1, 128, 0, stream>>>(scal_d_.p, scal_len, mode, scal_host_dev_, pub_seq_dev_, pub_seq_);
         launches++;
+        g_d2h_bytes += (long long)sizeof(double) * scal_len;
+        volatile unsigned long long* seq = pub_seq_host_;
+        unsigned long long spins = 0;
+        while (*seq != pub_seq_) {
+            if ((++spins & 0x3fff) == 0) {
+                cudaError_t q = cudaStreamQuery(stream);
+                if (q == cudaSuccess) { if (*seq == pub_seq_) break; if (spins > (1ULL << 26)) throw CudaError(-100, "iteration record never arrived"); }
+                else if (q != cudaErrorNotReady) throw CudaError(-100 - (int)q, std::string("kernel failed: ") + cudaGetErrorString(q));
+            }
+        }
+        scal_clean_ = iteration_end && scal_host[S_POISON] == 0.0 && (!opt.line_search_flag || scal_host[S_LS_ACCEPTED] != 0.0);
     }
-    PB_CUDA(cudaMemcpyAsync(scal_host, scal_d_.p, sizeof(double) * (size_t)scal_len, cudaMemcpyDeviceToHost, stream));
-    g_d2h_bytes += (long long)sizeof(double) * scal_len;
-    PB_CUDA(cudaStreamSynchronize(stream));
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) throw CudaError(-100 - (int)e, std::string("kernel launch failed: ") + cudaGetErrorString(e));
 }
@@ -1253,102 +1140,107 @@ void Solver::host_reduce(double* vals, int count, int op) {
 }
 
 // ---------------------------------------------------------------------------
-// result assembly (pdhg.jl:678-787), host side
+// result assembly (pdhg.jl:678-787), on the device
 // ---------------------------------------------------------------------------
-double Solver::dual_feas_host(const std::vector<double>& y, const std::vector<double>& cvec,
-                              std::vector<double>* dual_cone_out) {
-    // get_duals (pdhg.jl:701-710): dual_cone = c + A'y_eq + G'y_in (unscaled), off-diagonals / 2
-    std::vector<double> dc((size_t)n);
-    for (long long j = 0; j < n; ++j) {
-        double s = 0.0;
-        for (long long q = mt_colptr_[(size_t)j]; q < mt_colptr_[(size_t)j + 1]; ++q)
-            s += mt_val_orig_[(size_t)q] * y[(size_t)mt_rowidx_[(size_t)q]];
-        dc[(size_t)j] = cvec[(size_t)j] + s;
+double Solver::dual_feas_device(const double* y_dev, double c_factor) {
+    // get_duals (pdhg.jl:701-710): dual_cone = c + A'y_eq + G'y_in (un-scaled), off-diagonals / 2
+    if (res_dc_d_.n < (size_t)n) res_dc_d_.alloc_raw((size_t)n);
+    double* dc = res_dc_d_.p;
+    const int blocks_n = std::max(1, std::min(reduce_blocks_, ceil_div(n, 256)));
+    if (n > 0) {
+        k_scale_copy<<<blocks_n, 256, 0, stream>>>(c_orig_d_.p, c_factor, n, dc);
+        launches++;
+        if (Mt_.n_nz > 0) {
+            k_dual_cone_rows<<<std::max(1, std::min(reduce_blocks_, ceil_div((long long)Mt_.n_nz * 32, 256))), 256, 0, stream>>>(
+                Mt_.n_nz, Mt_.nz_rows.p, Mt_.rowptr.p, Mt_.colidx.p, Mt_.val_orig.p, y_dev, dc);
+            launches++;
+        }
+        if (n_sdp > 0) {
+            k_scale_offdiag_copy<<<blocks_n, 256, 0, stream>>>(dc, n, psd_end_, cone_off_d_.p, n_sdp, 2.0, 1, dc);
+            launches++;
+        }
     }
+    // dual_feas (pdhg.jl:716-732): inequality multipliers, free-variable part
+    PB_CUDA(cudaMemsetAsync(feas_d_.p, 0, sizeof(double) * FS_COUNT, stream));
     {
-        long long cont = 0;
-        for (int k = 0; k < n_sdp; ++k) {
-            long long side = cones[(size_t)k].side;
-            for (long long j = 0; j < side; ++j)
-                for (long long i = 0; i <= j; ++i) { if (i != j) dc[(size_t)cont] /= 2.0; cont++; }
-        }
+        const long long work = std::max<long long>(m, n - listed_end_);
+        k_feas_ineq_tail<<<std::max(1, std::min(reduce_blocks_, ceil_div(work, 256))), 256, 0, stream>>>(
+            y_dev + p, m, dc, listed_end_, n, feas_d_.p, ws_);
+        launches++;
     }
-    if (dual_cone_out) *dual_cone_out = dc;
-    // dual_feas (pdhg.jl:716-732)
-    double ineq_viol = 0.0;
-    if (m > 0) {
-        double mn = y[(size_t)p];
-        for (long long i = 1; i < m; ++i) mn = std::min(mn, y[(size_t)(p + i)]);
-        ineq_viol = -std::min(0.0, mn);
+    // cone_feas (pdhg.jl:678-699): min eigenvalue of mat(dual_cone) with off-diagonals / sqrt(2); SOC: t - ||v||
+    if (n_soc > 0) {
+        k_feas_soc<<<n_soc, 256, 0, stream>>>(dc, soc_off_d_.p, soc_len_d_.p, soc_gap_d_.p);
+        k_feas_max<<<1, 256, 0, stream>>>(soc_gap_d_.p, nullptr, n_soc, 0, feas_d_.p, FS_SOC);
+        launches += 2;
     }
-    // cone_feas (pdhg.jl:678-699): min eigenvalue of mat(dual_cone) with off-diagonals / sqrt(2)
+    if (!small_ids_.empty()) {
+        SmallConeArgs a{};
+        a.cone_ids = small_ids_d_.p; a.cone_side = cone_side_d_.p; a.cone_off = cone_off_d_.p;
+        a.x = dc; a.Mty = dc; a.c = dc; a.tau = 0.0; a.tol_psd = opt.tol_psd; a.x_out = nullptr;
+        a.scal = scal_scratch_d_.p; a.mode = 1; a.scale = 1.0; a.out_min = out_min_d_.p;
+        size_t sb = max_small_side_ > 1 ? small_cone_smem_bytes(max_small_side_, small_fast_) : 0;
+        a.fast = small_fast_;
+        k_small_cone_proj<<<(int)small_ids_.size(), small_fast_ ? 512 : 256, sb, stream>>>(a);
+        k_feas_max<<<1, 256, 0, stream>>>(out_min_d_.p, small_ids_d_.p, (int)small_ids_.size(), 1, feas_d_.p, FS_SMALL_PSD);
+        launches += 2;
+    }
     double cone_viol = 0.0;
-    if (n_sdp > 0) {
-        DBuf<double> dcd;
-        dcd.upload(dc);
-        if (!small_ids_.empty()) {
-            SmallConeArgs a{};
-            a.cone_ids = small_ids_d_.p; a.cone_side = cone_side_d_.p; a.cone_off = cone_off_d_.p;
-            a.x = dcd.p; a.Mty = dcd.p; a.c = dcd.p; a.tau = 0.0; a.tol_psd = opt.tol_psd; a.x_out = nullptr;
-            a.scal = scal_d_.p; a.mode = 1; a.scale = 1.0; a.out_min = out_min_d_.p;
-            size_t sb = max_small_side_ > 1 ? small_cone_smem_bytes(max_small_side_, small_fast_) : 0;
-            a.fast = small_fast_;
-            k_small_cone_proj<<<(int)small_ids_.size(), small_fast_ ? 512 : 256, sb, stream>>>(a);
-            launches++;
-            PB_CUDA(cudaStreamSynchronize(stream));
-            std::vector<double> mins = out_min_d_.download();
-            for (int k : small_ids_) cone_viol = std::max(cone_viol, -std::min(0.0, mins[(size_t)k]));
+    // large cones: lambda_min(Z) = -lambda_max(-Z) by Lanczos (nev = 1) on the negated matrix.  The eigen kernels write
+    // their bookkeeping to a scratch record so that the live per-iteration record is left alone.
+    scal_target_ = scal_scratch_d_.p;
+    struct Restore { double*& t; double* v; double& stop; ~Restore() { t = v; stop = 1e300; } } restore{scal_target_, scal_d_.p, lz_stop_above_};
+    for (int k : large_ids_) {
+        ConeDev& cd = cones[(size_t)k];
+        int nt = (cd.side + 31) / 32;
+        int tiles = nt * (nt + 1) / 2;
+        k_svec_to_mat<false><<<tiles, dim3(32, 8), 0, stream>>>(dc + cd.off, nullptr, nullptr, 0.0, -1.0, cd.side, cd.ld, cd.X.p);
+        launches++;
+        // Only the sign of lambda_min relative to tol_feasibility_dual is consumed (dual_feasible_user_tol,
+        // pdhg.jl:712-732), so the extreme eigenvalue is resolved to 1e-3 of that tolerance, not to 1e-10 ...
+        int K = (int)std::max<long long>(opt.eigsolver_min_lanczos, 3);
+        const double tol_ev = std::max(1e-10, 1e-3 * std::min(opt.tol_feasibility_dual, 1.0));
+        // ... and a Ritz value of -Z above the tolerance already proves the violation (Ritz values are lower bounds
+        // of lambda_max), so the eigsolve may stop there instead of converging an interior-looking extreme pair
+        lz_stop_above_ = opt.tol_feasibility_dual;
+        PB_CUDA(cudaMemsetAsync(scal_scratch_d_.p, 0, sizeof(double) * (size_t)scal_len, stream));
+        lanczos_launch(cd, k, 1, K, 60, tol_ev);
+        lz_stop_above_ = 1e300;
+        int info[4] = {0, 0, 0, 0};
+        double top = 0.0;
+        PB_CUDA(cudaMemcpyAsync(info, cd.info.p, sizeof(info), cudaMemcpyDeviceToHost, stream));
+        PB_CUDA(cudaMemcpyAsync(&top, cd.vals.p, sizeof(double), cudaMemcpyDeviceToHost, stream));
+        PB_CUDA(cudaStreamSynchronize(stream));
+        g_d2h_bytes += 24;
+        double lmin;
+        if (info[0] >= 1 && info[1] >= 1) {
+            lmin = -top;
+        } else {
+            // not converged (or the launch gave up): the reference takes the exact spectrum here (eigen!, pdhg.jl:685)
+            std::vector<double> w = full_eig_device(cd);      // X still holds -Z: Lanczos only reads it
+            double mx = w.empty() ? 0.0 : w[0];
+            for (double v : w) mx = std::max(mx, v);
+            lmin = -mx;
         }
-        for (int k : large_ids_) {
-            ConeDev& cd = cones[(size_t)k];
-            int nt = (cd.side + 31) / 32;
-            int tiles = nt * (nt + 1) / 2;
-            // lambda_min(Z) = -lambda_max(-Z): Lanczos (nev = 1) on the negated matrix
-            k_svec_to_mat<false><<<tiles, dim3(32, 8), 0, stream>>>(dcd.p + cd.off, nullptr, nullptr, 0.0, -1.0,
-                                                                    cd.side, cd.ld, cd.X.p);
-            launches++;
-            // Only the sign of lambda_min relative to tol_feasibility_dual is consumed (dual_feasible_user_tol,
-            // pdhg.jl:712-732), so the extreme eigenvalue is resolved to 1e-3 of that tolerance, not to 1e-10.
-            int K = (int)std::max<long long>(opt.eigsolver_min_lanczos, 3);
-            const double tol_ev = std::max(1e-10, 1e-3 * std::min(opt.tol_feasibility_dual, 1.0));
-            // ... and a Ritz value of -Z above the tolerance already proves the violation (Ritz values are lower bounds
-            // of lambda_max), so the eigsolve may stop there instead of converging an interior-looking extreme pair
-            lz_stop_above_ = opt.tol_feasibility_dual;
-            lanczos_launch(cd, k, 1, K, 60, tol_ev);
-            lz_stop_above_ = 1e300;
-            PB_CUDA(cudaStreamSynchronize(stream));
-            std::vector<double> vals = cd.vals.download();
-            double lmin = -vals[0];
-            cone_viol = std::max(cone_viol, -std::min(0.0, lmin));
-        }
+        cone_viol = std::max(cone_viol, -std::min(0.0, lmin));
     }
-    long long cont = psd_end_;
-    for (int k = 0; k < n_soc; ++k) {
-        long long len = soc_len_h_[(size_t)k];
-        double sv = dc[(size_t)cont], nv = 0.0;
-        for (long long i = 1; i < len; ++i) nv += dc[(size_t)(cont + i)] * dc[(size_t)(cont + i)];
-        cone_viol = std::max(cone_viol, -std::min(0.0, sv - std::sqrt(nv)));
-        cont += len;
-    }
-    double zero_viol = 0.0;
-    for (long long i = cont; i < n; ++i) zero_viol = std::max(zero_viol, std::fabs(dc[(size_t)i]));
-    return std::max(cone_viol, std::max(ineq_viol, zero_viol));
+    PB_CUDA(cudaMemcpyAsync(feas_host_, feas_d_.p, sizeof(double) * FS_COUNT, cudaMemcpyDeviceToHost, stream));
+    PB_CUDA(cudaStreamSynchronize(stream));
+    g_d2h_bytes += (long long)sizeof(double) * FS_COUNT;
+    cone_viol = std::max(cone_viol, std::max(feas_host_[FS_SOC], feas_host_[FS_SMALL_PSD]));
+    return std::max(cone_viol, std::max(feas_host_[FS_INEQ], feas_host_[FS_ZERO]));
 }
 
-// off-diagonal svec entries of every PSD block: x /= num (divide != 0, fix_diag_scaling pdhg.jl:734-743)
-// or x *= num (divide == 0, norm_scaling scaling.jl:28-58)
-__global__ void k_scale_offdiag(double* __restrict__ x, const int* __restrict__ cone_side,
-                                const long long* __restrict__ cone_off, int n_sdp, double num, int divide) {
-    int cone = blockIdx.y;
-    if (cone >= n_sdp) return;
-    int side = cone_side[cone];
-    long long tri = (long long)side * (side + 1) / 2;
-    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < tri; k += (long long)gridDim.x * blockDim.x) {
-        long long j = (long long)((sqrt(8.0 * (double)k + 1.0) - 1.0) * 0.5);
-        while ((j + 1) * (j + 2) / 2 <= k) ++j;
-        while (j * (j + 1) / 2 > k) --j;
-        long long i = k - j * (j + 1) / 2;
-        if (i != j) { if (divide) x[cone_off[cone] + k] /= num; else x[cone_off[cone] + k] = __dmul_rn(x[cone_off[cone] + k], num); }
+// dst = src with the off-diagonal svec entries of every PSD block divided by num (divide != 0: fix_diag_scaling,
+// pdhg.jl:734-743) or multiplied by num (divide == 0: norm_scaling, scaling.jl:28-58); src == dst is allowed
+__global__ void k_scale_offdiag_copy(const double* __restrict__ src, long long n, long long psd_end,
+                                     const long long* __restrict__ cone_off, int n_sdp, double num, int divide,
+                                     double* __restrict__ dst) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) {
+        double v = src[k];
+        if (offdiag_position(k, psd_end, cone_off, n_sdp)) v = divide ? v / num : __dmul_rn(v, num);
+        dst[k] = v;
     }
 }
 
@@ -1357,40 +1249,49 @@ __global__ void k_scale_copy(const double* __restrict__ src, double a, long long
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = __dmul_rn(a, src[i]);
 }
 
-// cache_solution (pdhg.jl:745-787).  Like the reference it rescales pair.x IN PLACE.
-void Solver::cache_solution(const double* c_res, proxsdp_result_t* out) {
-    StageTimer st("finish: fix scaling+download");
-    if (n_sdp > 0) {
-        k_scale_offdiag<<<dim3(64, n_sdp), 256, 0, stream>>>(x_[cur_].p, cone_side_d_.p, cone_off_d_.p, n_sdp, std::sqrt(2.0), 1);
+// cache_solution (pdhg.jl:745-787).  Like the reference it rescales pair.x IN PLACE.  Slacks, duals and the dual
+// feasibility are computed by the kernels of kernels_result.cuh; every output vector is downloaded once, straight
+// into the caller's buffer (pinned or pageable).
+void Solver::cache_solution(double c_factor, proxsdp_result_t* out) {
+    StageTimer st("finish: scaling + slack");
+    const int blocks_n = std::max(1, std::min(reduce_blocks_, ceil_div(n, 256)));
+    if (n_sdp > 0 && n > 0) {
+        k_scale_offdiag_copy<<<blocks_n, 256, 0, stream>>>(x_[cur_].p, n, psd_end_, cone_off_d_.p, n_sdp, std::sqrt(2.0), 1, x_[cur_].p);
         launches++;
     }
-    PB_CUDA(cudaStreamSynchronize(stream));
-    std::vector<double> x = x_[cur_].download(), y = y_[cur_].download();
-    st.lap("finish: slack");
-    std::vector<double> slack((size_t)R, 0.0);
-    for (long long j = 0; j < n; ++j) {
-        double xj = x[(size_t)j];
-        for (long long q = mt_colptr_[(size_t)j]; q < mt_colptr_[(size_t)j + 1]; ++q)
-            slack[(size_t)mt_rowidx_[(size_t)q]] += mt_val_orig_[(size_t)q] * xj;
+    const double* xw = x_[cur_].p;
+    const double* yw = y_[cur_].p;
+    if (res_slack_d_.n < (size_t)R) res_slack_d_.alloc_raw((size_t)R);
+    if (R > 0 && !cones_only_) {
+        k_slack<<<std::max(1, std::min(reduce_blocks_, ceil_div(R * 32, 256))), 256, 0, stream>>>(
+            (int)R, M_.rowptr.p, M_.colidx.p, M_.val_orig.p, xw, b_orig_d_.p, (int)p, h_orig_d_.p, res_slack_d_.p);
+        launches++;
     }
     st.lap("finish: dual_feas");
-    std::vector<double> cvec(c_res, c_res + n), dual_cone;
-    double dfeas = dual_feas_host(y, cvec, &dual_cone);
+    double dfeas = dual_feas_device(yw, c_factor);
     host_reduce(&dfeas, 1, 1);
     st.lap("finish: outputs");
     out->status = stop_reason_;
     snprintf(out->status_string, PROXSDP_STATUS_STRING_LEN, "%s", stop_reason_string_.c_str());
+    auto d2h = [&](double* dst, const double* src, long long cnt) {
+        if (!dst || cnt <= 0) return;
+        PB_CUDA(cudaMemcpyAsync(dst, src, sizeof(double) * (size_t)cnt, cudaMemcpyDeviceToHost, stream));
+        g_d2h_bytes += (long long)sizeof(double) * cnt;
+    };
     if (identity_) {
-        if (out->primal && n > 0) std::memcpy(out->primal, x.data(), sizeof(double) * (size_t)n);
-        if (out->dual_cone && n > 0) std::memcpy(out->dual_cone, dual_cone.data(), sizeof(double) * (size_t)n);
+        d2h(out->primal, xw, n);
+        d2h(out->dual_cone, res_dc_d_.p, n);
     } else {
-        if (out->primal) for (long long i = 0; i < n; ++i) out->primal[i] = x[(size_t)var_ordering_[(size_t)i]];
-        if (out->dual_cone) for (long long i = 0; i < n; ++i) out->dual_cone[i] = dual_cone[(size_t)var_ordering_[(size_t)i]];
+        // user order: result[i] = v[var_ordering[i]] (pdhg.jl:768-769)
+        if (res_user_d_.n < (size_t)(2 * n)) res_user_d_.alloc_raw((size_t)(2 * n));
+        if (out->primal) { launch_gather(xw, var_ordering_d_.p, n, res_user_d_.p, stream); launches++; d2h(out->primal, res_user_d_.p, n); }
+        if (out->dual_cone) { launch_gather(res_dc_d_.p, var_ordering_d_.p, n, res_user_d_.p + n, stream); launches++; d2h(out->dual_cone, res_user_d_.p + n, n); }
     }
-    if (out->dual_eq) for (long long i = 0; i < p; ++i) out->dual_eq[i] = y[(size_t)i];
-    if (out->dual_in) for (long long i = 0; i < m; ++i) out->dual_in[i] = y[(size_t)(p + i)];
-    if (out->slack_eq) for (long long i = 0; i < p; ++i) out->slack_eq[i] = slack[(size_t)i] - b_orig_[(size_t)i];
-    if (out->slack_in) for (long long i = 0; i < m; ++i) out->slack_in[i] = slack[(size_t)(p + i)] - h_orig_[(size_t)i];
+    d2h(out->dual_eq, yw, p);
+    d2h(out->dual_in, yw + p, m);
+    d2h(out->slack_eq, res_slack_d_.p, p);
+    d2h(out->slack_in, res_slack_d_.p + p, m);
+    PB_CUDA(cudaStreamSynchronize(stream));
     out->primal_residual = equa_feasibility_;
     out->dual_residual = ineq_feasibility_;
     out->objval = prim_obj_.get(iter_);
@@ -1493,13 +1394,13 @@ bool Solver::run(long long max_steps, bool flush_l2) {
             PB_CUDA(cudaEventRecord(ev_fl1_, stream));
         }
         // ------------------------------------------------------------------ device work
-        reset_scalars();
+        if (!scal_clean_) reset_scalars();
         double tau_primal = primal_step_;                       // pdhg.jl:622 uses the current step
         psd_projection_launch(k, tau_primal, false);
         double tau0 = opt.line_search_flag ? primal_step_ * std::sqrt(1.0 + theta_) : primal_step_;   // pdhg.jl:541
         launch_post_eig(tau0, true);
         PB_CUDA(cudaEventRecord(ev_post1_, stream));
-        sync_scalars();
+        sync_scalars(true);
         {
             float ms = 0.f;
             if (n_sdp > 0) {
@@ -1515,23 +1416,35 @@ bool Solver::run(long long max_steps, bool flush_l2) {
             fallback_projection(k);
             launch_post_eig(tau0, false);
             double keep_ops = scal_host[S_NUMOPS];
-            sync_scalars();
+            sync_scalars(true);
             scal_host[S_NUMOPS] = keep_ops;
         }
         // ---- linesearch beyond the speculative ladder (pdhg.jl:543-571)
         long long evals = (long long)scal_host[S_LS_EVALS];
+        bool ls_exhausted = false;
+        double ls_last_tau = 0.0;
         if (opt.line_search_flag && scal_host[S_LS_ACCEPTED] == 0.0) {
-            long long t = sharded() ? 1 : ladder_;
+            long long t = sharded() ? 1 : std::min<long long>(ladder_, std::max<long long>(opt.max_linsearch_steps, 1));
+            const double keep_ops = scal_host[S_NUMOPS];
             while (scal_host[S_LS_ACCEPTED] == 0.0 && t < opt.max_linsearch_steps) {
-                launch_dual_trial((int)t, tau0);
-                sync_scalars();
-                ++t;
+                if (!sharded() && fused_ladder_) {
+                    // the next batch of trials, again side by side
+                    const int T = (int)std::min<long long>(ladder_, opt.max_linsearch_steps - t);
+                    launch_ladder((int)t, T, tau0);
+                    sync_scalars();
+                    t = (long long)scal_host[S_LS_EVALS];
+                } else {
+                    launch_dual_trial((int)t, tau0);
+                    sync_scalars();
+                    ++t;
+                }
             }
             evals = t;
             if (scal_host[S_LS_ACCEPTED] == 0.0) {
                 // loop exhausted: the reference keeps the last trial's y/Mty and the once-more decayed step
                 double tau = tau0;
-                for (long long q = 0; q < opt.max_linsearch_steps; ++q) tau *= opt.linsearch_decay;
+                for (long long q = 0; q < opt.max_linsearch_steps; ++q) { if (q == opt.max_linsearch_steps - 1) ls_last_tau = tau; tau *= opt.linsearch_decay; }
+                ls_exhausted = true;
                 double rec[3] = {1.0, (double)(opt.max_linsearch_steps - 1), tau};
                 PB_CUDA(cudaMemcpyAsync(scal_d_.p + S_LS_ACCEPTED, rec, sizeof(rec), cudaMemcpyHostToDevice, stream));
                 PB_CUDA(cudaStreamSynchronize(stream));
@@ -1542,7 +1455,8 @@ bool Solver::run(long long max_steps, bool flush_l2) {
             k_residual_dual<<<blocksR, 256, 0, stream>>>((int)p, (int)m, beta_, 1, dual_step_, y_[1 - cur_].p, y_[cur_].p,
                                                          Mx_[1 - cur_].p, Mx_[cur_].p, b_.p, h_.p, scal_d_.p, ws_);
             launches += 2;
-            sync_scalars();
+            sync_scalars(true);
+            scal_host[S_NUMOPS] = keep_ops;
         }
         linesearch_trials += std::max<long long>(evals, 1);
         lanczos_matvecs += (long long)scal_host[S_NUMOPS];
@@ -1551,7 +1465,9 @@ bool Solver::run(long long max_steps, bool flush_l2) {
         // linesearch! epilogue (pdhg.jl:577-579) / dual_step! (pdhg.jl:606)
         if (opt.line_search_flag) {
             primal_step_ = scal_host[S_TAU];
-            theta_ = primal_step_ / primal_step_old_;
+            // theta belongs to the last trial that was evaluated (pdhg.jl:544): when the loop runs out of trials the
+            // step is decayed once more (pdhg.jl:569) but theta is not recomputed
+            theta_ = (ls_exhausted ? ls_last_tau : primal_step_) / primal_step_old_;
             primal_step_old_ = primal_step_;
             dual_step_ = beta_ * primal_step_;
         } else {
@@ -1586,10 +1502,7 @@ bool Solver::run(long long max_steps, bool flush_l2) {
 
         if (opt.check_dual_feas && (k % opt.check_dual_feas_freq) == 0) {     // pdhg.jl:166-173
             double f = stop_reason_ == 6 ? 0.0 : 1.0;
-            std::vector<double> cc((size_t)n);
-            for (long long i = 0; i < n; ++i) cc[(size_t)i] = f * c_orig_[(size_t)i];
-            std::vector<double> y = y_[cur_].download();
-            dual_feasibility_ = dual_feas_host(y, cc, nullptr);
+            dual_feasibility_ = dual_feas_device(y_[cur_].p, f);
             host_reduce(&dual_feasibility_, 1, 1);
             dual_feasibility_check_ = true;
         } else {
@@ -1602,9 +1515,7 @@ bool Solver::run(long long max_steps, bool flush_l2) {
         if (opt.certificate_search && certificate_search_) {                  // pdhg.jl:184-244
             if (stop_reason_ == 6) {
                 if (dual_obj_.get(k) > +opt.certificate_obj_tol) {
-                    std::vector<double> cc((size_t)n, 0.0);
-                    std::vector<double> y = y_[cur_].download();
-                    dual_feasibility_ = dual_feas_host(y, cc, nullptr);
+                    dual_feasibility_ = dual_feas_device(y_[cur_].p, 0.0);
                     host_reduce(&dual_feasibility_, 1, 1);
                     dual_feasibility_check_ = true;
                     if (dual_feasibility_ < opt.tol_feasibility_dual) {
@@ -1693,7 +1604,7 @@ bool Solver::run(long long max_steps, bool flush_l2) {
             certificate_search_ = true;
             opt.time_limit *= 1.1;
             opt.max_iter_local = opt.max_iter_local + opt.max_iter_local / 10;
-            cache_solution(c_orig_.data(), out); have_cached = true;
+            cache_solution(1.0, out); have_cached = true;
         };
         auto start_cert_dual_infeas = [&]() {  // certificate_dual_infeasibility (pdhg.jl:639-653)
             std::fill(b_host_.begin(), b_host_.end(), 0.0);
@@ -1704,7 +1615,7 @@ bool Solver::run(long long max_steps, bool flush_l2) {
             certificate_search_ = true;
             opt.time_limit *= 1.1;
             opt.max_iter_local = opt.max_iter_local + opt.max_iter_local / 10;
-            cache_solution(c_orig_.data(), out); have_cached = true;
+            cache_solution(1.0, out); have_cached = true;
         };
 
         // max_iter or time limit (pdhg.jl:335-382)
@@ -1804,13 +1715,12 @@ void Solver::finish(proxsdp_result_t* out) {
     // results (pdhg.jl:486-529)
     if (opt.certificate_search && certificate_search_) {
         if (certificate_found_) {
-            if (stop_reason_ == 6) std::fill(c_orig_.begin(), c_orig_.end(), 0.0);
-            cache_solution(c_orig_.data(), out);
+            cache_solution(stop_reason_ == 6 ? 0.0 : 1.0, out);     // pdhg.jl:515-517: c_orig .*= 0 for a dual ray
         } else if (!have_cached_) {
-            cache_solution(c_orig_.data(), out);
+            cache_solution(1.0, out);
         }
     } else {
-        cache_solution(c_orig_.data(), out);
+        cache_solution(1.0, out);
     }
     out->time_psd_proj = time_psd_ms_ * 1e-3;
     out->n_psd_proj = n_psd_;
@@ -2172,6 +2082,25 @@ int proxsdp_b200_eigh(int64_t n, const double* A, double* w, double* Z) {
                 std::memcpy(Z + j * n, V.data() + (size_t)order[(size_t)j] * (size_t)n, sizeof(double) * (size_t)n);
         }
     });
+}
+
+// page-locked host memory from the library's cache: result / input vectors that live in it are copied at full PCIe
+// rate without staging (and without first-touch page faults on a fresh 16 MB result vector)
+void* proxsdp_b200_host_alloc(int64_t bytes) {
+    if (bytes < 0) { g_last_error = "invalid argument"; return nullptr; }
+    void* p = nullptr;
+    int rc = guarded([&]() {
+        int ndev = 0;
+        if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) throw CudaError(-5, "no CUDA device available");
+        p = pb_host_alloc((size_t)std::max<int64_t>(bytes, 1));
+    });
+    return rc == 0 ? p : nullptr;
+}
+int proxsdp_b200_host_free(void* ptr) {
+    return guarded([&]() { pb_host_free(ptr); });
+}
+int proxsdp_b200_trim_caches(void) {
+    return guarded([&]() { cudaDeviceSynchronize(); pb_cache_trim(); });
 }
 
 int proxsdp_b200_device_count(void) {

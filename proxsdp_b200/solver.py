@@ -57,8 +57,52 @@ def lib():
     L.proxsdp_b200_eigh.argtypes = [c_int64, _pd, _pd, _pd]
     L.proxsdp_b200_eigh.restype = c_int
     L.proxsdp_b200_device_count.restype = c_int
+    L.proxsdp_b200_host_alloc.argtypes = [c_int64]
+    L.proxsdp_b200_host_alloc.restype = ctypes.c_void_p
+    L.proxsdp_b200_host_free.argtypes = [ctypes.c_void_p]
+    L.proxsdp_b200_host_free.restype = c_int
     _lib = L
     return L
+
+
+def pinned_empty(count: int, dtype=np.float64) -> np.ndarray:
+    """Uninitialised array in page-locked host memory from the library's cache (`proxsdp_b200_host_alloc`); the
+    block goes back to the cache when the last view of the array is collected."""
+    import weakref
+    L = lib()
+    dt = np.dtype(dtype)
+    nbytes = max(int(count) * dt.itemsize, 1)
+    ptr = L.proxsdp_b200_host_alloc(nbytes)
+    if not ptr:
+        raise RuntimeError(f"proxsdp_b200_host_alloc failed: {L.proxsdp_b200_last_error().decode()}")
+    raw = (ctypes.c_char * nbytes).from_address(ptr)
+    weakref.finalize(raw, L.proxsdp_b200_host_free, ctypes.c_void_p(ptr))
+    return np.frombuffer(raw, dtype=dt, count=int(count))
+
+
+def pinned_copy(a) -> np.ndarray:
+    a = np.ascontiguousarray(a)
+    out = pinned_empty(a.size, a.dtype)
+    out[...] = a.ravel()
+    return out.reshape(a.shape)
+
+
+def pin_problem(aff: AffineSets, con: ConicSets):
+    """The same problem with every array of the `chambolle_pock` arguments in page-locked memory and the matrices as
+    SparseMatrixCSC{Float64,Int64} (what a Julia caller holds): the C ABI then reads the caller's buffers in place."""
+    from .structs import SDPSet, SOCSet, SparseMatrixCSC
+
+    def mat(M):
+        M = M if isinstance(M, SparseMatrixCSC) else SparseMatrixCSC.from_scipy(M)
+        return SparseMatrixCSC(M.m, M.n, pinned_copy(M.colptr), pinned_copy(M.rowval), pinned_copy(M.nzval))
+
+    def vec(v, dtype=np.float64):
+        return pinned_copy(np.asarray(v, dtype=dtype))
+
+    aff2 = AffineSets(aff.n, aff.p, aff.m, aff.extra, mat(aff.A), mat(aff.G), vec(aff.b), vec(aff.h), vec(aff.c))
+    con2 = ConicSets([SDPSet(vec(s.vec_i, np.int64), s.tri_len, s.sq_side) for s in con.sdpcone],
+                     [SOCSet(vec(s.idx, np.int64), s.len) for s in con.socone])
+    return aff2, con2
 
 
 def _check(rc: int):
@@ -82,7 +126,7 @@ def chambolle_pock(aff: AffineSets, con: ConicSets, opt: Options, eig_resid=None
     """Drop-in for reference src/pdhg.jl:1 `chambolle_pock(affine_sets, conic_sets, opt)::Result`."""
     L = lib()
     fn = bind_solve(L, "proxsdp_b200_solve")
-    return call_solve(fn, aff, con, opt, eig_resid, err_fn=L.proxsdp_b200_last_error)
+    return call_solve(fn, aff, con, opt, eig_resid, err_fn=L.proxsdp_b200_last_error, empty=pinned_empty)
 
 
 class Solve:

@@ -13,9 +13,44 @@ import numpy as np
 import scipy.sparse as sp
 
 
+class SparseMatrixCSC:
+    """Julia's `SparseMatrixCSC{Float64,Int64}` (the type of `AffineSets.A` / `.G`, structs.jl:32-42) as three flat
+    arrays: colptr (n + 1, int64), rowval (nnz, int64), nzval (nnz, float64), 0-based.  scipy down-casts index arrays
+    to int32, so a scipy matrix has to be widened on every call of the C ABI; a problem held in this form crosses the
+    boundary without a copy."""
+
+    __slots__ = ("m", "n", "colptr", "rowval", "nzval")
+
+    def __init__(self, m: int, n: int, colptr, rowval, nzval):
+        self.m, self.n = int(m), int(n)
+        self.colptr = np.ascontiguousarray(colptr, dtype=np.int64)
+        self.rowval = np.ascontiguousarray(rowval, dtype=np.int64)
+        self.nzval = np.ascontiguousarray(nzval, dtype=np.float64)
+        assert self.colptr.shape == (self.n + 1,) and self.rowval.shape == self.nzval.shape
+
+    @property
+    def shape(self):
+        return (self.m, self.n)
+
+    @property
+    def nnz(self) -> int:
+        return int(self.nzval.size)
+
+    @classmethod
+    def from_scipy(cls, M) -> "SparseMatrixCSC":
+        M = sp.csc_matrix(M)
+        if not M.has_canonical_format:
+            M = M.copy()
+            M.sum_duplicates()
+        return cls(M.shape[0], M.shape[1], M.indptr, M.indices, M.data)
+
+    def to_scipy(self) -> sp.csc_matrix:
+        return sp.csc_matrix((self.nzval, self.rowval, self.colptr), shape=(self.m, self.n))
+
+
 @dataclass
 class AffineSets:
-    """structs.jl:32-42.  A is p x n, G is m x n (scipy CSC), b (p), h (m), c (n)."""
+    """structs.jl:32-42.  A is p x n, G is m x n (scipy CSC or SparseMatrixCSC), b (p), h (m), c (n)."""
 
     n: int
     p: int

@@ -1,0 +1,343 @@
+"""GPU parity tests, part 2: whole solves to termination and the branches of the hot path that part 1 does not reach.
+
+Everything is compared with the CPU oracle (oracle/: the restated reference — Julia itself is not installed, so this is
+"parity vs the restated reference"), through the C ABI, on identical inputs:
+
+  * full solves of the headline instance (Max-Cut ER n = 2000, config C2) and of SDPLIB maxG32 / mcp500-1 (exact mode);
+  * the Krylov-failure fallback of `psd_projection!` (reference src/prox_operators.jl:55-57);
+  * line searches that need more trials than the speculative ladder, and exhausted line searches (src/pdhg.jl:543-571);
+  * `check_dual_feas = true` (src/pdhg.jl:166-173) and the device-side `get_duals` / `dual_feas` (src/pdhg.jl:701-732);
+  * infeasible / unbounded problems with certificate search: statuses, rays and duals (src/pdhg.jl:184-244, 639-676);
+  * `min_size_krylov_eigs` below 100: small cones on the Krylov path (src/prox_operators.jl:46-49);
+  * problems whose variable order is not [PSD | SOC | free] (device-side `preprocess!`, src/scaling.jl:2-26), 1-based
+    indices, problems held as SparseMatrixCSC{Float64,Int64} in page-locked memory;
+  * the FP64 / two-pass switch of the Lanczos step (PROXSDP_B200_LZ_STRICT=1): the suite passes both ways.
+
+Tolerances: 1e-6 relative on objective, gap, feasibility and residuals (the north_star bar) wherever the two
+implementations walk through the same iterations; where a truncated-projection trajectory separates by rounding
+ the test says so and falls back to the band the solver tolerances imply.
+"""
+import os
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from proxsdp_b200 import Options
+from proxsdp_b200.problems import load_problem, maxcut_er_problem, mimo_problem, sensorloc_problem, stack_problems
+from proxsdp_b200.structs import AffineSets, ConicSets, SDPSet, SOCSet, SparseMatrixCSC, ivec
+
+pytestmark = pytest.mark.gpu
+
+SCALARS = ("objval", "dual_objval", "gap", "primal_residual", "dual_residual", "final_primal_res", "final_dual_res")
+
+
+def _rel(a, b):
+    return abs(a - b) / max(1.0, abs(b))
+
+
+def _vec_close(a, b, rtol):
+    a, b = np.asarray(a), np.asarray(b)
+    if a.size == 0:
+        return True
+    return np.abs(a - b).max() <= rtol * max(1.0, np.abs(b).max())
+
+
+def _same_solution(rg, ro, rtol=1e-6, vectors=True):
+    assert rg.status == ro.status, (rg.status_string, ro.status_string)
+    assert rg.iter == ro.iter
+    for name in SCALARS:
+        assert _rel(getattr(rg, name), getattr(ro, name)) <= rtol, (name, getattr(rg, name), getattr(ro, name))
+    if vectors:
+        for name in ("primal", "dual_cone", "dual_eq", "dual_in", "slack_eq", "slack_in"):
+            assert _vec_close(getattr(rg, name), getattr(ro, name), rtol), name
+    assert rg.primal_feasible_user_tol == ro.primal_feasible_user_tol
+    assert rg.dual_feasible_user_tol == ro.dual_feasible_user_tol
+    assert rg.certificate_found == ro.certificate_found
+    assert rg.final_rank == ro.final_rank
+
+
+@pytest.fixture(params=["default", "strict"])
+def lz_mode(request, monkeypatch):
+    """Run the test with the default Lanczos step and with KrylovKit's arithmetic to the letter (FP64 alpha, two
+    Gram-Schmidt passes every step)."""
+    if request.param == "strict":
+        monkeypatch.setenv("PROXSDP_B200_LZ_STRICT", "1")
+    else:
+        monkeypatch.delenv("PROXSDP_B200_LZ_STRICT", raising=False)
+    return request.param
+
+
+# ------------------------------------------------------------------ full solves of the headline instances
+def _full_solve_check(gpu, oracle_mod, golden_dir, name, aff, con, sdplib_optimum=None):
+    z = np.load(f"{golden_dir}/full_{name}.npz")
+    opt = Options(trace_cap=int(z["iters"]) + 2000)
+    rg = gpu.chambolle_pock(aff, con, opt)
+    assert rg.status == int(z["status"]) == 1
+    tr_o, tr_g = z["trace"], rg.trace
+    # how long do the two runs walk through the same iterations?  (identical Lanczos mat-vec counts and 1e-6 traces)
+    k = min(len(tr_o), len(tr_g))
+    same = np.abs(tr_g[:k, 1:7] - tr_o[:k, 1:7]) <= 1e-6 * np.maximum(1.0, np.abs(tr_o[:k, 1:7]))
+    agree = int(np.argmin(same.all(axis=1))) if not same.all() else k
+    print(f"{name}: GPU {rg.iter} iterations, oracle {int(z['iters'])}; traces agree to 1e-6 for the first {agree} iterations")
+    assert agree >= min(k, 40)
+    if rg.iter == int(z["iters"]) and agree == k:
+        for key in SCALARS:
+            assert _rel(getattr(rg, key), float(z[key])) <= 1e-6, key
+    else:
+        # the trajectories separated by rounding at a truncated projection: both runs stop where the reference's
+        # tolerances (tol_gap = tol_feasibility = 1e-4 relative) let them
+        assert abs(rg.iter - int(z["iters"])) <= 0.25 * int(z["iters"])
+        assert _rel(rg.objval, float(z["objval"])) <= 5e-4
+    assert rg.gap <= opt.tol_gap and rg.primal_residual <= opt.tol_feasibility
+    assert rg.primal_feasible_user_tol
+    if sdplib_optimum is not None:
+        assert abs(rg.objval - sdplib_optimum) <= 5e-3 * abs(sdplib_optimum)
+    return rg
+
+
+def test_full_solve_c2_headline(gpu, oracle_mod, golden_dir, lz_mode):
+    """BASELINE config C2 to termination: status, iterations, objective, gap, feasibility, residuals vs the oracle's run
+    (tests/golden/full_c2.npz, written by tests/golden/make_full_solves.py)."""
+    aff, con = maxcut_er_problem(2000, 0.01, 0)
+    rg = _full_solve_check(gpu, oracle_mod, golden_dir, "c2", aff, con)
+    X = ivec(rg.primal)
+    assert np.abs(np.diag(X) - 1.0).max() <= 1e-3                           # diag(X) = 1
+    w = np.linalg.eigvalsh(X)
+    assert w.min() >= -1e-4 * w.max()                                       # minus_rank == 0 (test/moi_sdplib.jl:53-56)
+
+
+def test_full_solve_maxG32(gpu, oracle_mod, golden_dir):
+    """SDPLIB maxG32 (n = 2000, reference test/data/maxG32.dat-s): full solve vs the oracle's run and the SDPLIB optimum."""
+    aff, con = load_problem(f"{golden_dir}/sdplib_maxG32.npz")
+    _full_solve_check(gpu, oracle_mod, golden_dir, "maxG32", aff, con, sdplib_optimum=-1567.640)
+
+
+def test_full_solve_exact_mode_mcp500(gpu, oracle_mod, golden_dir):
+    """SURVEY 8(d) parity gate: exact-projection mode on mcp500-1 to termination (block-Jacobi full eigendecomposition of
+    the 500 x 500 cone in every iteration) against the oracle's run."""
+    aff, con = load_problem(f"{golden_dir}/sdplib_mcp500-1.npz")
+    z = np.load(f"{golden_dir}/full_mcp500-1_exact.npz")
+    opt = Options(full_eig_decomp=True, trace_cap=int(z["iters"]) + 10)
+    rg = gpu.chambolle_pock(aff, con, opt)
+    assert rg.status == int(z["status"]) == 1 and rg.iter == int(z["iters"])
+    ref = z["trace"][:, 1:9]
+    assert np.abs(rg.trace[:, 1:9] - ref).max() <= 1e-6 * max(1.0, np.abs(ref).max())
+    for key in SCALARS:
+        assert _rel(getattr(rg, key), float(z[key])) <= 1e-6, key
+    assert abs(rg.objval - (-598.1485)) <= 5e-3 * 598.1485                   # SDPLIB optimum of mcp500-1
+
+
+# ------------------------------------------------------------------ branches of the projection dispatcher
+def test_krylov_failure_falls_back_to_full_eig(gpu, oracle_mod, golden_dir):
+    """converged == 0 => full_eig! (prox_operators.jl:55-57): krylovkit_max_iter = 1 with an unreachable tolerance makes
+    every eigsolve fail, so every projection is redone exactly; traces equal the oracle's, which takes the same branch."""
+    aff, con = load_problem(f"{golden_dir}/sdplib_mcp124-1.npz")
+    opt = Options(krylovkit_max_iter=1, krylovkit_tol=1e-30, max_iter=60, trace_cap=60)
+    rg = gpu.chambolle_pock(aff, con, opt)
+    ro = oracle_mod.chambolle_pock(aff, con, opt)
+    assert ro.full_eig_calls >= 55 and rg.full_eig_calls == ro.full_eig_calls and rg.lanczos_calls == ro.lanczos_calls
+    assert np.abs(rg.trace[:, 1:9] - ro.trace[:, 1:9]).max() <= 1e-6 * max(1.0, np.abs(ro.trace[:, 1:9]).max())
+    assert list(rg.trace[:, 12]) == list(ro.trace[:, 12])
+    _same_solution(rg, ro)
+
+
+@pytest.mark.parametrize("side,nev", [(3, 2), (7, 2), (24, 3), (40, 2), (64, 2), (65, 4), (100, 5)])
+def test_lanczos_small_sides(gpu, oracle_mod, side, nev):
+    """Krylov dimension above the matrix size (KrylovKit runs into an invariant subspace) and the hand-over between the
+    one-CTA row kernel (side < 64) and the cluster kernels."""
+    rng = np.random.default_rng(side)
+    B = rng.standard_normal((side, min(side, 3)))
+    S = rng.standard_normal((side, side))
+    A = B @ B.T - 0.1 * np.eye(side) + 0.01 * (S + S.T)
+    x0 = oracle_mod.eig_resid(side)
+    vo, Vo, io = oracle_mod.lanczos(np.triu(A), x0, nev, 25)
+    vg, Vg, ig = gpu.lanczos(A, x0, nev, 25)
+    assert (ig["converged"], ig["numops"], ig["numiter"]) == (io["converged"], io["numops"], io["numiter"])
+    assert len(vg) == len(vo) and np.abs(vo - vg).max() <= 1e-9 * max(1.0, np.abs(vo).max())
+    assert np.abs(A @ Vg - Vg * vg).max() <= 1e-8 * max(1.0, np.abs(vo).max())
+
+
+def test_min_size_krylov_eigs_is_honoured_for_small_cones(gpu, oracle_mod):
+    """prox_operators.jl:46-49 with min_size_krylov_eigs below the cone side: cones of side <= 100 take the Krylov
+    path (truncated projection, target rank and min_eig tracking) exactly like the reference."""
+    import problems_ref
+    from proxsdp_b200 import Optimizer
+    # reference test/moi_proxsdp_unit.jl:359-369: sdp_wiki (3 x 3 cone) with min_size_krylov_eigs = 1
+    og = Optimizer(min_size_krylov_eigs=1, eigsolver=2)
+    problems_ref.check(problems_ref.sdp_wiki(og))
+    oo = Optimizer(backend=oracle_mod.chambolle_pock, min_size_krylov_eigs=1, eigsolver=2)
+    problems_ref.sdp_wiki(oo)
+    assert og.sol.lanczos_calls == oo.sol.lanczos_calls > 0 and og.sol.full_eig_calls == oo.sol.full_eig_calls
+    _same_solution(og.sol, oo.sol)
+    # a 31 x 31 and a stack of 17 x 17 cones
+    for aff, con in (mimo_problem(7, 30), stack_problems([mimo_problem(40 + s, 16) for s in range(5)])):
+        opt = Options(min_size_krylov_eigs=10, trace_cap=3000)
+        rg = gpu.chambolle_pock(aff, con, opt)
+        ro = oracle_mod.chambolle_pock(aff, con, opt)
+        assert ro.lanczos_calls > 0 and rg.lanczos_calls == ro.lanczos_calls and rg.lanczos_matvecs == ro.lanczos_matvecs
+        assert list(rg.trace[:, 12]) == list(ro.trace[:, 12])
+        _same_solution(rg, ro)
+
+
+# ------------------------------------------------------------------ line search
+@pytest.mark.parametrize("kw", [dict(linsearch_decay=0.97),                     # up to 16 trials: beyond the 4-trial ladder
+                                dict(max_linsearch_steps=2, delta=0.3),         # exhausted line searches (theta of the last trial)
+                                dict(max_linsearch_steps=1),
+                                dict(linsearch_decay=0.97, max_linsearch_steps=3)], ids=str)
+def test_linesearch_beyond_the_ladder_and_exhausted(gpu, oracle_mod, kw):
+    aff, con = mimo_problem(7, 16)
+    opt = Options(trace_cap=5000, **kw)
+    rg = gpu.chambolle_pock(aff, con, opt)
+    ro = oracle_mod.chambolle_pock(aff, con, opt)
+    assert list(rg.trace[:, 13]) == list(ro.trace[:, 13])                       # identical trial counts, every iteration
+    if "linsearch_decay" in kw and "max_linsearch_steps" not in kw:
+        assert ro.trace[:, 13].max() > 4
+    assert np.abs(rg.trace[:, 1:9] - ro.trace[:, 1:9]).max() <= 1e-6 * max(1.0, np.abs(ro.trace[:, 1:9]).max())
+    _same_solution(rg, ro)
+
+
+# ------------------------------------------------------------------ dual feasibility on the device
+def test_check_dual_feas_option(gpu, oracle_mod, golden_dir):
+    """check_dual_feas = true (pdhg.jl:166-173, 249): termination additionally waits for dual feasibility, evaluated
+    by the device-side get_duals / cone_feas every check_dual_feas_freq iterations."""
+    aff, con = mimo_problem(11, 12)
+    opt = Options(check_dual_feas=True, check_dual_feas_freq=7, trace_cap=5000)
+    rg = gpu.chambolle_pock(aff, con, opt)
+    ro = oracle_mod.chambolle_pock(aff, con, opt)
+    _same_solution(rg, ro)
+    # large cone: Lanczos-based cone_feas (sign of lambda_min) must take the same decisions as the oracle's exact eigen!
+    aff, con = load_problem(f"{golden_dir}/sdplib_mcp124-1.npz")
+    opt = Options(check_dual_feas=True, check_dual_feas_freq=10, max_iter=400, trace_cap=400)
+    rg = gpu.chambolle_pock(aff, con, opt)
+    ro = oracle_mod.chambolle_pock(aff, con, opt)
+    assert rg.iter == ro.iter and rg.status == ro.status
+    k = 40
+    assert np.abs(rg.trace[:k, 1:9] - ro.trace[:k, 1:9]).max() <= 1e-6 * max(1.0, np.abs(ro.trace[:k, 1:9]).max())
+    assert rg.dual_feasible_user_tol == ro.dual_feasible_user_tol
+
+
+def test_duals_slacks_and_dual_cone_vs_oracle(gpu, oracle_mod):
+    """get_duals / cache_solution (pdhg.jl:701-787) on the device: mixed SOC + PSD problem with free variables, an
+    inequality block and a non-trivial variable order."""
+    aff, con = sensorloc_problem(0, 10, soc_variant=True)
+    rg = gpu.chambolle_pock(aff, con, Options())
+    ro = oracle_mod.chambolle_pock(aff, con, Options())
+    _same_solution(rg, ro)
+    aff, con = stack_problems([mimo_problem(3, 6), mimo_problem(4, 9)])
+    rg = gpu.chambolle_pock(aff, con, Options())
+    ro = oracle_mod.chambolle_pock(aff, con, Options())
+    _same_solution(rg, ro)
+
+
+# ------------------------------------------------------------------ infeasible / unbounded, certificates
+def _infeasible_sdp():      # X PSD 2 x 2 with X11 = -1
+    A = sp.csc_matrix(np.array([[1.0, 0.0, 0.0]]))
+    return (AffineSets(3, 1, 0, 0, A, sp.csc_matrix((0, 3)), np.array([-1.0]), np.zeros(0), np.array([1.0, 0.0, 1.0])),
+            ConicSets([SDPSet(np.arange(3), 3, 2)], []))
+
+
+def _unbounded_sdp():       # min -X11 s.t. X22 = 1, X PSD
+    A = sp.csc_matrix(np.array([[0.0, 0.0, 1.0]]))
+    return (AffineSets(3, 1, 0, 0, A, sp.csc_matrix((0, 3)), np.array([1.0]), np.zeros(0), np.array([-1.0, 0.0, 0.0])),
+            ConicSets([SDPSet(np.arange(3), 3, 2)], []))
+
+
+def _unbounded_lp():        # min -x s.t. -x <= 0
+    G = sp.csc_matrix(np.array([[-1.0]]))
+    return (AffineSets(1, 0, 1, 0, sp.csc_matrix((0, 1)), G, np.zeros(0), np.array([0.0]), np.array([-1.0])), ConicSets())
+
+
+@pytest.mark.parametrize("make,status", [(_infeasible_sdp, 6), (_unbounded_sdp, 5), (_unbounded_lp, 5)],
+                         ids=["infeasible_sdp", "unbounded_sdp", "unbounded_lp"])
+@pytest.mark.parametrize("certificate_search", [False, True], ids=["plain", "certificate"])
+def test_infeasible_unbounded_and_rays(gpu, oracle_mod, make, status, certificate_search):
+    """statuses 5 / 6, the certificate search (pdhg.jl:184-244, 639-676) and the returned rays / duals vs the oracle."""
+    aff, con = make()
+    opt = Options(certificate_search=certificate_search)
+    rg = gpu.chambolle_pock(aff, con, opt)
+    ro = oracle_mod.chambolle_pock(aff, con, opt)
+    assert rg.status == ro.status == status
+    assert rg.status_string.split(" = ")[0] == ro.status_string.split(" = ")[0]
+    assert rg.iter == ro.iter and rg.certificate_found == ro.certificate_found == certificate_search
+    for name in ("primal", "dual_cone", "dual_eq", "dual_in", "slack_eq", "slack_in"):
+        a, b = getattr(rg, name), getattr(ro, name)
+        if a.size:
+            with np.errstate(over="ignore", invalid="ignore"):
+                assert np.all(np.abs(a - b) <= 1e-6 * np.maximum(1.0, np.abs(b))), (name, a, b)
+    assert _rel(rg.dual_objval, ro.dual_objval) <= 1e-6 and _rel(rg.objval, ro.objval) <= 1e-6 * max(1.0, abs(ro.objval))
+    assert rg.dual_feasible_user_tol == ro.dual_feasible_user_tol
+
+
+# ------------------------------------------------------------------ device-side ingest (preprocess!, norm_scaling)
+def _scrambled(aff, con, seed):
+    """The same problem with its variables renumbered at random (so that preprocess! has a real permutation to undo)."""
+    rng = np.random.default_rng(seed)
+    n = aff.n
+    new_of_old = rng.permutation(n)
+    P = sp.csc_matrix((np.ones(n), (np.arange(n), new_of_old)), shape=(n, n))      # (A P)[:, new] = A[:, old]
+    A2 = sp.csc_matrix(sp.csc_matrix(aff.A) @ P) if aff.p else sp.csc_matrix((0, n))
+    G2 = sp.csc_matrix(sp.csc_matrix(aff.G) @ P) if aff.m else sp.csc_matrix((0, n))
+    c2 = np.zeros(n)
+    c2[new_of_old] = aff.c
+    con2 = ConicSets([SDPSet(new_of_old[s.vec_i], s.tri_len, s.sq_side) for s in con.sdpcone],
+                     [SOCSet(new_of_old[s.idx], s.len) for s in con.socone])
+    return AffineSets(n, aff.p, aff.m, 0, A2, G2, aff.b, aff.h, c2), con2, new_of_old
+
+
+def test_ingest_permuted_variables(gpu, oracle_mod):
+    aff, con = sensorloc_problem(1, 8, soc_variant=True)
+    aff2, con2, new_of_old = _scrambled(aff, con, 5)
+    r1 = gpu.chambolle_pock(aff, con, Options())
+    r2 = gpu.chambolle_pock(aff2, con2, Options())
+    ro = oracle_mod.chambolle_pock(aff2, con2, Options())
+    _same_solution(r2, ro)
+    assert r1.iter == r2.iter and _vec_close(r2.primal[new_of_old], r1.primal, 1e-9)
+    assert _vec_close(r2.dual_cone[new_of_old], r1.dual_cone, 1e-9)
+
+
+def test_ingest_rejects_malformed_cones(gpu):
+    aff, con = mimo_problem(3, 4)
+    bad = ConicSets([SDPSet(con.sdpcone[0].vec_i.copy(), con.sdpcone[0].tri_len, con.sdpcone[0].sq_side)], [])
+    bad.sdpcone[0].vec_i[3] = aff.n + 5                                        # out of range
+    with pytest.raises(RuntimeError):
+        gpu.chambolle_pock(aff, bad, Options(max_iter=5))
+    bad.sdpcone[0].vec_i[3] = bad.sdpcone[0].vec_i[2]                          # a variable listed twice
+    with pytest.raises(RuntimeError):
+        gpu.chambolle_pock(aff, bad, Options(max_iter=5))
+    Abad = sp.csc_matrix(aff.A).copy()
+    Abad.indices[0] = aff.p + 3                                                # row index out of range
+    M = SparseMatrixCSC(aff.p, aff.n, Abad.indptr, Abad.indices, Abad.data)
+    with pytest.raises(RuntimeError):
+        gpu.chambolle_pock(AffineSets(aff.n, aff.p, aff.m, 0, M, aff.G, aff.b, aff.h, aff.c), con, Options(max_iter=5))
+
+
+def test_pinned_int64_problem_equals_scipy_problem(gpu):
+    """SparseMatrixCSC{Float64,Int64} in page-locked memory (the zero-copy form bench.py's e2e leg uses) gives
+    bit-identical results to the scipy form."""
+    aff, con = stack_problems([mimo_problem(9, 7), mimo_problem(10, 5)])
+    aff2, con2 = gpu.pin_problem(aff, con)
+    assert isinstance(aff2.A, SparseMatrixCSC) and aff2.A.colptr.dtype == np.int64
+    r1 = gpu.chambolle_pock(aff, con, Options())
+    r2 = gpu.chambolle_pock(aff2, con2, Options())
+    assert r1.iter == r2.iter and np.array_equal(r1.primal, r2.primal) and np.array_equal(r1.dual_cone, r2.dual_cone)
+    assert np.array_equal(r1.slack_in, r2.slack_in) and r1.objval == r2.objval
+
+
+def test_many_small_cones_grid_limits(gpu, oracle_mod):
+    """more PSD blocks than a grid dimension would allow per axis is not needed to see the flat off-diagonal scaling
+    work: 300 cones of side 2-3, compared with the oracle."""
+    rng = np.random.default_rng(0)
+    probs = []
+    for s in range(300):
+        side = 2 + (s % 2)
+        N = side * (side + 1) // 2
+        diag = np.array([j * (j + 1) // 2 + j for j in range(side)])
+        A = sp.csc_matrix((np.ones(side), (np.arange(side), diag)), shape=(side, N))
+        c = rng.standard_normal(N)
+        probs.append((AffineSets(N, side, 0, 0, A, sp.csc_matrix((0, N)), np.ones(side), np.zeros(0), c),
+                      ConicSets([SDPSet(np.arange(N), N, side)], [])))
+    aff, con = stack_problems(probs)
+    rg = gpu.chambolle_pock(aff, con, Options())
+    ro = oracle_mod.chambolle_pock(aff, con, Options())
+    _same_solution(rg, ro)
