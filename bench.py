@@ -28,6 +28,7 @@ import os
 import sys
 import threading
 import time
+from types import SimpleNamespace
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
@@ -258,7 +259,13 @@ def run_b200(args):
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         e2e_walls.append(float(te[0]))
-        e2e_runs.append(r2_)
+        # keep the scalars only: a Result holds 32 MB of page-locked vectors, and holding five of them would make every
+        # call allocate fresh pinned memory instead of re-using the library's cache
+        e2e_runs.append(SimpleNamespace(iter=int(r2_.iter), objval=float(r2_.objval), gap=float(r2_.gap),
+                                        h2d_bytes=int(r2_.h2d_bytes), d2h_bytes=int(r2_.d2h_bytes),
+                                        time_setup=float(r2_.time_setup), time_loop=float(r2_.time_loop),
+                                        lanczos_matvecs=int(r2_.lanczos_matvecs)))
+        del r2_
     order = sorted(range(5), key=lambda i: e2e_walls[i])
     r2 = e2e_runs[order[2]]
     e2e_wall = e2e_walls[order[2]]

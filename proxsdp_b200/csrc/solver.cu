@@ -9,6 +9,7 @@
 #include <cmath>
 #include <cstring>
 #include <memory>
+#include <mutex>
 #include <numeric>
 #include <vector>
 
@@ -350,11 +351,25 @@ Solver::Solver(const proxsdp_problem_t* prob, const proxsdp_options_t* opt_in, b
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) throw CudaError(-5, "no CUDA device available");
     dev_ = (int)opt.device_id;
     if (dev_ < 0 || dev_ >= ndev) throw CudaError(-1, "device_id out of range");
+    StageTimer st0("ctor: device");
     PB_CUDA(cudaSetDevice(dev_));
-    cudaDeviceProp prop;
-    PB_CUDA(cudaGetDeviceProperties(&prop, dev_));
-    num_sms_ = prop.multiProcessorCount;
-    smem_optin_ = prop.sharedMemPerBlockOptin;
+    {
+        // cudaGetDeviceProperties costs milliseconds: two attributes, cached per process and device
+        static std::mutex mu;
+        static int sms[64], smem[64];
+        static bool have[64] = {false};
+        std::lock_guard<std::mutex> g(mu);
+        const int d = dev_ & 63;
+        if (!have[d]) {
+            PB_CUDA(cudaDeviceGetAttribute(&sms[d], cudaDevAttrMultiProcessorCount, dev_));
+            PB_CUDA(cudaDeviceGetAttribute(&smem[d], cudaDevAttrMaxSharedMemoryPerBlockOptin, dev_));
+            size_t lim = 0;
+            if (cudaDeviceGetLimit(&lim, cudaLimitStackSize) == cudaSuccess && lim < 4096) cudaDeviceSetLimit(cudaLimitStackSize, 4096);
+            have[d] = true;
+        }
+        num_sms_ = sms[d]; smem_optin_ = (size_t)smem[d];
+    }
+    st0.lap("ctor: stream+events");
     PB_CUDA(cudaStreamCreate(&stream));   // blocking stream: ordered against the synchronous setup copies on the legacy stream
     PB_CUDA(cudaEventCreate(&ev_psd0_));
     PB_CUDA(cudaEventCreate(&ev_psd1_));
@@ -367,8 +382,8 @@ Solver::Solver(const proxsdp_problem_t* prob, const proxsdp_options_t* opt_in, b
     if (const char* e = getenv("PROXSDP_B200_LZ_XRES")) lz_xres_ = atoi(e);
     if (const char* e = getenv("PROXSDP_B200_LZ_STRICT")) lz_strict_ = atoi(e) != 0 ? 1 : 0;
     if (const char* e = getenv("PROXSDP_B200_RITZ_BI")) lz_bi_ = atoi(e);
-    { size_t lim = 0; if (cudaDeviceGetLimit(&lim, cudaLimitStackSize) == cudaSuccess && lim < 4096) cudaDeviceSetLimit(cudaLimitStackSize, 4096); }
     g_h2d_bytes = 0; g_d2h_bytes = 0;
+    st0.lap("ctor: done");
     setup_host(prob);
 }
 
