@@ -53,8 +53,8 @@ constexpr int LZ3_GMAX = 256;    // largest grid the per-CTA alpha partials are 
 
 // shared-memory layout, in doubles from the start of dynamic shared memory (host-computed, read from the constant bank)
 struct Lz3Layout {
-    int part;    // (round_rows + 1) * LZ_THREADS   per-thread partial sums of the slab symv, [row][thread]; last row: alpha
-    int red2;    // 32 * 16                half-warp partials of the row reduction
+    int wpart;   // 2 * 32 * LZ_NW         per-warp totals of the slab symv, [buffer][row of the round][warp]
+    int aprod;   // 32                     w[r] v[r] of my slab rows (this CTA's share of alpha)
     int dpart;   // LZ_NW * (K+2)          per-warp partial Gram-Schmidt dots
     int vbuf;    // cpr * 64               newest Lanczos vector (written by the cluster peers)
     int Vs;      // (K+1) * VNp            basis rows owned by this CTA
@@ -66,16 +66,19 @@ struct Lz3Layout {
     int JA, JB, JU;           // Kp * Kp each (JA and JB contiguous: bisection scratch)
     int order;   // K ints
     int jscratch;
+    int xres;    // nres * cpr * 64        the LAST nres rows of my slab of X, staged once per launch by the TMA engine
+    int nres;
     int total;   // doubles
 };
 
-__host__ inline Lz3Layout lanczos_cl3_layout(int K, int round_rows, int vn_max, int n, int C) {
+// everything except the resident slab rows
+__host__ inline Lz3Layout lanczos_cl3_layout(int K, int nres, int vn_max, int n, int C) {
     Lz3Layout L{};
     const int Kp = lanczos_kp(K), VNp = lanczos_cl_vnp(vn_max), cpr = lanczos_cpr(n);
     int d = 0;
     auto take = [&](int cnt) { int o = d; d += (cnt + 1) & ~1; return o; };     // keep everything 16-byte aligned
-    L.part = take((round_rows + 1) * LZ_THREADS);
-    L.red2 = take(32 * 16);
+    L.wpart = take(2 * 32 * LZ_NW);
+    L.aprod = take(32);
     L.dpart = take(LZ_NW * (K + 2));
     L.vbuf = take(cpr * 64);
     L.Vs = take((K + 1) * VNp);
@@ -87,6 +90,8 @@ __host__ inline Lz3Layout lanczos_cl3_layout(int K, int round_rows, int vn_max, 
     L.JA = take(Kp * Kp); L.JB = take(Kp * Kp); L.JU = take(Kp * Kp);
     L.order = take((K + 3) / 2 + 2);
     L.jscratch = take((int)((jacobi_scratch_bytes(Kp) + 7) / 8));
+    L.nres = nres;
+    L.xres = take(nres * cpr * 64);
     L.total = d;
     return L;
 }
@@ -98,7 +103,8 @@ struct LanczosCl3Args {
     uint4* wg;                 // [2][ld] mat-vec result, flagged ("LL") words: data and ready-signal in one 16-byte store
     uint4* apart;              // [2][LZ3_GMAX] per-CTA partial alpha = v_j[slab] . w[slab], flagged words
     unsigned int epoch_base;   // the g-th exchange of this launch is tagged epoch_base + g (unique over launches: no memset)
-    int round_rows;            // slab rows whose partial sums fit the shared-memory table at once (<= 31)
+    int res_begin_off;         // rl - res_begin_off is the first RESIDENT row of a slab of rl rows (the last L.nres rows of the
+                               // shortest slab live in shared memory; a slab that is one row longer streams one row more)
     const double* ritz_rd;     // optional warm start of the Ritz eigenproblem (see LanczosClArgs)
     double* ritz_wr;
     int nev, K, maxiter;
@@ -152,25 +158,50 @@ __device__ __forceinline__ bool mbar_wait(unsigned long long* bar, unsigned int 
     }
 }
 
-// One batch of the strip symv: RB rows x CPW chunks of X (16 bytes per lane each) against the warp's piece of v.
-// Branch-free when the strip is full (nch == CPW): all loads are issued back to back, then the FMAs; a batch short
-// of rows simply re-reads its last valid row (the caller ignores those sums).  Only a ragged last strip pays a
-// predicate per load.
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned int bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
+                 "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// One step of the transposing butterfly that sums per-lane partials of N rows over the warp: lanes with the mask bit
+// clear keep the lower half [0, H) of the rows, lanes with the bit set the upper half [H, N); after the five steps
+// (masks 16 ... 1) every lane holds the warp total of at most one row.
+template <int N, int NMAX>
+__device__ __forceinline__ void bfly_step(double (&v)[NMAX], const bool hi, const int mask) {
+    constexpr int H = (N + 1) / 2;
+#pragma unroll
+    for (int i = 0; i < H; ++i) {
+        const double upper = (H + i < N) ? v[H + i] : 0.0;
+        const double send = hi ? v[i] : upper;
+        const double recv = __shfl_xor_sync(0xffffffffu, send, mask);
+        v[i] = (hi ? upper : v[i]) + recv;
+    }
+}
+// acc[i]: this lane's partial of row i (i < nrows <= NMAX <= 32).  On return acc[0] is the warp total of row `off` when
+// valid != 0.  H1 + ... + H5 (20 for NMAX = 18) 64-bit shuffles instead of 5 per row.
+template <int NMAX>
+__device__ __forceinline__ void bfly_reduce(double (&acc)[NMAX], const int lane, const int nrows, int& off, int& valid) {
+    constexpr int N1 = NMAX, H1 = (N1 + 1) / 2, H2 = (H1 + 1) / 2, H3 = (H2 + 1) / 2, H4 = (H3 + 1) / 2, H5 = (H4 + 1) / 2;
+    static_assert(NMAX <= 32 && H5 == 1, "at most 32 rows per round");
+    int cnt = nrows;
+    off = 0;
+    { const bool hi = (lane & 16) != 0; bfly_step<N1, NMAX>(acc, hi, 16); off += hi ? H1 : 0; cnt = hi ? max(cnt - H1, 0) : min(cnt, H1); }
+    { const bool hi = (lane & 8) != 0;  bfly_step<H1, NMAX>(acc, hi, 8);  off += hi ? H2 : 0; cnt = hi ? max(cnt - H2, 0) : min(cnt, H2); }
+    { const bool hi = (lane & 4) != 0;  bfly_step<H2, NMAX>(acc, hi, 4);  off += hi ? H3 : 0; cnt = hi ? max(cnt - H3, 0) : min(cnt, H3); }
+    { const bool hi = (lane & 2) != 0;  bfly_step<H3, NMAX>(acc, hi, 2);  off += hi ? H4 : 0; cnt = hi ? max(cnt - H4, 0) : min(cnt, H4); }
+    { const bool hi = (lane & 1) != 0;  bfly_step<H4, NMAX>(acc, hi, 1);  off += hi ? H5 : 0; cnt = hi ? max(cnt - H5, 0) : min(cnt, H5); }
+    valid = cnt >= 1;
+}
+
+// loads of one chunk of RB streamed rows (rows first, first + 1, ... below `stream_end`): CPW 16-byte loads per row and lane
 template <int CPW, int RB>
-__device__ __forceinline__ void strip_batch(const double* __restrict__ gp, const size_t gstride, const int nrows, const int nch,
-                                            const double2 (&vr)[CPW], double (&acc)[RB]) {
-    double2 x[RB][CPW];
-    if (nch == CPW) {
+__device__ __forceinline__ void strip_load(double2 (&x)[RB][CPW], const double* __restrict__ gcol, const int ld, const int first,
+                                           const int stream_end, const int nch) {
 #pragma unroll
-        for (int i = 0; i < RB; ++i) {
-            const double* rp = gp + (size_t)min(i, nrows - 1) * gstride;
-#pragma unroll
-            for (int c = 0; c < CPW; ++c) x[i][c] = ld_stream_d2(reinterpret_cast<const double2*>(rp + c * 64));
-        }
-    } else {
-#pragma unroll
-        for (int i = 0; i < RB; ++i) {
-            const double* rp = gp + (size_t)min(i, nrows - 1) * gstride;
+    for (int i = 0; i < RB; ++i) {
+        if (first + i < stream_end) {
+            const double* rp = gcol + (size_t)(first + i) * ld;
 #pragma unroll
             for (int c = 0; c < CPW; ++c) {
                 x[i][c] = make_double2(0.0, 0.0);
@@ -178,97 +209,132 @@ __device__ __forceinline__ void strip_batch(const double* __restrict__ gp, const
             }
         }
     }
-#pragma unroll
-    for (int i = 0; i < RB; ++i) {
-        double t = 0.0;
-#pragma unroll
-        for (int c = 0; c < CPW; ++c) { t = fma(x[i][c].x, vr[c].x, t); t = fma(x[i][c].y, vr[c].y, t); }
-        acc[i] = t;
-    }
 }
 
-// sum of cnt doubles at p[l], p[l + 16], ... (l = lane within the half-warp), four chains
-__device__ __forceinline__ double strided16_sum(const double* p, const int l, const int cnt) {
-    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0, s4 = 0.0, s5 = 0.0, s6 = 0.0, s7 = 0.0;      // eight chains: 4 adds deep for 512 partials
-    int i = l;
-    for (; i + 112 < cnt; i += 128) {
-        s0 += p[i]; s1 += p[i + 16]; s2 += p[i + 32]; s3 += p[i + 48];
-        s4 += p[i + 64]; s5 += p[i + 80]; s6 += p[i + 96]; s7 += p[i + 112];
+// up to NMAX STREAMED rows first .. first + count - 1 of the slab: strip loads, RB rows per chunk, the next chunk in flight
+// while the current one is multiplied; warp totals of the rows -> wrow[row - first][warp]
+template <int CPW, int RB, int NMAX>
+__device__ __forceinline__ void symv_sub_streamed(const double* __restrict__ gcol, const int ld, const int first, const int count,
+                                                  const int nch, const double2 (&vr)[CPW], double* wrow, const int lane, const int warp) {
+    double acc[NMAX];
+    const int stream_end = first + count;
+    double2 x[RB][CPW];
+    strip_load<CPW, RB>(x, gcol, ld, first, stream_end, nch);
+#pragma unroll
+    for (int c0 = 0; c0 < NMAX; c0 += RB) {
+        double2 xn[RB][CPW];
+        if (c0 + RB < NMAX) strip_load<CPW, RB>(xn, gcol, ld, first + c0 + RB, stream_end, nch);
+#pragma unroll
+        for (int i = 0; i < RB; ++i) {
+            if (c0 + i < NMAX) {
+                double t = 0.0;
+                if (c0 + i < count) {
+#pragma unroll
+                    for (int c = 0; c < CPW; ++c) { t = fma(x[i][c].x, vr[c].x, t); t = fma(x[i][c].y, vr[c].y, t); }
+                }
+                acc[c0 + i] = t;
+            }
+        }
+        if (c0 + RB < NMAX) {
+#pragma unroll
+            for (int i = 0; i < RB; ++i)
+#pragma unroll
+                for (int c = 0; c < CPW; ++c) x[i][c] = xn[i][c];
+        }
     }
-    for (; i < cnt; i += 16) s0 += p[i];
-    return ((s0 + s1) + (s2 + s3)) + ((s4 + s5) + (s6 + s7));
+    int off, valid;
+    bfly_reduce<NMAX>(acc, lane, count, off, valid);
+    if (valid) wrow[off * LZ_NW + warp] = acc[0];
+}
+
+// up to NMAX RESIDENT rows: srow points at this lane's piece of the first of them in shared memory
+template <int CPW, int NMAX>
+__device__ __forceinline__ void symv_sub_resident(const double* srow, const int rstride, const int count, const int nch,
+                                                  const double2 (&vr)[CPW], double* wrow, const int lane, const int warp) {
+    double acc[NMAX];
+#pragma unroll
+    for (int i = 0; i < NMAX; ++i) {
+        double t = 0.0;
+        if (i < count) {
+            const double* rp = srow + (size_t)i * rstride;
+#pragma unroll
+            for (int c = 0; c < CPW; ++c) {
+                if (c < nch) { const double2 q = *reinterpret_cast<const double2*>(rp + c * 64); t = fma(q.x, vr[c].x, t); t = fma(q.y, vr[c].y, t); }
+            }
+        }
+        acc[i] = t;
+    }
+    int off, valid;
+    bfly_reduce<NMAX>(acc, lane, count, off, valid);
+    if (valid) wrow[off * LZ_NW + warp] = acc[0];
 }
 
 // Slab symv w[r0 : r0 + rl] = X[r0 : r0 + rl, :] v plus this CTA's share of alpha = v[slab] . w[slab], written straight
-// to global memory (wg_slab[row], *alpha_out).  Warp (strip s, row group rg) owns the columns of CPW chunks for the
-// rows rg, rg + nrg, ... ; the slab is walked in rounds of round_rows rows (one round at n = 2000): every thread parks
-// its per-row partial sums in part[row][thread], one block barrier, half-warp h reduces row h and publishes it as a
-// flagged word.  All threads of the block must call it.
-template <int CPW, int RB>
+// to global memory as flagged words (wg_slab[row], *alpha_out).
+//   * Warp s owns the column strip of CPW 64-double chunks for ALL rows of the slab; its piece of v sits in registers.
+//   * The last rows of the slab (from res_begin on) are RESIDENT in shared memory: the TMA engine staged them once when
+//     the kernel started (cp.async.bulk + mbarrier, see the kernel prologue); at n = 2000 that takes ~40 % of the matrix
+//     off the L2 -> SM path of every mat-vec.  The rows before them are streamed with 128-bit loads, RB rows per chunk,
+//     the next chunk in flight while the current one is multiplied.
+//   * Every lane keeps one partial sum per row of a sub-round (NMAX rows) in registers; a transposing butterfly (12
+//     shuffles for 9 rows instead of 5 per row) leaves one warp total per row in one lane, the NS <= 16 warp totals of
+//     a row go through a 4 KB table, and after one block barrier per 32 rows thread r of warp 0 publishes row r.
+//     (The first generation parked 512 partials per row in a 70 KB shared-memory table that half-warps summed after a
+//     block barrier: 1.2 us per mat-vec, and the table took the room the resident rows now use.)
+// All threads of the block must call it.
+template <int CPW, int RB, int NMAX>
 __device__ __forceinline__ void symv_slab(const double* __restrict__ X, const int ld, const int r0, const int rl, const int cpr,
-                                          const double* vbuf, double* part, double* red2, const int round_rows,
+                                          const double* vbuf, const double* xres, const int res_begin, double* wpart, double* aprod,
                                           uint4* wg_slab, uint4* alpha_out, const unsigned int tag, long long* prof) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     long long tp = (prof && tid == 0) ? clock64() : 0;
     const int NS = (cpr + CPW - 1) / CPW;
-    const int nrg = LZ_NW / NS;
-    const int s = warp % NS, rg = warp / NS;
-    const bool active = warp < NS * nrg;
-    const int nch = min(CPW, cpr - s * CPW);
+    const bool active = warp < NS;
+    const int nch = min(CPW, cpr - warp * CPW);
     double2 vr[CPW];
 #pragma unroll
-    for (int c = 0; c < CPW; ++c) vr[c] = (active && c < nch) ? *reinterpret_cast<const double2*>(vbuf + (s * CPW + c) * 64 + 2 * lane) : make_double2(0.0, 0.0);
-    const double* gcol = X + (size_t)r0 * ld + (size_t)s * CPW * 64 + 2 * lane;
-    const size_t gstride = (size_t)nrg * ld;
-    double pa = 0.0;
-    for (int rbeg = 0; rbeg < rl; rbeg += round_rows) {
-        const int rend = min(rl, rbeg + round_rows);
+    for (int c = 0; c < CPW; ++c) vr[c] = (active && c < nch) ? *reinterpret_cast<const double2*>(vbuf + (warp * CPW + c) * 64 + 2 * lane) : make_double2(0.0, 0.0);
+    if (tid < 32) aprod[tid] = 0.0;      // (the same warp reads and updates it below: no barrier needed)
+    for (int rbeg = 0; rbeg < rl; rbeg += 32) {          // one block barrier per 32 rows
+        const int rend = min(rl, rbeg + 32);
+        const int buf = (rbeg >> 5) & 1;                 // two tables: the writers of round r + 2 are behind the barrier of
+        double* wtab = wpart + buf * 32 * LZ_NW;         // round r + 1, which warp 0 passes only after reading round r
         if (active) {
-            int row = rbeg + ((rg - rbeg) % nrg + nrg) % nrg;        // my first row of this round: row = rg (mod nrg)
-            for (; row < rend; row += RB * nrg) {
-                const int nrows = min(RB, (rend - row + nrg - 1) / nrg);
-                double acc[RB];
-                strip_batch<CPW, RB>(gcol + (size_t)row * ld, gstride, nrows, nch, vr, acc);
-                double p0 = 0.0, p1 = 0.0, p2 = 0.0;
-#pragma unroll
-                for (int i = 0; i < RB; ++i) {
-                    if (i < nrows) {
-                        const int ri = row + i * nrg;
-                        part[(ri - rbeg) * LZ_THREADS + tid] = acc[i];
-                        const double vi = vbuf[r0 + ri];
-                        if (i % 3 == 0) p0 = fma(acc[i], vi, p0); else if (i % 3 == 1) p1 = fma(acc[i], vi, p1); else p2 = fma(acc[i], vi, p2);
-                    }
-                }
-                pa += (p0 + p1) + p2;
-            }
+            const int se = min(rend, res_begin);
+            const double* gcol = X + (size_t)r0 * ld + (size_t)warp * CPW * 64 + 2 * lane;
+            for (int f = rbeg; f < se; f += NMAX)
+                symv_sub_streamed<CPW, RB, NMAX>(gcol, ld, f, min(NMAX, se - f), nch, vr, wtab + (f - rbeg) * LZ_NW, lane, warp);
+            const int rstride = cpr * 64;
+            const double* scol = xres + (size_t)warp * CPW * 64 + 2 * lane;
+            for (int f = max(rbeg, res_begin); f < rend; f += NMAX)
+                symv_sub_resident<CPW, NMAX>(scol + (size_t)(f - res_begin) * rstride, rstride, min(NMAX, rend - f), nch, vr,
+                                             wtab + (f - rbeg) * LZ_NW, lane, warp);
         }
-        const bool last_round = (rend == rl);
-        if (last_round) part[(rend - rbeg) * LZ_THREADS + tid] = pa;      // alpha: one more row of the table
-        if (prof && tid == 0) { const long long tn = clock64(); prof[15] += tn - tp; tp = tn; }      // warp 0: loads + FMAs + parking
+        if (prof && tid == 0) { const long long tn = clock64(); prof[15] += tn - tp; tp = tn; }          // warp 0: loads + FMAs + butterflies
         __syncthreads();
-        if (prof && tid == 0) { const long long tn = clock64(); prof[16] += tn - tp; tp = tn; }      // waiting for the slowest warp
-        {
-            const int h = tid >> 4, l = tid & 15;
-            const int nred = (rend - rbeg) + (last_round ? 1 : 0);
-            if (h < nred) {
-                const bool is_alpha = (h == rend - rbeg);
-                const int row = rbeg + h;
-                // a row gets partials only from the NS warps of its row group; alpha from every thread
-                const int base = is_alpha ? 0 : 32 * NS * (row % nrg);
-                const int cnt = is_alpha ? LZ_THREADS : 32 * NS;
-                red2[h * 16 + l] = strided16_sum(part + h * LZ_THREADS + base, l, cnt);
-            }
-            __syncwarp();
-            if (h < nred && l == 0) {
-                const double* q = red2 + h * 16;
-                const double sres = ((q[0] + q[4]) + (q[8] + q[12])) + ((q[1] + q[5]) + (q[9] + q[13])) +
-                                    (((q[2] + q[6]) + (q[10] + q[14])) + ((q[3] + q[7]) + (q[11] + q[15])));
-                if (h == rend - rbeg) ll_store(alpha_out, sres, tag); else ll_store(wg_slab + rbeg + h, sres, tag);
-            }
+        if (prof && tid == 0) { const long long tn = clock64(); prof[16] += tn - tp; tp = tn; }          // waiting for the slowest warp
+        if (tid < rend - rbeg) {
+            const double* q = wtab + tid * LZ_NW;
+            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+            int w = 0;
+            for (; w + 3 < NS; w += 4) { s0 += q[w]; s1 += q[w + 1]; s2 += q[w + 2]; s3 += q[w + 3]; }
+            for (; w < NS; ++w) s0 += q[w];
+            const double sres = (s0 + s1) + (s2 + s3);
+            ll_store(wg_slab + rbeg + tid, sres, tag);
+            aprod[tid] = fma(sres, vbuf[r0 + rbeg + tid], aprod[tid]);
         }
-        if (prof && tid == 0) { const long long tn = clock64(); prof[17] += tn - tp; tp = tn; }      // row reduction + publish
-        if (!last_round) __syncthreads();          // the table is rewritten by the next round
     }
+    // alpha: the products of my rows (threads 0 .. 31, all in warp 0), summed in four chains by lane 0
+    if (tid < 32) {
+        __syncwarp();
+        if (tid == 0) {
+            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) { s0 += aprod[i]; s1 += aprod[i + 1]; s2 += aprod[i + 2]; s3 += aprod[i + 3]; }
+            ll_store(alpha_out, (s0 + s1) + (s2 + s3), tag);
+        }
+    }
+    if (prof && tid == 0) { const long long tn = clock64(); prof[17] += tn - tp; tp = tn; }              // row totals + publish
 }
 
 // Ritz analysis + thick restart, out of line: it runs once or twice per launch, and keeping its ~100 KB of code
@@ -388,7 +454,7 @@ __device__ __noinline__ void lz3_ritz(const LanczosCl3Args& a, double* sbase, in
 #undef SMD
 }
 
-template <int CPW, int RB>
+template <int CPW, int RB, int NMAX>
 __global__ void __launch_bounds__(LZ_THREADS, 1) k_lanczos_cl3(const __grid_constant__ LanczosCl3Args a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cg::cluster_group cluster = cg::this_cluster();
@@ -424,7 +490,8 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) k_lanczos_cl3(const __grid_cons
     __shared__ int s_ok;
     __shared__ int s_state[10];
     __shared__ double s_beta;
-    __shared__ __align__(8) unsigned long long s_mbar[2];      // [0] Gram-Schmidt dots exchange, [1] publication of v_{j+1}
+    __shared__ __align__(8) unsigned long long s_mbar[3];      // [0] Gram-Schmidt dots exchange, [1] publication of v_{j+1},
+                                                               // [2] TMA staging of the resident slab rows
     unsigned int ph_dots = 0;                                  // dots exchanges completed so far (parity = phase & 1); the
                                                                // publication phase is the step number: parity (gsync - 1) & 1
     const int prow = (cta == 0) ? 0 : (cta == C - 1) ? 1 : (cta == G / 2) ? 2 : (cta == G - 1) ? 3 : -1;
@@ -447,9 +514,21 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) k_lanczos_cl3(const __grid_cons
     if (tid == 0) {
         mbar_init(&s_mbar[0], 1);
         mbar_init(&s_mbar[1], 1);
+        mbar_init(&s_mbar[2], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        // stage the resident rows of my slab (the last a.res_begin_off of its rl rows) into shared memory: one bulk
+        // copy per row on the TMA engine (row = cpr * 64 doubles = ld doubles: X is zero-padded to ld columns),
+        // completion counted in bytes on s_mbar[2]; the copies run while the cluster barrier below is crossed
+        const int nres = min(a.res_begin_off, rl);
+        if (nres > 0) {
+            const unsigned int rowbytes = (unsigned int)(cpr * 64 * sizeof(double));
+            mbar_expect_tx(&s_mbar[2], (unsigned int)nres * rowbytes);
+            for (int q = 0; q < nres; ++q)
+                bulk_g2s(SMD(xres) + (size_t)q * cpr * 64, a.X + (size_t)(r0 + rl - nres + q) * a.ld, rowbytes, &s_mbar[2]);
+        }
     }
     cluster.sync();       // everybody's shared memory and barriers are initialised before any peer writes into them
+    if (min(a.res_begin_off, rl) > 0 && !mbar_wait(&s_mbar[2], 0)) s_ok = 0;
     if (profiling && tid == 0) tprev = clock64();
 
     while (!finished) {
@@ -463,9 +542,9 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) k_lanczos_cl3(const __grid_cons
         }
         // ================= symv on my slab of rows: w slab and my share of alpha straight to global =================
         // (gsync still counts the exchanges done so far: this step's buffers have parity (gsync + 1) & 1)
-        symv_slab<CPW, RB>(a.X, a.ld, r0, rl, cpr, SMD(vbuf), SMD(part), SMD(red2), a.round_rows,
-                           a.wg + (size_t)((gsync + 1) & 1) * a.ld + r0, a.apart + (size_t)((gsync + 1) & 1) * LZ3_GMAX + cta,
-                           a.epoch_base + gsync + 1, profiling ? s_prof : nullptr);
+        symv_slab<CPW, RB, NMAX>(a.X, a.ld, r0, rl, cpr, SMD(vbuf), SMD(xres), max(rl - a.res_begin_off, 0), SMD(wpart), SMD(aprod),
+                                 a.wg + (size_t)((gsync + 1) & 1) * a.ld + r0, a.apart + (size_t)((gsync + 1) & 1) * LZ3_GMAX + cta,
+                                 a.epoch_base + gsync + 1, profiling ? s_prof : nullptr);
         // (no block barrier here: the state words were written a whole step ago)
         k = s_state[0]; gsync = (unsigned int)s_state[1]; arrow = s_state[2]; howmany = s_state[3]; numiter = s_state[4];
         first_analysis = s_state[5] != 0; ph_dots = (unsigned int)s_state[8]; beta = s_beta;

@@ -69,16 +69,18 @@ static NcclApi& nccl_api() {
     } while (0)
 
 
-// the strip width (64-double chunks per warp) selects the kernel instance: cpw = ceil(ceil(n / 64) / 16)
+// the strip width (64-double chunks per warp) selects the kernel instance: cpw = ceil(ceil(n / 64) / 16);
+// <strip width, streamed rows per load chunk (two chunks in flight), rows per butterfly>: the widest choice that ptxas
+// fits into 128 registers without spilling on the per-step path
 static const void* lanczos_cl3_kernel(int cpw) {
     switch (cpw) {
-        case 1: return (const void*)k_lanczos_cl3<1, 15>;
-        case 2: return (const void*)k_lanczos_cl3<2, 9>;
-        case 3: return (const void*)k_lanczos_cl3<3, 6>;
-        case 4: return (const void*)k_lanczos_cl3<4, 3>;
-        case 5: return (const void*)k_lanczos_cl3<5, 3>;
-        case 6: return (const void*)k_lanczos_cl3<6, 3>;
-        case 8: return (const void*)k_lanczos_cl3<8, 2>;
+        case 1: return (const void*)k_lanczos_cl3<1, 3, 9>;
+        case 2: return (const void*)k_lanczos_cl3<2, 2, 8>;
+        case 3: return (const void*)k_lanczos_cl3<3, 1, 8>;
+        case 4: return (const void*)k_lanczos_cl3<4, 1, 6>;
+        case 5: return (const void*)k_lanczos_cl3<5, 1, 6>;
+        case 6: return (const void*)k_lanczos_cl3<6, 1, 6>;
+        case 8: return (const void*)k_lanczos_cl3<8, 1, 4>;
         default: return nullptr;
     }
 }
@@ -225,7 +227,7 @@ class Solver {
     DBuf<double> small_warm_d_;
     int lz_kernel_ = 3;        // 3 = third-generation cluster kernel (lanczos_cl3.cuh), 2 = second generation (lanczos_cl.cuh)
     int lz_strict_ = 0;        // cl3 kernel: FP64 alpha + two Gram-Schmidt passes on every step (PROXSDP_B200_LZ_STRICT=1)
-    int lz_xres_ = 1;          // > 1: cap the cl3 symv partial-sum table at lz_xres_ - 1 rows per round (experiments / tests)
+    int lz_xres_ = 0;          // >= 1: cap the resident slab rows of the cl3 symv at lz_xres_ - 1 (experiments / tests)
     size_t lz_cl3_smem_max_ = 0;
     int lz_mode_ = 0;          // 0 = cluster-replicated kernel when it fits, 1 = row-distributed kernel only
     int lz_cluster_ = 8;       // cluster size of the replicated kernel
@@ -720,25 +722,21 @@ bool Solver::lanczos_launch_cluster3(ConeDev& cd, int cone_idx, int nev, int K, 
     cfg.blockDim = dim3(LZ_THREADS); cfg.stream = stream; cfg.attrs = attr; cfg.numAttrs = 1;
     int G = std::min(std::min(want, (num_sms_ / C) * C), (LZ3_GMAX / C) * C);
     if (G < C) return false;
-    int rows_max = (nside + G - 1) / G;
-    // the partial-sum table of the symv takes what the basis replica leaves: at least one row + alpha must fit
-    auto fit_rounds = [&](int rmax, Lz3Layout& Lout, size_t& bytes) -> int {
-        Lz3Layout L1 = lanczos_cl3_layout(K, 1, vn_max, nside, C);
-        if ((size_t)L1.total * sizeof(double) > lz_cl3_smem_max_) return 0;
-        const long long spare_rows = (long long)((lz_cl3_smem_max_ - (size_t)L1.total * sizeof(double)) / ((size_t)LZ_THREADS * sizeof(double)));
-        int rr = (int)std::min<long long>(std::min(rmax, 31), 1 + spare_rows);
-        if (lz_xres_ > 1) rr = std::min(rr, lz_xres_ - 1);        // PROXSDP_B200_LZ_XRES = rows + 1: cap for experiments
-        Lout = lanczos_cl3_layout(K, rr, vn_max, nside, C);
+    // resident slab rows: whatever shared memory the basis replica and the Ritz scratch leave, at most the shortest slab
+    const size_t rowbytes = (size_t)cpr * 64 * sizeof(double);
+    auto fit_resident = [&](int grid, Lz3Layout& Lout, size_t& bytes) -> bool {
+        Lz3Layout L0 = lanczos_cl3_layout(K, 0, vn_max, nside, C);
+        if ((size_t)L0.total * sizeof(double) > lz_cl3_smem_max_) return false;
+        long long nres = (long long)((lz_cl3_smem_max_ - (size_t)L0.total * sizeof(double)) / rowbytes);
+        nres = std::min<long long>(nres, nside / grid);
+        if (lz_xres_ >= 1) nres = std::min<long long>(nres, lz_xres_ - 1);      // PROXSDP_B200_LZ_XRES = rows + 1: cap for experiments
+        Lout = lanczos_cl3_layout(K, (int)std::max<long long>(nres, 0), vn_max, nside, C);
         bytes = (size_t)Lout.total * sizeof(double);
-        return rr;
+        return true;
     };
     Lz3Layout L{};
     size_t smem = 0;
-    int round_rows = fit_rounds(rows_max, L, smem);
-    // more than two rounds per mat-vec (side >~ 4500 at K = 25: the basis replica leaves no room for the partial-sum
-    // table) cost more block barriers than the strip symv saves: measured 62.7 vs 51.5 us per mat-vec at side 5000
-    // (scripts/lz_large.py), so those cones go to the second-generation kernel
-    if (round_rows < 1 || (lz_xres_ <= 1 && 2 * round_rows < rows_max)) return false;
+    if (!fit_resident(G, L, smem)) return false;
     cfg.gridDim = dim3((unsigned)G); cfg.dynamicSmemBytes = smem;
     const void* kfn = lanczos_cl3_kernel(cpw);
     int max_clusters = 0;
@@ -748,11 +746,10 @@ bool Solver::lanczos_launch_cluster3(ConeDev& cd, int cone_idx, int nev, int K, 
     }
     if (max_clusters * C < G) {
         G = max_clusters * C;
-        rows_max = (nside + G - 1) / G;
-        round_rows = fit_rounds(rows_max, L, smem);
-        if (round_rows < 1 || (lz_xres_ <= 1 && 2 * round_rows < rows_max)) return false;
+        if (!fit_resident(G, L, smem)) return false;
     }
     cfg.gridDim = dim3((unsigned)G); cfg.dynamicSmemBytes = smem;
+    const int rows_max = (nside + G - 1) / G;
     if ((size_t)cd.ld * (size_t)(K + 1) > cd.Y.n) cd.Y.alloc((size_t)cd.ld * (size_t)(K + 1));
     // flagged-exchange buffers (shared by all cones of this solver; launches are stream ordered); tags are unique over
     // launches, freshly zeroed buffers carry tag 0, which is never used
@@ -768,7 +765,7 @@ bool Solver::lanczos_launch_cluster3(ConeDev& cd, int cone_idx, int nev, int K, 
     LanczosCl3Args a{};
     a.X = cd.X.p; a.n = nside; a.ld = cd.ld; a.x0 = cd.resid.p; a.Y = cd.Y.p;
     a.wg = lz3_wg_.p; a.apart = lz3_apart_.p; a.epoch_base = (unsigned int)lz3_epoch_;
-    a.round_rows = round_rows;
+    a.res_begin_off = L.nres;
     const int flip = (int)(cd.ritz_launches & 1);
     a.ritz_rd = (lz_warm_ && cd.ritz_launches > 0 && (cd.ritz_launches % 32) != 0) ? cd.ritz_ws[flip].p : nullptr;
     a.ritz_wr = lz_warm_ ? cd.ritz_ws[1 - flip].p : nullptr;
@@ -787,8 +784,8 @@ bool Solver::lanczos_launch_cluster3(ConeDev& cd, int cone_idx, int nev, int K, 
         return false;
     }
     if (getenv("PROXSDP_B200_DEBUG") && cd.ritz_launches == 0)
-        fprintf(stderr, "[lanczos] cl3 kernel: side %d, K %d, grid %d x %d, strip width %d chunks, %d symv rows per round (of %d), %zu KB shared memory\n",
-                nside, K, G / C, C, cpw, round_rows, rows_max, smem >> 10);
+        fprintf(stderr, "[lanczos] cl3 kernel: side %d, K %d, grid %d x %d, strip width %d chunks, %d of %d slab rows resident in shared memory, %zu KB shared memory\n",
+                nside, K, G / C, C, cpw, L.nres, rows_max, smem >> 10);
     cd.ritz_launches++;
     lz3_epoch_ += bound;
     launches += 1;

@@ -325,11 +325,13 @@ def test_lanczos_kernel_variants_agree(gpu, oracle_mod, monkeypatch):
     for tag, env in (("cluster+bi", {}), ("cluster+jacobi", {"PROXSDP_B200_RITZ_BI": "0"}),
                      ("cluster cold jacobi", {"PROXSDP_B200_RITZ_BI": "0", "PROXSDP_B200_RITZ_WARM": "0"}),
                      ("rows", {"PROXSDP_B200_LANCZOS": "rows"}), ("cluster4", {"PROXSDP_B200_CLUSTER": "4"}),
-                     ("gen3 small symv rounds", {"PROXSDP_B200_LZ_XRES": "4"}),
+                     ("gen3, 3 slab rows resident", {"PROXSDP_B200_LZ_XRES": "4"}),
+                     ("gen3, no slab row resident", {"PROXSDP_B200_LZ_XRES": "1"}),
+                     ("gen3 strict arithmetic", {"PROXSDP_B200_LZ_STRICT": "1"}),
                      ("gen3 cluster4", {"PROXSDP_B200_CLUSTER": "4"}), ("gen2", {"PROXSDP_B200_LZ_KERNEL": "2"}),
                      ("gen2 cluster4", {"PROXSDP_B200_LZ_KERNEL": "2", "PROXSDP_B200_CLUSTER": "4"})):
         for k_ in ("PROXSDP_B200_RITZ_BI", "PROXSDP_B200_RITZ_WARM", "PROXSDP_B200_LANCZOS", "PROXSDP_B200_CLUSTER",
-                   "PROXSDP_B200_LZ_KERNEL", "PROXSDP_B200_LZ_XRES"):
+                   "PROXSDP_B200_LZ_KERNEL", "PROXSDP_B200_LZ_XRES", "PROXSDP_B200_LZ_STRICT"):
             monkeypatch.delenv(k_, raising=False)
         for k_, v_ in env.items():
             monkeypatch.setenv(k_, v_)

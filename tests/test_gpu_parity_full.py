@@ -71,7 +71,10 @@ def lz_mode(request, monkeypatch):
 # ------------------------------------------------------------------ full solves of the headline instances
 def _full_solve_check(gpu, oracle_mod, golden_dir, name, aff, con, sdplib_optimum=None):
     z = np.load(f"{golden_dir}/full_{name}.npz")
-    opt = Options(trace_cap=int(z["iters"]) + 2000)
+    # the reference's own max_target_rank_krylov_eigs raised from 16 to 32: with the default both instances end with a
+    # few hundred FULL 2000 x 2000 eigendecompositions (target rank 17 > 16, prox_operators.jl:47): 30 minutes for the CPU
+    # oracle, 4 minutes for the GPU's block-Jacobi fallback (measured: 6589 iterations, 369 of them full, 246 s)
+    opt = Options(trace_cap=int(z["iters"]) + 2000, max_target_rank_krylov_eigs=32)
     rg = gpu.chambolle_pock(aff, con, opt)
     assert rg.status == int(z["status"]) == 1
     tr_o, tr_g = z["trace"], rg.trace
@@ -183,8 +186,11 @@ def test_min_size_krylov_eigs_is_honoured_for_small_cones(gpu, oracle_mod):
 # ------------------------------------------------------------------ line search
 @pytest.mark.parametrize("kw", [dict(linsearch_decay=0.97),                     # up to 16 trials: beyond the 4-trial ladder
                                 dict(max_linsearch_steps=2, delta=0.3),         # exhausted line searches (theta of the last trial)
-                                dict(max_linsearch_steps=1),
-                                dict(linsearch_decay=0.97, max_linsearch_steps=3)], ids=str)
+                                # every line search exhausted.  These two runs DIVERGE (the dual objective passes 1e11 after
+                                # 20 iterations and overflows later), so rounding differences are amplified without bound:
+                                # compared over the iterations before that happens
+                                dict(max_linsearch_steps=1, max_iter=20),
+                                dict(linsearch_decay=0.97, max_linsearch_steps=3, max_iter=40)], ids=str)
 def test_linesearch_beyond_the_ladder_and_exhausted(gpu, oracle_mod, kw):
     aff, con = mimo_problem(7, 16)
     opt = Options(trace_cap=5000, **kw)
@@ -193,7 +199,7 @@ def test_linesearch_beyond_the_ladder_and_exhausted(gpu, oracle_mod, kw):
     assert list(rg.trace[:, 13]) == list(ro.trace[:, 13])                       # identical trial counts, every iteration
     if "linsearch_decay" in kw and "max_linsearch_steps" not in kw:
         assert ro.trace[:, 13].max() > 4
-    assert np.abs(rg.trace[:, 1:9] - ro.trace[:, 1:9]).max() <= 1e-6 * max(1.0, np.abs(ro.trace[:, 1:9]).max())
+    assert np.all(np.abs(rg.trace[:, 1:9] - ro.trace[:, 1:9]) <= 1e-6 * np.maximum(1.0, np.abs(ro.trace[:, 1:9])))
     _same_solution(rg, ro)
 
 
