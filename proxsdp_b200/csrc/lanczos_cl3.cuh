@@ -116,6 +116,7 @@ struct LanczosCl3Args {
     int use_bi;
     double stop_above;         // finish as soon as the largest Ritz value exceeds this (it is a lower bound of lambda_max);
                                // 1e300 = never: used by cone_feas, which only needs to know whether lambda_min < -tol
+    int poll_ns;               // back-off between two polls of the flagged exchange words (PROXSDP_B200_LZ_POLL_NS)
     int strict;                // 1: KrylovKit's arithmetic to the letter — alpha of the local step summed in FP64 and two
                                // Gram-Schmidt passes on every step (PROXSDP_B200_LZ_STRICT=1); 0: FP32 tree for the provisional
                                // alpha and a second pass only when the DGKS test asks for it (same counts)
@@ -353,24 +354,169 @@ __device__ __noinline__ void lz3_ritz(const LanczosCl3Args& a, double* sbase, in
     const int lda = lanczos_kp(K);
     const int m = (k + 1) & ~1;
     long long t_in = prof ? clock64() : 0;
-    // ---- fast path: leading pairs of the plain tridiagonal by bisection + twisted vectors ----
+    bool first_out = first_analysis;
+    // Thick restart as KrylovKit does it: keep the `keep` leading Ritz pairs (theta_t, y_t = V u_t) and the residual
+    // vector r.  In the basis [y_0 .. y_keep-1, r] the Rayleigh quotient is diag(theta) bordered by the row
+    // f_t = beta u_t[K-1]; an orthogonal change of basis inside span(y) turns it back into a TRIDIAGONAL matrix:
+    // Lanczos on diag(theta) started from f / ||f|| (full re-orthogonalisation, keep <= 16 steps on vectors of length
+    // keep: one warp, lane <-> component) gives Q~ with Q~' diag(theta) Q~ = T~ and Q~' f = ||f|| e_0; taken in
+    // reverse order the coupling to r sits in the last row, as the three-term recurrence expects.  The basis is
+    // rotated once by U Q~, the recurrence carries on with a plain tridiagonal (so every later Ritz analysis takes the
+    // bisection path), and nothing downstream knows an arrow ever existed.
+    auto thick_restart_tridiag = [&](const int keep) {
+        double* Vs = SMD(Vs);
+        const int* order = reinterpret_cast<const int*>(SMD(order));
+        double* Wc = SMD(JA);                    // K x keep coefficients of the new basis vectors in the old Lanczos basis
+        double* Qs = SMD(JB);                    // keep x MP: Qs[j * MP + c] = component c of Lanczos vector j
+        const int MP = 17;
+        double* ta = Qs + 16 * MP;               // diagonal of T~
+        double* tb = ta + 16;                    // off-diagonal of T~
+        double* ws = tb + 16;                    // work vector
+        double* hs = ws + 32;                    // re-orthogonalisation coefficients
+        __syncthreads();                         // D, f, order, JU are final; the bisection / Jacobi scratch in JA, JB is dead
+        if (tid < 32) {
+            const int c = tid;
+            const double th = (c < keep) ? SMD(D)[c] : 0.0;
+            const double fc = (c < keep) ? SMD(f)[c] : 0.0;
+            const double nf = sqrt(warp_sum(fc * fc));
+            double qprev = 0.0, qcur = (nf > 0.0) ? fc / nf : ((c == 0) ? 1.0 : 0.0);
+            double bprev = 0.0;
+            for (int j = 0; j < keep; ++j) {
+                if (c < keep) Qs[j * MP + c] = qcur;
+                double w = th * qcur;
+                const double aj = warp_sum(qcur * w);
+                w -= aj * qcur + bprev * qprev;
+                if (c == 0) ta[j] = aj;
+                if (j == keep - 1) break;
+                // two classical Gram-Schmidt passes of w against q_0 .. q_j: lane i <-> coefficient of q_i
+                auto reorth = [&]() {
+                    for (int pass = 0; pass < 2; ++pass) {
+                        __syncwarp();
+                        ws[c] = (c < keep) ? w : 0.0;
+                        __syncwarp();
+                        double h = 0.0;
+                        if (c <= j) for (int t = 0; t < keep; ++t) h = fma(Qs[c * MP + t], ws[t], h);
+                        hs[c] = (c <= j) ? h : 0.0;
+                        __syncwarp();
+                        if (c < keep) for (int i = 0; i <= j; ++i) w = fma(-hs[i], Qs[i * MP + c], w);
+                    }
+                    return sqrt(warp_sum((c < keep) ? w * w : 0.0));
+                };
+                double nb = reorth();
+                double bj = nb;
+                if (!(nb > 1e-200)) {
+                    // exact breakdown (an f_t that is exactly zero, or a repeated theta): carry on with any direction
+                    // orthogonal to the q's — T~ decouples there (off-diagonal 0)
+                    for (int t0 = 0; t0 < keep; ++t0) {
+                        w = (c == t0) ? 1.0 : 0.0;
+                        nb = reorth();
+                        if (nb > 0.5) break;
+                    }
+                    bj = 0.0;
+                }
+                if (c == 0) tb[j] = bj;
+                qprev = qcur;
+                qcur = w / nb;
+                bprev = bj;
+            }
+            if (c == 0) tb[keep - 1] = nf;         // coupling of the last rotated vector to the residual vector
+        }
+        __syncthreads();
+        // new basis vector i = sum_t y_t Q~[t][keep-1-i]  =>  coefficients in the old Lanczos basis
+        for (int idx = tid; idx < K * keep; idx += LZ_THREADS) {
+            const int r = idx % K, i = idx / K;
+            const double* qv = Qs + (keep - 1 - i) * MP;
+            double sacc = 0.0;
+            for (int t = 0; t < keep; ++t) sacc = fma(SMD(JU)[r + order[t] * lda], qv[t], sacc);
+            Wc[r + i * K] = sacc;
+        }
+        __syncthreads();
+        for (int t = tid; t < vn; t += LZ_THREADS) {
+            double row[LZC_KMAX];
+            for (int i = 0; i < K; ++i) row[i] = Vs[i * VNp + t];
+            for (int q = 0; q < keep; ++q) {
+                const double* u = Wc + q * K;
+                double sacc = 0.0;
+                for (int i = 0; i < K; ++i) sacc = fma(row[i], u[i], sacc);
+                Vs[q * VNp + t] = sacc;
+            }
+            Vs[keep * VNp + t] = Vs[K * VNp + t];
+        }
+        __syncthreads();
+        for (int i = tid; i < K; i += LZ_THREADS) {
+            SMD(Hd)[i] = (i < keep) ? ta[keep - 1 - i] : 0.0;
+            SMD(He)[i] = (i < keep - 1) ? tb[keep - 2 - i] : ((i == keep - 1) ? tb[keep - 1] : 0.0);
+            SMD(Harr)[i] = 0.0;
+        }
+        arrow = -1;
+        k = keep;                       // the caller's k++ makes it keep + 1
+        numiter++;
+    };
+    // restart that keeps the arrowhead form (large Krylov dimensions: keep > 16 does not fit the one-warp reduction above;
+    // the dense Jacobi solver diagonalises arrow + tridiagonal tail directly, which is the same Krylov space)
+    auto thick_restart_arrow = [&](const int keep) {
+        double* Vs = SMD(Vs);
+        const int* order = reinterpret_cast<const int*>(SMD(order));
+        for (int t = tid; t < vn; t += LZ_THREADS) {
+            double row[LZC_KMAX];
+            for (int i = 0; i < K; ++i) row[i] = Vs[i * VNp + t];
+            for (int q = 0; q < keep; ++q) {
+                const double* u = SMD(JU) + order[q] * lda;
+                double sacc = 0.0;
+                for (int i = 0; i < K; ++i) sacc = fma(row[i], u[i], sacc);
+                Vs[q * VNp + t] = sacc;
+            }
+            Vs[keep * VNp + t] = Vs[K * VNp + t];
+        }
+        __syncthreads();
+        for (int i = tid; i < K; i += LZ_THREADS) {
+            double d = (i < keep) ? SMD(D)[i] : 0.0;
+            double fa = (i < keep) ? SMD(f)[i] : 0.0;
+            SMD(Hd)[i] = d; SMD(Harr)[i] = fa; SMD(He)[i] = 0.0;
+        }
+        arrow = keep;
+        k = keep;
+        numiter++;
+    };
+    // ---- fast path: the leading pairs of the tridiagonal Rayleigh quotient by bisection + twisted vectors ----
     bool done_bi = false;
     if (a.use_bi && arrow < 0 && 2 * (size_t)lda * lda >= ritz_bi_scratch_doubles(K)) {
         RitzBiScratch bs = ritz_bi_carve(SMD(JA), K);          // JA and JB are contiguous and unused here
-        const int mb = ritz_top_bi(k, SMD(Hd), SMD(He), howmany + 4, SMD(D), SMD(JU), lda, bs, prof);
-        if (mb > 0) {
-            int* order = reinterpret_cast<int*>(SMD(order));
-            for (int i = tid; i < mb; i += LZ_THREADS) { order[i] = i; SMD(f)[i] = beta * SMD(JU)[(k - 1) + i * lda]; }
+        auto solve = [&](const int want) -> int {
+            const int got = ritz_top_bi(k, SMD(Hd), SMD(He), want, SMD(D), SMD(JU), lda, bs, prof);
+            if (got > 0) {
+                int* order = reinterpret_cast<int*>(SMD(order));
+                for (int i = tid; i < got; i += LZ_THREADS) { order[i] = i; SMD(f)[i] = beta * SMD(JU)[(k - 1) + i * lda]; }
+            }
             __syncthreads();
+            return got;
+        };
+        int mb = solve(howmany + 4);
+        if (mb > 0) {
             int cv = 0;
             while (cv < mb && fabs(SMD(f)[cv]) <= a.tol) cv++;
             if (cv >= howmany && cv < mb) { converged = cv; finished = 1; done_bi = true; }
             else if (SMD(D)[0] > a.stop_above) { converged = max(cv, 1); finished = 1; done_bi = true; }      // bound certified
+            else if (cv < howmany && k == K && numiter < a.maxiter) {
+                // not converged at the end of a Krylov cycle: the restart needs the `keep` leading pairs — one warp each
+                const int keep = (3 * K + 2 * cv) / 5;
+                if (keep <= RITZ_BI_MAXM && keep < k) {
+                    __syncthreads();
+                    if (mb < keep) mb = solve(keep);
+                    int cv2 = 0;
+                    while (cv2 < mb && fabs(SMD(f)[cv2]) <= a.tol) cv2++;
+                    if (mb >= keep && cv2 == cv) {
+                        converged = cv;
+                        thick_restart_tridiag(keep);
+                        done_bi = true;
+                        first_out = false;
+                    }
+                }
+            }
             __syncthreads();
         }
     }
     if (prof && tid == 0) { prof[8 + (done_bi ? 0 : 1)] += 1; prof[10] += clock64() - t_in; }
-    bool first_out = first_analysis;
     if (!done_bi) {
         {
             double* JA = SMD(JA);
@@ -421,29 +567,8 @@ __device__ __noinline__ void lz3_ritz(const LanczosCl3Args& a, double* sbase, in
             if (numiter == a.maxiter) {
                 finished = 1;
             } else {
-                // ---- thick restart: V[:, 0:keep] <- V U[:, order[0:keep]], in place row by row ----
                 const int keep = (3 * K + 2 * converged) / 5;
-                double* Vs = SMD(Vs);
-                for (int t = tid; t < vn; t += LZ_THREADS) {
-                    double row[LZC_KMAX];
-                    for (int i = 0; i < K; ++i) row[i] = Vs[i * VNp + t];
-                    for (int q = 0; q < keep; ++q) {
-                        const double* u = SMD(JU) + order[q] * lda;
-                        double s = 0.0;
-                        for (int i = 0; i < K; ++i) s = fma(row[i], u[i], s);
-                        Vs[q * VNp + t] = s;
-                    }
-                    Vs[keep * VNp + t] = Vs[K * VNp + t];
-                }
-                __syncthreads();
-                for (int i = tid; i < K; i += LZ_THREADS) {
-                    double d = (i < keep) ? SMD(D)[i] : 0.0;
-                    double fa = (i < keep) ? SMD(f)[i] : 0.0;
-                    SMD(Hd)[i] = d; SMD(Harr)[i] = fa; SMD(He)[i] = 0.0;
-                }
-                arrow = keep;
-                k = keep;                       // the caller's k++ makes it keep + 1
-                numiter++;
+                if (keep <= 16 && arrow < 0) thick_restart_tridiag(keep); else thick_restart_arrow(keep);
             }
         }
     }
@@ -581,6 +706,9 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) k_lanczos_cl3(const __grid_cons
                     }
                     if (__all_sync(0xffffffffu, have[0] && have[1])) break;
                     if (clock64() - tw > 4000000000LL) { s_ok = 0; break; }      // ~2 s: a peer died; give up instead of hanging
+                    // back off between polls: 120 CTAs x 16 warps spinning on L2 take request slots from the CTAs that are
+                    // still streaming their slab (measured: profiles/r2_poll_sweep.txt)
+                    if (a.poll_ns > 0) __nanosleep((unsigned int)a.poll_ns);
                 }
 #pragma unroll
                 for (int u = 0; u < 2; ++u) wreg[u] = (t_lo + lane + 32 * u < t_hi) ? ll_value(rr[u]) : 0.0;
@@ -604,6 +732,7 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) k_lanczos_cl3(const __grid_cons
                         }
                         if (__all_sync(0xffffffffu, all)) break;
                         if (clock64() - tw > 4000000000LL) { s_ok = 0; break; }
+                        if (a.poll_ns > 0) __nanosleep((unsigned int)a.poll_ns);
                     }
 #pragma unroll
                     for (int u = 0; u < 4; ++u) if (cb + lane + 32 * u < G) sd += ll_value(pr[u]);

@@ -102,9 +102,9 @@ __device__ inline int ritz_top_bi(int k, const double* d, const double* e, int m
         emin = fmin(emin, __shfl_xor_sync(0xffffffffu, emin, o));
     }
     const double tnorm = fmax(fabs(gl), fabs(gu));
-    if (!(tnorm > 0.0) || !(tnorm < 1e140) || !(emin > 1e-9 * tnorm)) return 0;     // (nearly) decoupled or degenerate: decline
+    if (!(tnorm > 0.0) || !(tnorm < 1e140)) return 0;     // degenerate: decline
     const double inv_t = 1.0 / tnorm;
-    for (int j = tid; j < k - 1; j += blockDim.x) { sc.ie[j] = 1.0 / e[j]; const double es = e[j] * inv_t; sc.e2s[j] = es * es; }
+    for (int j = tid; j < k - 1; j += blockDim.x) { const double es = e[j] * inv_t; sc.e2s[j] = es * es; }
     if (tid == 0) *sc.fail = 0;
     __syncthreads();
     RITZ_TICK(11);
@@ -139,35 +139,39 @@ __device__ inline int ritz_top_bi(int k, const double* d, const double* e, int m
     }
     RITZ_TICK(12);
 
-    // ---- eigenvector `warp` : forward (lane 0) and backward (lane 1) recurrences, same instruction stream ----
+    // ---- eigenvector `warp` by the twisted factorisation in its qd form (Parlett & Dhillon): lane 0 runs the
+    // stationary transform T - lam I = L D+ L' from the top, lane 1 the progressive one U D- U' from the bottom;
+    // gamma_r = D+_r + D-_r - (d_r - lam) is the one residual left when both are glued at row r, the twist goes to the
+    // smallest |gamma_r|, and z follows from the multipliers: z_j = -L_j z_{j+1} above the twist, z_{j+1} = -U_j z_j
+    // below it.  No division by an off-diagonal entry: a (nearly) decoupled tridiagonal — the Rayleigh quotient right
+    // after a thick restart with converged Ritz pairs has couplings of 1e-13 — is handled like any other.
     if (warp < m) {
-        double* zf = sc.zf + (size_t)warp * k;
-        double* zb = sc.zb + (size_t)warp * k;
-        if (lane < 2) {
-            const bool rev = (lane == 1);
-            double* z = rev ? zb : zf;
-            // reversed problem: d'[j] = d[k-1-j], e'[j] = e[k-2-j]; z'[j] is stored at its natural position
-            double zm1 = 1.0;
-            z[rev ? k - 1 : 0] = 1.0;
-            double z0 = -(d[rev ? k - 1 : 0] - lam) * sc.ie[rev ? k - 2 : 0];
-            z[rev ? k - 2 : 1] = z0;
-            for (int j = 1; j < k - 1; ++j) {
-                const int jd = rev ? k - 1 - j : j;            // d'[j]
-                const int je = rev ? k - 2 - j : j;            // e'[j]
-                const int jm = rev ? k - 1 - j : j - 1;        // e'[j-1]
-                const double zn = -fma(d[jd] - lam, z0, e[jm] * zm1) * sc.ie[je];
-                z[rev ? k - 2 - j : j + 1] = zn;
-                zm1 = z0; z0 = zn;
+        double* Dp = sc.zf + (size_t)warp * k;
+        double* Dm = sc.zb + (size_t)warp * k;
+        const double pivmin = 1e-290 + 1e-30 * tnorm;
+        if (lane == 0) {
+            double q = d[0] - lam;
+            for (int j = 0; j < k - 1; ++j) {
+                if (fabs(q) < pivmin) q = -pivmin;
+                Dp[j] = q;
+                q = (d[j + 1] - lam) - (e[j] / q) * e[j];
             }
+            if (fabs(q) < pivmin) q = -pivmin;
+            Dp[k - 1] = q;
+        } else if (lane == 1) {
+            double q = d[k - 1] - lam;
+            for (int j = k - 2; j >= 0; --j) {
+                if (fabs(q) < pivmin) q = -pivmin;
+                Dm[j + 1] = q;
+                q = (d[j] - lam) - (e[j] / q) * e[j];
+            }
+            if (fabs(q) < pivmin) q = -pivmin;
+            Dm[0] = q;
         }
         __syncwarp();
-        // gamma_r = (d_r - lam) + e_{r-1} zf_{r-1}/zf_r + e_r zb_{r+1}/zb_r ; twist at the smallest |gamma|
         double best = 1e300; int bestr = 0;
         for (int r = lane; r < k; r += 32) {
-            double g = d[r] - lam;
-            if (r > 0) g += e[r - 1] * zf[r - 1] / zf[r];
-            if (r < k - 1) g += e[r] * zb[r + 1] / zb[r];
-            double ag = fabs(g);
+            double ag = fabs(Dp[r] + Dm[r] - (d[r] - lam));
             if (!(ag < 1e300)) ag = 1e300;                    // NaN / inf: never chosen
             if (ag < best) { best = ag; bestr = r; }
         }
@@ -176,16 +180,21 @@ __device__ inline int ritz_top_bi(int k, const double* d, const double* e, int m
             const int orr = __shfl_xor_sync(0xffffffffu, bestr, o);
             if (ob < best || (ob == best && orr < bestr)) { best = ob; bestr = orr; }
         }
-        const double sf = 1.0 / zf[bestr], sb = 1.0 / zb[bestr];
-        double nrm2 = 0.0;
-        for (int j = lane; j < k; j += 32) {
-            const double zj = (j <= bestr) ? zf[j] * sf : zb[j] * sb;
-            nrm2 = fma(zj, zj, nrm2);
+        double* u = U + (size_t)warp * ldu;
+        if (lane == 0) {
+            double z = 1.0;
+            u[bestr] = 1.0;
+            for (int j = bestr - 1; j >= 0; --j) { z = -(e[j] / Dp[j]) * z; u[j] = z; }
+        } else if (lane == 1) {
+            double z = 1.0;
+            for (int j = bestr; j < k - 1; ++j) { z = -(e[j] / Dm[j + 1]) * z; u[j + 1] = z; }
         }
+        __syncwarp();
+        double nrm2 = 0.0;
+        for (int j = lane; j < k; j += 32) nrm2 = fma(u[j], u[j], nrm2);
         nrm2 = warp_sum(nrm2);
         const double inrm = rsqrt(nrm2);
-        double* u = U + (size_t)warp * ldu;
-        for (int j = lane; j < k; j += 32) u[j] = ((j <= bestr) ? zf[j] * sf : zb[j] * sb) * inrm;
+        for (int j = lane; j < k; j += 32) u[j] *= inrm;
         __syncwarp();
         // residual check || T u - lam u ||_inf <= 1e-13 ||T||
         double res = 0.0;
