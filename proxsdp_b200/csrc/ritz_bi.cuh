@@ -139,40 +139,41 @@ __device__ inline int ritz_top_bi(int k, const double* d, const double* e, int m
     }
     RITZ_TICK(12);
 
-    // ---- eigenvector `warp` by the twisted factorisation in its qd form (Parlett & Dhillon): lane 0 runs the
-    // stationary transform T - lam I = L D+ L' from the top, lane 1 the progressive one U D- U' from the bottom;
-    // gamma_r = D+_r + D-_r - (d_r - lam) is the one residual left when both are glued at row r, the twist goes to the
-    // smallest |gamma_r|, and z follows from the multipliers: z_j = -L_j z_{j+1} above the twist, z_{j+1} = -U_j z_j
-    // below it.  No division by an off-diagonal entry: a (nearly) decoupled tridiagonal — the Rayleigh quotient right
-    // after a thick restart with converged Ritz pairs has couplings of 1e-13 — is handled like any other.
+    // ---- eigenvector `warp` by the twisted factorisation (Parlett & Dhillon), written on the leading / trailing
+    // principal minors of (T - lam I) / ||T|| so that its dependent chains are division-free: lane 0 runs
+    // p_j = dx_j p_{j-1} - e_{j-1}^2 p_{j-2} from the top (p_j / p_{j-1} is the pivot D+_j of L D+ L'), lane 1 the same
+    // from the bottom (q_j / q_{j+1} = D-_j of U D- U').  gamma_r = D+_r + D-_r - dx_r is the one residual left when both
+    // factorisations are glued at row r; the twist goes to the smallest |gamma_r| and
+    //     z_j = (-1)^{r-j} e_j ... e_{r-1} p_{j-1} q_{r+1}  (j <= r),   z_j = (-1)^{j-r} e_r ... e_{j-1} q_{j+1} p_{r-1}  (j >= r).
+    // Nothing is ever divided by an off-diagonal entry: a (nearly) decoupled tridiagonal — the Rayleigh quotient right
+    // after a thick restart with converged Ritz pairs has couplings of 1e-13 — is handled like any other (entries of
+    // the scaled matrix are <= 2 in modulus and k <= 101, so the minors stay far from the overflow threshold).
     if (warp < m) {
-        double* Dp = sc.zf + (size_t)warp * k;
-        double* Dm = sc.zb + (size_t)warp * k;
-        const double pivmin = 1e-290 + 1e-30 * tnorm;
+        double* pf = sc.zf + (size_t)warp * k;      // pf[j] = p_j   (p_{-1} = 1)
+        double* pb = sc.zb + (size_t)warp * k;      // pb[j] = q_j   (q_k = 1)
         if (lane == 0) {
-            double q = d[0] - lam;
-            for (int j = 0; j < k - 1; ++j) {
-                if (fabs(q) < pivmin) q = -pivmin;
-                Dp[j] = q;
-                q = (d[j + 1] - lam) - (e[j] / q) * e[j];
+            double p0 = 1.0, p1 = (d[0] - lam) * inv_t;
+            pf[0] = p1;
+            for (int j = 1; j < k; ++j) {
+                const double p2 = fma((d[j] - lam) * inv_t, p1, -sc.e2s[j - 1] * p0);
+                pf[j] = p2;
+                p0 = p1; p1 = p2;
             }
-            if (fabs(q) < pivmin) q = -pivmin;
-            Dp[k - 1] = q;
         } else if (lane == 1) {
-            double q = d[k - 1] - lam;
+            double q0 = 1.0, q1 = (d[k - 1] - lam) * inv_t;
+            pb[k - 1] = q1;
             for (int j = k - 2; j >= 0; --j) {
-                if (fabs(q) < pivmin) q = -pivmin;
-                Dm[j + 1] = q;
-                q = (d[j] - lam) - (e[j] / q) * e[j];
+                const double q2 = fma((d[j] - lam) * inv_t, q1, -sc.e2s[j] * q0);
+                pb[j] = q2;
+                q0 = q1; q1 = q2;
             }
-            if (fabs(q) < pivmin) q = -pivmin;
-            Dm[0] = q;
         }
         __syncwarp();
         double best = 1e300; int bestr = 0;
         for (int r = lane; r < k; r += 32) {
-            double ag = fabs(Dp[r] + Dm[r] - (d[r] - lam));
-            if (!(ag < 1e300)) ag = 1e300;                    // NaN / inf: never chosen
+            const double pm = (r > 0) ? pf[r - 1] : 1.0, qp = (r < k - 1) ? pb[r + 1] : 1.0;
+            double ag = fabs(pf[r] / pm + pb[r] / qp - (d[r] - lam) * inv_t);
+            if (!(ag < 1e300)) ag = 1e300;                    // NaN / inf (a vanishing minor): never chosen
             if (ag < best) { best = ag; bestr = r; }
         }
         for (int o = 16; o > 0; o >>= 1) {
@@ -181,13 +182,16 @@ __device__ inline int ritz_top_bi(int k, const double* d, const double* e, int m
             if (ob < best || (ob == best && orr < bestr)) { best = ob; bestr = orr; }
         }
         double* u = U + (size_t)warp * ldu;
-        if (lane == 0) {
-            double z = 1.0;
-            u[bestr] = 1.0;
-            for (int j = bestr - 1; j >= 0; --j) { z = -(e[j] / Dp[j]) * z; u[j] = z; }
-        } else if (lane == 1) {
-            double z = 1.0;
-            for (int j = bestr; j < k - 1; ++j) { z = -(e[j] / Dm[j + 1]) * z; u[j + 1] = z; }
+        {
+            const double pm = (bestr > 0) ? pf[bestr - 1] : 1.0, qp = (bestr < k - 1) ? pb[bestr + 1] : 1.0;
+            if (lane == 0) {
+                double E = qp;
+                u[bestr] = pm * qp;
+                for (int j = bestr - 1; j >= 0; --j) { E = -(e[j] * inv_t) * E; u[j] = E * ((j > 0) ? pf[j - 1] : 1.0); }
+            } else if (lane == 1) {
+                double E = pm;
+                for (int j = bestr + 1; j < k; ++j) { E = -(e[j - 1] * inv_t) * E; u[j] = E * ((j < k - 1) ? pb[j + 1] : 1.0); }
+            }
         }
         __syncwarp();
         double nrm2 = 0.0;

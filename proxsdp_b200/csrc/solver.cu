@@ -70,16 +70,22 @@ static NcclApi& nccl_api() {
 
 
 // the strip width (64-double chunks per warp) selects the kernel instance: cpw = ceil(ceil(n / 64) / 16);
-// <strip width, streamed rows per load chunk (two chunks in flight), rows per butterfly>: the widest choice that ptxas
-// fits into 128 registers without spilling on the per-step path
-static const void* lanczos_cl3_kernel(int cpw) {
+// <strip width, streamed rows per load batch (all of them in flight at once), resident rows per butterfly>.
+// rb_override (PROXSDP_B200_LZ_RB, experiments): other batch sizes of the n <= 2048 instance.
+static const void* lanczos_cl3_kernel(int cpw, int rb_override = 0) {
     switch (cpw) {
-        case 1: return (const void*)k_lanczos_cl3<1, 3, 9>;
-        case 2: return (const void*)k_lanczos_cl3<2, 2, 8>;
-        case 3: return (const void*)k_lanczos_cl3<3, 1, 8>;
-        case 4: return (const void*)k_lanczos_cl3<4, 1, 6>;
-        case 5: return (const void*)k_lanczos_cl3<5, 1, 6>;
-        case 6: return (const void*)k_lanczos_cl3<6, 1, 6>;
+        case 1: return (const void*)k_lanczos_cl3<1, 6, 9>;
+        case 2:
+            switch (rb_override) {
+                case 3: return (const void*)k_lanczos_cl3<2, 3, 8>;
+                case 6: return (const void*)k_lanczos_cl3<2, 6, 8>;
+                case 9: return (const void*)k_lanczos_cl3<2, 9, 8>;
+                default: return (const void*)k_lanczos_cl3<2, 5, 8>;
+            }
+        case 3: return (const void*)k_lanczos_cl3<3, 3, 8>;
+        case 4: return (const void*)k_lanczos_cl3<4, 3, 6>;
+        case 5: return (const void*)k_lanczos_cl3<5, 2, 6>;
+        case 6: return (const void*)k_lanczos_cl3<6, 2, 6>;
         case 8: return (const void*)k_lanczos_cl3<8, 1, 4>;
         default: return nullptr;
     }
@@ -226,6 +232,7 @@ class Solver {
     long long small_warm_calls_ = 0;
     DBuf<double> small_warm_d_;
     int lz_kernel_ = 3;        // 3 = third-generation cluster kernel (lanczos_cl3.cuh), 2 = second generation (lanczos_cl.cuh)
+    int lz_rb_ = 0;            // cl3 kernel, experiments: streamed rows per load batch of the n <= 2048 instance
     int lz_poll_ns_ = 0;       // cl3 kernel: nanoseconds of back-off between polls of the exchange words
     int lz_strict_ = 0;        // cl3 kernel: FP64 alpha + two Gram-Schmidt passes on every step (PROXSDP_B200_LZ_STRICT=1)
     int lz_xres_ = 0;          // >= 1: cap the resident slab rows of the cl3 symv at lz_xres_ - 1 (experiments / tests)
@@ -385,6 +392,7 @@ Solver::Solver(const proxsdp_problem_t* prob, const proxsdp_options_t* opt_in, b
     if (const char* e = getenv("PROXSDP_B200_LZ_XRES")) lz_xres_ = atoi(e);
     if (const char* e = getenv("PROXSDP_B200_LZ_STRICT")) lz_strict_ = atoi(e) != 0 ? 1 : 0;
     if (const char* e = getenv("PROXSDP_B200_LZ_POLL_NS")) lz_poll_ns_ = std::max(0, atoi(e));
+    if (const char* e = getenv("PROXSDP_B200_LZ_RB")) lz_rb_ = atoi(e);
     if (const char* e = getenv("PROXSDP_B200_RITZ_BI")) lz_bi_ = atoi(e);
     g_h2d_bytes = 0; g_d2h_bytes = 0;
     st0.lap("ctor: done");
@@ -584,16 +592,15 @@ void Solver::setup_host(const proxsdp_problem_t* prob) {
         static thread_local bool attr_nonportable = false;
         if (attr_dev != dev_ || (lz_cluster_ > 8 && !attr_nonportable)) {
             size_t mx = smem_optin_;
-            for (int cpw = 1; cpw <= 8; ++cpw) {
-                const void* fn = lanczos_cl3_kernel(cpw);
-                if (!fn) continue;
+            std::vector<const void*> fns;
+            for (int cpw = 1; cpw <= 8; ++cpw) if (const void* fn = lanczos_cl3_kernel(cpw)) fns.push_back(fn);
+            for (int rb : {3, 6, 9}) fns.push_back(lanczos_cl3_kernel(2, rb));
+            for (const void* fn : fns) {
                 cudaFuncAttributes fa{};
                 PB_CUDA(cudaFuncGetAttributes(&fa, fn));
                 mx = std::min(mx, smem_optin_ - fa.sharedSizeBytes);
             }
-            for (int cpw = 1; cpw <= 8; ++cpw) {
-                const void* fn = lanczos_cl3_kernel(cpw);
-                if (!fn) continue;
+            for (const void* fn : fns) {
                 PB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mx));
                 if (lz_cluster_ > 8) PB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
             }
@@ -740,7 +747,7 @@ bool Solver::lanczos_launch_cluster3(ConeDev& cd, int cone_idx, int nev, int K, 
     size_t smem = 0;
     if (!fit_resident(G, L, smem)) return false;
     cfg.gridDim = dim3((unsigned)G); cfg.dynamicSmemBytes = smem;
-    const void* kfn = lanczos_cl3_kernel(cpw);
+    const void* kfn = lanczos_cl3_kernel(cpw, lz_rb_);
     int max_clusters = 0;
     if (cudaOccupancyMaxActiveClusters(&max_clusters, kfn, &cfg) != cudaSuccess || max_clusters < 1) {
         cudaGetLastError();
