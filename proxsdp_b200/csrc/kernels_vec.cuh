@@ -330,7 +330,9 @@ struct LadderArgs {
     double tau0, decay, tau_old, beta, sigma_fixed, delta;
     int use_theta;           // 1: line search (theta from the trial step); 0: fixed-step dual_step! (pdhg.jl:584-609)
     int ntrials;             // T: trials evaluated by this launch (1 .. LS_MAXT)
-    int do_test;             // 0: accept trial 0 unconditionally (fixed step)
+    int do_test;             // 0: accept trial 0 unconditionally (fixed step); 2: sharded run — only publish this rank's
+                             // partial sums (partial_out), k_ls_decide_gathered applies the test to the sums over all ranks
+    double* partial_out;     // [2 * LS_MAXT]: ||y_t - y||^2, ||M'y_t - M'y||^2 per trial (do_test == 2)
     // M' in DCSR
     const int* nz_rows; const int* nz_ptr; const int* colidx; const double* val; int n_nz;
     int long_threshold; const int* long_rows; int n_long;
@@ -436,7 +438,9 @@ __global__ void __launch_bounds__(256) k_ls_ladder(LadderArgs a, double* __restr
             for (int b = threadIdx.x; b < nb; b += blockDim.x) v += __ldcg(ws.partials + t * nb + b);
             tot[t] = block_sum(v, red);
         }
-        if (threadIdx.x == 0) {
+        if (threadIdx.x == 0 && a.do_test == 2) {
+            for (int t = 0; t < 2 * LS_MAXT; ++t) a.partial_out[t] = tot[t];
+        } else if (threadIdx.x == 0) {
             int chosen = -1;
             for (int t = 0; t < a.ntrials && chosen < 0; ++t) {
                 const double lhs = mul_rn(mul_rn(sqrt(a.beta), c[t].tau), sqrt(tot[2 * t + 1]));
@@ -451,6 +455,30 @@ __global__ void __launch_bounds__(256) k_ls_ladder(LadderArgs a, double* __restr
             if (chosen >= 0) scal[S_LS_ACCEPTED] = 1.0;
         }
     }
+}
+
+// sharded line search: the per-rank partial sums of every trial of the ladder arrive in ONE all-gather
+// ([nranks][2 * LS_MAXT]); every rank adds them up in rank order and applies the accept test of pdhg.jl:566 to trial
+// 0, 1, ... exactly as the last block of k_ls_ladder does on a single GPU, so all ranks record the same trial.
+__global__ void k_ls_decide_gathered(LadderArgs a, const double* __restrict__ gathered, int nranks, double* __restrict__ scal, int trial0) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    if (scal[S_POISON] != 0.0 || scal[S_LS_ACCEPTED] != 0.0) return;
+    int chosen = -1, last = a.ntrials - 1;
+    double yn_l = 0.0, mn_l = 0.0, tau_l = 0.0;
+    for (int t = 0; t < a.ntrials; ++t) {
+        double yn = 0.0, mn = 0.0;
+        for (int r = 0; r < nranks; ++r) { yn += gathered[(size_t)r * 2 * LS_MAXT + 2 * t]; mn += gathered[(size_t)r * 2 * LS_MAXT + 2 * t + 1]; }
+        const TrialCoef c = ls_trial_coef(a, trial0 + t);
+        const double lhs = mul_rn(mul_rn(sqrt(a.beta), c.tau), sqrt(mn));
+        const double rhs = mul_rn(a.delta, sqrt(yn));
+        const bool ok = lhs <= rhs;
+        if (ok || t == last) { yn_l = yn; mn_l = mn; tau_l = c.tau; if (ok) chosen = t; last = t; break; }
+    }
+    scal[S_YNORM2] = yn_l; scal[S_MTYNORM2] = mn_l;
+    scal[S_TAU] = tau_l;
+    scal[S_LS_EVALS] = (double)(trial0 + last + 1);
+    scal[S_LS_TRIAL] = (double)(trial0 + last);
+    if (chosen >= 0) scal[S_LS_ACCEPTED] = 1.0;
 }
 
 // writes y_new / Mty_new of trial scal[S_LS_TRIAL] (set by k_ls_ladder of the same ladder)

@@ -285,7 +285,7 @@ class Solver {
     bool scal_clean_ = false;                      // the header of the device record is already zero (reset by the last publish)
     bool spin_sync_ = true;                        // PROXSDP_B200_SYNC=memcpy: cudaMemcpyAsync + cudaStreamSynchronize instead
     int fused_ladder_ = 1;                         // PROXSDP_B200_LADDER_FUSED=0: one launch pair per trial (first-round path)
-    DBuf<double> ls_long_sums_;
+    DBuf<double> ls_long_sums_, ls_partial_d_;
     double* feas_host_ = nullptr;
     DBuf<int> cone_side_d_, small_ids_d_;
     DBuf<long long> cone_off_d_, soc_off_d_;
@@ -1021,7 +1021,9 @@ void Solver::launch_ladder(int trial0, int T, double tau0) {
     a.p = (int)p; a.m = (int)m;
     a.tau0 = tau0; a.decay = opt.linsearch_decay; a.tau_old = primal_step_old_; a.beta = beta_;
     a.sigma_fixed = dual_step_; a.delta = opt.delta;
-    a.use_theta = opt.line_search_flag ? 1 : 0; a.do_test = opt.line_search_flag ? 1 : 0;
+    a.use_theta = opt.line_search_flag ? 1 : 0; a.do_test = opt.line_search_flag ? (sharded() ? 2 : 1) : 0;
+    if (sharded() && ls_partial_d_.n == 0) ls_partial_d_.alloc(2 * LS_MAXT);
+    a.partial_out = ls_partial_d_.p;
     a.ntrials = std::max(1, std::min(T, LS_MAXT));
     a.nz_rows = Mt_.nz_rows.p; a.nz_ptr = Mt_.rowptr.p; a.colidx = Mt_.colidx.p; a.val = Mt_.val.p; a.n_nz = Mt_.n_nz;
     a.long_threshold = Mt_.long_threshold; a.long_rows = Mt_.long_rows.p; a.n_long = Mt_.n_long;
@@ -1035,6 +1037,13 @@ void Solver::launch_ladder(int trial0, int T, double tau0) {
     const long long work = std::max<long long>(R, Mt_.n_nz);
     const int blocks = std::max(1, std::min(reduce_blocks_ / 2, ceil_div(work, 256)));
     k_ls_ladder<<<blocks, 256, 0, stream>>>(a, scal_d_.p, ws_, trial0);
+    if (a.do_test == 2) {
+        // one exchange for the whole ladder: 2 * LS_MAXT doubles per rank
+        if (red_d_.n < (size_t)nranks_ * 2 * LS_MAXT) red_d_.alloc((size_t)nranks_ * 2 * LS_MAXT);
+        PB_NCCL(nccl_api().AllGather(ls_partial_d_.p, red_d_.p, 2 * LS_MAXT, ncclDouble, comm_->comm, stream));
+        k_ls_decide_gathered<<<1, 32, 0, stream>>>(a, red_d_.p, nranks_, scal_d_.p, trial0);
+        launches++;
+    }
     k_ls_apply<<<blocks, 256, 0, stream>>>(a, scal_d_.p, trial0);
     launches += 2;
 }
@@ -1060,8 +1069,8 @@ void Solver::launch_post_eig(double tau0, bool first_pass) {
         launches += 2;
     }
     launch_spmv(M_, xn, Mx_[1 - cur_].p);
-    int ntr = opt.line_search_flag ? (sharded() ? 1 : (int)std::min<long long>(ladder_, std::max<long long>(opt.max_linsearch_steps, 1))) : 1;
-    if (!sharded() && fused_ladder_) launch_ladder(0, ntr, tau0);
+    int ntr = opt.line_search_flag ? (int)std::min<long long>(ladder_, std::max<long long>(opt.max_linsearch_steps, 1)) : 1;
+    if (fused_ladder_) launch_ladder(0, ntr, tau0);
     else for (int t = 0; t < ntr; ++t) launch_dual_trial(t, tau0);
     int blocksN = std::max(1, std::min(reduce_blocks_, ceil_div(n, 512)));
     k_residual_primal<<<blocksN, 256, 0, stream>>>(n, xn, x_[cur_].p, Mty_[1 - cur_].p, Mty_[cur_].p, c_.p, scal_d_.p, ws_);
@@ -1105,22 +1114,24 @@ void Solver::fallback_projection(long long iter) {
 }
 
 void Solver::sync_scalars(bool iteration_end) {
-    if (sharded() || !spin_sync_) {
-        if (sharded()) {
-            if (gather_d_.n < (size_t)nranks_ * S_HEADER) gather_d_.alloc((size_t)nranks_ * S_HEADER);
-            PB_NCCL(nccl_api().AllGather(scal_d_.p, gather_d_.p, S_HEADER, ncclDouble, comm_->comm, stream));
-            k_fold_header<<<1, 32, 0, stream>>>(gather_d_.p, nranks_, scal_d_.p);
-            launches++;
-        }
+    if (sharded()) {
+        // whole-problem record: one all-gather of the per-rank headers, folded in rank order on every rank
+        if (gather_d_.n < (size_t)nranks_ * S_HEADER) gather_d_.alloc((size_t)nranks_ * S_HEADER);
+        PB_NCCL(nccl_api().AllGather(scal_d_.p, gather_d_.p, S_HEADER, ncclDouble, comm_->comm, stream));
+        k_fold_header<<<1, 32, 0, stream>>>(gather_d_.p, nranks_, scal_d_.p);
+        launches++;
+    }
+    if (!spin_sync_) {
         PB_CUDA(cudaMemcpyAsync(scal_host, scal_d_.p, sizeof(double) * (size_t)scal_len, cudaMemcpyDeviceToHost, stream));
         g_d2h_bytes += (long long)sizeof(double) * scal_len;
         PB_CUDA(cudaStreamSynchronize(stream));
         scal_clean_ = false;
     } else {
-        // single GPU: the last kernel of the sequence writes the record into mapped host memory and bumps a sequence
-        // word; the host spins on it (a D2H copy + stream synchronisation costs 25-40 us per iteration, this ~3)
+        // the last kernel of the sequence writes the record into mapped host memory and bumps a sequence word; the
+        // host spins on it (a D2H copy + stream synchronisation costs 25-40 us per iteration, this ~3).  Sharded runs
+        // re-initialise the record every iteration (elapsed time, SOC identity), so nothing is reset here for them.
         ++pub_seq_;
-        const int mode = iteration_end ? (opt.line_search_flag ? 1 : 2) : 0;
+        const int mode = (iteration_end && !sharded()) ? (opt.line_search_flag ? 1 : 2) : 0;
         k_publish_record<<<1, 128, 0, stream>>>(scal_d_.p, scal_len, mode, scal_host_dev_, pub_seq_dev_, pub_seq_);
         launches++;
         g_d2h_bytes += (long long)sizeof(double) * scal_len;
@@ -1133,7 +1144,7 @@ void Solver::sync_scalars(bool iteration_end) {
                 else if (q != cudaErrorNotReady) throw CudaError(-100 - (int)q, std::string("kernel failed: ") + cudaGetErrorString(q));
             }
         }
-        scal_clean_ = iteration_end && scal_host[S_POISON] == 0.0 && (!opt.line_search_flag || scal_host[S_LS_ACCEPTED] != 0.0);
+        scal_clean_ = mode != 0 && scal_host[S_POISON] == 0.0 && (!opt.line_search_flag || scal_host[S_LS_ACCEPTED] != 0.0);
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) throw CudaError(-100 - (int)e, std::string("kernel launch failed: ") + cudaGetErrorString(e));
@@ -1445,10 +1456,10 @@ bool Solver::run(long long max_steps, bool flush_l2) {
         bool ls_exhausted = false;
         double ls_last_tau = 0.0;
         if (opt.line_search_flag && scal_host[S_LS_ACCEPTED] == 0.0) {
-            long long t = sharded() ? 1 : std::min<long long>(ladder_, std::max<long long>(opt.max_linsearch_steps, 1));
+            long long t = std::min<long long>(ladder_, std::max<long long>(opt.max_linsearch_steps, 1));
             const double keep_ops = scal_host[S_NUMOPS];
             while (scal_host[S_LS_ACCEPTED] == 0.0 && t < opt.max_linsearch_steps) {
-                if (!sharded() && fused_ladder_) {
+                if (fused_ladder_) {
                     // the next batch of trials, again side by side
                     const int T = (int)std::min<long long>(ladder_, opt.max_linsearch_steps - t);
                     launch_ladder((int)t, T, tau0);
