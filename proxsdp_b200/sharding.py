@@ -197,6 +197,30 @@ def _nccl_comm(device_id: int, group=None):
     return comm
 
 
+def solve_local_shard(aff_loc: AffineSets, con_loc: ConicSets, opt: Options, rank: int, world: int,
+                      global_n: int, global_p: int, global_m: int, group=None, device_id: Optional[int] = None) -> Result:
+    """`proxsdp_b200_solve_sharded` on this rank's blocks: the local sub-problem plus the sizes of the whole problem.
+    For callers that generate their shard directly (e.g. a weak-scaling batch: every rank builds its own instances)."""
+    from . import solver
+    from ._abi import MarshalledProblem, MarshalledResult, OptionsPOD, ProblemPOD, ResultPOD
+    L = solver.lib()
+    if device_id is None:
+        import torch
+        device_id = torch.cuda.current_device()
+    comm = _nccl_comm(device_id, group) if world > 1 else c_void_p()
+    shard = ShardPOD(rank, world, global_n, global_p, global_m, comm, ctypes.cast(None, REDUCE_FN), None)
+    mp = MarshalledProblem(aff_loc, con_loc)
+    mr = MarshalledResult(mp.n, mp.p, mp.m, mp.n_sdp, int(opt.trace_cap))
+    o = opt.copy()
+    o.device_id = device_id
+    opod = o.to_pod()
+    L.proxsdp_b200_solve_sharded.argtypes = [POINTER(ProblemPOD), POINTER(OptionsPOD), POINTER(ShardPOD), POINTER(ResultPOD)]
+    L.proxsdp_b200_solve_sharded.restype = ctypes.c_int
+    solver._check(L.proxsdp_b200_solve_sharded(ctypes.byref(mp.pod), ctypes.byref(opod), ctypes.byref(shard),
+                                               ctypes.byref(mr.pod)))
+    return mr.to_result()
+
+
 def chambolle_pock_sharded(aff: AffineSets, con: ConicSets, opt: Options, group=None, device_id: Optional[int] = None,
                            local_solve: Optional[Callable] = None, gather: bool = True) -> Result:
     """`chambolle_pock` on the whole problem, executed by all ranks of a torch.distributed group.
@@ -210,25 +234,8 @@ def chambolle_pock_sharded(aff: AffineSets, con: ConicSets, opt: Options, group=
     if local_solve is not None:
         res = local_solve(aff_loc, con_loc, opt, info)
     else:
-        from . import solver
-        from ._abi import MarshalledProblem, MarshalledResult, OptionsPOD, ProblemPOD, ResultPOD
-        L = solver.lib()
-        if device_id is None:
-            import torch
-            device_id = torch.cuda.current_device()
-        comm = _nccl_comm(device_id, group) if world > 1 else c_void_p()
-        shard = ShardPOD(rank, world, info.global_n, info.global_p, info.global_m, comm,
-                         ctypes.cast(None, REDUCE_FN), None)
-        mp = MarshalledProblem(aff_loc, con_loc)
-        mr = MarshalledResult(mp.n, mp.p, mp.m, mp.n_sdp, int(opt.trace_cap))
-        o = opt.copy()
-        o.device_id = device_id
-        opod = o.to_pod()
-        L.proxsdp_b200_solve_sharded.argtypes = [POINTER(ProblemPOD), POINTER(OptionsPOD), POINTER(ShardPOD), POINTER(ResultPOD)]
-        L.proxsdp_b200_solve_sharded.restype = ctypes.c_int
-        solver._check(L.proxsdp_b200_solve_sharded(ctypes.byref(mp.pod), ctypes.byref(opod), ctypes.byref(shard),
-                                                   ctypes.byref(mr.pod)))
-        res = mr.to_result()
+        res = solve_local_shard(aff_loc, con_loc, opt, rank, world, info.global_n, info.global_p, info.global_m,
+                                group=group, device_id=device_id)
     if not gather:
         return res
     pieces = [None] * world
