@@ -160,11 +160,15 @@ __global__ void __launch_bounds__(512) k_small_cone_proj(SmallConeArgs a) {
 //
 // The matrix (padded to NP = 32*nb rows/cols with zeros) is cut into nb blocks of 32.
 // A sweep is a round-robin tournament over block pairs (I, J); per round
-//   1. k_bj_pair_eig : one CTA per pair diagonalises the 64x64 pivot sub-matrix
-//                      [A_II A_IJ; A_JI A_JJ] in shared memory (cyclic Jacobi) -> Q, lambda
+//   1. k_bj_pair_eig : one CTA per pair rotates the 64x64 pivot sub-matrix [A_II A_IJ; A_JI A_JJ] in shared
+//                      memory: `inner_sweeps` cyclic Jacobi sweeps (double-buffered two-sided rounds), NOT to
+//                      convergence — every rotation lowers the off-diagonal norm of the whole matrix by exactly
+//                      2 a_pq^2, so the outer iteration converges whatever the inner effort, and one or two inner
+//                      sweeps cost 60-130 dependent rounds instead of ~500 -> Q and the rotated pivot block P
 //   2. k_bj_apply<COLS>: A[:, I∪J] <- A[:, I∪J] Q ;  V[:, I∪J] <- V[:, I∪J] Q
-//   3. k_bj_apply<ROWS>: A[I∪J, :] <- Q' A[I∪J, :]   (pivot block set to diag(lambda))
-// Pairs of one round touch disjoint block rows/columns, so each pass is one launch.
+//   3. k_bj_apply<ROWS>: A[I∪J, :] <- Q' A[I∪J, :]   (pivot block set to P, which is symmetric to the last bit)
+// Pairs of one round touch disjoint block rows/columns, so each pass is one launch; the pair of a CTA is computed
+// from (round, blockIdx) on the device — the host only launches.
 // Used for full_eig! on cones with side > SMALL_CONE_MAX (Krylov fallback,
 // full_eig_decomp = true, target_rank > max_target_rank_krylov_eigs) and for cone_feas.
 // ===========================================================================
@@ -172,64 +176,76 @@ constexpr int BJ_B = 32;          // block size
 constexpr int BJ_P = 2 * BJ_B;    // pivot size
 constexpr int BJ_LD = BJ_P + 1;
 
-struct BjPairs {       // device arrays for the current round
-    const int* pi;     // block index I (I < J), -1 for a pair with the dummy block
-    const int* pj;
+struct BjRound {       // the tournament round: CTA t handles the pair below
+    int round, mplayers, nb;
 };
-
-__host__ __device__ inline size_t bj_pair_smem_bytes() {
-    return sizeof(double) * (2 * (size_t)BJ_P * BJ_LD) + jacobi_scratch_bytes(BJ_P) + 64;
+__device__ __forceinline__ void bj_pair_of(const BjRound& r, int t, int& I, int& J) {
+    int a_, b_;
+    if (r.mplayers == 2) { a_ = 0; b_ = 1; }
+    else if (t == 0) { a_ = r.mplayers - 1; b_ = r.round; }
+    else { a_ = (r.round + t) % (r.mplayers - 1); b_ = (r.round - t + (r.mplayers - 1)) % (r.mplayers - 1); }
+    I = min(a_, b_); J = max(a_, b_);
+    if (J >= r.nb) { I = -1; J = -1; }        // pair with the dummy player of an odd tournament
 }
 
-// Q layout: per pair, BJ_P x BJ_P column-major (ld = BJ_P), followed by BJ_P eigenvalues.
-constexpr int BJ_QSTRIDE = BJ_P * BJ_P + BJ_P;
+__host__ __device__ inline size_t bj_pair_smem_bytes() {
+    return sizeof(double) * (3 * (size_t)BJ_P * BJ_LD) + jacobi_scratch_bytes(BJ_P) + 64;
+}
+
+// Q layout: per pair, Q (BJ_P x BJ_P column-major, ld = BJ_P) followed by the rotated pivot block P (same layout).
+constexpr int BJ_QSTRIDE = 2 * BJ_P * BJ_P;
 constexpr size_t BJ_APPLY_SMEM = sizeof(double) * 2 * BJ_P * (BJ_P + 1);
 
-__global__ void __launch_bounds__(256)
-k_bj_pair_eig(double* __restrict__ A, int ld, BjPairs pr, double* __restrict__ Qbuf, int* __restrict__ rotated) {
+__global__ void __launch_bounds__(512)
+k_bj_pair_eig(double* __restrict__ A, int ld, BjRound pr, int inner_sweeps, double* __restrict__ Qbuf, int* __restrict__ rotated) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int I = pr.pi[blockIdx.x], J = pr.pj[blockIdx.x];
+    int I, J;
+    bj_pair_of(pr, blockIdx.x, I, J);
     if (I < 0) return;
-    double* S = reinterpret_cast<double*>(smem_raw);
-    double* U = S + (size_t)BJ_P * BJ_LD;
+    double* S0 = reinterpret_cast<double*>(smem_raw);
+    double* S1 = S0 + (size_t)BJ_P * BJ_LD;
+    double* U = S1 + (size_t)BJ_P * BJ_LD;
     JacobiScratch js = jacobi_carve(reinterpret_cast<void*>(U + (size_t)BJ_P * BJ_LD), BJ_P);
-    const int tid = threadIdx.x;
-    for (int idx = tid; idx < BJ_P * BJ_P; idx += 256) {
+    const int tid = threadIdx.x, nt = blockDim.x;
+    for (int idx = tid; idx < BJ_P * BJ_P; idx += nt) {
         int r = idx % BJ_P, c = idx / BJ_P;
         int gr = (r < BJ_B ? I * BJ_B + r : J * BJ_B + (r - BJ_B));
         int gc = (c < BJ_B ? I * BJ_B + c : J * BJ_B + (c - BJ_B));
-        S[r + c * BJ_LD] = A[(size_t)gr + (size_t)gc * ld];
+        S0[r + c * BJ_LD] = A[(size_t)gr + (size_t)gc * ld];
     }
     __syncthreads();
     // symmetrise (the two triangles may differ by rounding after the GEMM passes)
-    for (int idx = tid; idx < BJ_P * BJ_P; idx += 256) {
+    for (int idx = tid; idx < BJ_P * BJ_P; idx += nt) {
         int r = idx % BJ_P, c = idx / BJ_P;
         if (r < c) {
-            double v = 0.5 * (S[r + c * BJ_LD] + S[c + r * BJ_LD]);
-            S[r + c * BJ_LD] = v; S[c + r * BJ_LD] = v;
+            double v = 0.5 * (S0[r + c * BJ_LD] + S0[c + r * BJ_LD]);
+            S0[r + c * BJ_LD] = v; S0[c + r * BJ_LD] = v;
         }
     }
     __syncthreads();
-    int sweeps = jacobi_eigh_smem(BJ_P, S, BJ_LD, U, BJ_LD, js);
+    const double* P = jacobi_eigh_smem_fast(BJ_P, S0, S1, BJ_LD, U, BJ_LD, js, inner_sweeps);
     __syncthreads();
+    const int nrounds = (int)js.red[38];
     double* Q = Qbuf + (size_t)blockIdx.x * BJ_QSTRIDE;
-    for (int idx = tid; idx < BJ_P * BJ_P; idx += 256) {
+    for (int idx = tid; idx < BJ_P * BJ_P; idx += nt) {
         int r = idx % BJ_P, c = idx / BJ_P;
         Q[idx] = U[r + c * BJ_LD];
+        // rotated pivot block, symmetrised (both triangles carry the same rotations up to rounding)
+        Q[BJ_P * BJ_P + idx] = (r == c) ? P[r + c * BJ_LD] : 0.5 * (P[r + c * BJ_LD] + P[c + r * BJ_LD]);
     }
-    for (int i = tid; i < BJ_P; i += 256) Q[BJ_P * BJ_P + i] = S[i + i * BJ_LD];
-    if (tid == 0 && sweeps > 0) atomicAdd(rotated, 1);
+    if (tid == 0 && nrounds > 0) atomicAdd(rotated, 1);
 }
 
 // MODE 0: columns of A and V;  MODE 1: rows of A.  grid = (pairs, NP/64 chunks, MODE==0 ? 2 : 1)
 template <int MODE>
 __global__ void __launch_bounds__(256)
-k_bj_apply(double* __restrict__ A, double* __restrict__ V, int ld, int NP, BjPairs pr,
+k_bj_apply(double* __restrict__ A, double* __restrict__ V, int ld, int NP, BjRound pr,
            const double* __restrict__ Qbuf) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double (*Qs)[BJ_P + 1] = reinterpret_cast<double (*)[BJ_P + 1]>(smem_raw);
     double (*Ts)[BJ_P + 1] = Qs + BJ_P;
-    const int I = pr.pi[blockIdx.x], J = pr.pj[blockIdx.x];
+    int I, J;
+    bj_pair_of(pr, blockIdx.x, I, J);
     if (I < 0) return;
     const double* Q = Qbuf + (size_t)blockIdx.x * BJ_QSTRIDE;
     const int tid = threadIdx.x;
@@ -272,7 +288,7 @@ k_bj_apply(double* __restrict__ A, double* __restrict__ V, int ld, int NP, BjPai
 #pragma unroll
             for (int v = 0; v < 4; ++v) acc[u][v] = fma(av[u], bv[v], acc[u][v]);
     }
-    const double* lam = Q + BJ_P * BJ_P;
+    const double* Pm = Q + BJ_P * BJ_P;
 #pragma unroll
     for (int u = 0; u < 4; ++u)
 #pragma unroll
@@ -287,15 +303,65 @@ k_bj_apply(double* __restrict__ A, double* __restrict__ V, int ld, int NP, BjPai
                 int gc = chunk0 + b_;
                 if (gc < NP) {
                     double val = acc[u][v];
-                    // pivot block: exactly diag(lambda)
+                    // pivot block: the block the pair kernel rotated in shared memory (exactly symmetric)
                     int pc = -1;
                     if (gc >= I * BJ_B && gc < (I + 1) * BJ_B) pc = gc - I * BJ_B;
                     else if (gc >= J * BJ_B && gc < (J + 1) * BJ_B) pc = BJ_B + gc - J * BJ_B;
-                    if (pc >= 0) val = (pc == a_) ? lam[a_] : 0.0;
+                    if (pc >= 0) val = Pm[a_ + pc * BJ_P];
                     M[(size_t)gr + (size_t)gc * ld] = val;
                 }
             }
         }
+}
+
+// C = op(A) B for NP x NP matrices (NP a multiple of 64, column-major, leading dimension ld), op = transpose when TA.
+// Plain tiled FP64 product (64 x 64 tile per CTA, 4 x 4 patch per thread, k in slices of 16): used twice per warm-started
+// eigendecomposition (W' (A W)), i.e. a few % of it; FP64 has no tcgen05 kind, so this is CUDA-core FMA by construction.
+template <bool TA>
+__global__ void __launch_bounds__(256)
+k_gemm64(const double* __restrict__ A, const double* __restrict__ B, double* __restrict__ C, int NP, int ld) {
+    __shared__ double As[16][64 + 4];     // As[k][i] = op(A)(i0 + i, k0 + k)
+    __shared__ double Bs[16][64 + 4];     // Bs[k][j] = B(k0 + k, j0 + j)
+    const int tid = threadIdx.x;
+    const int i0 = blockIdx.x * 64, j0 = blockIdx.y * 64;
+    const int tr = (tid % 16) * 4, tc = (tid / 16) * 4;
+    double acc[4][4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int v = 0; v < 4; ++v) acc[u][v] = 0.0;
+    for (int k0 = 0; k0 < NP; k0 += 16) {
+        for (int idx = tid; idx < 16 * 64; idx += 256) {
+            if (TA) { const int k = idx % 16, i = idx / 16; As[k][i] = A[(size_t)(k0 + k) + (size_t)(i0 + i) * ld]; }      // A'(i, k) = A(k, i): k contiguous
+            else    { const int i = idx % 64, k = idx / 64; As[k][i] = A[(size_t)(i0 + i) + (size_t)(k0 + k) * ld]; }
+            { const int k = idx % 16, j = idx / 16; Bs[k][j] = B[(size_t)(k0 + k) + (size_t)(j0 + j) * ld]; }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            double av[4], bv[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { av[u] = As[k][tr + u]; bv[u] = Bs[k][tc + u]; }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int v = 0; v < 4; ++v) acc[u][v] = fma(av[u], bv[v], acc[u][v]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int v = 0; v < 4; ++v) C[(size_t)(i0 + tr + u) + (size_t)(j0 + tc + v) * ld] = acc[u][v];
+}
+
+// zero padding of A beyond n (warm start: V keeps the previous eigenvectors)
+__global__ void k_bj_pad(double* __restrict__ A, int ld, int n, int NP) {
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long tot = (long long)NP * NP;
+    if (idx >= tot) return;
+    int r = (int)(idx % NP), c = (int)(idx / NP);
+    if (r >= n || c >= n) A[(size_t)r + (size_t)c * ld] = 0.0;
 }
 
 // V = I (NP x NP), zero padding of A beyond n

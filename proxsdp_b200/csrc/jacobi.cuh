@@ -158,7 +158,7 @@ __device__ __forceinline__ double fast_rcp_pos(double x) {
 
 // rotation sweeps shared by the cold and warm entry points (V already initialised)
 __device__ inline double* jacobi_sweeps_fast(int m, double* A0, double* A1, int lda, double* V, int ldv,
-                                             JacobiScratch js, double fro2) {
+                                             JacobiScratch js, double fro2, int max_sweeps = 40) {
     const int tid = threadIdx.x, nt = blockDim.x;
     if (m < 2 || fro2 == 0.0) return A0;
     const double skip = sqrt(fro2) * 1.0e-17;
@@ -176,7 +176,7 @@ __device__ inline double* jacobi_sweeps_fast(int m, double* A0, double* A1, int 
     double* A = A0;
     double* B = A1;
     int nrounds = 0;
-    for (int sweep = 0; sweep < 40; ++sweep) {
+    for (int sweep = 0; sweep < max_sweeps; ++sweep) {
         int rotated_in_sweep = 0;
         for (int round = 0; round < m - 1; ++round) {
             int any = 0;
@@ -250,7 +250,7 @@ __device__ inline double* jacobi_sweeps_fast(int m, double* A0, double* A1, int 
 }
 
 __device__ inline double* jacobi_eigh_smem_fast(int m, double* A0, double* A1, int lda, double* V, int ldv,
-                                                JacobiScratch js) {
+                                                JacobiScratch js, int max_sweeps = 40) {
     const int tid = threadIdx.x, nt = blockDim.x;
     double fro2 = 0.0;
     for (int idx = tid; idx < m * m; idx += nt) {
@@ -260,7 +260,7 @@ __device__ inline double* jacobi_eigh_smem_fast(int m, double* A0, double* A1, i
         fro2 += a * a;
     }
     fro2 = block_sum(fro2, js.red);
-    return jacobi_sweeps_fast(m, A0, A1, lda, V, ldv, js, fro2);
+    return jacobi_sweeps_fast(m, A0, A1, lda, V, ldv, js, fro2, max_sweeps);
 }
 
 // Warm start: W (m x m, leading dimension ldv, global memory) is an orthogonal basis that nearly diagonalises

@@ -212,22 +212,39 @@ __device__ __forceinline__ void strip_load(double2 (&x)[RB][CPW], const double* 
     }
 }
 
-// one batch of up to RB STREAMED rows whose loads are already in flight in x: multiply, butterfly, warp totals -> wrow
-template <int CPW, int RB>
-__device__ __forceinline__ void symv_batch_streamed(const double2 (&x)[RB][CPW], const int count, const double2 (&vr)[CPW], double* wrow,
-                                                    const int lane, const int warp) {
-    double acc[RB];
+// up to NMAX STREAMED rows first .. first + count - 1 of the slab: strip loads, RB rows per chunk, the next chunk in flight
+// while the current one is multiplied; warp totals of the rows -> wrow[row - first][warp]
+template <int CPW, int RB, int NMAX>
+__device__ __forceinline__ void symv_sub_streamed(const double* __restrict__ gcol, const int ld, const int first, const int count,
+                                                  const int nch, const double2 (&vr)[CPW], double* wrow, const int lane, const int warp) {
+    double acc[NMAX];
+    const int stream_end = first + count;
+    double2 x[RB][CPW];
+    strip_load<CPW, RB>(x, gcol, ld, first, stream_end, nch);
 #pragma unroll
-    for (int i = 0; i < RB; ++i) {
-        double t = 0.0;
-        if (i < count) {
+    for (int c0 = 0; c0 < NMAX; c0 += RB) {
+        double2 xn[RB][CPW];
+        if (c0 + RB < NMAX) strip_load<CPW, RB>(xn, gcol, ld, first + c0 + RB, stream_end, nch);
 #pragma unroll
-            for (int c = 0; c < CPW; ++c) { t = fma(x[i][c].x, vr[c].x, t); t = fma(x[i][c].y, vr[c].y, t); }
+        for (int i = 0; i < RB; ++i) {
+            if (c0 + i < NMAX) {
+                double t = 0.0;
+                if (c0 + i < count) {
+#pragma unroll
+                    for (int c = 0; c < CPW; ++c) { t = fma(x[i][c].x, vr[c].x, t); t = fma(x[i][c].y, vr[c].y, t); }
+                }
+                acc[c0 + i] = t;
+            }
         }
-        acc[i] = t;
+        if (c0 + RB < NMAX) {
+#pragma unroll
+            for (int i = 0; i < RB; ++i)
+#pragma unroll
+                for (int c = 0; c < CPW; ++c) x[i][c] = xn[i][c];
+        }
     }
     int off, valid;
-    bfly_reduce<RB>(acc, lane, count, off, valid);
+    bfly_reduce<NMAX>(acc, lane, count, off, valid);
     if (valid) wrow[off * LZ_NW + warp] = acc[0];
 }
 
@@ -258,8 +275,8 @@ __device__ __forceinline__ void symv_sub_resident(const double* srow, const int 
 //   * Warp s owns the column strip of CPW 64-double chunks for ALL rows of the slab; its piece of v sits in registers.
 //   * The last rows of the slab (from res_begin on) are RESIDENT in shared memory: the TMA engine staged them once when
 //     the kernel started (cp.async.bulk + mbarrier, see the kernel prologue); at n = 2000 that takes ~40 % of the matrix
-//     off the L2 -> SM path of every mat-vec.  The rows before them are streamed with 128-bit loads in batches of RB rows
-//     (a whole batch in flight at once; the first one flies while the resident rows are multiplied).
+//     off the L2 -> SM path of every mat-vec.  The rows before them are streamed with 128-bit loads, RB rows per chunk,
+//     the next chunk in flight while the current one is multiplied.
 //   * Every lane keeps one partial sum per row of a sub-round (NMAX rows) in registers; a transposing butterfly (12
 //     shuffles for 9 rows instead of 5 per row) leaves one warp total per row in one lane, the NS <= 16 warp totals of
 //     a row go through a 4 KB table, and after one block barrier per 32 rows thread r of warp 0 publishes row r.
@@ -284,21 +301,15 @@ __device__ __forceinline__ void symv_slab(const double* __restrict__ X, const in
         const int buf = (rbeg >> 5) & 1;                 // two tables: the writers of round r + 2 are behind the barrier of
         double* wtab = wpart + buf * 32 * LZ_NW;         // round r + 1, which warp 0 passes only after reading round r
         if (active) {
-            // streamed rows [rbeg, se): batches of RB rows, RB * CPW 16-byte loads per lane in flight (the whole batch is
-            // issued before anything is consumed); the first batch flies while the resident rows are multiplied
             const int se = min(rend, res_begin);
             const double* gcol = X + (size_t)r0 * ld + (size_t)warp * CPW * 64 + 2 * lane;
-            double2 x[RB][CPW];
-            strip_load<CPW, RB>(x, gcol, ld, rbeg, se, nch);
+            for (int f = rbeg; f < se; f += NMAX)
+                symv_sub_streamed<CPW, RB, NMAX>(gcol, ld, f, min(NMAX, se - f), nch, vr, wtab + (f - rbeg) * LZ_NW, lane, warp);
             const int rstride = cpr * 64;
             const double* scol = xres + (size_t)warp * CPW * 64 + 2 * lane;
             for (int f = max(rbeg, res_begin); f < rend; f += NMAX)
                 symv_sub_resident<CPW, NMAX>(scol + (size_t)(f - res_begin) * rstride, rstride, min(NMAX, rend - f), nch, vr,
                                              wtab + (f - rbeg) * LZ_NW, lane, warp);
-            for (int f = rbeg; f < se; f += RB) {
-                if (f > rbeg) strip_load<CPW, RB>(x, gcol, ld, f, se, nch);
-                symv_batch_streamed<CPW, RB>(x, min(RB, se - f), vr, wtab + (f - rbeg) * LZ_NW, lane, warp);
-            }
         }
         if (prof && tid == 0) { const long long tn = clock64(); prof[15] += tn - tp; tp = tn; }          // warp 0: loads + FMAs + butterflies
         __syncthreads();

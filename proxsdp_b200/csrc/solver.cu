@@ -70,22 +70,17 @@ static NcclApi& nccl_api() {
 
 
 // the strip width (64-double chunks per warp) selects the kernel instance: cpw = ceil(ceil(n / 64) / 16);
-// <strip width, streamed rows per load batch (all of them in flight at once), resident rows per butterfly>.
-// rb_override (PROXSDP_B200_LZ_RB, experiments): other batch sizes of the n <= 2048 instance.
-static const void* lanczos_cl3_kernel(int cpw, int rb_override = 0) {
+// <strip width, streamed rows per load chunk (two chunks in flight), rows per butterfly>: the widest choice that ptxas
+// fits into 128 registers without spilling on the per-step path.  Deeper load batches were measured and are slower
+// (profiles/r2_rb_sweep.txt): the mat-vec is not limited by the bytes in flight.
+static const void* lanczos_cl3_kernel(int cpw) {
     switch (cpw) {
-        case 1: return (const void*)k_lanczos_cl3<1, 6, 9>;
-        case 2:
-            switch (rb_override) {
-                case 3: return (const void*)k_lanczos_cl3<2, 3, 8>;
-                case 6: return (const void*)k_lanczos_cl3<2, 6, 8>;
-                case 9: return (const void*)k_lanczos_cl3<2, 9, 8>;
-                default: return (const void*)k_lanczos_cl3<2, 5, 8>;
-            }
-        case 3: return (const void*)k_lanczos_cl3<3, 3, 8>;
-        case 4: return (const void*)k_lanczos_cl3<4, 3, 6>;
-        case 5: return (const void*)k_lanczos_cl3<5, 2, 6>;
-        case 6: return (const void*)k_lanczos_cl3<6, 2, 6>;
+        case 1: return (const void*)k_lanczos_cl3<1, 3, 9>;
+        case 2: return (const void*)k_lanczos_cl3<2, 2, 8>;
+        case 3: return (const void*)k_lanczos_cl3<3, 1, 8>;
+        case 4: return (const void*)k_lanczos_cl3<4, 1, 6>;
+        case 5: return (const void*)k_lanczos_cl3<5, 1, 6>;
+        case 6: return (const void*)k_lanczos_cl3<6, 1, 6>;
         case 8: return (const void*)k_lanczos_cl3<8, 1, 4>;
         default: return nullptr;
     }
@@ -176,6 +171,9 @@ struct ConeDev {
     bool small = false;
     DBuf<double> X;             // ld x ld, large cones only
     DBuf<double> Vfull;         // ld x ld eigenvectors for the block-Jacobi path (allocated lazily)
+    DBuf<double> Vtmp;          // ld x ld scratch of the warm start (A W)
+    bool have_V = false;        // Vfull holds the eigenvectors of this cone's previous full projection
+    long long full_calls = 0;
     DBuf<double> Y;             // ld x (Kmax)
     DBuf<double> resid, vals, kept_lam;
     DBuf<double> ritz_ws[2];    // warm start of the K x K Ritz eigenproblem (ping-pong between launches)
@@ -222,7 +220,10 @@ class Solver {
 
     // device full eigendecomposition of the matrix currently in cone.X (destroys X):
     // eigenvalues -> host vector (unsorted), eigenvectors in cone.Vfull
-    std::vector<double> full_eig_device(ConeDev& cd);
+    // warm: start from the eigenvector basis of the cone's previous decomposition (consecutive PDHG iterates have nearly
+    // the same eigenvectors, so W' A W is nearly diagonal and 2-3 sweeps replace ~10); every 32nd call starts cold
+    std::vector<double> full_eig_device(ConeDev& cd, bool warm = false);
+    int bj_warm_ = 1;          // PROXSDP_B200_BJ_WARM=0 disables the warm start
     void lanczos_launch(ConeDev& cd, int cone_idx, int nev, int K, int maxiter, double tol);
     bool lanczos_launch_cluster(ConeDev& cd, int cone_idx, int nev, int K, int maxiter, double tol);
     bool lanczos_launch_cluster3(ConeDev& cd, int cone_idx, int nev, int K, int maxiter, double tol);
@@ -232,7 +233,6 @@ class Solver {
     long long small_warm_calls_ = 0;
     DBuf<double> small_warm_d_;
     int lz_kernel_ = 3;        // 3 = third-generation cluster kernel (lanczos_cl3.cuh), 2 = second generation (lanczos_cl.cuh)
-    int lz_rb_ = 0;            // cl3 kernel, experiments: streamed rows per load batch of the n <= 2048 instance
     int lz_poll_ns_ = 0;       // cl3 kernel: nanoseconds of back-off between polls of the exchange words
     int lz_strict_ = 0;        // cl3 kernel: FP64 alpha + two Gram-Schmidt passes on every step (PROXSDP_B200_LZ_STRICT=1)
     int lz_xres_ = 0;          // >= 1: cap the resident slab rows of the cl3 symv at lz_xres_ - 1 (experiments / tests)
@@ -293,7 +293,8 @@ class Solver {
     DBuf<double> soc_gap_d_, scal_d_, partials_d_, out_min_d_, offnorm_d_;
     DBuf<unsigned int> counters_d_;
     DBuf<double> bj_Q_;
-    DBuf<int> bj_pi_, bj_pj_, bj_rot_;
+    DBuf<int> bj_rot_;
+    int bj_inner_sweeps_ = 2;      // cyclic Jacobi sweeps on a 64 x 64 pivot block per visit (PROXSDP_B200_BJ_INNER)
     std::vector<int> small_ids_, large_ids_;
     int max_small_side_ = 0, Kmax_ = 25;
     ReduceWs ws_{};
@@ -392,7 +393,8 @@ Solver::Solver(const proxsdp_problem_t* prob, const proxsdp_options_t* opt_in, b
     if (const char* e = getenv("PROXSDP_B200_LZ_XRES")) lz_xres_ = atoi(e);
     if (const char* e = getenv("PROXSDP_B200_LZ_STRICT")) lz_strict_ = atoi(e) != 0 ? 1 : 0;
     if (const char* e = getenv("PROXSDP_B200_LZ_POLL_NS")) lz_poll_ns_ = std::max(0, atoi(e));
-    if (const char* e = getenv("PROXSDP_B200_LZ_RB")) lz_rb_ = atoi(e);
+    if (const char* e = getenv("PROXSDP_B200_BJ_INNER")) bj_inner_sweeps_ = std::max(1, atoi(e));
+    if (const char* e = getenv("PROXSDP_B200_BJ_WARM")) bj_warm_ = atoi(e) != 0 ? 1 : 0;
     if (const char* e = getenv("PROXSDP_B200_RITZ_BI")) lz_bi_ = atoi(e);
     g_h2d_bytes = 0; g_d2h_bytes = 0;
     st0.lap("ctor: done");
@@ -594,7 +596,6 @@ void Solver::setup_host(const proxsdp_problem_t* prob) {
             size_t mx = smem_optin_;
             std::vector<const void*> fns;
             for (int cpw = 1; cpw <= 8; ++cpw) if (const void* fn = lanczos_cl3_kernel(cpw)) fns.push_back(fn);
-            for (int rb : {3, 6, 9}) fns.push_back(lanczos_cl3_kernel(2, rb));
             for (const void* fn : fns) {
                 cudaFuncAttributes fa{};
                 PB_CUDA(cudaFuncGetAttributes(&fa, fn));
@@ -747,7 +748,7 @@ bool Solver::lanczos_launch_cluster3(ConeDev& cd, int cone_idx, int nev, int K, 
     size_t smem = 0;
     if (!fit_resident(G, L, smem)) return false;
     cfg.gridDim = dim3((unsigned)G); cfg.dynamicSmemBytes = smem;
-    const void* kfn = lanczos_cl3_kernel(cpw, lz_rb_);
+    const void* kfn = lanczos_cl3_kernel(cpw);
     int max_clusters = 0;
     if (cudaOccupancyMaxActiveClusters(&max_clusters, kfn, &cfg) != cudaSuccess || max_clusters < 1) {
         cudaGetLastError();
@@ -846,47 +847,41 @@ void Solver::launch_reconstruct(ConeDev& cd, double* x_out) {
 
 // Block-Jacobi eigendecomposition of cd.X (destroyed).  Returns the eigenvalues (unsorted);
 // eigenvectors are the columns of cd.Vfull.
-std::vector<double> Solver::full_eig_device(ConeDev& cd) {
+std::vector<double> Solver::full_eig_device(ConeDev& cd, bool warm) {
     const int nside = cd.side, ld = cd.ld, NP = ld;
-    if (cd.Vfull.n < (size_t)ld * ld) cd.Vfull.alloc((size_t)ld * ld);
+    if (cd.Vfull.n < (size_t)ld * ld) { cd.Vfull.alloc((size_t)ld * ld); cd.have_V = false; }
+    warm = warm && bj_warm_ && cd.have_V && (cd.full_calls % 32) != 0;
+    cd.full_calls++;
     int nb = NP / BJ_B;
     int mplayers = (nb + 1) & ~1;
     int npairs = mplayers / 2;
     if (bj_Q_.n < (size_t)npairs * BJ_QSTRIDE) bj_Q_.alloc((size_t)npairs * BJ_QSTRIDE);
-    if (bj_pi_.n < (size_t)npairs) { bj_pi_.alloc((size_t)npairs); bj_pj_.alloc((size_t)npairs); }
     if (bj_rot_.n < 1) bj_rot_.alloc(1);
     {
         long long tot = (long long)NP * NP;
-        k_bj_init<<<ceil_div(tot, 256), 256, 0, stream>>>(cd.X.p, cd.Vfull.p, ld, nside, NP);
-        launches++;
+        if (warm) {
+            // A <- W' (A W) with W = the previous eigenvectors (orthogonal to working precision); V starts as W
+            if (cd.Vtmp.n < (size_t)ld * ld) cd.Vtmp.alloc_raw((size_t)ld * ld);
+            k_bj_pad<<<ceil_div(tot, 256), 256, 0, stream>>>(cd.X.p, ld, nside, NP);
+            k_gemm64<false><<<dim3(NP / 64, NP / 64), 256, 0, stream>>>(cd.X.p, cd.Vfull.p, cd.Vtmp.p, NP, ld);
+            k_gemm64<true><<<dim3(NP / 64, NP / 64), 256, 0, stream>>>(cd.Vfull.p, cd.Vtmp.p, cd.X.p, NP, ld);
+            launches += 3;
+        } else {
+            k_bj_init<<<ceil_div(tot, 256), 256, 0, stream>>>(cd.X.p, cd.Vfull.p, ld, nside, NP);
+            launches++;
+        }
     }
-    std::vector<int> pi((size_t)npairs), pj((size_t)npairs);
+    cd.have_V = true;
     std::vector<double> offn(2);
     const int chunks = (NP + BJ_P - 1) / BJ_P;
-    for (int sweep = 0; sweep < 40; ++sweep) {
+    for (int sweep = 0; sweep < 60; ++sweep) {
         PB_CUDA(cudaMemsetAsync(bj_rot_.p, 0, sizeof(int), stream));
-        if (nb == 1) {
-            // single block: one pivot problem on the 32x32 matrix embedded in a 64x64 pair with the dummy
-        }
         for (int round = 0; round < std::max(1, mplayers - 1); ++round) {
-            for (int t = 0; t < npairs; ++t) {
-                int a_, b_;
-                if (mplayers == 2) { a_ = 0; b_ = 1; }
-                else if (t == 0) { a_ = mplayers - 1; b_ = round; }
-                else { a_ = (round + t) % (mplayers - 1); b_ = (round - t + (mplayers - 1)) % (mplayers - 1); }
-                int I = std::min(a_, b_), J = std::max(a_, b_);
-                if (J >= nb) { I = -1; J = -1; }
-                pi[(size_t)t] = I; pj[(size_t)t] = J;
-            }
-            PB_CUDA(cudaMemcpyAsync(bj_pi_.p, pi.data(), sizeof(int) * (size_t)npairs, cudaMemcpyHostToDevice, stream));
-            PB_CUDA(cudaMemcpyAsync(bj_pj_.p, pj.data(), sizeof(int) * (size_t)npairs, cudaMemcpyHostToDevice, stream));
-            BjPairs pr{bj_pi_.p, bj_pj_.p};
-            k_bj_pair_eig<<<npairs, 256, bj_pair_smem_bytes(), stream>>>(cd.X.p, ld, pr, bj_Q_.p, bj_rot_.p);
+            BjRound pr{round, mplayers, nb};
+            k_bj_pair_eig<<<npairs, 512, bj_pair_smem_bytes(), stream>>>(cd.X.p, ld, pr, bj_inner_sweeps_, bj_Q_.p, bj_rot_.p);
             k_bj_apply<0><<<dim3(npairs, chunks, 2), 256, BJ_APPLY_SMEM, stream>>>(cd.X.p, cd.Vfull.p, ld, NP, pr, bj_Q_.p);
             k_bj_apply<1><<<dim3(npairs, chunks, 1), 256, BJ_APPLY_SMEM, stream>>>(cd.X.p, cd.Vfull.p, ld, NP, pr, bj_Q_.p);
             launches += 3;
-            // pi/pj host buffers are reused next round: the async copies above were issued from pageable
-            // memory (staged synchronously by the runtime), so reuse is safe.
         }
         k_bj_offnorm<<<std::min(reduce_blocks_, ceil_div((long long)nside * nside, 256)), 256, 0, stream>>>(
             cd.X.p, ld, nside, offnorm_d_.p, ws_);
@@ -908,7 +903,7 @@ std::vector<double> Solver::full_eig_device(ConeDev& cd) {
 // full_eig! for a large cone (prox_operators.jl:111-126) on the matrix in cones[k].X
 void Solver::launch_full_projection_large(int k) {
     ConeDev& cd = cones[(size_t)k];
-    std::vector<double> w = full_eig_device(cd);
+    std::vector<double> w = full_eig_device(cd, /*warm=*/true);
     std::vector<int> idx;
     std::vector<double> lam;
     long long rk = 0;
@@ -1250,6 +1245,7 @@ double Solver::dual_feas_device(const double* y_dev, double c_factor) {
         } else {
             // not converged (or the launch gave up): the reference takes the exact spectrum here (eigen!, pdhg.jl:685)
             std::vector<double> w = full_eig_device(cd);      // X still holds -Z: Lanczos only reads it
+            cd.have_V = false;                                // (the basis of -Z is no warm start for the next projection)
             double mx = w.empty() ? 0.0 : w[0];
             for (double v : w) mx = std::max(mx, v);
             lmin = -mx;

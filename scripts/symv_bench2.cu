@@ -208,17 +208,23 @@ __global__ void __launch_bounds__(T, 1) k(const double* __restrict__ X, int n, i
     if (sink == 123.456) out[cta * T + tid] = sink;
 }
 
+__global__ void k_touch(double* X, size_t n) {      // rewrite every element: all lines of X become DIRTY in L2
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) X[i] = X[i] * 1.0;
+}
+static bool g_dirty = false;
 template <int MODE, int RES, int RB>
 void run(const char* name, const double* X, int n, int ld, uint4* wg, uint4* flags, double* out, long long* cyc, double* host_w) {
     static unsigned tag0 = 16;
+    if (g_dirty) { k_touch<<<148 * 8, 256>>>(const_cast<double*>(X), (size_t)ld * ld); cudaDeviceSynchronize(); }
     size_t smem = (2048 + 512 + 32) * sizeof(double) + (MODE == 0 ? (size_t)(18 * 512 + 512) * sizeof(double) : (size_t)RES * 2048 * sizeof(double));
     cudaFuncSetAttribute(k<MODE, RES, RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const int G = 120;
     k<MODE, RES, RB><<<G, T, smem>>>(X, n, ld, 5, wg, flags, tag0, out, cyc); tag0 += 5;
     cudaDeviceSynchronize();
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-    cudaEventRecord(e0); k<MODE, RES, RB><<<G, T, smem>>>(X, n, ld, 200, wg, flags, tag0, out, cyc); cudaEventRecord(e1); cudaDeviceSynchronize();
-    tag0 += 200;
+    if (g_dirty) { k_touch<<<148 * 8, 256>>>(const_cast<double*>(X), (size_t)ld * ld); }
+    cudaEventRecord(e0); k<MODE, RES, RB><<<G, T, smem>>>(X, n, ld, 25, wg, flags, tag0, out, cyc); cudaEventRecord(e1); cudaDeviceSynchronize();
+    tag0 += 25;
     float ms; cudaEventElapsedTime(&ms, e0, e1);
     // check the published mat-vec result of the last pass against the host's
     uint4* h = new uint4[2 * ld];
@@ -232,7 +238,7 @@ void run(const char* name, const double* X, int n, int ld, uint4* wg, uint4* fla
     }
     delete[] h;
     printf("%-58s smem %3zu KB  %6.2f us/pass (events)  CTA0 %5lld cyc/pass: symv %5lld reduce+publish %5lld  max rel err %.1e [%s]\n", name, smem >> 10,
-           ms * 1e3 / 200, cyc[0], cyc[1], cyc[2], err, cudaGetErrorString(cudaGetLastError()));
+           ms * 1e3 / 25, cyc[0], cyc[1], cyc[2], err, cudaGetErrorString(cudaGetLastError()));
 }
 int main() {
     const int n = 2000, ld = 2048;
@@ -245,6 +251,9 @@ int main() {
     for (int r = 0; r < n; ++r) for (int c = 0; c < n; ++c) hX[(size_t)r * ld + c] = ((r * 131 + c * 71) % 97 - 48) * 0.01;
     for (int r = 0; r < n; ++r) { double s = 0; for (int c = 0; c < n; ++c) s += hX[(size_t)r * ld + c] * (1.0 + 1e-3 * c); hw[r] = s; }
     cudaMemcpy(X, hX, (size_t)ld * ld * 8, cudaMemcpyHostToDevice);
+    for (int dirty = 0; dirty < 2; ++dirty) {
+    g_dirty = dirty != 0;
+    printf("---- X %s before the timed launch (25 passes per launch, like one eigsolve)\n", dirty ? "REWRITTEN by a kernel (dirty in L2)" : "clean");
     run<0, 0, 9>("r1 symv: strip loads, [row][thread] table", X, n, ld, wg, flags, out, cyc, hw);
     run<1, 0, 9>("butterfly reduce, nothing resident (RB 9)", X, n, ld, wg, flags, out, cyc, hw);
     run<1, 0, 6>("butterfly reduce, nothing resident (RB 6)", X, n, ld, wg, flags, out, cyc, hw);
@@ -255,5 +264,6 @@ int main() {
     run<1, 9, 4>("TMA-staged: 9 rows resident, 8 streamed (RB 4)", X, n, ld, wg, flags, out, cyc, hw);
     run<1, 10, 4>("TMA-staged: 10 rows resident, 7 streamed (RB 4)", X, n, ld, wg, flags, out, cyc, hw);
     run<1, 12, 3>("TMA-staged: 12 rows resident, 5 streamed (RB 3)", X, n, ld, wg, flags, out, cyc, hw);
+    }
     return 0;
 }
