@@ -77,6 +77,20 @@ int proxsdp_b200_psd_project(int64_t n_sdp, const int64_t* sides, double* x,
  * (lens[k] entries each, the first being t).  x: in/out. */
 int proxsdp_b200_soc_project(int64_t n_soc, const int64_t* lens, double* x);
 
+/* `linesearch!` (options->line_search_flag != 0) or `dual_step!` (reference src/pdhg.jl:532-609) on explicit state.
+ * rows: only n, p, m, index_base, A, G of the problem are read — M = [A; G] is taken AS IS (working representation, no
+ * cone scaling), b and h come from `st`.  In: st->y, Mx, Mx_old, Mty (the current M'y, called Mty_old inside
+ * linesearch!), primal_step, primal_step_old, theta, beta, dual_step.  Out: y_new (p + m), Mty_new (n) and
+ * scalars_out[4] = {primal_step, theta, dual_step, primal_step_old} as the function leaves them; *trials = line-search
+ * trials evaluated. */
+int proxsdp_b200_dual_step(const proxsdp_problem_t* rows, const proxsdp_options_t* options,
+                           const proxsdp_step_state_t* st, double* y_new, double* Mty_new,
+                           double* scalars_out, int64_t* trials);
+
+/* `compute_residual!` + `compute_gap!` (reference src/residuals.jl:2-71) on explicit state.  out[8] =
+ * {primal_residual, dual_residual, comb_residual, equa_feasibility, ineq_feasibility, prim_obj, dual_obj, dual_gap}. */
+int proxsdp_b200_residuals(const proxsdp_options_t* options, const proxsdp_step_state_t* st, double* out);
+
 /* Kernel-level seam of the eigen back-end: KrylovKit.eigsolve(A, x0, howmany, :LR,
  * Lanczos(orth, krylovdim, maxiter, tol)) as used at reference src/eigsolver.jl:802-812.
  * A: n x n column-major, both triangles valid.  vals: krylovdim doubles; vecs: n x krylovdim

@@ -217,6 +217,21 @@ typedef struct proxsdp_result {
     int64_t d2h_bytes;           /* device->host bytes copied during this solve                           */
 } proxsdp_result_t;
 
+/* ---- step-level seams: the slice of PrimalDual / AuxiliaryData / Params (structs.jl:83-192) that `linesearch!` /
+ * `dual_step!` (pdhg.jl:532-609) and `compute_residual!` / `compute_gap!` (residuals.jl:2-71) read.  All vectors are in
+ * the solver's WORKING representation (permuted, off-diagonal svec entries scaled): these seams exist for kernel-level
+ * parity tests, the same way the reference's functions operate on its internal state. */
+typedef struct proxsdp_step_state {
+    int64_t n, p, m;                       /* variables, equality rows, inequality rows */
+    const double* b; const double* h; const double* c;
+    const double* x; const double* x_old;              /* (n)      */
+    const double* y; const double* y_old;              /* (p + m)  */
+    const double* Mx; const double* Mx_old;            /* (p + m)  */
+    const double* Mty; const double* Mty_old;          /* (n)      */
+    double primal_step, primal_step_old, dual_step, theta, beta;
+    double norm_b, norm_h, norm_c;
+} proxsdp_step_state_t;
+
 /* ---- sharded solves (independent blocks of a stacked problem, one block set per GPU) --------------
  * The reference is single-process; this is the B200 extension of SURVEY.md section 8(e).  Each rank passes
  * the sub-problem made of its blocks (variables, cones and rows that are coupled only among themselves:

@@ -116,6 +116,18 @@ def psd_project(sides, x, target_rank, opt: Options, iter: int = 1, mode: int = 
     return x, cur, mineig, conv, nops.value
 
 
+def dual_step(A, G, n, p, m, opt: Options, **state):
+    """Oracle counterpart of `proxsdp_b200_dual_step` (reference src/pdhg.jl:532-609)."""
+    from proxsdp_b200._abi import call_dual_step
+    return call_dual_step(lib().proxsdp_oracle_dual_step, A, G, n, p, m, opt, **state)
+
+
+def residuals(n, p, m, opt: Options, **state):
+    """Oracle counterpart of `proxsdp_b200_residuals` (reference src/residuals.jl:2-71)."""
+    from proxsdp_b200._abi import call_residuals
+    return call_residuals(lib().proxsdp_oracle_residuals, n, p, m, opt, **state)
+
+
 def soc_project(lens, x):
     lens = np.ascontiguousarray(lens, dtype=np.int64)
     x = np.ascontiguousarray(x, dtype=np.float64).copy()

@@ -1257,6 +1257,75 @@ int proxsdp_oracle_psd_project(int64_t n_sdp, const int64_t* sides, double* x,
     return 0;
 }
 
+/* helpers of the two step seams */
+static double* dup_vec(const double* v, int64_t n) {
+    double* d = (double*)calloc((size_t)(n > 0 ? n : 1), sizeof(double));
+    if (v && n > 0) memcpy(d, v, sizeof(double) * (size_t)n);
+    return d;
+}
+static void circ_init1(circ_t* c) { c->l = 2; c->v = (double*)calloc(2, sizeof(double)); }
+
+/* linesearch! / dual_step! (pdhg.jl:532-609) on explicit state: the counterpart of proxsdp_b200_dual_step.
+ * rows: A (p x n) and G (m x n) of the working problem, M = [A; G] taken as is. */
+int proxsdp_oracle_dual_step(const proxsdp_problem_t* rows, const proxsdp_options_t* opt, const proxsdp_step_state_t* st,
+                             double* y_new, double* Mty_new, double* scalars_out, int64_t* trials) {
+    state_t S; memset(&S, 0, sizeof(S));
+    state_t* s = &S;
+    s->n = st->n; s->p = st->p; s->m = st->m; s->R = st->p + st->m;
+    int64_t n = s->n, R = s->R;
+    s->A = csc_from_input(s->p, n, rows->A_colptr, rows->A_rowval, rows->A_nzval, rows->index_base);
+    s->G = csc_from_input(s->m, n, rows->G_colptr, rows->G_rowval, rows->G_nzval, rows->index_base);
+    s->M = csc_vstack(&s->A, &s->G);
+    s->Mt = csc_transpose(&s->M);
+    s->b = dup_vec(st->b, s->p); s->h = dup_vec(st->h, s->m);
+    s->y = dup_vec(st->y, R); s->y_old = dup_vec(st->y, R);          /* pair.y_old == pair.y when linesearch! runs */
+    s->Mx = dup_vec(st->Mx, R); s->Mx_old = dup_vec(st->Mx_old, R);
+    s->Mty = dup_vec(NULL, n); s->Mty_old = dup_vec(st->Mty, n);
+    s->y_half = dup_vec(NULL, R); s->y_temp = dup_vec(NULL, R);
+    s->primal_step = st->primal_step; s->primal_step_old = st->primal_step_old; s->theta = st->theta;
+    s->beta = st->beta; s->dual_step = st->dual_step;
+    if (opt->line_search_flag) linesearch(s, opt); else { s->linesearch_trials = 1; dual_step(s); }
+    memcpy(y_new, s->y, sizeof(double) * (size_t)R);
+    memcpy(Mty_new, s->Mty, sizeof(double) * (size_t)n);
+    if (scalars_out) { scalars_out[0] = s->primal_step; scalars_out[1] = s->theta; scalars_out[2] = s->dual_step; scalars_out[3] = s->primal_step_old; }
+    if (trials) *trials = s->linesearch_trials;
+    csc_free(&s->A); csc_free(&s->G); csc_free(&s->M); csc_free(&s->Mt);
+    free(s->b); free(s->h); free(s->y); free(s->y_old); free(s->Mx); free(s->Mx_old); free(s->Mty); free(s->Mty_old);
+    free(s->y_half); free(s->y_temp);
+    return 0;
+}
+
+/* compute_residual! + compute_gap! (residuals.jl:2-71) on explicit state: the counterpart of proxsdp_b200_residuals.
+ * out[8] = primal_residual, dual_residual, comb_residual, equa_feasibility, ineq_feasibility, prim_obj, dual_obj, gap */
+int proxsdp_oracle_residuals(const proxsdp_options_t* opt, const proxsdp_step_state_t* st, double* out) {
+    (void)opt;
+    state_t S; memset(&S, 0, sizeof(S));
+    state_t* s = &S;
+    s->n = st->n; s->p = st->p; s->m = st->m; s->R = st->p + st->m;
+    int64_t n = s->n, R = s->R;
+    s->b = dup_vec(st->b, s->p); s->h = dup_vec(st->h, s->m); s->c = dup_vec(st->c, n);
+    s->x = dup_vec(st->x, n); s->x_old = dup_vec(st->x_old, n);
+    s->y = dup_vec(st->y, R); s->y_old = dup_vec(st->y_old, R);
+    s->Mx = dup_vec(st->Mx, R); s->Mx_old = dup_vec(st->Mx_old, R);
+    s->Mty = dup_vec(st->Mty, n); s->Mty_old = dup_vec(st->Mty_old, n);
+    s->primal_step = st->primal_step; s->dual_step = st->dual_step; s->beta = st->beta;
+    s->norm_b = st->norm_b; s->norm_h = st->norm_h; s->norm_c = st->norm_c;
+    s->iter = 1;
+    circ_init1(&s->dual_gap); circ_init1(&s->prim_obj); circ_init1(&s->dual_obj); circ_init1(&s->feasibility);
+    circ_init1(&s->primal_residual); circ_init1(&s->dual_residual); circ_init1(&s->comb_residual);
+    compute_residual(s);
+    /* compute_residual! has copied the new iterates over the old ones; compute_gap! reads only the new ones */
+    compute_gap(s);
+    out[0] = circ_get(&s->primal_residual, 1); out[1] = circ_get(&s->dual_residual, 1); out[2] = circ_get(&s->comb_residual, 1);
+    out[3] = s->equa_feasibility; out[4] = s->ineq_feasibility;
+    out[5] = circ_get(&s->prim_obj, 1); out[6] = circ_get(&s->dual_obj, 1); out[7] = circ_get(&s->dual_gap, 1);
+    free(s->b); free(s->h); free(s->c); free(s->x); free(s->x_old); free(s->y); free(s->y_old); free(s->Mx); free(s->Mx_old);
+    free(s->Mty); free(s->Mty_old);
+    free(s->dual_gap.v); free(s->prim_obj.v); free(s->dual_obj.v); free(s->feasibility.v);
+    free(s->primal_residual.v); free(s->dual_residual.v); free(s->comb_residual.v);
+    return 0;
+}
+
 /* soc_projection! over concatenated SOC blocks (prox_operators.jl:138-158) */
 int proxsdp_oracle_soc_project(int64_t n_soc, const int64_t* lens, double* x) {
     state_t S; memset(&S, 0, sizeof(S));

@@ -60,6 +60,75 @@ class ResultPOD(ctypes.Structure):
     ]
 
 
+class StepStatePOD(ctypes.Structure):
+    """include/proxsdp_b200_types.h: proxsdp_step_state_t."""
+    _fields_ = [
+        ("n", c_int64), ("p", c_int64), ("m", c_int64),
+        ("b", _pd), ("h", _pd), ("c", _pd),
+        ("x", _pd), ("x_old", _pd), ("y", _pd), ("y_old", _pd),
+        ("Mx", _pd), ("Mx_old", _pd), ("Mty", _pd), ("Mty_old", _pd),
+        ("primal_step", c_double), ("primal_step_old", c_double), ("dual_step", c_double), ("theta", c_double),
+        ("beta", c_double), ("norm_b", c_double), ("norm_h", c_double), ("norm_c", c_double),
+    ]
+
+
+class MarshalledStepState:
+    """Owns the buffers a StepStatePOD points into.  Vectors that a seam does not read may be omitted (NULL)."""
+    VECS = ("b", "h", "c", "x", "x_old", "y", "y_old", "Mx", "Mx_old", "Mty", "Mty_old")
+    SCALARS = ("primal_step", "primal_step_old", "dual_step", "theta", "beta", "norm_b", "norm_h", "norm_c")
+
+    def __init__(self, n: int, p: int, m: int, **kw):
+        self.bufs = {}
+        pod = StepStatePOD()
+        pod.n, pod.p, pod.m = int(n), int(p), int(m)
+        for name in self.VECS:
+            v = kw.get(name)
+            if v is None:
+                setattr(pod, name, ctypes.cast(None, _pd))
+            else:
+                a = np.ascontiguousarray(np.asarray(v, dtype=np.float64).ravel())
+                self.bufs[name] = a
+                setattr(pod, name, a.ctypes.data_as(_pd) if a.size else ctypes.cast(None, _pd))
+        for name in self.SCALARS:
+            setattr(pod, name, float(kw.get(name, 0.0)))
+        self.pod = pod
+
+
+def call_dual_step(fn, A, G, n, p, m, opt: Options, err_fn=None, **state):
+    """Invoke `int dual_step(const proxsdp_problem_t* rows, options*, step_state*, y_new, Mty_new, scalars[4], trials*)`.
+    Returns (y_new, Mty_new, dict(primal_step, theta, dual_step, primal_step_old), trials)."""
+    aff = AffineSets(n, p, m, 0, A, G, np.zeros(p), np.zeros(m), np.zeros(n))
+    mp = MarshalledProblem(aff, ConicSets())
+    ms = MarshalledStepState(n, p, m, **state)
+    y_new, Mty_new, sc = np.zeros(p + m), np.zeros(n), np.zeros(4)
+    trials = c_int64(0)
+    opod = opt.to_pod()
+    fn.argtypes = [POINTER(ProblemPOD), POINTER(OptionsPOD), POINTER(StepStatePOD), _pd, _pd, _pd, _pi]
+    fn.restype = ctypes.c_int
+    rc = fn(ctypes.byref(mp.pod), ctypes.byref(opod), ctypes.byref(ms.pod), _ptr_d(y_new), _ptr_d(Mty_new), _ptr_d(sc),
+            ctypes.byref(trials))
+    if rc != 0:
+        raise RuntimeError(f"dual_step failed with code {rc}: {err_fn().decode() if err_fn else ''}")
+    return y_new, Mty_new, dict(primal_step=sc[0], theta=sc[1], dual_step=sc[2], primal_step_old=sc[3]), int(trials.value)
+
+
+RESIDUAL_NAMES = ("primal_residual", "dual_residual", "comb_residual", "equa_feasibility", "ineq_feasibility",
+                  "prim_obj", "dual_obj", "dual_gap")
+
+
+def call_residuals(fn, n, p, m, opt: Options, err_fn=None, **state):
+    """Invoke `int residuals(options*, step_state*, out[8])`; returns a dict keyed by RESIDUAL_NAMES."""
+    ms = MarshalledStepState(n, p, m, **state)
+    out = np.zeros(8)
+    opod = opt.to_pod()
+    fn.argtypes = [POINTER(OptionsPOD), POINTER(StepStatePOD), _pd]
+    fn.restype = ctypes.c_int
+    rc = fn(ctypes.byref(opod), ctypes.byref(ms.pod), _ptr_d(out))
+    if rc != 0:
+        raise RuntimeError(f"residuals failed with code {rc}: {err_fn().decode() if err_fn else ''}")
+    return dict(zip(RESIDUAL_NAMES, (float(v) for v in out)))
+
+
 def _f64(a) -> np.ndarray:
     return np.ascontiguousarray(np.asarray(a, dtype=np.float64).ravel())
 

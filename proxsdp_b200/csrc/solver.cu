@@ -253,6 +253,14 @@ class Solver {
     void launch_post_eig(double tau0, bool first_pass);
     void launch_dual_trial(int trial, double tau0);
     void launch_ladder(int trial0, int T, double tau0);
+    long long linesearch_continue(double tau0, bool& exhausted, double& last_tau);
+    void host_residuals(long long k);
+  public:
+    // step-level seams (proxsdp_b200_dual_step / proxsdp_b200_residuals): one linesearch! / dual_step!, one
+    // compute_residual! + compute_gap!, on state the caller has placed in the ping-pong buffers
+    long long seam_dual_step(double primal_step, double primal_step_old, double theta, double beta, double dual_step, double* out4);
+    void seam_residuals(double primal_step, double dual_step, double beta, double norm_b, double norm_h, double norm_c, double* out8);
+  private:
     void cache_solution(double c_factor, proxsdp_result_t* out);
     // get_duals + dual_feas (pdhg.jl:701-732) on the device: dual_cone = c_factor * c + M'y (un-scaled, off-diagonals / 2)
     // is left in res_dc_d_ (position order); returns the dual infeasibility measure
@@ -1367,6 +1375,104 @@ void Solver::record_trace(proxsdp_result_t* out) {
     out->trace_len++;
 }
 
+long long Solver::seam_dual_step(double primal_step, double primal_step_old, double theta, double beta, double dual_step, double* out4) {
+    primal_step_ = primal_step; primal_step_old_ = primal_step_old; theta_ = theta; beta_ = beta; dual_step_ = dual_step;
+    reset_scalars();
+    const double tau0 = opt.line_search_flag ? primal_step_ * std::sqrt(1.0 + theta_) : primal_step_;   // pdhg.jl:541
+    int ntr = opt.line_search_flag ? (int)std::min<long long>(ladder_, std::max<long long>(opt.max_linsearch_steps, 1)) : 1;
+    if (fused_ladder_) launch_ladder(0, ntr, tau0);
+    else for (int t = 0; t < ntr; ++t) launch_dual_trial(t, tau0);
+    sync_scalars();
+    long long evals = (long long)scal_host[S_LS_EVALS];
+    bool exhausted = false;
+    double last_tau = 0.0;
+    if (opt.line_search_flag && scal_host[S_LS_ACCEPTED] == 0.0) evals = linesearch_continue(tau0, exhausted, last_tau);
+    if (opt.line_search_flag) {       // linesearch! epilogue (pdhg.jl:577-579)
+        primal_step_ = scal_host[S_TAU];
+        theta_ = (exhausted ? last_tau : primal_step_) / primal_step_old_;
+        primal_step_old_ = primal_step_;
+        dual_step_ = beta_ * primal_step_;
+    } else {                          // dual_step! (pdhg.jl:606)
+        primal_step_old_ = primal_step_;
+    }
+    out4[0] = primal_step_; out4[1] = theta_; out4[2] = dual_step_; out4[3] = primal_step_old_;
+    return std::max<long long>(evals, 1);
+}
+
+void Solver::seam_residuals(double primal_step, double dual_step, double beta, double norm_b, double norm_h, double norm_c, double* out8) {
+    primal_step_ = primal_step; dual_step_ = dual_step; beta_ = beta; norm_b_ = norm_b; norm_h_ = norm_h; norm_c_ = norm_c;
+    reset_scalars();
+    // the kernels take the accepted step from the record (what the line search leaves there)
+    double rec[3] = {1.0, 0.0, primal_step};
+    PB_CUDA(cudaMemcpyAsync(scal_d_.p + S_LS_ACCEPTED, rec, sizeof(rec), cudaMemcpyHostToDevice, stream));
+    int blocksN = std::max(1, std::min(reduce_blocks_, ceil_div(n, 512)));
+    k_residual_primal<<<blocksN, 256, 0, stream>>>(n, x_[1].p, x_[0].p, Mty_[1].p, Mty_[0].p, c_.p, scal_d_.p, ws_);
+    int blocksR = std::max(1, std::min(reduce_blocks_, ceil_div(R, 256)));
+    k_residual_dual<<<blocksR, 256, 0, stream>>>((int)p, (int)m, beta_, 0, dual_step_, y_[1].p, y_[0].p, Mx_[1].p, Mx_[0].p,
+                                                 b_.p, h_.p, scal_d_.p, ws_);
+    launches += 2;
+    sync_scalars();
+    iter_ = 1;
+    host_residuals(1);
+    out8[0] = primal_residual_.get(1); out8[1] = dual_residual_.get(1); out8[2] = comb_residual_.get(1);
+    out8[3] = equa_feasibility_; out8[4] = ineq_feasibility_; out8[5] = prim_obj_.get(1); out8[6] = dual_obj_.get(1);
+    out8[7] = dual_gap_.get(1);
+}
+
+// The line search after its first ladder of trials came back without an accepted step (pdhg.jl:543-571): further
+// ladders, and — when max_linsearch_steps is exhausted — the reference's exit state (last trial's vectors, the step
+// decayed once more).  Returns the number of trials evaluated.
+long long Solver::linesearch_continue(double tau0, bool& exhausted, double& last_tau) {
+    long long t = std::min<long long>(ladder_, std::max<long long>(opt.max_linsearch_steps, 1));
+    while (scal_host[S_LS_ACCEPTED] == 0.0 && t < opt.max_linsearch_steps) {
+        if (fused_ladder_) {
+            // the next batch of trials, again side by side
+            const int T = (int)std::min<long long>(ladder_, opt.max_linsearch_steps - t);
+            launch_ladder((int)t, T, tau0);
+            sync_scalars();
+            t = (long long)scal_host[S_LS_EVALS];
+        } else {
+            launch_dual_trial((int)t, tau0);
+            sync_scalars();
+            ++t;
+        }
+    }
+    if (scal_host[S_LS_ACCEPTED] == 0.0) {
+        // loop exhausted: the reference keeps the last trial's y/Mty and the once-more decayed step
+        double tau = tau0;
+        for (long long q = 0; q < opt.max_linsearch_steps; ++q) { if (q == opt.max_linsearch_steps - 1) last_tau = tau; tau *= opt.linsearch_decay; }
+        exhausted = true;
+        double rec[3] = {1.0, (double)(opt.max_linsearch_steps - 1), tau};
+        PB_CUDA(cudaMemcpyAsync(scal_d_.p + S_LS_ACCEPTED, rec, sizeof(rec), cudaMemcpyHostToDevice, stream));
+        PB_CUDA(cudaStreamSynchronize(stream));
+        scal_host[S_LS_ACCEPTED] = 1.0; scal_host[S_TAU] = tau;
+    }
+    return t;
+}
+
+// compute_residual! (residuals.jl:37-71) and compute_gap! (residuals.jl:2-35): the scalar part, on the record of
+// iteration k that the residual kernels filled
+void Solver::host_residuals(long long k) {
+    {
+        double den = jl_max(jl_max(scal_host[S_RES_P_DEN], norm_b_), jl_max(norm_h_, 1.0));
+        double pr = std::sqrt((double)(sharded() ? global_n_ : n)) * scal_host[S_RES_P_NUM] / den;
+        double den2 = jl_max(jl_max(scal_host[S_RES_D_DEN], norm_c_), 1.0);
+        double dr = std::sqrt((double)(sharded() ? global_R_ : R)) * scal_host[S_RES_D_NUM] / den2;
+        primal_residual_.set(k, pr); dual_residual_.set(k, dr); comb_residual_.set(k, jl_max(pr, dr));
+    }
+    {
+        const long long gp = sharded() ? global_p_ : p, gm = sharded() ? global_m_ : m;
+        if (gp > 0) equa_feasibility_ = scal_host[S_EQ_MAX] / (1.0 + norm_b_);
+        if (gm > 0) ineq_feasibility_ = scal_host[S_IN_MAX] / (1.0 + norm_h_);
+        feasibility_.set(k, std::max(equa_feasibility_, ineq_feasibility_));
+        double po = scal_host[S_PRIM_OBJ], dobj = 0.0;
+        if (gp > 0) dobj -= scal_host[S_BY];
+        if (gm > 0) dobj -= scal_host[S_HY];
+        prim_obj_.set(k, po); dual_obj_.set(k, dobj);
+        dual_gap_.set(k, std::fabs(po - dobj) / (1.0 + std::fabs(po) + std::fabs(dobj)));
+    }
+}
+
 // ---------------------------------------------------------------------------
 // chambolle_pock main loop (pdhg.jl:145-530)
 // ---------------------------------------------------------------------------
@@ -1452,31 +1558,8 @@ bool Solver::run(long long max_steps, bool flush_l2) {
         bool ls_exhausted = false;
         double ls_last_tau = 0.0;
         if (opt.line_search_flag && scal_host[S_LS_ACCEPTED] == 0.0) {
-            long long t = std::min<long long>(ladder_, std::max<long long>(opt.max_linsearch_steps, 1));
             const double keep_ops = scal_host[S_NUMOPS];
-            while (scal_host[S_LS_ACCEPTED] == 0.0 && t < opt.max_linsearch_steps) {
-                if (fused_ladder_) {
-                    // the next batch of trials, again side by side
-                    const int T = (int)std::min<long long>(ladder_, opt.max_linsearch_steps - t);
-                    launch_ladder((int)t, T, tau0);
-                    sync_scalars();
-                    t = (long long)scal_host[S_LS_EVALS];
-                } else {
-                    launch_dual_trial((int)t, tau0);
-                    sync_scalars();
-                    ++t;
-                }
-            }
-            evals = t;
-            if (scal_host[S_LS_ACCEPTED] == 0.0) {
-                // loop exhausted: the reference keeps the last trial's y/Mty and the once-more decayed step
-                double tau = tau0;
-                for (long long q = 0; q < opt.max_linsearch_steps; ++q) { if (q == opt.max_linsearch_steps - 1) ls_last_tau = tau; tau *= opt.linsearch_decay; }
-                ls_exhausted = true;
-                double rec[3] = {1.0, (double)(opt.max_linsearch_steps - 1), tau};
-                PB_CUDA(cudaMemcpyAsync(scal_d_.p + S_LS_ACCEPTED, rec, sizeof(rec), cudaMemcpyHostToDevice, stream));
-                PB_CUDA(cudaStreamSynchronize(stream));
-            }
+            evals = linesearch_continue(tau0, ls_exhausted, ls_last_tau);
             int blocksN = std::max(1, std::min(reduce_blocks_, ceil_div(n, 512)));
             k_residual_primal<<<blocksN, 256, 0, stream>>>(n, x_[1 - cur_].p, x_[cur_].p, Mty_[1 - cur_].p, Mty_[cur_].p, c_.p, scal_d_.p, ws_);
             int blocksR = std::max(1, std::min(reduce_blocks_, ceil_div(R, 256)));
@@ -1506,26 +1589,7 @@ bool Solver::run(long long max_steps, bool flush_l2) {
             min_eig[(size_t)q] = scal_host[S_HEADER + 3 * q + 1];
         }
         soc_gap_max_ = (n_soc > 0 || global_has_soc_) ? scal_host[S_SOC_GAP] : -1.0;
-        // compute_residual! (residuals.jl:37-71)
-        {
-            double den = jl_max(jl_max(scal_host[S_RES_P_DEN], norm_b_), jl_max(norm_h_, 1.0));
-            double pr = std::sqrt((double)(sharded() ? global_n_ : n)) * scal_host[S_RES_P_NUM] / den;
-            double den2 = jl_max(jl_max(scal_host[S_RES_D_DEN], norm_c_), 1.0);
-            double dr = std::sqrt((double)(sharded() ? global_R_ : R)) * scal_host[S_RES_D_NUM] / den2;
-            primal_residual_.set(k, pr); dual_residual_.set(k, dr); comb_residual_.set(k, jl_max(pr, dr));
-        }
-        // compute_gap! (residuals.jl:2-35)
-        {
-            const long long gp = sharded() ? global_p_ : p, gm = sharded() ? global_m_ : m;
-            if (gp > 0) equa_feasibility_ = scal_host[S_EQ_MAX] / (1.0 + norm_b_);
-            if (gm > 0) ineq_feasibility_ = scal_host[S_IN_MAX] / (1.0 + norm_h_);
-            feasibility_.set(k, std::max(equa_feasibility_, ineq_feasibility_));
-            double po = scal_host[S_PRIM_OBJ], dobj = 0.0;
-            if (gp > 0) dobj -= scal_host[S_BY];
-            if (gm > 0) dobj -= scal_host[S_HY];
-            prim_obj_.set(k, po); dual_obj_.set(k, dobj);
-            dual_gap_.set(k, std::fabs(po - dobj) / (1.0 + std::fabs(po) + std::fabs(dobj)));
-        }
+        host_residuals(k);
         cur_ = 1 - cur_;    // keep-old copies (residuals.jl:65-68) are a pointer swap
 
         if (opt.check_dual_feas && (k % opt.check_dual_feas_freq) == 0) {     // pdhg.jl:166-173
@@ -2038,6 +2102,77 @@ int proxsdp_b200_soc_project(int64_t n_soc, const int64_t* lens, double* x) {
         s.launch_soc_only();
         s.sync_scalars();
         PB_CUDA(cudaMemcpy(x, s.x_[1].p, sizeof(double) * (size_t)cp.pr.n, cudaMemcpyDeviceToHost));
+    });
+}
+
+// a problem without cones and without objective: only the rows M = [A; G] (taken as they are), b, h
+static proxsdp_problem_t rows_only_problem(const proxsdp_problem_t* rows, const proxsdp_step_state_t* st, std::vector<double>& zeros,
+                                           std::vector<int64_t>& colptr0) {
+    proxsdp_problem_t pr{};
+    pr.n = st->n; pr.p = st->p; pr.m = st->m;
+    zeros.assign((size_t)std::max<int64_t>(st->n, 1), 0.0);
+    if (rows) {
+        pr.index_base = rows->index_base;
+        pr.A_colptr = rows->A_colptr; pr.A_rowval = rows->A_rowval; pr.A_nzval = rows->A_nzval;
+        pr.G_colptr = rows->G_colptr; pr.G_rowval = rows->G_rowval; pr.G_nzval = rows->G_nzval;
+    } else {
+        colptr0.assign((size_t)st->n + 1, 0);
+        pr.index_base = 0;
+        pr.A_colptr = colptr0.data(); pr.G_colptr = colptr0.data();
+    }
+    pr.b = st->b; pr.h = st->h; pr.c = st->c ? st->c : zeros.data();
+    return pr;
+}
+
+int proxsdp_b200_dual_step(const proxsdp_problem_t* rows, const proxsdp_options_t* options, const proxsdp_step_state_t* st,
+                           double* y_new, double* Mty_new, double* scalars_out, int64_t* trials) {
+    if (!rows || !options || !st || !y_new || !Mty_new) { g_last_error = "null argument"; return -1; }
+    return guarded([&]() {
+        std::vector<double> zeros; std::vector<int64_t> cp0;
+        proxsdp_problem_t pr = rows_only_problem(rows, st, zeros, cp0);
+        pr.c = zeros.data();
+        Solver s(&pr, options);
+        const size_t Rb = sizeof(double) * (size_t)(st->p + st->m), Nb = sizeof(double) * (size_t)st->n;
+        // linesearch! reads pair.y, a.Mx, a.Mx_old and a.Mty_old (the current M'y)
+        s.cur_ = 0;
+        if (Rb) {
+            PB_CUDA(cudaMemcpy(s.y_[0].p, st->y, Rb, cudaMemcpyHostToDevice));
+            PB_CUDA(cudaMemcpy(s.Mx_[1].p, st->Mx, Rb, cudaMemcpyHostToDevice));
+            PB_CUDA(cudaMemcpy(s.Mx_[0].p, st->Mx_old, Rb, cudaMemcpyHostToDevice));
+        }
+        if (Nb) PB_CUDA(cudaMemcpy(s.Mty_[0].p, st->Mty, Nb, cudaMemcpyHostToDevice));
+        double out4[4];
+        long long ev = s.seam_dual_step(st->primal_step, st->primal_step_old, st->theta, st->beta, st->dual_step, out4);
+        if (Rb) PB_CUDA(cudaMemcpy(y_new, s.y_[1].p, Rb, cudaMemcpyDeviceToHost));
+        if (Nb) PB_CUDA(cudaMemcpy(Mty_new, s.Mty_[1].p, Nb, cudaMemcpyDeviceToHost));
+        if (scalars_out) for (int i = 0; i < 4; ++i) scalars_out[i] = out4[i];
+        if (trials) *trials = ev;
+    });
+}
+
+int proxsdp_b200_residuals(const proxsdp_options_t* options, const proxsdp_step_state_t* st, double* out) {
+    if (!options || !st || !out) { g_last_error = "null argument"; return -1; }
+    return guarded([&]() {
+        std::vector<double> zeros; std::vector<int64_t> cp0;
+        proxsdp_problem_t pr = rows_only_problem(nullptr, st, zeros, cp0);
+        pr.c = zeros.data();                 // the working objective is uploaded below exactly as given
+        Solver s(&pr, options);
+        const size_t Rb = sizeof(double) * (size_t)(st->p + st->m), Nb = sizeof(double) * (size_t)st->n;
+        s.cur_ = 0;     // new iterates in slot 1, old ones in slot 0 (the layout at the end of an iteration)
+        if (Nb) {
+            PB_CUDA(cudaMemcpy(s.x_[1].p, st->x, Nb, cudaMemcpyHostToDevice));
+            PB_CUDA(cudaMemcpy(s.x_[0].p, st->x_old, Nb, cudaMemcpyHostToDevice));
+            PB_CUDA(cudaMemcpy(s.Mty_[1].p, st->Mty, Nb, cudaMemcpyHostToDevice));
+            PB_CUDA(cudaMemcpy(s.Mty_[0].p, st->Mty_old, Nb, cudaMemcpyHostToDevice));
+            PB_CUDA(cudaMemcpy(s.c_.p, st->c, Nb, cudaMemcpyHostToDevice));
+        }
+        if (Rb) {
+            PB_CUDA(cudaMemcpy(s.y_[1].p, st->y, Rb, cudaMemcpyHostToDevice));
+            PB_CUDA(cudaMemcpy(s.y_[0].p, st->y_old, Rb, cudaMemcpyHostToDevice));
+            PB_CUDA(cudaMemcpy(s.Mx_[1].p, st->Mx, Rb, cudaMemcpyHostToDevice));
+            PB_CUDA(cudaMemcpy(s.Mx_[0].p, st->Mx_old, Rb, cudaMemcpyHostToDevice));
+        }
+        s.seam_residuals(st->primal_step, st->dual_step, st->beta, st->norm_b, st->norm_h, st->norm_c, out);
     });
 }
 

@@ -216,6 +216,22 @@ def psd_project(sides, x, target_rank, opt: Options, iter: int = 1, mode: int = 
     return x, cur[:k], mineig[:k], conv[:k], nops.value, ms.value
 
 
+def dual_step(A, G, n, p, m, opt: Options, **state):
+    """`linesearch!` / `dual_step!` (reference src/pdhg.jl:532-609) on explicit working-space state: A (p x n), G (m x n)
+    and y, Mx, Mx_old, Mty, b, h, primal_step, primal_step_old, theta, beta, dual_step as keywords.
+    Returns (y_new, Mty_new, scalars, trials)."""
+    from ._abi import call_dual_step
+    L = lib()
+    return call_dual_step(L.proxsdp_b200_dual_step, A, G, n, p, m, opt, err_fn=L.proxsdp_b200_last_error, **state)
+
+
+def residuals(n, p, m, opt: Options, **state):
+    """`compute_residual!` + `compute_gap!` (reference src/residuals.jl:2-71) on explicit working-space state."""
+    from ._abi import call_residuals
+    L = lib()
+    return call_residuals(L.proxsdp_b200_residuals, n, p, m, opt, err_fn=L.proxsdp_b200_last_error, **state)
+
+
 def soc_project(lens, x):
     """`soc_projection!` (reference src/prox_operators.jl:138-158)."""
     lens = np.ascontiguousarray(lens, dtype=np.int64)

@@ -347,3 +347,40 @@ def test_many_small_cones_grid_limits(gpu, oracle_mod):
     rg = gpu.chambolle_pock(aff, con, Options())
     ro = oracle_mod.chambolle_pock(aff, con, Options())
     _same_solution(rg, ro)
+
+
+# ------------------------------------------------------------------ step-level seams: linesearch! / residuals
+def _step_state(seed, n, p, m):
+    rng = np.random.default_rng(seed)
+    A = sp.random(p, n, 0.3, random_state=seed + 1, format="csc") if p else sp.csc_matrix((0, n))
+    G = sp.random(m, n, 0.3, random_state=seed + 2, format="csc") if m else sp.csc_matrix((0, n))
+    st = dict(b=rng.standard_normal(p), h=rng.standard_normal(m), c=rng.standard_normal(n), x=rng.standard_normal(n),
+              x_old=rng.standard_normal(n), y=rng.standard_normal(p + m), y_old=rng.standard_normal(p + m),
+              Mx=rng.standard_normal(p + m), Mx_old=rng.standard_normal(p + m), Mty=rng.standard_normal(n),
+              Mty_old=rng.standard_normal(n), primal_step=0.3, primal_step_old=0.25, dual_step=0.2, theta=1.0, beta=0.8,
+              norm_b=1.5, norm_h=0.7, norm_c=2.0)
+    return A, G, st
+
+
+@pytest.mark.parametrize("n,p,m", [(40, 7, 9), (300, 0, 50), (5000, 700, 0), (64, 1, 1)])
+@pytest.mark.parametrize("kw", [dict(), dict(line_search_flag=False), dict(linsearch_decay=0.97), dict(max_linsearch_steps=2, delta=0.05)], ids=str)
+def test_dual_step_seam(gpu, oracle_mod, n, p, m, kw):
+    """proxsdp_b200_dual_step == linesearch! / dual_step! (pdhg.jl:532-609): same trial count, same vectors, same steps."""
+    A, G, st = _step_state(n + p, n, p, m)
+    opt = Options(**kw)
+    yo, Mo, so, to = oracle_mod.dual_step(A, G, n, p, m, opt, **st)
+    yg, Mg, sg, tg = gpu.dual_step(A, G, n, p, m, opt, **st)
+    assert tg == to
+    assert _vec_close(yg, yo, 1e-12) and _vec_close(Mg, Mo, 1e-12)
+    for k_ in so:
+        assert abs(sg[k_] - so[k_]) <= 1e-13 * max(1.0, abs(so[k_])), k_
+
+
+@pytest.mark.parametrize("n,p,m", [(40, 7, 9), (300, 0, 50), (100001, 700, 0), (64, 1, 1)])
+def test_residuals_seam(gpu, oracle_mod, n, p, m):
+    """proxsdp_b200_residuals == compute_residual! + compute_gap! (residuals.jl:2-71)."""
+    _, _, st = _step_state(n + m, n, p, m)
+    ro = oracle_mod.residuals(n, p, m, Options(), **st)
+    rg = gpu.residuals(n, p, m, Options(), **st)
+    for k_ in ro:
+        assert abs(rg[k_] - ro[k_]) <= 1e-12 * max(1.0, abs(ro[k_])), (k_, rg[k_], ro[k_])

@@ -202,3 +202,51 @@ def test_randsdp_mini_benchmark(oracle_mod):
     assert r.status in (1, 3)
     X = ivec(r.primal)
     assert np.linalg.eigvalsh(X).min() > -1e-5
+
+
+def test_step_seams_against_numpy_restatement(oracle_mod):
+    """The oracle's linesearch! / compute_residual! / compute_gap! seams against a direct numpy restatement of
+    reference src/pdhg.jl:532-582 and src/residuals.jl:2-71."""
+    import scipy.sparse as sp
+    rng = np.random.default_rng(0)
+    n, p, m = 40, 7, 9
+    A = sp.random(p, n, 0.3, random_state=1, format="csc")
+    G = sp.random(m, n, 0.3, random_state=2, format="csc")
+    M = sp.vstack([A, G]).tocsc()
+    st = dict(b=rng.standard_normal(p), h=rng.standard_normal(m), c=rng.standard_normal(n), x=rng.standard_normal(n),
+              x_old=rng.standard_normal(n), y=rng.standard_normal(p + m), y_old=rng.standard_normal(p + m),
+              Mx=rng.standard_normal(p + m), Mx_old=rng.standard_normal(p + m), Mty=rng.standard_normal(n),
+              Mty_old=rng.standard_normal(n), primal_step=0.3, primal_step_old=0.25, dual_step=0.2, theta=1.0, beta=0.8,
+              norm_b=1.5, norm_h=0.7, norm_c=2.0)
+    # residuals.jl:37-71
+    r = oracle_mod.residuals(n, p, m, Options(), **st)
+    tau, sig = st["primal_step"], st["dual_step"]
+    pold = st["x_old"] - tau * st["Mty_old"]
+    pr = np.sqrt(n) * np.abs((st["x"] - tau * st["Mty"]) - pold).max() / max(np.abs(pold).max(), st["norm_b"], st["norm_h"], 1.0)
+    dold = st["y_old"] - sig * st["Mx_old"]
+    dr = np.sqrt(p + m) * np.abs((st["y"] - sig * st["Mx"]) - dold).max() / max(np.abs(dold).max(), st["norm_c"], 1.0)
+    assert abs(r["primal_residual"] - pr) <= 1e-13 * pr and abs(r["dual_residual"] - dr) <= 1e-13 * dr
+    # residuals.jl:2-35
+    eq = np.abs(st["Mx"][:p] - st["b"]).max() / (1 + st["norm_b"])
+    ineq = max(0.0, (st["Mx"][p:] - st["h"]).max()) / (1 + st["norm_h"])
+    po = st["c"] @ st["x"]
+    do = -(st["b"] @ st["y"][:p]) - (st["h"] @ st["y"][p:])
+    assert abs(r["equa_feasibility"] - eq) <= 1e-14 and abs(r["ineq_feasibility"] - ineq) <= 1e-14
+    assert abs(r["prim_obj"] - po) <= 1e-12 and abs(r["dual_obj"] - do) <= 1e-12
+    assert abs(r["dual_gap"] - abs(po - do) / (1 + abs(po) + abs(do))) <= 1e-14
+    # pdhg.jl:532-582
+    opt = Options()
+    yn, Mn, sc, trials = oracle_mod.dual_step(A, G, n, p, m, opt, **st)
+    t = st["primal_step"] * np.sqrt(1 + st["theta"])
+    for it in range(int(opt.max_linsearch_steps)):
+        theta = t / st["primal_step_old"]
+        bt = st["beta"] * t
+        yh = st["y"] + bt * ((1 + theta) * st["Mx"] - theta * st["Mx_old"])
+        proj = np.concatenate([st["b"], np.minimum(yh[p:] / bt, st["h"])])
+        yt = yh - bt * proj
+        Mt = M.T @ yt
+        if np.sqrt(st["beta"]) * t * np.linalg.norm(Mt - st["Mty"]) <= opt.delta * np.linalg.norm(yt - st["y"]):
+            break
+        t *= opt.linsearch_decay
+    assert trials == it + 1 and abs(sc["primal_step"] - t) <= 1e-15 and abs(sc["theta"] - theta) <= 1e-15
+    assert np.abs(yn - yt).max() <= 1e-13 and np.abs(Mn - Mt).max() <= 1e-13
