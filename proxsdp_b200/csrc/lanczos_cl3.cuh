@@ -116,6 +116,8 @@ struct LanczosCl3Args {
     int use_bi;
     double stop_above;         // finish as soon as the largest Ritz value exceeds this (it is a lower bound of lambda_max);
                                // 1e300 = never: used by cone_feas, which only needs to know whether lambda_min < -tol
+    int debug;                 // PROXSDP_B200_LZ_DEBUG=1: CTA 0 prints every Ritz analysis / restart (device printf)
+    int arrow_restart;         // 1: keep the arrowhead form after a thick restart (dense Jacobi Ritz solves; PROXSDP_B200_LZ_ARROW=1)
     int poll_ns;               // back-off between two polls of the flagged exchange words (PROXSDP_B200_LZ_POLL_NS)
     int strict;                // 1: KrylovKit's arithmetic to the letter — alpha of the local step summed in FP64 and two
                                // Gram-Schmidt passes on every step (PROXSDP_B200_LZ_STRICT=1); 0: FP32 tree for the provisional
@@ -363,51 +365,58 @@ __device__ __noinline__ void lz3_ritz(const LanczosCl3Args& a, double* sbase, in
     // reverse order the coupling to r sits in the last row, as the three-term recurrence expects.  The basis is
     // rotated once by U Q~, the recurrence carries on with a plain tridiagonal (so every later Ritz analysis takes the
     // bisection path), and nothing downstream knows an arrow ever existed.
-    auto thick_restart_tridiag = [&](const int keep) {
+    auto thick_restart_tridiag = [&](const int keep, const int nlock) {
+        // nlock: leading Ritz pairs that have converged (|f_t| <= tol).  They are LOCKED: kept as decoupled 1 x 1 blocks
+        // at the front of the new tridiagonal, their residual coupling (<= tol) dropped.  Feeding them to the small
+        // Lanczos run below would be numerically fatal: their components of f are ~1e-15 of the others and shrink by
+        // that factor at every restart, so the run exhausts its Krylov space early and rounding noise along the dominant
+        // locked eigenvector is amplified ~100x per step until it pollutes the rotated basis (seen on Max-Cut n = 2000
+        // once two of three wanted pairs had converged: the locked Ritz value moved from 1283.66 to 1275.47).
         double* Vs = SMD(Vs);
         const int* order = reinterpret_cast<const int*>(SMD(order));
         double* Wc = SMD(JA);                    // K x keep coefficients of the new basis vectors in the old Lanczos basis
-        double* Qs = SMD(JB);                    // keep x MP: Qs[j * MP + c] = component c of Lanczos vector j
+        double* Qs = SMD(JB);                    // m2 x MP: Qs[j * MP + c] = component c of Lanczos vector j
         const int MP = 17;
         double* ta = Qs + 16 * MP;               // diagonal of T~
         double* tb = ta + 16;                    // off-diagonal of T~
         double* ws = tb + 16;                    // work vector
         double* hs = ws + 32;                    // re-orthogonalisation coefficients
+        const int m2 = keep - nlock;             // pairs that take part in the re-tridiagonalisation (>= 1)
         __syncthreads();                         // D, f, order, JU are final; the bisection / Jacobi scratch in JA, JB is dead
         if (tid < 32) {
-            const int c = tid;
-            const double th = (c < keep) ? SMD(D)[c] : 0.0;
-            const double fc = (c < keep) ? SMD(f)[c] : 0.0;
+            const int c = tid;                   // component c <-> kept pair nlock + c
+            const double th = (c < m2) ? SMD(D)[nlock + c] : 0.0;
+            const double fc = (c < m2) ? SMD(f)[nlock + c] : 0.0;
             const double nf = sqrt(warp_sum(fc * fc));
             double qprev = 0.0, qcur = (nf > 0.0) ? fc / nf : ((c == 0) ? 1.0 : 0.0);
             double bprev = 0.0;
-            for (int j = 0; j < keep; ++j) {
-                if (c < keep) Qs[j * MP + c] = qcur;
+            for (int j = 0; j < m2; ++j) {
+                if (c < m2) Qs[j * MP + c] = qcur;
                 double w = th * qcur;
                 const double aj = warp_sum(qcur * w);
                 w -= aj * qcur + bprev * qprev;
                 if (c == 0) ta[j] = aj;
-                if (j == keep - 1) break;
+                if (j == m2 - 1) break;
                 // two classical Gram-Schmidt passes of w against q_0 .. q_j: lane i <-> coefficient of q_i
                 auto reorth = [&]() {
                     for (int pass = 0; pass < 2; ++pass) {
                         __syncwarp();
-                        ws[c] = (c < keep) ? w : 0.0;
+                        ws[c] = (c < m2) ? w : 0.0;
                         __syncwarp();
                         double h = 0.0;
-                        if (c <= j) for (int t = 0; t < keep; ++t) h = fma(Qs[c * MP + t], ws[t], h);
+                        if (c <= j) for (int t = 0; t < m2; ++t) h = fma(Qs[c * MP + t], ws[t], h);
                         hs[c] = (c <= j) ? h : 0.0;
                         __syncwarp();
-                        if (c < keep) for (int i = 0; i <= j; ++i) w = fma(-hs[i], Qs[i * MP + c], w);
+                        if (c < m2) for (int i = 0; i <= j; ++i) w = fma(-hs[i], Qs[i * MP + c], w);
                     }
-                    return sqrt(warp_sum((c < keep) ? w * w : 0.0));
+                    return sqrt(warp_sum((c < m2) ? w * w : 0.0));
                 };
                 double nb = reorth();
                 double bj = nb;
                 if (!(nb > 1e-200)) {
                     // exact breakdown (an f_t that is exactly zero, or a repeated theta): carry on with any direction
                     // orthogonal to the q's — T~ decouples there (off-diagonal 0)
-                    for (int t0 = 0; t0 < keep; ++t0) {
+                    for (int t0 = 0; t0 < m2; ++t0) {
                         w = (c == t0) ? 1.0 : 0.0;
                         nb = reorth();
                         if (nb > 0.5) break;
@@ -419,15 +428,20 @@ __device__ __noinline__ void lz3_ritz(const LanczosCl3Args& a, double* sbase, in
                 qcur = w / nb;
                 bprev = bj;
             }
-            if (c == 0) tb[keep - 1] = nf;         // coupling of the last rotated vector to the residual vector
+            if (c == 0) tb[m2 - 1] = nf;           // coupling of the last rotated vector to the residual vector
         }
         __syncthreads();
-        // new basis vector i = sum_t y_t Q~[t][keep-1-i]  =>  coefficients in the old Lanczos basis
+        // new basis: the locked Ritz vectors first, then vector nlock + i = sum_t y_{nlock + t} Q~[m2 - 1 - i][t]
         for (int idx = tid; idx < K * keep; idx += LZ_THREADS) {
             const int r = idx % K, i = idx / K;
-            const double* qv = Qs + (keep - 1 - i) * MP;
-            double sacc = 0.0;
-            for (int t = 0; t < keep; ++t) sacc = fma(SMD(JU)[r + order[t] * lda], qv[t], sacc);
+            double sacc;
+            if (i < nlock) {
+                sacc = SMD(JU)[r + order[i] * lda];
+            } else {
+                const double* qv = Qs + (m2 - 1 - (i - nlock)) * MP;
+                sacc = 0.0;
+                for (int t = 0; t < m2; ++t) sacc = fma(SMD(JU)[r + order[nlock + t] * lda], qv[t], sacc);
+            }
             Wc[r + i * K] = sacc;
         }
         __syncthreads();
@@ -443,10 +457,19 @@ __device__ __noinline__ void lz3_ritz(const LanczosCl3Args& a, double* sbase, in
             Vs[keep * VNp + t] = Vs[K * VNp + t];
         }
         __syncthreads();
+        if (a.debug && cta == 0 && tid == 0)
+            printf("[lz] restart keep %d locked %d  ||f|| %.3e  T~ diag %.6g ... %.6g  off %.3e ... %.3e\n", keep, nlock, tb[m2 - 1], ta[0], ta[m2 - 1],
+                   tb[0], m2 > 1 ? tb[m2 - 2] : 0.0);
+        // (the locked values are read before anything is overwritten: D is a separate array)
         for (int i = tid; i < K; i += LZ_THREADS) {
-            SMD(Hd)[i] = (i < keep) ? ta[keep - 1 - i] : 0.0;
-            SMD(He)[i] = (i < keep - 1) ? tb[keep - 2 - i] : ((i == keep - 1) ? tb[keep - 1] : 0.0);
-            SMD(Harr)[i] = 0.0;
+            double hd = 0.0, he = 0.0;
+            if (i < nlock) { hd = SMD(D)[i]; he = 0.0; }
+            else if (i < keep) {
+                const int q = i - nlock;
+                hd = ta[m2 - 1 - q];
+                he = (q < m2 - 1) ? tb[m2 - 2 - q] : tb[m2 - 1];
+            }
+            SMD(Hd)[i] = hd; SMD(He)[i] = he; SMD(Harr)[i] = 0.0;
         }
         arrow = -1;
         k = keep;                       // the caller's k++ makes it keep + 1
@@ -495,19 +518,22 @@ __device__ __noinline__ void lz3_ritz(const LanczosCl3Args& a, double* sbase, in
         if (mb > 0) {
             int cv = 0;
             while (cv < mb && fabs(SMD(f)[cv]) <= a.tol) cv++;
+            if (a.debug && cta == 0 && tid == 0)
+                printf("[lz] analysis numiter %d k %d beta %.3e bisection mb %d cv %d  D %.9g %.9g %.9g %.9g  f %.2e %.2e %.2e %.2e\n", numiter, k, beta,
+                       mb, cv, SMD(D)[0], SMD(D)[1], SMD(D)[2], SMD(D)[3], SMD(f)[0], SMD(f)[1], SMD(f)[2], SMD(f)[3]);
             if (cv >= howmany && cv < mb) { converged = cv; finished = 1; done_bi = true; }
             else if (SMD(D)[0] > a.stop_above) { converged = max(cv, 1); finished = 1; done_bi = true; }      // bound certified
             else if (cv < howmany && k == K && numiter < a.maxiter) {
                 // not converged at the end of a Krylov cycle: the restart needs the `keep` leading pairs — one warp each
                 const int keep = (3 * K + 2 * cv) / 5;
-                if (keep <= RITZ_BI_MAXM && keep < k) {
+                if (keep <= RITZ_BI_MAXM && keep < k && !a.arrow_restart) {
                     __syncthreads();
                     if (mb < keep) mb = solve(keep);
                     int cv2 = 0;
                     while (cv2 < mb && fabs(SMD(f)[cv2]) <= a.tol) cv2++;
                     if (mb >= keep && cv2 == cv) {
                         converged = cv;
-                        thick_restart_tridiag(keep);
+                        thick_restart_tridiag(keep, cv);
                         done_bi = true;
                         first_out = false;
                     }
@@ -558,6 +584,9 @@ __device__ __noinline__ void lz3_ritz(const LanczosCl3Args& a, double* sbase, in
         __syncthreads();
         converged = 0;
         while (converged < k && fabs(SMD(f)[converged]) <= a.tol) converged++;
+        if (a.debug && cta == 0 && tid == 0)
+            printf("[lz] analysis numiter %d k %d arrow %d beta %.3e dense cv %d  D %.9g %.9g %.9g %.9g  f %.2e %.2e %.2e %.2e\n", numiter, k, arrow, beta,
+                   converged, SMD(D)[0], SMD(D)[1], SMD(D)[2], SMD(D)[3], SMD(f)[0], SMD(f)[1], SMD(f)[2], SMD(f)[3]);
         if (converged >= howmany) {
             finished = 1;
         } else if (SMD(D)[0] > a.stop_above) {      // the largest Ritz value never exceeds lambda_max: bound certified
@@ -568,7 +597,7 @@ __device__ __noinline__ void lz3_ritz(const LanczosCl3Args& a, double* sbase, in
                 finished = 1;
             } else {
                 const int keep = (3 * K + 2 * converged) / 5;
-                if (keep <= 16 && arrow < 0) thick_restart_tridiag(keep); else thick_restart_arrow(keep);
+                if (keep <= 16 && arrow < 0 && !a.arrow_restart) thick_restart_tridiag(keep, min(converged, keep - 1)); else thick_restart_arrow(keep);
             }
         }
     }

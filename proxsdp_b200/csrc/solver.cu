@@ -233,6 +233,7 @@ class Solver {
     long long small_warm_calls_ = 0;
     DBuf<double> small_warm_d_;
     int lz_kernel_ = 3;        // 3 = third-generation cluster kernel (lanczos_cl3.cuh), 2 = second generation (lanczos_cl.cuh)
+    int lz_arrow_ = 0;         // cl3 kernel: 1 = arrowhead thick restart + dense Ritz solves (first-round behaviour)
     int lz_poll_ns_ = 0;       // cl3 kernel: nanoseconds of back-off between polls of the exchange words
     int lz_strict_ = 0;        // cl3 kernel: FP64 alpha + two Gram-Schmidt passes on every step (PROXSDP_B200_LZ_STRICT=1)
     int lz_xres_ = 0;          // >= 1: cap the resident slab rows of the cl3 symv at lz_xres_ - 1 (experiments / tests)
@@ -401,6 +402,7 @@ Solver::Solver(const proxsdp_problem_t* prob, const proxsdp_options_t* opt_in, b
     if (const char* e = getenv("PROXSDP_B200_LZ_XRES")) lz_xres_ = atoi(e);
     if (const char* e = getenv("PROXSDP_B200_LZ_STRICT")) lz_strict_ = atoi(e) != 0 ? 1 : 0;
     if (const char* e = getenv("PROXSDP_B200_LZ_POLL_NS")) lz_poll_ns_ = std::max(0, atoi(e));
+    if (const char* e = getenv("PROXSDP_B200_LZ_ARROW")) lz_arrow_ = atoi(e) != 0 ? 1 : 0;
     if (const char* e = getenv("PROXSDP_B200_BJ_INNER")) bj_inner_sweeps_ = std::max(1, atoi(e));
     if (const char* e = getenv("PROXSDP_B200_BJ_WARM")) bj_warm_ = atoi(e) != 0 ? 1 : 0;
     if (const char* e = getenv("PROXSDP_B200_RITZ_BI")) lz_bi_ = atoi(e);
@@ -788,7 +790,7 @@ bool Solver::lanczos_launch_cluster3(ConeDev& cd, int cone_idx, int nev, int K, 
     a.ritz_rd = (lz_warm_ && cd.ritz_launches > 0 && (cd.ritz_launches % 32) != 0) ? cd.ritz_ws[flip].p : nullptr;
     a.ritz_wr = lz_warm_ ? cd.ritz_ws[1 - flip].p : nullptr;
     a.nev = nev; a.K = K; a.maxiter = maxiter; a.tol = tol;
-    a.vn_max = vn_max; a.use_bi = lz_bi_; a.stop_above = lz_stop_above_; a.strict = lz_strict_; a.poll_ns = lz_poll_ns_;
+    a.vn_max = vn_max; a.use_bi = lz_bi_; a.stop_above = lz_stop_above_; a.strict = lz_strict_; a.poll_ns = lz_poll_ns_; a.arrow_restart = lz_arrow_; a.debug = getenv("PROXSDP_B200_LZ_DEBUG") ? 1 : 0;
     a.rbase = nside / G; a.rrem = nside % G; a.vbase = nside / C; a.vrem = nside % C;
     a.vals = cd.vals.p; a.info = cd.info.p; a.scal = scal_target_; a.cone = cone_idx;
     a.L = L;

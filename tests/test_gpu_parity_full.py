@@ -105,7 +105,7 @@ def test_full_solve_c2_headline(gpu, oracle_mod, golden_dir, lz_mode):
     aff, con = maxcut_er_problem(2000, 0.01, 0)
     rg = _full_solve_check(gpu, oracle_mod, golden_dir, "c2", aff, con)
     X = ivec(rg.primal)
-    assert np.abs(np.diag(X) - 1.0).max() <= 1e-3                           # diag(X) = 1
+    assert np.abs(np.diag(X) - 1.0).max() <= 1e-4 * (1.0 + np.sqrt(2000.0))    # diag(X) = 1 to tol_feasibility (1 + ||b||)
     w = np.linalg.eigvalsh(X)
     assert w.min() >= -1e-4 * w.max()                                       # minus_rank == 0 (test/moi_sdplib.jl:53-56)
 
@@ -356,9 +356,12 @@ def _step_state(seed, n, p, m):
     G = sp.random(m, n, 0.3, random_state=seed + 2, format="csc") if m else sp.csc_matrix((0, n))
     st = dict(b=rng.standard_normal(p), h=rng.standard_normal(m), c=rng.standard_normal(n), x=rng.standard_normal(n),
               x_old=rng.standard_normal(n), y=rng.standard_normal(p + m), y_old=rng.standard_normal(p + m),
-              Mx=rng.standard_normal(p + m), Mx_old=rng.standard_normal(p + m), Mty=rng.standard_normal(n),
-              Mty_old=rng.standard_normal(n), primal_step=0.3, primal_step_old=0.25, dual_step=0.2, theta=1.0, beta=0.8,
-              norm_b=1.5, norm_h=0.7, norm_c=2.0)
+              Mx=rng.standard_normal(p + m), Mx_old=rng.standard_normal(p + m), primal_step=0.3, primal_step_old=0.25,
+              dual_step=0.2, theta=1.0, beta=0.8, norm_b=1.5, norm_h=0.7, norm_c=2.0)
+    # M'y of a real state vanishes on the columns of M that hold no entry (the device walks M' through its non-empty rows)
+    M = sp.vstack([A, G]).tocsc()
+    st["Mty"] = np.asarray(M.T @ rng.standard_normal(p + m)).ravel()
+    st["Mty_old"] = np.asarray(M.T @ rng.standard_normal(p + m)).ravel()
     return A, G, st
 
 
