@@ -233,6 +233,8 @@ class Solver {
     long long small_warm_calls_ = 0;
     DBuf<double> small_warm_d_;
     int lz_kernel_ = 3;        // 3 = third-generation cluster kernel (lanczos_cl3.cuh), 2 = second generation (lanczos_cl.cuh)
+    int lz_coop_ = 1;          // cluster kernels are launched with cudaLaunchAttributeCooperative (PROXSDP_B200_LZ_COOP=0: plain launch)
+    bool lz_demoted_ = false;
     int lz_arrow_ = 0;         // cl3 kernel: 1 = arrowhead thick restart + dense Ritz solves (first-round behaviour)
     int lz_poll_ns_ = 0;       // cl3 kernel: nanoseconds of back-off between polls of the exchange words
     int lz_strict_ = 0;        // cl3 kernel: FP64 alpha + two Gram-Schmidt passes on every step (PROXSDP_B200_LZ_STRICT=1)
@@ -403,6 +405,7 @@ Solver::Solver(const proxsdp_problem_t* prob, const proxsdp_options_t* opt_in, b
     if (const char* e = getenv("PROXSDP_B200_LZ_STRICT")) lz_strict_ = atoi(e) != 0 ? 1 : 0;
     if (const char* e = getenv("PROXSDP_B200_LZ_POLL_NS")) lz_poll_ns_ = std::max(0, atoi(e));
     if (const char* e = getenv("PROXSDP_B200_LZ_ARROW")) lz_arrow_ = atoi(e) != 0 ? 1 : 0;
+    if (const char* e = getenv("PROXSDP_B200_LZ_COOP")) lz_coop_ = atoi(e) != 0 ? 1 : 0;
     if (const char* e = getenv("PROXSDP_B200_BJ_INNER")) bj_inner_sweeps_ = std::max(1, atoi(e));
     if (const char* e = getenv("PROXSDP_B200_BJ_WARM")) bj_warm_ = atoi(e) != 0 ? 1 : 0;
     if (const char* e = getenv("PROXSDP_B200_RITZ_BI")) lz_bi_ = atoi(e);
@@ -664,10 +667,14 @@ bool Solver::lanczos_launch_cluster(ConeDev& cd, int cone_idx, int nev, int K, i
     // grid: as many clusters as can be co-resident, but no more CTAs than there are 8-row slabs
     int want = std::max(C, ((std::max(1, (nside + 7) / 8) + C - 1) / C) * C);
     cudaLaunchConfig_t cfg{};
-    cudaLaunchAttribute attr[1];
+    // The kernel spins on words written by other CTAs, so the whole grid has to be co-resident: the cooperative attribute
+    // makes the launch FAIL (instead of spinning into its 2 s time-out) when another tenant of the device holds SMs.
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = (unsigned)C; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.blockDim = dim3(LZ_THREADS); cfg.stream = stream; cfg.attrs = attr; cfg.numAttrs = 1;
+    attr[1].id = cudaLaunchAttributeCooperative;
+    attr[1].val.cooperative = 1;
+    cfg.blockDim = dim3(LZ_THREADS); cfg.stream = stream; cfg.attrs = attr; cfg.numAttrs = lz_coop_ ? 2 : 1;
     // shared memory depends on rows_max = ceil(n / G); G depends on occupancy, which depends on shared memory:
     // size for the smallest plausible grid first (largest rows_max), then shrink
     int G = std::min(want, (num_sms_ / C) * C);
@@ -709,6 +716,11 @@ bool Solver::lanczos_launch_cluster(ConeDev& cd, int cone_idx, int nev, int K, i
     a.vals = cd.vals.p; a.info = cd.info.p; a.scal = scal_target_; a.cone = cone_idx;
     if (getenv("PROXSDP_B200_LZ_PROF")) { if (lz_prof_.n == 0) lz_prof_.alloc(8 + 8 * 256); a.prof = lz_prof_.p; }
     cudaError_t e = cudaLaunchKernelEx(&cfg, k_lanczos_cl, a);
+    if (e != cudaSuccess && lz_coop_ && (e == cudaErrorNotSupported || e == cudaErrorInvalidValue)) {
+        cudaGetLastError();
+        lz_coop_ = 0; cfg.numAttrs = 1;
+        e = cudaLaunchKernelEx(&cfg, k_lanczos_cl, a);
+    }
     if (e != cudaSuccess) {
         cudaGetLastError();
         if (!lz_cluster_warned_) { fprintf(stderr, "[proxsdp_b200] cluster Lanczos launch failed (%s); using the row-distributed kernel\n", cudaGetErrorString(e)); lz_cluster_warned_ = true; }
@@ -736,10 +748,14 @@ bool Solver::lanczos_launch_cluster3(ConeDev& cd, int cone_idx, int nev, int K, 
     if ((vn_max + LZ_NW - 1) / LZ_NW > 64) return false;      // the gather keeps two rows per lane in registers
     int want = std::max(C, ((std::max(1, (nside + 7) / 8) + C - 1) / C) * C);
     cudaLaunchConfig_t cfg{};
-    cudaLaunchAttribute attr[1];
+    // The kernel spins on words written by other CTAs, so the whole grid has to be co-resident: the cooperative attribute
+    // makes the launch FAIL (instead of spinning into its 2 s time-out) when another tenant of the device holds SMs.
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = (unsigned)C; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.blockDim = dim3(LZ_THREADS); cfg.stream = stream; cfg.attrs = attr; cfg.numAttrs = 1;
+    attr[1].id = cudaLaunchAttributeCooperative;
+    attr[1].val.cooperative = 1;
+    cfg.blockDim = dim3(LZ_THREADS); cfg.stream = stream; cfg.attrs = attr; cfg.numAttrs = lz_coop_ ? 2 : 1;
     int G = std::min(std::min(want, (num_sms_ / C) * C), (LZ3_GMAX / C) * C);
     if (G < C) return false;
     // resident slab rows: whatever shared memory the basis replica and the Ritz scratch leave, at most the shortest slab
@@ -797,6 +813,13 @@ bool Solver::lanczos_launch_cluster3(ConeDev& cd, int cone_idx, int nev, int K, 
     if (getenv("PROXSDP_B200_LZ_PROF")) { if (lz_prof_.n == 0) lz_prof_.alloc(8 + 8 * 256); a.prof = lz_prof_.p; }
     void* kargs[] = {&a};
     cudaError_t e = cudaLaunchKernelExC(&cfg, kfn, kargs);
+    if (e != cudaSuccess && lz_coop_ && (e == cudaErrorNotSupported || e == cudaErrorInvalidValue)) {
+        // this driver does not combine the cooperative attribute with cluster launches: plain launch, co-residency is
+        // then only what cudaOccupancyMaxActiveClusters promised (and the in-kernel time-outs remain the guard)
+        cudaGetLastError();
+        lz_coop_ = 0; cfg.numAttrs = 1;
+        e = cudaLaunchKernelExC(&cfg, kfn, kargs);
+    }
     if (e != cudaSuccess) {
         cudaGetLastError();
         if (!lz_cluster_warned_) { fprintf(stderr, "[proxsdp_b200] cl3 Lanczos launch failed (%s); using the second-generation kernel\n", cudaGetErrorString(e)); lz_cluster_warned_ = true; }
@@ -1107,6 +1130,19 @@ void Solver::fallback_projection(long long iter) {
     for (int kk : large_ids_) {
         if (!krylov_eligible(kk, iter)) continue;
         if (scal_host[S_HEADER + 3 * kk + 2] == 0.0) {
+            if (!lz_demoted_ && lz_mode_ == 0) {
+                // converged == 0 is either KrylovKit's "nothing converged" or an eigsolve that gave up because a peer CTA
+                // never answered (info[0] == 0: part of the grid was not resident).  The latter would repeat its 2 s
+                // time-out on every iteration: switch to the cooperative row-distributed kernel for the rest of the solve.
+                int info[4] = {1, 0, 0, 0};
+                PB_CUDA(cudaMemcpyAsync(info, cones[(size_t)kk].info.p, sizeof(info), cudaMemcpyDeviceToHost, stream));
+                PB_CUDA(cudaStreamSynchronize(stream));
+                if (info[0] == 0 && info[2] > 0) {
+                    fprintf(stderr, "[proxsdp_b200] a cluster eigsolve timed out waiting for a peer CTA (device shared with another "
+                                    "tenant?): using the cooperative row-distributed Lanczos kernel from here on\n");
+                    lz_mode_ = 1; lz_demoted_ = true;
+                }
+            }
             launch_full_projection_large(kk);
         } else {
             ConeDev& cd = cones[(size_t)kk];

@@ -112,6 +112,8 @@ def test_full_solve_c2_headline(gpu, oracle_mod, golden_dir, lz_mode):
 
 def test_full_solve_maxG32(gpu, oracle_mod, golden_dir):
     """SDPLIB maxG32 (n = 2000, reference test/data/maxG32.dat-s): full solve vs the oracle's run and the SDPLIB optimum."""
+    if not os.path.exists(f"{golden_dir}/full_maxG32.npz"):
+        pytest.skip("tests/golden/full_maxG32.npz not generated (hours of CPU oracle time: tests/golden/make_full_solves.py maxG32)")
     aff, con = load_problem(f"{golden_dir}/sdplib_maxG32.npz")
     _full_solve_check(gpu, oracle_mod, golden_dir, "maxG32", aff, con, sdplib_optimum=-1567.640)
 
@@ -387,3 +389,22 @@ def test_residuals_seam(gpu, oracle_mod, n, p, m):
     rg = gpu.residuals(n, p, m, Options(), **st)
     for k_ in ro:
         assert abs(rg[k_] - ro[k_]) <= 1e-12 * max(1.0, abs(ro[k_])), (k_, rg[k_], ro[k_])
+
+
+# ------------------------------------------------------------------ eigsolver = 1 (ARPACK mode) on a large cone
+def test_arpack_mode_large_cone(gpu, oracle_mod, golden_dir):
+    """eigsolver = 1 (reference src/eigsolver.jl:668-770): the device serves it with the same thick-restart Lanczos and
+    the same converged quantities; on mcp124-1 (side 124 > min_size_krylov_eigs: the Krylov path really
+    runs) the solve must agree with the oracle's eigsolver = 1 run — same status and iterations over the first 60
+    iterations, traces to 1e-6 — and with the KrylovKit mode of the device itself."""
+    aff, con = load_problem(f"{golden_dir}/sdplib_mcp124-1.npz")
+    opt1 = Options(eigsolver=1, max_iter=60, trace_cap=60)
+    rg = gpu.chambolle_pock(aff, con, opt1)
+    ro = oracle_mod.chambolle_pock(aff, con, opt1)
+    assert rg.lanczos_calls == ro.lanczos_calls == 60 and rg.full_eig_calls == ro.full_eig_calls
+    assert np.all(np.abs(rg.trace[:, 1:9] - ro.trace[:, 1:9]) <= 1e-6 * np.maximum(1.0, np.abs(ro.trace[:, 1:9])))
+    r2 = gpu.chambolle_pock(aff, con, Options(eigsolver=2, max_iter=60, trace_cap=60))
+    assert np.all(np.abs(rg.trace[:, 1:9] - r2.trace[:, 1:9]) <= 1e-6 * np.maximum(1.0, np.abs(r2.trace[:, 1:9])))
+    # to termination: same status, objective within the solver tolerance of the SDPLIB optimum
+    rg = gpu.chambolle_pock(aff, con, Options(eigsolver=1))
+    assert rg.status == 1 and abs(rg.objval - (-141.9905)) <= 5e-3 * 141.9905
