@@ -160,6 +160,10 @@ typedef struct proxsdp_options {
     int64_t freeze_target_rank;    /* 1 => never bump target_rank (rank-sweep measurement) */
     int64_t device_id;             /* CUDA device ordinal (product only)                   */
     int64_t trace_cap;             /* record up to this many iterations into result trace  */
+    int64_t implicit_psd_operator; /* 1 => Krylov projections of large cones apply the matrix IMPLICITLY as
+                                      Y diag(lam) Y' - tau mat(M'y + c) (low rank + sparse) whenever the
+                                      previous projection left a low-rank iterate: no dense n x n matrix is formed or
+                                      read, the eigsolve runs inside one thread-block cluster (product only)            */
 } proxsdp_options_t;
 
 /* ---- Result (structs.jl:60-81) ------------------------------------------
@@ -215,6 +219,7 @@ typedef struct proxsdp_result {
     int64_t lanczos_timed_calls; /* launches covered by time_lanczos                                      */
     int64_t h2d_bytes;           /* host->device bytes copied during this solve                           */
     int64_t d2h_bytes;           /* device->host bytes copied during this solve                           */
+    int64_t implicit_calls;      /* eigsolves that ran on the implicit low-rank + sparse operator         */
 } proxsdp_result_t;
 
 /* ---- step-level seams: the slice of PrimalDual / AuxiliaryData / Params (structs.jl:83-192) that `linesearch!` /

@@ -57,6 +57,7 @@ class ResultPOD(ctypes.Structure):
         ("trace", _pd), ("trace_len", c_int64),
         ("time_lanczos", c_double), ("time_rest", c_double), ("time_l2_flush", c_double),
         ("lanczos_timed_calls", c_int64), ("h2d_bytes", c_int64), ("d2h_bytes", c_int64),
+        ("implicit_calls", c_int64),
     ]
 
 
@@ -257,6 +258,7 @@ class MarshalledResult:
             trace=self.trace[: int(q.trace_len)].copy(),
             time_lanczos=q.time_lanczos, time_rest=q.time_rest, time_l2_flush=q.time_l2_flush,
             lanczos_timed_calls=int(q.lanczos_timed_calls), h2d_bytes=int(q.h2d_bytes), d2h_bytes=int(q.d2h_bytes),
+            implicit_calls=int(q.implicit_calls),
         )
 
 

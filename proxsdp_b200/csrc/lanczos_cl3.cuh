@@ -68,11 +68,23 @@ struct Lz3Layout {
     int jscratch;
     int xres;    // nres * cpr * 64        the LAST nres rows of my slab of X, staged once per launch by the TMA engine
     int nres;
+    // implicit-operator mode (k_lanczos_cl3<..., true>): instead of slab rows the region holds
+    int imp_Ys;     // LZ3_RMAX * VNp      my rows of the previous iterate's kept eigenvectors
+    int imp_lam;    // LZ3_RMAX            their eigenvalues
+    int imp_tq;     // LZ3_RMAX            lambda_q (Y_q . v)
+    int imp_tpart;  // C * LZ3_RMAX        per-peer partial Y' v (written by the peers)
+    int imp_twarp;  // LZ_NW * LZ3_RMAX    per-warp partials
+    int imp_apart;  // C + LZ_NW           per-peer partial alpha (written by the peers), per-warp partials
+    int imp_sval;   // imp_cap             values of my rows of the sparse part, tau folded in
+    int imp_scol;   // imp_cap ints
+    int imp_sptr;   // VNp + 1 ints
+    int imp_cap;
     int total;   // doubles
 };
+constexpr int LZ3_RMAX = 32;     // kept eigenpairs of the previous iterate the implicit operator can carry
 
 // everything except the resident slab rows
-__host__ inline Lz3Layout lanczos_cl3_layout(int K, int nres, int vn_max, int n, int C) {
+__host__ inline Lz3Layout lanczos_cl3_layout(int K, int nres, int vn_max, int n, int C, int imp_cap = -1) {
     Lz3Layout L{};
     const int Kp = lanczos_kp(K), VNp = lanczos_cl_vnp(vn_max), cpr = lanczos_cpr(n);
     int d = 0;
@@ -92,6 +104,18 @@ __host__ inline Lz3Layout lanczos_cl3_layout(int K, int nres, int vn_max, int n,
     L.jscratch = take((int)((jacobi_scratch_bytes(Kp) + 7) / 8));
     L.nres = nres;
     L.xres = take(nres * cpr * 64);
+    if (imp_cap >= 0) {
+        L.imp_Ys = take(LZ3_RMAX * VNp);
+        L.imp_lam = take(LZ3_RMAX);
+        L.imp_tq = take(LZ3_RMAX);
+        L.imp_tpart = take(C * LZ3_RMAX);
+        L.imp_twarp = take(LZ_NW * LZ3_RMAX);
+        L.imp_apart = take(C + LZ_NW);
+        L.imp_sval = take(imp_cap);
+        L.imp_scol = take((imp_cap + 1) / 2 + 1);
+        L.imp_sptr = take((VNp + 2) / 2 + 1);
+        L.imp_cap = imp_cap;
+    }
     L.total = d;
     return L;
 }
@@ -116,6 +140,12 @@ struct LanczosCl3Args {
     int use_bi;
     double stop_above;         // finish as soon as the largest Ritz value exceeds this (it is a lower bound of lambda_max);
                                // 1e300 = never: used by cone_feas, which only needs to know whether lambda_min < -tol
+    // implicit operator: the matrix is NOT stored; it is  Y diag(lam) Y' - tau S  with Y, lam the kept
+    // eigenpairs of the previous projection (x_k = svec(Y lam Y')) and S = mat(M'y + c), sparse
+    const double* imp_Y; const int* imp_kept_idx; const double* imp_kept_lam; const int* imp_nkept;
+    const int* imp_rowptr; const int* imp_col; const int* imp_pos; const double* imp_coef;   // CSR by row of the pattern of S
+    const double* imp_Mty; const double* imp_c;      // this cone's svec blocks of M'y and of the (scaled) objective
+    double imp_tau;
     int debug;                 // PROXSDP_B200_LZ_DEBUG=1: CTA 0 prints every Ritz analysis / restart (device printf)
     int arrow_restart;         // 1: keep the arrowhead form after a thick restart (dense Jacobi Ritz solves; PROXSDP_B200_LZ_ARROW=1)
     int poll_ns;               // back-off between two polls of the flagged exchange words (PROXSDP_B200_LZ_POLL_NS)
@@ -457,9 +487,11 @@ __device__ __noinline__ void lz3_ritz(const LanczosCl3Args& a, double* sbase, in
             Vs[keep * VNp + t] = Vs[K * VNp + t];
         }
         __syncthreads();
+#ifdef PROXSDP_B200_LZ_DEBUG_PRINTF
         if (a.debug && cta == 0 && tid == 0)
             printf("[lz] restart keep %d locked %d  ||f|| %.3e  T~ diag %.6g ... %.6g  off %.3e ... %.3e\n", keep, nlock, tb[m2 - 1], ta[0], ta[m2 - 1],
                    tb[0], m2 > 1 ? tb[m2 - 2] : 0.0);
+#endif
         // (the locked values are read before anything is overwritten: D is a separate array)
         for (int i = tid; i < K; i += LZ_THREADS) {
             double hd = 0.0, he = 0.0;
@@ -518,9 +550,11 @@ __device__ __noinline__ void lz3_ritz(const LanczosCl3Args& a, double* sbase, in
         if (mb > 0) {
             int cv = 0;
             while (cv < mb && fabs(SMD(f)[cv]) <= a.tol) cv++;
+#ifdef PROXSDP_B200_LZ_DEBUG_PRINTF
             if (a.debug && cta == 0 && tid == 0)
                 printf("[lz] analysis numiter %d k %d beta %.3e bisection mb %d cv %d  D %.9g %.9g %.9g %.9g  f %.2e %.2e %.2e %.2e\n", numiter, k, beta,
                        mb, cv, SMD(D)[0], SMD(D)[1], SMD(D)[2], SMD(D)[3], SMD(f)[0], SMD(f)[1], SMD(f)[2], SMD(f)[3]);
+#endif
             if (cv >= howmany && cv < mb) { converged = cv; finished = 1; done_bi = true; }
             else if (SMD(D)[0] > a.stop_above) { converged = max(cv, 1); finished = 1; done_bi = true; }      // bound certified
             else if (cv < howmany && k == K && numiter < a.maxiter) {
@@ -584,9 +618,11 @@ __device__ __noinline__ void lz3_ritz(const LanczosCl3Args& a, double* sbase, in
         __syncthreads();
         converged = 0;
         while (converged < k && fabs(SMD(f)[converged]) <= a.tol) converged++;
+#ifdef PROXSDP_B200_LZ_DEBUG_PRINTF
         if (a.debug && cta == 0 && tid == 0)
             printf("[lz] analysis numiter %d k %d arrow %d beta %.3e dense cv %d  D %.9g %.9g %.9g %.9g  f %.2e %.2e %.2e %.2e\n", numiter, k, arrow, beta,
                    converged, SMD(D)[0], SMD(D)[1], SMD(D)[2], SMD(D)[3], SMD(f)[0], SMD(f)[1], SMD(f)[2], SMD(f)[3]);
+#endif
         if (converged >= howmany) {
             finished = 1;
         } else if (SMD(D)[0] > a.stop_above) {      // the largest Ritz value never exceeds lambda_max: bound certified
@@ -608,7 +644,7 @@ __device__ __noinline__ void lz3_ritz(const LanczosCl3Args& a, double* sbase, in
 #undef SMD
 }
 
-template <int CPW, int RB, int NMAX>
+template <int CPW, int RB, int NMAX, bool IMP = false>
 __global__ void __launch_bounds__(LZ_THREADS, 1) k_lanczos_cl3(const __grid_constant__ LanczosCl3Args a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cg::cluster_group cluster = cg::this_cluster();
@@ -644,8 +680,9 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) k_lanczos_cl3(const __grid_cons
     __shared__ int s_ok;
     __shared__ int s_state[10];
     __shared__ double s_beta;
-    __shared__ __align__(8) unsigned long long s_mbar[3];      // [0] Gram-Schmidt dots exchange, [1] publication of v_{j+1},
-                                                               // [2] TMA staging of the resident slab rows
+    __shared__ __align__(8) unsigned long long s_mbar[5];      // [0] Gram-Schmidt dots exchange, [1] publication of v_{j+1},
+                                                               // [2] TMA staging of the resident slab rows,
+                                                               // implicit operator: [3] Y'v exchange, [4] alpha exchange
     unsigned int ph_dots = 0;                                  // dots exchanges completed so far (parity = phase & 1); the
                                                                // publication phase is the step number: parity (gsync - 1) & 1
     const int prow = (cta == 0) ? 0 : (cta == C - 1) ? 1 : (cta == G / 2) ? 2 : (cta == G - 1) ? 3 : -1;
@@ -669,11 +706,13 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) k_lanczos_cl3(const __grid_cons
         mbar_init(&s_mbar[0], 1);
         mbar_init(&s_mbar[1], 1);
         mbar_init(&s_mbar[2], 1);
+        mbar_init(&s_mbar[3], 1);
+        mbar_init(&s_mbar[4], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         // stage the resident rows of my slab (the last a.res_begin_off of its rl rows) into shared memory: one bulk
         // copy per row on the TMA engine (row = cpr * 64 doubles = ld doubles: X is zero-padded to ld columns),
         // completion counted in bytes on s_mbar[2]; the copies run while the cluster barrier below is crossed
-        const int nres = min(a.res_begin_off, rl);
+        const int nres = IMP ? 0 : min(a.res_begin_off, rl);
         if (nres > 0) {
             const unsigned int rowbytes = (unsigned int)(cpr * 64 * sizeof(double));
             mbar_expect_tx(&s_mbar[2], (unsigned int)nres * rowbytes);
@@ -681,8 +720,30 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) k_lanczos_cl3(const __grid_cons
                 bulk_g2s(SMD(xres) + (size_t)q * cpr * 64, a.X + (size_t)(r0 + rl - nres + q) * a.ld, rowbytes, &s_mbar[2]);
         }
     }
+    int imp_nk = 0;
+    if constexpr (IMP) {
+        // my rows of the kept eigenvectors of the previous projection, their eigenvalues, and my rows of the sparse part
+        // with (M'y + c) and -tau folded into the values: all of it stays in shared memory for the whole eigsolve
+        imp_nk = min(*a.imp_nkept, LZ3_RMAX);
+        double* Ys = SMD(imp_Ys);
+        for (int idx = tid; idx < imp_nk * vn; idx += LZ_THREADS) {
+            const int q = idx / vn, t = idx - q * vn;
+            Ys[q * VNp + t] = a.imp_Y[(size_t)(v0 + t) + (size_t)a.imp_kept_idx[q] * a.ld];
+        }
+        for (int q = tid; q < LZ3_RMAX; q += LZ_THREADS) SMD(imp_lam)[q] = (q < imp_nk) ? a.imp_kept_lam[q] : 0.0;
+        int* sptr = reinterpret_cast<int*>(SMD(imp_sptr));
+        int* scol = reinterpret_cast<int*>(SMD(imp_scol));
+        const int base = a.imp_rowptr[v0];
+        for (int t = tid; t <= vn; t += LZ_THREADS) sptr[t] = a.imp_rowptr[v0 + t] - base;
+        const int cnt = min(a.imp_rowptr[v0 + vn] - base, a.L.imp_cap);
+        for (int e = tid; e < cnt; e += LZ_THREADS) {
+            const int pos = a.imp_pos[base + e];
+            scol[e] = a.imp_col[base + e];
+            SMD(imp_sval)[e] = -a.imp_tau * (a.imp_coef[base + e] * (a.imp_Mty[pos] + a.imp_c[pos]));
+        }
+    }
     cluster.sync();       // everybody's shared memory and barriers are initialised before any peer writes into them
-    if (min(a.res_begin_off, rl) > 0 && !mbar_wait(&s_mbar[2], 0)) s_ok = 0;
+    if (!IMP && min(a.res_begin_off, rl) > 0 && !mbar_wait(&s_mbar[2], 0)) s_ok = 0;
     if (profiling && tid == 0) tprev = clock64();
 
     while (!finished) {
@@ -696,9 +757,12 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) k_lanczos_cl3(const __grid_cons
         }
         // ================= symv on my slab of rows: w slab and my share of alpha straight to global =================
         // (gsync still counts the exchanges done so far: this step's buffers have parity (gsync + 1) & 1)
-        symv_slab<CPW, RB, NMAX>(a.X, a.ld, r0, rl, cpr, SMD(vbuf), SMD(xres), max(rl - a.res_begin_off, 0), SMD(wpart), SMD(aprod),
-                                 a.wg + (size_t)((gsync + 1) & 1) * a.ld + r0, a.apart + (size_t)((gsync + 1) & 1) * LZ3_GMAX + cta,
-                                 a.epoch_base + gsync + 1, profiling ? s_prof : nullptr);
+        if constexpr (!IMP)
+            symv_slab<CPW, RB, NMAX>(a.X, a.ld, r0, rl, cpr, SMD(vbuf), SMD(xres), max(rl - a.res_begin_off, 0), SMD(wpart), SMD(aprod),
+                                     a.wg + (size_t)((gsync + 1) & 1) * a.ld + r0, a.apart + (size_t)((gsync + 1) & 1) * LZ3_GMAX + cta,
+                                     a.epoch_base + gsync + 1, profiling ? s_prof : nullptr);
+        else
+            __syncthreads();      // the state words just parked are re-read below
         // (no block barrier here: the state words were written a whole step ago)
         k = s_state[0]; gsync = (unsigned int)s_state[1]; arrow = s_state[2]; howmany = s_state[3]; numiter = s_state[4];
         first_analysis = s_state[5] != 0; ph_dots = (unsigned int)s_state[8]; beta = s_beta;
@@ -722,6 +786,83 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) k_lanczos_cl3(const __grid_cons
             const double* Vs = SMD(Vs);
             double* wv = SMD(wv);
             double wreg[2];                                  // RW <= 64 rows per warp is checked on the host
+            if constexpr (IMP) {
+                // ---- w = Y (lam (Y' v)) - tau S v on my basis rows; no grid exchange: the cluster is the whole grid ----
+                const double* Ys = SMD(imp_Ys);
+                const double* vb = SMD(vbuf);
+                {   // (1) Y' v: lane <-> eigenvector q, warp <-> its rows, then across warps and across the cluster
+                    double s0 = 0.0, s1 = 0.0;
+                    if (lane < imp_nk) {
+                        const double* yq = Ys + lane * VNp;
+                        int t = t_lo;
+                        for (; t + 1 < t_hi; t += 2) { s0 = fma(yq[t], vb[v0 + t], s0); s1 = fma(yq[t + 1], vb[v0 + t + 1], s1); }
+                        if (t < t_hi) s0 = fma(yq[t], vb[v0 + t], s0);
+                    }
+                    SMD(imp_twarp)[warp * LZ3_RMAX + lane] = s0 + s1;
+                }
+                __syncthreads();
+                if (tid < imp_nk) {
+                    const double* tw = SMD(imp_twarp) + tid;
+                    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll
+                    for (int w = 0; w < LZ_NW; w += 4) { s0 += tw[w * LZ3_RMAX]; s1 += tw[(w + 1) * LZ3_RMAX]; s2 += tw[(w + 2) * LZ3_RMAX]; s3 += tw[(w + 3) * LZ3_RMAX]; }
+                    const double sres = (s0 + s1) + (s2 + s3);
+                    const unsigned int dst = smem_u32(SMD(imp_tpart) + crank * LZ3_RMAX + tid), mb = smem_u32(&s_mbar[3]);
+                    for (int c = 0; c < C; ++c) st_async_f64(mapa_u32(dst, c), sres, mapa_u32(mb, c));
+                }
+                if (tid == 0) mbar_expect_tx(&s_mbar[3], (unsigned int)(C * imp_nk * 8));
+                if (imp_nk > 0 && !mbar_wait(&s_mbar[3], (gsync - 1) & 1)) s_ok = 0;
+                if (tid < imp_nk) {
+                    double sres = 0.0;
+                    for (int c = 0; c < C; ++c) sres += SMD(imp_tpart)[c * LZ3_RMAX + tid];      // rank order: same bits in every CTA
+                    SMD(imp_tq)[tid] = SMD(imp_lam)[tid] * sres;
+                }
+                __syncthreads();
+                // (2) my rows of w, and my share of alpha = v . w
+                const int* sptr = reinterpret_cast<const int*>(SMD(imp_sptr));
+                const int* scol = reinterpret_cast<const int*>(SMD(imp_scol));
+                const double* sval = SMD(imp_sval);
+                const double* tq = SMD(imp_tq);
+                double ap = 0.0;
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int t = t_lo + lane + 32 * u;
+                    double w = 0.0;
+                    if (t < t_hi) {
+                        double w0 = 0.0, w1 = 0.0;
+                        int q = 0;
+                        for (; q + 1 < imp_nk; q += 2) { w0 = fma(Ys[q * VNp + t], tq[q], w0); w1 = fma(Ys[(q + 1) * VNp + t], tq[q + 1], w1); }
+                        if (q < imp_nk) w0 = fma(Ys[q * VNp + t], tq[q], w0);
+                        double z0 = 0.0, z1 = 0.0;
+                        int e = sptr[t];
+                        const int ee = min(sptr[t + 1], a.L.imp_cap);
+                        for (; e + 1 < ee; e += 2) { z0 = fma(sval[e], vb[scol[e]], z0); z1 = fma(sval[e + 1], vb[scol[e + 1]], z1); }
+                        if (e < ee) z0 = fma(sval[e], vb[scol[e]], z0);
+                        w = (w0 + w1) + (z0 + z1);
+                        ap = fma(w, vb[v0 + t], ap);
+                    }
+                    wreg[u] = w;
+                }
+                ap = warp_sum(ap);
+                if (lane == 0) SMD(imp_apart)[C + warp] = ap;
+                __syncthreads();
+                if (tid == 0) {
+                    const double* aw = SMD(imp_apart) + C;
+                    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll
+                    for (int w = 0; w < LZ_NW; w += 4) { s0 += aw[w]; s1 += aw[w + 1]; s2 += aw[w + 2]; s3 += aw[w + 3]; }
+                    const double sres = (s0 + s1) + (s2 + s3);
+                    const unsigned int dst = smem_u32(SMD(imp_apart) + crank), mb = smem_u32(&s_mbar[4]);
+                    for (int c = 0; c < C; ++c) st_async_f64(mapa_u32(dst, c), sres, mapa_u32(mb, c));
+                    mbar_expect_tx(&s_mbar[4], (unsigned int)(C * 8));
+                }
+                if (!mbar_wait(&s_mbar[4], (gsync - 1) & 1)) s_ok = 0;
+                if (tid == 0) {
+                    double sres = 0.0;
+                    for (int c = 0; c < C; ++c) sres += SMD(imp_apart)[c];
+                    SMD(hred)[K + 1] = sres;
+                }
+            } else {
             {
                 uint4 rr[2];
                 bool have[2];
@@ -776,6 +917,7 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) k_lanczos_cl3(const __grid_cons
                     if (lane == 0) SMD(hred)[K + 1] = (double)sf;
                 }
             }
+            }      // dense operator
             if (j == arrow) {
 #pragma unroll
                 for (int u = 0; u < 2; ++u) {

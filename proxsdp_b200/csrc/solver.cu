@@ -172,6 +172,13 @@ struct ConeDev {
     DBuf<double> X;             // ld x ld, large cones only
     DBuf<double> Vfull;         // ld x ld eigenvectors for the block-Jacobi path (allocated lazily)
     DBuf<double> Vtmp;          // ld x ld scratch of the warm start (A W)
+    // implicit operator (opt.implicit_psd_operator): CSR by row of the sparsity pattern of mat(M'y + c) inside this cone
+    DBuf<int> imp_rowptr, imp_col, imp_pos;
+    DBuf<double> imp_coef;
+    int imp_cap = 0;            // largest number of pattern entries in one CTA's rows (cluster split)
+    bool imp_tried = false, imp_ready = false;
+    bool lowrank_valid = false; // x holds svec(Y diag(lam) Y') of the previous Krylov projection (Y, kept_* still on the device)
+    bool used_implicit = false; // this iteration's eigsolve ran on the implicit operator (X was not formed)
     bool have_V = false;        // Vfull holds the eigenvectors of this cone's previous full projection
     long long full_calls = 0;
     DBuf<double> Y;             // ld x (Kmax)
@@ -227,6 +234,10 @@ class Solver {
     void lanczos_launch(ConeDev& cd, int cone_idx, int nev, int K, int maxiter, double tol);
     bool lanczos_launch_cluster(ConeDev& cd, int cone_idx, int nev, int K, int maxiter, double tol);
     bool lanczos_launch_cluster3(ConeDev& cd, int cone_idx, int nev, int K, int maxiter, double tol);
+    bool lanczos_launch_implicit(ConeDev& cd, int cone_idx, int nev, int K, int maxiter, double tol, double tau);
+    bool implicit_pattern(ConeDev& cd);
+    double last_tau_ = 0.0;
+    long long implicit_calls = 0;
     double lz_stop_above_ = 1e300;   // cl3 kernel: early exit once the top Ritz value exceeds this (cone_feas only)
     int small_fast_ = 0;       // small cones: double-buffered Jacobi when three matrices fit shared memory
     int small_warm_ = 1;       // small cones: warm-start the Jacobi sweeps from the previous projection's eigenvectors
@@ -609,6 +620,7 @@ void Solver::setup_host(const proxsdp_problem_t* prob) {
             size_t mx = smem_optin_;
             std::vector<const void*> fns;
             for (int cpw = 1; cpw <= 8; ++cpw) if (const void* fn = lanczos_cl3_kernel(cpw)) fns.push_back(fn);
+            fns.push_back((const void*)k_lanczos_cl3<1, 1, 1, true>);
             for (const void* fn : fns) {
                 cudaFuncAttributes fa{};
                 PB_CUDA(cudaFuncGetAttributes(&fa, fn));
@@ -836,6 +848,110 @@ bool Solver::lanczos_launch_cluster3(ConeDev& cd, int cone_idx, int nev, int K, 
     return true;
 }
 
+// Sparsity pattern of S = mat(M'y + c) inside one cone, as CSR by matrix row (built once per solve, on first use): entry
+// (row, col, svec position, coefficient) with coefficient 1 on the diagonal and 1/sqrt(2) off it (prox_operators.jl:1-16).
+// M'y + c vanishes outside supp(c) ∪ {non-empty rows of M'}, whatever y is.
+bool Solver::implicit_pattern(ConeDev& cd) {
+    if (cd.imp_tried) return cd.imp_ready;
+    cd.imp_tried = true;
+    const long long tri = (long long)cd.side * (cd.side + 1) / 2;
+    std::vector<double> cblk((size_t)tri);
+    PB_CUDA(cudaMemcpy(cblk.data(), c_orig_d_.p + cd.off, sizeof(double) * (size_t)tri, cudaMemcpyDeviceToHost));
+    g_d2h_bytes += (long long)sizeof(double) * tri;
+    std::vector<int> nzr((size_t)Mt_.n_nz);
+    if (Mt_.n_nz > 0) PB_CUDA(cudaMemcpy(nzr.data(), Mt_.nz_rows.p, sizeof(int) * (size_t)Mt_.n_nz, cudaMemcpyDeviceToHost));
+    std::vector<long long> pos;
+    for (long long k = 0; k < tri; ++k) if (cblk[(size_t)k] != 0.0) pos.push_back(k);
+    for (int r : nzr) if (r >= cd.off && r < cd.off + tri) pos.push_back((long long)r - cd.off);
+    std::sort(pos.begin(), pos.end());
+    pos.erase(std::unique(pos.begin(), pos.end()), pos.end());
+    if ((long long)pos.size() * 2 > (1LL << 30)) return false;
+    const int nside = cd.side;
+    std::vector<int> rp((size_t)nside + 1, 0);
+    struct E { int row, col, pos; double coef; };
+    std::vector<E> ent;
+    ent.reserve(pos.size() * 2);
+    const double isq2 = 1.0 / std::sqrt(2.0);
+    for (long long k : pos) {
+        long long j = (long long)((std::sqrt(8.0 * (double)k + 1.0) - 1.0) * 0.5);
+        while ((j + 1) * (j + 2) / 2 <= k) ++j;
+        while (j * (j + 1) / 2 > k) --j;
+        const long long i = k - j * (j + 1) / 2;
+        if (i == j) ent.push_back({(int)i, (int)j, (int)k, 1.0});
+        else { ent.push_back({(int)i, (int)j, (int)k, isq2}); ent.push_back({(int)j, (int)i, (int)k, isq2}); }
+    }
+    for (const E& e : ent) rp[(size_t)e.row + 1]++;
+    for (int r = 0; r < nside; ++r) rp[(size_t)r + 1] += rp[(size_t)r];
+    std::vector<int> next(rp.begin(), rp.end() - 1), col(ent.size()), ps(ent.size());
+    std::vector<double> cf(ent.size());
+    for (const E& e : ent) { const int d = next[(size_t)e.row]++; col[(size_t)d] = e.col; ps[(size_t)d] = e.pos; cf[(size_t)d] = e.coef; }
+    // entries per CTA of the cluster split (rows v0 .. v0 + vn)
+    const int C = lz_cluster_;
+    int cap = 0;
+    for (int c = 0; c < C; ++c) {
+        const int vb = nside / C, vr = nside % C;
+        const int v0 = c * vb + std::min(c, vr), vn = vb + (c < vr ? 1 : 0);
+        cap = std::max(cap, rp[(size_t)(v0 + vn)] - rp[(size_t)v0]);
+    }
+    cd.imp_cap = std::max(cap, 1);
+    cd.imp_rowptr.upload(rp); cd.imp_col.upload(col); cd.imp_pos.upload(ps); cd.imp_coef.upload(cf);
+    cd.imp_ready = true;
+    return true;
+}
+
+// One eigsolve on the implicit operator  Y diag(lam) Y' - tau mat(M'y + c): a single thread-block cluster, no grid
+// exchange, no dense matrix (lanczos_cl3.cuh, IMP = true).  Returns false when the configuration does not fit.
+bool Solver::lanczos_launch_implicit(ConeDev& cd, int cone_idx, int nev, int K, int maxiter, double tol, double tau) {
+    if (lz_mode_ == 1 || lz_kernel_ != 3 || K > LZC_KMAX || cd.side < 64) return false;
+    if (!implicit_pattern(cd)) return false;
+    const int nside = cd.side;
+    const int C = lz_cluster_;
+    const int vn_max = (nside + C - 1) / C;
+    if ((vn_max + LZ_NW - 1) / LZ_NW > 64) return false;
+    Lz3Layout L = lanczos_cl3_layout(K, 0, vn_max, nside, C, cd.imp_cap);
+    const size_t smem = (size_t)L.total * sizeof(double);
+    if (smem > lz_cl3_smem_max_) return false;
+    cudaLaunchConfig_t cfg{};
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)C; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeCooperative;
+    attr[1].val.cooperative = 1;
+    cfg.blockDim = dim3(LZ_THREADS); cfg.stream = stream; cfg.attrs = attr; cfg.numAttrs = lz_coop_ ? 2 : 1;
+    cfg.gridDim = dim3((unsigned)C); cfg.dynamicSmemBytes = smem;
+    if ((size_t)cd.ld * (size_t)(K + 1) > cd.Y.n) return false;      // (Y must not be re-allocated: it holds the operator)
+    const size_t ws_len = 1 + (size_t)lanczos_kp(Kmax_ > K ? Kmax_ : K) * (size_t)lanczos_kp(Kmax_ > K ? Kmax_ : K);
+    for (int q = 0; q < 2; ++q) if (cd.ritz_ws[q].n < ws_len) { cd.ritz_ws[q].alloc(ws_len); cd.ritz_launches = 0; }
+    LanczosCl3Args a{};
+    a.X = nullptr; a.n = nside; a.ld = cd.ld; a.x0 = cd.resid.p; a.Y = cd.Y.p;
+    a.wg = nullptr; a.apart = nullptr; a.epoch_base = 0; a.res_begin_off = 0;
+    const int flip = (int)(cd.ritz_launches & 1);
+    a.ritz_rd = (lz_warm_ && cd.ritz_launches > 0 && (cd.ritz_launches % 32) != 0) ? cd.ritz_ws[flip].p : nullptr;
+    a.ritz_wr = lz_warm_ ? cd.ritz_ws[1 - flip].p : nullptr;
+    a.nev = nev; a.K = K; a.maxiter = maxiter; a.tol = tol;
+    a.vn_max = vn_max; a.use_bi = lz_bi_; a.stop_above = 1e300; a.strict = lz_strict_; a.poll_ns = 0; a.arrow_restart = lz_arrow_; a.debug = 0;
+    a.rbase = nside / C; a.rrem = nside % C; a.vbase = nside / C; a.vrem = nside % C;
+    a.vals = cd.vals.p; a.info = cd.info.p; a.scal = scal_target_; a.cone = cone_idx;
+    a.L = L;
+    a.imp_Y = cd.Y.p; a.imp_kept_idx = cd.kept_idx.p; a.imp_kept_lam = cd.kept_lam.p; a.imp_nkept = cd.nkept.p;
+    a.imp_rowptr = cd.imp_rowptr.p; a.imp_col = cd.imp_col.p; a.imp_pos = cd.imp_pos.p; a.imp_coef = cd.imp_coef.p;
+    a.imp_Mty = Mty_[cur_].p + cd.off; a.imp_c = c_.p + cd.off; a.imp_tau = tau;
+    const void* kfn = (const void*)k_lanczos_cl3<1, 1, 1, true>;
+    void* kargs[] = {&a};
+    cudaError_t e = cudaLaunchKernelExC(&cfg, kfn, kargs);
+    if (e != cudaSuccess && lz_coop_ && (e == cudaErrorNotSupported || e == cudaErrorInvalidValue)) {
+        cudaGetLastError();
+        cfg.numAttrs = 1;
+        e = cudaLaunchKernelExC(&cfg, kfn, kargs);
+    }
+    if (e != cudaSuccess) { cudaGetLastError(); return false; }
+    cd.ritz_launches++;
+    launches += 1;
+    lz_cluster_launches_++;
+    implicit_calls++;
+    return true;
+}
+
 void Solver::lanczos_launch(ConeDev& cd, int cone_idx, int nev, int K, int maxiter, double tol) {
     if (lanczos_launch_cluster3(cd, cone_idx, nev, K, maxiter, tol)) return;
     if (lanczos_launch_cluster(cd, cone_idx, nev, K, maxiter, tol)) return;
@@ -985,26 +1101,43 @@ void Solver::psd_projection_launch(long long iter, double tau, bool force_full) 
         full_eig_calls += (long long)small_ids_.size();
     }
     std::vector<int> full_now;
+    last_tau_ = tau;
     for (int k : large_ids_) {
         ConeDev& cd = cones[(size_t)k];
         int nt = (cd.side + 31) / 32;
         int tiles = nt * (nt + 1) / 2;
-        k_svec_to_mat<true><<<tiles, dim3(32, 8), 0, stream>>>(x + cd.off, Mty + cd.off, c_.p + cd.off, tau, 1.0,
-                                                               cd.side, cd.ld, cd.X.p);
-        launches++;
-        if (!force_full && krylov_eligible(k, iter)) {
-            int nev = (int)target_rank[(size_t)k];
-            int K = (int)std::max<long long>(2 * nev + 1, opt.eigsolver_min_lanczos);   // eigsolver.jl:794
-            const bool timed = !lz_timed_;     // the per-kernel timer covers the first eigsolve of the iteration
+        const bool krylov = !force_full && krylov_eligible(k, iter);
+        const int nev = (int)target_rank[(size_t)k];
+        const int K = (int)std::max<long long>(2 * nev + 1, opt.eigsolver_min_lanczos);   // eigsolver.jl:794
+        // implicit operator: x_k is still the low-rank product of the previous Krylov projection, so the matrix
+        // x_k - tau (M'y + c) need not be formed at all (opt.implicit_psd_operator)
+        cd.used_implicit = false;
+        if (krylov && opt.implicit_psd_operator && cd.lowrank_valid && nev <= LZ3_RMAX && tau != 0.0) {
+            const bool timed = !lz_timed_;
             if (timed) PB_CUDA(cudaEventRecord(ev_lz0_, stream));
-            lanczos_launch(cd, k, nev, K, (int)opt.krylovkit_max_iter, opt.krylovkit_tol);
-            if (timed) { PB_CUDA(cudaEventRecord(ev_lz1_, stream)); lz_timed_ = true; }
+            cd.used_implicit = lanczos_launch_implicit(cd, k, nev, K, (int)opt.krylovkit_max_iter, opt.krylovkit_tol, tau);
+            if (cd.used_implicit && timed) { PB_CUDA(cudaEventRecord(ev_lz1_, stream)); lz_timed_ = true; }
+        }
+        if (!cd.used_implicit) {
+            k_svec_to_mat<true><<<tiles, dim3(32, 8), 0, stream>>>(x + cd.off, Mty + cd.off, c_.p + cd.off, tau, 1.0,
+                                                                   cd.side, cd.ld, cd.X.p);
+            launches++;
+        }
+        if (krylov) {
+            if (!cd.used_implicit) {
+                const bool timed = !lz_timed_;     // the per-kernel timer covers the first eigsolve of the iteration
+                if (timed) PB_CUDA(cudaEventRecord(ev_lz0_, stream));
+                lanczos_launch(cd, k, nev, K, (int)opt.krylovkit_max_iter, opt.krylovkit_tol);
+                if (timed) { PB_CUDA(cudaEventRecord(ev_lz1_, stream)); lz_timed_ = true; }
+            }
+            cd.lowrank_valid = true;           // (cleared again by the fallback when the eigsolve did not converge)
             lanczos_calls++;
             k_lanczos_select<<<1, 32, 0, stream>>>(cd.vals.p, cd.info.p, nev, cd.kept_idx.p, cd.kept_lam.p,
                                                    cd.nkept.p, scal_d_.p, k);
             launches++;
             launch_reconstruct(cd, xn);
         } else {
+            cd.lowrank_valid = false;
             full_now.push_back(k);
         }
     }
@@ -1142,6 +1275,16 @@ void Solver::fallback_projection(long long iter) {
                                     "tenant?): using the cooperative row-distributed Lanczos kernel from here on\n");
                     lz_mode_ = 1; lz_demoted_ = true;
                 }
+            }
+            {
+                ConeDev& cf = cones[(size_t)kk];
+                if (cf.used_implicit) {      // the eigsolve ran without the dense matrix: the exact projection needs it
+                    int nt = (cf.side + 31) / 32;
+                    k_svec_to_mat<true><<<nt * (nt + 1) / 2, dim3(32, 8), 0, stream>>>(x_[cur_].p + cf.off, Mty_[cur_].p + cf.off, c_.p + cf.off,
+                                                                                       last_tau_, 1.0, cf.side, cf.ld, cf.X.p);
+                    launches++;
+                }
+                cf.lowrank_valid = false;
             }
             launch_full_projection_large(kk);
         } else {
@@ -1328,6 +1471,7 @@ __global__ void k_scale_copy(const double* __restrict__ src, double a, long long
 // into the caller's buffer (pinned or pageable).
 void Solver::cache_solution(double c_factor, proxsdp_result_t* out) {
     StageTimer st("finish: scaling + slack");
+    for (ConeDev& cd : cones) cd.lowrank_valid = false;      // x is rescaled in place below: no longer svec(Y lam Y')
     const int blocks_n = std::max(1, std::min(reduce_blocks_, ceil_div(n, 256)));
     if (n_sdp > 0 && n > 0) {
         k_scale_offdiag_copy<<<blocks_n, 256, 0, stream>>>(x_[cur_].p, n, psd_end_, cone_off_d_.p, n_sdp, std::sqrt(2.0), 1, x_[cur_].p);
@@ -1865,6 +2009,7 @@ void Solver::finish(proxsdp_result_t* out) {
     out->lanczos_timed_calls = lanczos_timed_calls;
     out->h2d_bytes = g_h2d_bytes;
     out->d2h_bytes = g_d2h_bytes;
+    out->implicit_calls = implicit_calls;
     if (out->target_rank) for (int q = 0; q < n_sdp; ++q) out->target_rank[q] = target_rank[(size_t)q];
 }
 

@@ -97,6 +97,7 @@ OPTION_FIELDS = [
     ("freeze_target_rank", "b", False),
     ("device_id", "i", 0),
     ("trace_cap", "i", 0),
+    ("implicit_psd_operator", "b", False),
 ]
 
 N_REFERENCE_FIELDS = 80  # options.jl has 80 fields; the rest are extensions

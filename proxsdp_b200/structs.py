@@ -132,6 +132,7 @@ class Result:
     lanczos_timed_calls: int = 0
     h2d_bytes: int = 0
     d2h_bytes: int = 0
+    implicit_calls: int = 0
 
 
 def sympackedlen(n: int) -> int:
