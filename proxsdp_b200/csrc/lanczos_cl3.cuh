@@ -69,7 +69,7 @@ struct Lz3Layout {
     int xres;    // nres * cpr * 64        the LAST nres rows of my slab of X, staged once per launch by the TMA engine
     int nres;
     // implicit-operator mode (k_lanczos_cl3<..., true>): instead of slab rows the region holds
-    int imp_Ys;     // LZ3_RMAX * VNp      my rows of the previous iterate's kept eigenvectors
+    int imp_Ys;     // imp_r * VNp         my rows of the previous iterate's kept eigenvectors
     int imp_lam;    // LZ3_RMAX            their eigenvalues
     int imp_tq;     // LZ3_RMAX            lambda_q (Y_q . v)
     int imp_tpart;  // C * LZ3_RMAX        per-peer partial Y' v (written by the peers)
@@ -79,12 +79,13 @@ struct Lz3Layout {
     int imp_scol;   // imp_cap ints
     int imp_sptr;   // VNp + 1 ints
     int imp_cap;
+    int imp_r;      // kept eigenpairs the layout has room for
     int total;   // doubles
 };
 constexpr int LZ3_RMAX = 32;     // kept eigenpairs of the previous iterate the implicit operator can carry
 
 // everything except the resident slab rows
-__host__ inline Lz3Layout lanczos_cl3_layout(int K, int nres, int vn_max, int n, int C, int imp_cap = -1) {
+__host__ inline Lz3Layout lanczos_cl3_layout(int K, int nres, int vn_max, int n, int C, int imp_cap = -1, int imp_r = 0) {
     Lz3Layout L{};
     const int Kp = lanczos_kp(K), VNp = lanczos_cl_vnp(vn_max), cpr = lanczos_cpr(n);
     int d = 0;
@@ -105,7 +106,7 @@ __host__ inline Lz3Layout lanczos_cl3_layout(int K, int nres, int vn_max, int n,
     L.nres = nres;
     L.xres = take(nres * cpr * 64);
     if (imp_cap >= 0) {
-        L.imp_Ys = take(LZ3_RMAX * VNp);
+        L.imp_Ys = take((imp_r > 0 ? imp_r : LZ3_RMAX) * VNp);      // imp_r: kept pairs the launch can meet (<= target rank)
         L.imp_lam = take(LZ3_RMAX);
         L.imp_tq = take(LZ3_RMAX);
         L.imp_tpart = take(C * LZ3_RMAX);
@@ -115,6 +116,7 @@ __host__ inline Lz3Layout lanczos_cl3_layout(int K, int nres, int vn_max, int n,
         L.imp_scol = take((imp_cap + 1) / 2 + 1);
         L.imp_sptr = take((VNp + 2) / 2 + 1);
         L.imp_cap = imp_cap;
+        L.imp_r = imp_r > 0 ? imp_r : LZ3_RMAX;
     }
     L.total = d;
     return L;
@@ -724,7 +726,7 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) k_lanczos_cl3(const __grid_cons
     if constexpr (IMP) {
         // my rows of the kept eigenvectors of the previous projection, their eigenvalues, and my rows of the sparse part
         // with (M'y + c) and -tau folded into the values: all of it stays in shared memory for the whole eigsolve
-        imp_nk = min(*a.imp_nkept, LZ3_RMAX);
+        imp_nk = min(*a.imp_nkept, a.L.imp_r);
         double* Ys = SMD(imp_Ys);
         for (int idx = tid; idx < imp_nk * vn; idx += LZ_THREADS) {
             const int q = idx / vn, t = idx - q * vn;

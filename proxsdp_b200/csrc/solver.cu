@@ -908,9 +908,13 @@ bool Solver::lanczos_launch_implicit(ConeDev& cd, int cone_idx, int nev, int K, 
     const int C = lz_cluster_;
     const int vn_max = (nside + C - 1) / C;
     if ((vn_max + LZ_NW - 1) / LZ_NW > 64) return false;
-    Lz3Layout L = lanczos_cl3_layout(K, 0, vn_max, nside, C, cd.imp_cap);
+    // (the previous projection kept at most its own target rank pairs, which never exceeds the current one)
+    Lz3Layout L = lanczos_cl3_layout(K, 0, vn_max, nside, C, cd.imp_cap, std::min(nev, LZ3_RMAX));
     const size_t smem = (size_t)L.total * sizeof(double);
-    if (smem > lz_cl3_smem_max_) return false;
+    if (smem > lz_cl3_smem_max_) {
+        if (getenv("PROXSDP_B200_DEBUG")) fprintf(stderr, "[lanczos] implicit operator: %zu KB of shared memory needed, %zu available: dense path\n", smem >> 10, lz_cl3_smem_max_ >> 10);
+        return false;
+    }
     cudaLaunchConfig_t cfg{};
     cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -944,7 +948,11 @@ bool Solver::lanczos_launch_implicit(ConeDev& cd, int cone_idx, int nev, int K, 
         cfg.numAttrs = 1;
         e = cudaLaunchKernelExC(&cfg, kfn, kargs);
     }
-    if (e != cudaSuccess) { cudaGetLastError(); return false; }
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        if (getenv("PROXSDP_B200_DEBUG")) fprintf(stderr, "[lanczos] implicit operator: launch failed (%s): dense path\n", cudaGetErrorString(e));
+        return false;
+    }
     cd.ritz_launches++;
     launches += 1;
     lz_cluster_launches_++;
