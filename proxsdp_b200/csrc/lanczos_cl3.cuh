@@ -539,8 +539,8 @@ __device__ __noinline__ void lz3_ritz(const LanczosCl3Args& a, double* sbase, in
     bool done_bi = false;
     if (a.use_bi && arrow < 0 && 2 * (size_t)lda * lda >= ritz_bi_scratch_doubles(K)) {
         RitzBiScratch bs = ritz_bi_carve(SMD(JA), K);          // JA and JB are contiguous and unused here
-        auto solve = [&](const int want) -> int {
-            const int got = ritz_top_bi(k, SMD(Hd), SMD(He), want, SMD(D), SMD(JU), lda, bs, prof);
+        auto solve = [&](const int want, const int have) -> int {
+            const int got = ritz_top_bi(k, SMD(Hd), SMD(He), want, SMD(D), SMD(JU), lda, bs, prof, have);
             if (got > 0) {
                 int* order = reinterpret_cast<int*>(SMD(order));
                 for (int i = tid; i < got; i += LZ_THREADS) { order[i] = i; SMD(f)[i] = beta * SMD(JU)[(k - 1) + i * lda]; }
@@ -548,7 +548,7 @@ __device__ __noinline__ void lz3_ritz(const LanczosCl3Args& a, double* sbase, in
             __syncthreads();
             return got;
         };
-        int mb = solve(howmany + 4);
+        int mb = solve(howmany + 4, 0);
         if (mb > 0) {
             int cv = 0;
             while (cv < mb && fabs(SMD(f)[cv]) <= a.tol) cv++;
@@ -564,7 +564,7 @@ __device__ __noinline__ void lz3_ritz(const LanczosCl3Args& a, double* sbase, in
                 const int keep = (3 * K + 2 * cv) / 5;
                 if (keep <= RITZ_BI_MAXM && keep < k && !a.arrow_restart) {
                     __syncthreads();
-                    if (mb < keep) mb = solve(keep);
+                    if (mb < keep) mb = solve(keep, mb);      // the pairs of the first call stay
                     int cv2 = 0;
                     while (cv2 < mb && fabs(SMD(f)[cv2]) <= a.tol) cv2++;
                     if (mb >= keep && cv2 == cv) {
