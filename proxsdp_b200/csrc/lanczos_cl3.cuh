@@ -150,6 +150,8 @@ struct LanczosCl3Args {
     double imp_tau;
     int debug;                 // PROXSDP_B200_LZ_DEBUG=1: CTA 0 prints every Ritz analysis / restart (device printf)
     int arrow_restart;         // 1: keep the arrowhead form after a thick restart (dense Jacobi Ritz solves; PROXSDP_B200_LZ_ARROW=1)
+    int pf_rows;               // > 0: slab rows prefetched into L2 ahead of the register loads (matrices larger than L2;
+                               // PROXSDP_B200_LZ_PF overrides the host's choice)
     int poll_ns;               // back-off between two polls of the flagged exchange words (PROXSDP_B200_LZ_POLL_NS)
     int strict;                // 1: KrylovKit's arithmetic to the letter — alpha of the local step summed in FP64 and two
                                // Gram-Schmidt passes on every step (PROXSDP_B200_LZ_STRICT=1); 0: FP32 tree for the provisional
@@ -197,6 +199,11 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned in
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
                  "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
+}
+
+// L2 prefetch of `bytes` contiguous bytes (multiple of 16) by the TMA engine: no registers, no shared memory, no completion
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, unsigned int bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
 }
 
 // One step of the transposing butterfly that sums per-lane partials of N rows over the warp: lanes with the mask bit
@@ -317,10 +324,10 @@ __device__ __forceinline__ void symv_sub_resident(const double* srow, const int 
 //     (The first generation parked 512 partials per row in a 70 KB shared-memory table that half-warps summed after a
 //     block barrier: 1.2 us per mat-vec, and the table took the room the resident rows now use.)
 // All threads of the block must call it.
-template <int CPW, int RB, int NMAX>
+template <int CPW, int RB, int NMAX, bool PFL2>
 __device__ __forceinline__ void symv_slab(const double* __restrict__ X, const int ld, const int r0, const int rl, const int cpr,
                                           const double* vbuf, const double* xres, const int res_begin, double* wpart, double* aprod,
-                                          uint4* wg_slab, uint4* alpha_out, const unsigned int tag, long long* prof) {
+                                          uint4* wg_slab, uint4* alpha_out, const unsigned int tag, const int pf_rows, long long* prof) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     long long tp = (prof && tid == 0) ? clock64() : 0;
     const int NS = (cpr + CPW - 1) / CPW;
@@ -337,8 +344,17 @@ __device__ __forceinline__ void symv_slab(const double* __restrict__ X, const in
         if (active) {
             const int se = min(rend, res_begin);
             const double* gcol = X + (size_t)r0 * ld + (size_t)warp * CPW * 64 + 2 * lane;
-            for (int f = rbeg; f < se; f += NMAX)
+            for (int f = rbeg; f < se; f += NMAX) {
+                // matrices beyond L2: the TMA engine pulls the rows pf_rows ahead of the ones being multiplied into L2, so the
+                // register loads below see L2 latency instead of HBM latency (same bytes in flight -> more bandwidth)
+                // (a warp-uniform instruction: the whole warp issues it once per row)
+                if (PFL2 && pf_rows > 0 && warp == 0) {
+                    for (int q = 0; q < NMAX; ++q)
+                        if (f + pf_rows + q < min(rl, res_begin))
+                            bulk_prefetch_l2(X + (size_t)(r0 + f + pf_rows + q) * ld, (unsigned int)(cpr * 64 * sizeof(double)));
+                }
                 symv_sub_streamed<CPW, RB, NMAX>(gcol, ld, f, min(NMAX, se - f), nch, vr, wtab + (f - rbeg) * LZ_NW, lane, warp);
+            }
             const int rstride = cpr * 64;
             const double* scol = xres + (size_t)warp * CPW * 64 + 2 * lane;
             for (int f = max(rbeg, res_begin); f < rend; f += NMAX)
@@ -358,6 +374,11 @@ __device__ __forceinline__ void symv_slab(const double* __restrict__ X, const in
             ll_store(wg_slab + rbeg + tid, sres, tag);
             aprod[tid] = fma(sres, vbuf[r0 + rbeg + tid], aprod[tid]);
         }
+    }
+    // the first pf_rows rows of the slab for the NEXT mat-vec: HBM is idle during the exchange and Gram-Schmidt phases
+    if (PFL2 && pf_rows > 0 && warp == 1) {
+        for (int q = 0; q < min(pf_rows, min(rl, res_begin)); ++q)
+            bulk_prefetch_l2(X + (size_t)(r0 + q) * ld, (unsigned int)(cpr * 64 * sizeof(double)));
     }
     // alpha: the products of my rows (threads 0 .. 31, all in warp 0), summed in four chains by lane 0
     if (tid < 32) {
@@ -646,7 +667,7 @@ __device__ __noinline__ void lz3_ritz(const LanczosCl3Args& a, double* sbase, in
 #undef SMD
 }
 
-template <int CPW, int RB, int NMAX, bool IMP = false>
+template <int CPW, int RB, int NMAX, bool IMP = false, bool PFL2 = false>
 __global__ void __launch_bounds__(LZ_THREADS, 1) k_lanczos_cl3(const __grid_constant__ LanczosCl3Args a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cg::cluster_group cluster = cg::this_cluster();
@@ -760,9 +781,9 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) k_lanczos_cl3(const __grid_cons
         // ================= symv on my slab of rows: w slab and my share of alpha straight to global =================
         // (gsync still counts the exchanges done so far: this step's buffers have parity (gsync + 1) & 1)
         if constexpr (!IMP)
-            symv_slab<CPW, RB, NMAX>(a.X, a.ld, r0, rl, cpr, SMD(vbuf), SMD(xres), max(rl - a.res_begin_off, 0), SMD(wpart), SMD(aprod),
+            symv_slab<CPW, RB, NMAX, PFL2>(a.X, a.ld, r0, rl, cpr, SMD(vbuf), SMD(xres), max(rl - a.res_begin_off, 0), SMD(wpart), SMD(aprod),
                                      a.wg + (size_t)((gsync + 1) & 1) * a.ld + r0, a.apart + (size_t)((gsync + 1) & 1) * LZ3_GMAX + cta,
-                                     a.epoch_base + gsync + 1, profiling ? s_prof : nullptr);
+                                     a.epoch_base + gsync + 1, a.pf_rows, profiling ? s_prof : nullptr);
         else
             __syncthreads();      // the state words just parked are re-read below
         // (no block barrier here: the state words were written a whole step ago)

@@ -77,11 +77,13 @@ static const void* lanczos_cl3_kernel(int cpw) {
     switch (cpw) {
         case 1: return (const void*)k_lanczos_cl3<1, 3, 9>;
         case 2: return (const void*)k_lanczos_cl3<2, 2, 8>;
-        case 3: return (const void*)k_lanczos_cl3<3, 1, 8>;
-        case 4: return (const void*)k_lanczos_cl3<4, 1, 6>;
-        case 5: return (const void*)k_lanczos_cl3<5, 1, 6>;
-        case 6: return (const void*)k_lanczos_cl3<6, 1, 6>;
-        case 8: return (const void*)k_lanczos_cl3<8, 1, 4>;
+        // sides > 2048 (matrices of 34 MB and more): the variants with the L2 prefetch of the slab rows compiled in
+        // (profiles/r2_l2_prefetch.txt; at 32 MB it gains nothing and its code costs the per-step path a few per cent)
+        case 3: return (const void*)k_lanczos_cl3<3, 1, 8, false, true>;
+        case 4: return (const void*)k_lanczos_cl3<4, 1, 6, false, true>;
+        case 5: return (const void*)k_lanczos_cl3<5, 1, 6, false, true>;
+        case 6: return (const void*)k_lanczos_cl3<6, 1, 6, false, true>;
+        case 8: return (const void*)k_lanczos_cl3<8, 1, 4, false, true>;
         default: return nullptr;
     }
 }
@@ -248,6 +250,7 @@ class Solver {
     bool lz_demoted_ = false;
     int lz_arrow_ = 0;         // cl3 kernel: 1 = arrowhead thick restart + dense Ritz solves (first-round behaviour)
     int lz_poll_ns_ = 0;       // cl3 kernel: nanoseconds of back-off between polls of the exchange words
+    int lz_pf_ = -1;           // cl3 kernel: slab rows prefetched into L2 ahead of the loads (-1: 8 rows when the matrix exceeds L2)
     int lz_strict_ = 0;        // cl3 kernel: FP64 alpha + two Gram-Schmidt passes on every step (PROXSDP_B200_LZ_STRICT=1)
     int lz_xres_ = 0;          // >= 1: cap the resident slab rows of the cl3 symv at lz_xres_ - 1 (experiments / tests)
     size_t lz_cl3_smem_max_ = 0;
@@ -285,6 +288,7 @@ class Solver {
 
     bool cones_only_ = false;
     int dev_ = 0, num_sms_ = 148;
+    int l2_bytes_ = 126 << 20;
     size_t smem_optin_ = 0;
     // host problem data: only the right-hand sides (R doubles) and the cone table stay on the host
     std::vector<double> b_host_, h_host_;
@@ -389,18 +393,19 @@ Solver::Solver(const proxsdp_problem_t* prob, const proxsdp_options_t* opt_in, b
     {
         // cudaGetDeviceProperties costs milliseconds: two attributes, cached per process and device
         static std::mutex mu;
-        static int sms[64], smem[64];
+        static int sms[64], smem[64], l2b[64];
         static bool have[64] = {false};
         std::lock_guard<std::mutex> g(mu);
         const int d = dev_ & 63;
         if (!have[d]) {
             PB_CUDA(cudaDeviceGetAttribute(&sms[d], cudaDevAttrMultiProcessorCount, dev_));
             PB_CUDA(cudaDeviceGetAttribute(&smem[d], cudaDevAttrMaxSharedMemoryPerBlockOptin, dev_));
+            PB_CUDA(cudaDeviceGetAttribute(&l2b[d], cudaDevAttrL2CacheSize, dev_));
             size_t lim = 0;
             if (cudaDeviceGetLimit(&lim, cudaLimitStackSize) == cudaSuccess && lim < 4096) cudaDeviceSetLimit(cudaLimitStackSize, 4096);
             have[d] = true;
         }
-        num_sms_ = sms[d]; smem_optin_ = (size_t)smem[d];
+        num_sms_ = sms[d]; smem_optin_ = (size_t)smem[d]; l2_bytes_ = l2b[d];
     }
     st0.lap("ctor: stream+events");
     PB_CUDA(cudaStreamCreate(&stream));   // blocking stream: ordered against the synchronous setup copies on the legacy stream
@@ -415,6 +420,7 @@ Solver::Solver(const proxsdp_problem_t* prob, const proxsdp_options_t* opt_in, b
     if (const char* e = getenv("PROXSDP_B200_LZ_XRES")) lz_xres_ = atoi(e);
     if (const char* e = getenv("PROXSDP_B200_LZ_STRICT")) lz_strict_ = atoi(e) != 0 ? 1 : 0;
     if (const char* e = getenv("PROXSDP_B200_LZ_POLL_NS")) lz_poll_ns_ = std::max(0, atoi(e));
+    if (const char* e = getenv("PROXSDP_B200_LZ_PF")) lz_pf_ = std::max(0, atoi(e));
     if (const char* e = getenv("PROXSDP_B200_LZ_ARROW")) lz_arrow_ = atoi(e) != 0 ? 1 : 0;
     if (const char* e = getenv("PROXSDP_B200_LZ_COOP")) lz_coop_ = atoi(e) != 0 ? 1 : 0;
     if (const char* e = getenv("PROXSDP_B200_BJ_INNER")) bj_inner_sweeps_ = std::max(1, atoi(e));
@@ -822,6 +828,14 @@ bool Solver::lanczos_launch_cluster3(ConeDev& cd, int cone_idx, int nev, int K, 
     a.rbase = nside / G; a.rrem = nside % G; a.vbase = nside / C; a.vrem = nside % C;
     a.vals = cd.vals.p; a.info = cd.info.p; a.scal = scal_target_; a.cone = cone_idx;
     a.L = L;
+    // a matrix that does not stay in L2 between two mat-vecs is pulled in by the TMA engine a few rows ahead of the loads
+    {
+        // whole slab when the matrix fits L2 (the loads then hit the near L2 partition); a window of ~16 MB over the grid otherwise
+        const size_t mbytes = (size_t)nside * (size_t)cd.ld * sizeof(double);
+        int pf = 0;
+        if (cpw >= 3) pf = mbytes <= (size_t)l2_bytes_ * 3 / 4 ? 32 : (int)std::min<size_t>(32, std::max<size_t>(2, ((size_t)16 << 20) / (rowbytes * (size_t)G) + 1));
+        a.pf_rows = lz_pf_ >= 0 ? std::min(lz_pf_, 32) : pf;
+    }
     if (getenv("PROXSDP_B200_LZ_PROF")) { if (lz_prof_.n == 0) lz_prof_.alloc(8 + 8 * 256); a.prof = lz_prof_.p; }
     void* kargs[] = {&a};
     cudaError_t e = cudaLaunchKernelExC(&cfg, kfn, kargs);
@@ -2386,6 +2400,9 @@ int proxsdp_b200_lanczos(int64_t n, const double* A, const double* x0, int64_t h
         int64_t reps = std::max<int64_t>(repeat, 1);
         double total_ms = 0.0;
         for (int64_t r = 0; r < reps; ++r) {
+            // An untimed launch runs first when a time is wanted: the events and the timed launch are enqueued while it
+            // executes, so the elapsed time is the kernel's, not the host's launch latency on an idle stream.
+            if (ms_per_call && repeat > 1) s.lanczos_launch(cd, 0, (int)howmany, (int)krylovdim, (int)maxiter, tol);
             s.reset_scalars();
             PB_CUDA(cudaEventRecord(e0, s.stream));
             s.lanczos_launch(cd, 0, (int)howmany, (int)krylovdim, (int)maxiter, tol);
