@@ -512,7 +512,7 @@ __global__ void __launch_bounds__(256) k_ls_apply(LadderArgs a, const double* __
 //   num = max |(x - tau*Mty) - (x_old - tau*Mty_old)| ; den = max |x_old - tau*Mty_old|
 // tau is the accepted step (scal[S_TAU]).
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)      // 4 CTAs per SM = the whole grid in one resident wave (solver.cu: blocksN)
 k_residual_primal(long long N, const double* __restrict__ x, const double* __restrict__ x_old,
                   const double* __restrict__ Mty, const double* __restrict__ Mty_old,
                   const double* __restrict__ c, double* __restrict__ scal, ReduceWs ws) {

@@ -422,6 +422,10 @@ Solver::Solver(const proxsdp_problem_t* prob, const proxsdp_options_t* opt_in, b
     if (const char* e = getenv("PROXSDP_B200_LZ_POLL_NS")) lz_poll_ns_ = std::max(0, atoi(e));
     if (const char* e = getenv("PROXSDP_B200_LZ_PF")) lz_pf_ = std::max(0, atoi(e));
     if (const char* e = getenv("PROXSDP_B200_LZ_ARROW")) lz_arrow_ = atoi(e) != 0 ? 1 : 0;
+    // Nsight Compute cannot replay a launch that carries the cooperative attribute together with a cluster dimension
+    // (it reports LaunchFailed and tears the process down): under an injected profiler the launch is a plain cluster
+    // launch, co-residency then rests on cudaOccupancyMaxActiveClusters and the in-kernel time-outs
+    if (getenv("CUDA_INJECTION64_PATH") || getenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR") || getenv("NV_NSIGHT_INJECTION_PORT_BASE")) lz_coop_ = 0;
     if (const char* e = getenv("PROXSDP_B200_LZ_COOP")) lz_coop_ = atoi(e) != 0 ? 1 : 0;
     if (const char* e = getenv("PROXSDP_B200_BJ_INNER")) bj_inner_sweeps_ = std::max(1, atoi(e));
     if (const char* e = getenv("PROXSDP_B200_BJ_WARM")) bj_warm_ = atoi(e) != 0 ? 1 : 0;
@@ -1255,7 +1259,7 @@ void Solver::launch_post_eig(double tau0, bool first_pass) {
     int ntr = opt.line_search_flag ? (int)std::min<long long>(ladder_, std::max<long long>(opt.max_linsearch_steps, 1)) : 1;
     if (fused_ladder_) launch_ladder(0, ntr, tau0);
     else for (int t = 0; t < ntr; ++t) launch_dual_trial(t, tau0);
-    int blocksN = std::max(1, std::min(reduce_blocks_, ceil_div(n, 512)));
+    int blocksN = std::max(1, std::min(std::min(reduce_blocks_, 4 * num_sms_), ceil_div(n, 512)));      // one resident wave
     k_residual_primal<<<blocksN, 256, 0, stream>>>(n, xn, x_[cur_].p, Mty_[1 - cur_].p, Mty_[cur_].p, c_.p, scal_d_.p, ws_);
     int blocksR = std::max(1, std::min(reduce_blocks_, ceil_div(R, 256)));
     k_residual_dual<<<blocksR, 256, 0, stream>>>((int)p, (int)m, beta_, opt.line_search_flag ? 1 : 0, dual_step_,
@@ -1609,7 +1613,7 @@ void Solver::seam_residuals(double primal_step, double dual_step, double beta, d
     // the kernels take the accepted step from the record (what the line search leaves there)
     double rec[3] = {1.0, 0.0, primal_step};
     PB_CUDA(cudaMemcpyAsync(scal_d_.p + S_LS_ACCEPTED, rec, sizeof(rec), cudaMemcpyHostToDevice, stream));
-    int blocksN = std::max(1, std::min(reduce_blocks_, ceil_div(n, 512)));
+    int blocksN = std::max(1, std::min(std::min(reduce_blocks_, 4 * num_sms_), ceil_div(n, 512)));      // one resident wave
     k_residual_primal<<<blocksN, 256, 0, stream>>>(n, x_[1].p, x_[0].p, Mty_[1].p, Mty_[0].p, c_.p, scal_d_.p, ws_);
     int blocksR = std::max(1, std::min(reduce_blocks_, ceil_div(R, 256)));
     k_residual_dual<<<blocksR, 256, 0, stream>>>((int)p, (int)m, beta_, 0, dual_step_, y_[1].p, y_[0].p, Mx_[1].p, Mx_[0].p,
@@ -1764,7 +1768,7 @@ bool Solver::run(long long max_steps, bool flush_l2) {
         if (opt.line_search_flag && scal_host[S_LS_ACCEPTED] == 0.0) {
             const double keep_ops = scal_host[S_NUMOPS];
             evals = linesearch_continue(tau0, ls_exhausted, ls_last_tau);
-            int blocksN = std::max(1, std::min(reduce_blocks_, ceil_div(n, 512)));
+            int blocksN = std::max(1, std::min(std::min(reduce_blocks_, 4 * num_sms_), ceil_div(n, 512)));      // one resident wave
             k_residual_primal<<<blocksN, 256, 0, stream>>>(n, x_[1 - cur_].p, x_[cur_].p, Mty_[1 - cur_].p, Mty_[cur_].p, c_.p, scal_d_.p, ws_);
             int blocksR = std::max(1, std::min(reduce_blocks_, ceil_div(R, 256)));
             k_residual_dual<<<blocksR, 256, 0, stream>>>((int)p, (int)m, beta_, 1, dual_step_, y_[1 - cur_].p, y_[cur_].p,
