@@ -150,6 +150,8 @@ struct LanczosCl3Args {
     double imp_tau;
     int debug;                 // PROXSDP_B200_LZ_DEBUG=1: CTA 0 prints every Ritz analysis / restart (device printf)
     int arrow_restart;         // 1: keep the arrowhead form after a thick restart (dense Jacobi Ritz solves; PROXSDP_B200_LZ_ARROW=1)
+    long long spin_limit;      // cycles a spin loop waits for a peer before the launch gives up (~2 s; PROXSDP_B200_LZ_SPIN_S
+                               // stretches it for runs under compute-sanitizer, where a peer can be 100x slower)
     int pf_rows;               // > 0: slab rows prefetched into L2 ahead of the register loads (matrices larger than L2;
                                // PROXSDP_B200_LZ_PF overrides the host's choice)
     int poll_ns;               // back-off between two polls of the flagged exchange words (PROXSDP_B200_LZ_POLL_NS)
@@ -183,15 +185,15 @@ __device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
 __device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned int bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-// all threads call it; returns false after ~2 s (a peer died)
-__device__ __forceinline__ bool mbar_wait(unsigned long long* bar, unsigned int parity) {
+// all threads call it; returns false after `limit` cycles (~2 s by default: a peer died)
+__device__ __forceinline__ bool mbar_wait(unsigned long long* bar, unsigned int parity, const long long limit) {
     const unsigned int a = smem_u32(bar);
     unsigned int done = 0;
     const long long t0 = clock64();
     while (true) {
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(a), "r"(parity) : "memory");
         if (done) return true;
-        if (clock64() - t0 > 4000000000LL) return false;
+        if (clock64() - t0 > limit) return false;
     }
 }
 
@@ -667,7 +669,10 @@ __device__ __noinline__ void lz3_ritz(const LanczosCl3Args& a, double* sbase, in
 #undef SMD
 }
 
-template <int CPW, int RB, int NMAX, bool IMP = false, bool PFL2 = false>
+// OP selects the operator: 0 = dense matrix in global memory, row slabs over the whole grid (the default); 1 = implicit
+// low-rank + sparse operator on ONE cluster; 2 = dense matrix RESIDENT in the distributed shared memory of ONE cluster
+// (mid-size cones: CTA rank c holds rows [c n/C, (c+1) n/C) of X for the whole eigsolve, no grid exchange at all).
+template <int CPW, int RB, int NMAX, int OP = 0, bool PFL2 = false>
 __global__ void __launch_bounds__(LZ_THREADS, 1) k_lanczos_cl3(const __grid_constant__ LanczosCl3Args a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cg::cluster_group cluster = cg::this_cluster();
@@ -682,6 +687,7 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) k_lanczos_cl3(const __grid_cons
     const int rl = a.rbase + (cta < a.rrem ? 1 : 0);
     const int v0 = crank * a.vbase + min(crank, a.vrem);
     const int vn = a.vbase + (crank < a.vrem ? 1 : 0);
+    constexpr bool IMP = (OP == 1);
     const int VNp = lanczos_cl_vnp(a.vn_max);
     const int cpr = lanczos_cpr(n);
     const int Kp2 = K + 2;
@@ -735,12 +741,14 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) k_lanczos_cl3(const __grid_cons
         // stage the resident rows of my slab (the last a.res_begin_off of its rl rows) into shared memory: one bulk
         // copy per row on the TMA engine (row = cpr * 64 doubles = ld doubles: X is zero-padded to ld columns),
         // completion counted in bytes on s_mbar[2]; the copies run while the cluster barrier below is crossed
-        const int nres = IMP ? 0 : min(a.res_begin_off, rl);
+        // (OP == 2: ALL my basis rows of X, rows v0 .. v0 + vn - 1 — the matrix lives in the cluster's shared memory)
+        const int nres = (OP == 1) ? 0 : (OP == 2) ? vn : min(a.res_begin_off, rl);
+        const int first_res = (OP == 2) ? v0 : r0 + rl - nres;
         if (nres > 0) {
             const unsigned int rowbytes = (unsigned int)(cpr * 64 * sizeof(double));
             mbar_expect_tx(&s_mbar[2], (unsigned int)nres * rowbytes);
             for (int q = 0; q < nres; ++q)
-                bulk_g2s(SMD(xres) + (size_t)q * cpr * 64, a.X + (size_t)(r0 + rl - nres + q) * a.ld, rowbytes, &s_mbar[2]);
+                bulk_g2s(SMD(xres) + (size_t)q * cpr * 64, a.X + (size_t)(first_res + q) * a.ld, rowbytes, &s_mbar[2]);
         }
     }
     int imp_nk = 0;
@@ -766,7 +774,7 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) k_lanczos_cl3(const __grid_cons
         }
     }
     cluster.sync();       // everybody's shared memory and barriers are initialised before any peer writes into them
-    if (!IMP && min(a.res_begin_off, rl) > 0 && !mbar_wait(&s_mbar[2], 0)) s_ok = 0;
+    if ((OP == 2 ? vn : (OP == 0 ? min(a.res_begin_off, rl) : 0)) > 0 && !mbar_wait(&s_mbar[2], 0, a.spin_limit)) s_ok = 0;
     if (profiling && tid == 0) tprev = clock64();
 
     while (!finished) {
@@ -780,7 +788,7 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) k_lanczos_cl3(const __grid_cons
         }
         // ================= symv on my slab of rows: w slab and my share of alpha straight to global =================
         // (gsync still counts the exchanges done so far: this step's buffers have parity (gsync + 1) & 1)
-        if constexpr (!IMP)
+        if constexpr (OP == 0)
             symv_slab<CPW, RB, NMAX, PFL2>(a.X, a.ld, r0, rl, cpr, SMD(vbuf), SMD(xres), max(rl - a.res_begin_off, 0), SMD(wpart), SMD(aprod),
                                      a.wg + (size_t)((gsync + 1) & 1) * a.ld + r0, a.apart + (size_t)((gsync + 1) & 1) * LZ3_GMAX + cta,
                                      a.epoch_base + gsync + 1, a.pf_rows, profiling ? s_prof : nullptr);
@@ -809,10 +817,40 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) k_lanczos_cl3(const __grid_cons
             const double* Vs = SMD(Vs);
             double* wv = SMD(wv);
             double wreg[2];                                  // RW <= 64 rows per warp is checked on the host
-            if constexpr (IMP) {
-                // ---- w = Y (lam (Y' v)) - tau S v on my basis rows; no grid exchange: the cluster is the whole grid ----
-                const double* Ys = SMD(imp_Ys);
+            if constexpr (OP != 0) {
+                // ---- single-cluster operators: w on my basis rows, no grid exchange (the cluster is the whole grid) ----
                 const double* vb = SMD(vbuf);
+                double ap = 0.0;
+                if constexpr (OP == 2) {
+                    // dense rows resident in shared memory: warp <-> its RW <= 4 basis rows, lane <-> a double2 of every
+                    // 64-column chunk; the row totals end up in lanes 0 .. RW-1 (lane u <-> row t_lo + u)
+                    const double* xr = SMD(xres) + 2 * lane;
+                    const int rstride = cpr * 64;
+                    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+                    for (int c = 0; c < cpr; ++c) {
+                        const double2 vv = *reinterpret_cast<const double2*>(vb + c * 64 + 2 * lane);
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            if (t_lo + u < t_hi) {
+                                const double2 q = *reinterpret_cast<const double2*>(xr + (size_t)(t_lo + u) * rstride + c * 64);
+                                acc[u] = fma(q.x, vv.x, acc[u]);
+                                acc[u] = fma(q.y, vv.y, acc[u]);
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) acc[u] += __shfl_xor_sync(0xffffffffu, acc[u], o);
+                    }
+                    double w = 0.0;
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) if (lane == u && t_lo + u < t_hi) w = acc[u];
+                    wreg[0] = w; wreg[1] = 0.0;
+                    if (t_lo + lane < t_hi) ap = w * vb[v0 + t_lo + lane];
+                } else {
+                // ---- w = Y (lam (Y' v)) - tau S v ----
+                const double* Ys = SMD(imp_Ys);
                 {   // (1) Y' v: lane <-> eigenvector q, warp <-> its rows, then across warps and across the cluster
                     double s0 = 0.0, s1 = 0.0;
                     if (lane < imp_nk) {
@@ -834,7 +872,7 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) k_lanczos_cl3(const __grid_cons
                     for (int c = 0; c < C; ++c) st_async_f64(mapa_u32(dst, c), sres, mapa_u32(mb, c));
                 }
                 if (tid == 0) mbar_expect_tx(&s_mbar[3], (unsigned int)(C * imp_nk * 8));
-                if (imp_nk > 0 && !mbar_wait(&s_mbar[3], (gsync - 1) & 1)) s_ok = 0;
+                if (imp_nk > 0 && !mbar_wait(&s_mbar[3], (gsync - 1) & 1, a.spin_limit)) s_ok = 0;
                 if (tid < imp_nk) {
                     double sres = 0.0;
                     for (int c = 0; c < C; ++c) sres += SMD(imp_tpart)[c * LZ3_RMAX + tid];      // rank order: same bits in every CTA
@@ -846,7 +884,6 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) k_lanczos_cl3(const __grid_cons
                 const int* scol = reinterpret_cast<const int*>(SMD(imp_scol));
                 const double* sval = SMD(imp_sval);
                 const double* tq = SMD(imp_tq);
-                double ap = 0.0;
 #pragma unroll
                 for (int u = 0; u < 2; ++u) {
                     const int t = t_lo + lane + 32 * u;
@@ -866,6 +903,7 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) k_lanczos_cl3(const __grid_cons
                     }
                     wreg[u] = w;
                 }
+                }      // OP == 1
                 ap = warp_sum(ap);
                 if (lane == 0) SMD(imp_apart)[C + warp] = ap;
                 __syncthreads();
@@ -879,11 +917,14 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) k_lanczos_cl3(const __grid_cons
                     for (int c = 0; c < C; ++c) st_async_f64(mapa_u32(dst, c), sres, mapa_u32(mb, c));
                     mbar_expect_tx(&s_mbar[4], (unsigned int)(C * 8));
                 }
-                if (!mbar_wait(&s_mbar[4], (gsync - 1) & 1)) s_ok = 0;
+                if (!mbar_wait(&s_mbar[4], (gsync - 1) & 1, a.spin_limit)) s_ok = 0;
                 if (tid == 0) {
-                    double sres = 0.0;
-                    for (int c = 0; c < C; ++c) sres += SMD(imp_apart)[c];
-                    SMD(hred)[K + 1] = sres;
+                    const double* ap_ = SMD(imp_apart);
+                    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+                    int c = 0;
+                    for (; c + 3 < C; c += 4) { s0 += ap_[c]; s1 += ap_[c + 1]; s2 += ap_[c + 2]; s3 += ap_[c + 3]; }
+                    for (; c < C; ++c) s0 += ap_[c];
+                    SMD(hred)[K + 1] = (s0 + s1) + (s2 + s3);
                 }
             } else {
             {
@@ -898,7 +939,7 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) k_lanczos_cl3(const __grid_cons
                         if (!have[u]) { rr[u] = ll_peek(wgp + t_lo + lane + 32 * u); have[u] = (rr[u].y == tag && rr[u].w == tag); }
                     }
                     if (__all_sync(0xffffffffu, have[0] && have[1])) break;
-                    if (clock64() - tw > 4000000000LL) { s_ok = 0; break; }      // ~2 s: a peer died; give up instead of hanging
+                    if (clock64() - tw > a.spin_limit) { s_ok = 0; break; }      // ~2 s: a peer died; give up instead of hanging
                     // back off between polls: 120 CTAs x 16 warps spinning on L2 take request slots from the CTAs that are
                     // still streaming their slab (measured: profiles/r2_poll_sweep.txt)
                     if (a.poll_ns > 0) __nanosleep((unsigned int)a.poll_ns);
@@ -924,7 +965,7 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) k_lanczos_cl3(const __grid_cons
                             all = all && got[u];
                         }
                         if (__all_sync(0xffffffffu, all)) break;
-                        if (clock64() - tw > 4000000000LL) { s_ok = 0; break; }
+                        if (clock64() - tw > a.spin_limit) { s_ok = 0; break; }
                         if (a.poll_ns > 0) __nanosleep((unsigned int)a.poll_ns);
                     }
 #pragma unroll
@@ -997,7 +1038,7 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) k_lanczos_cl3(const __grid_cons
             }
             if (tid == 0) mbar_expect_tx(&s_mbar[0], (unsigned int)(C * (j + 2) * 8));      // j + 2 dots from each of the C peers (me included)
             LZ3_TICK(2);
-            if (!mbar_wait(&s_mbar[0], ph_dots & 1)) s_ok = 0;
+            if (!mbar_wait(&s_mbar[0], ph_dots & 1, a.spin_limit)) s_ok = 0;
             ++ph_dots;
             LZ3_TICK(3);
             // h[q] = sum over the C peers in rank order (fixed tree)
@@ -1007,8 +1048,12 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) k_lanczos_cl3(const __grid_cons
                 if (C == 8) {
                     sres = ((hp[0] + hp[Kp2]) + (hp[2 * Kp2] + hp[3 * Kp2])) + ((hp[4 * Kp2] + hp[5 * Kp2]) + (hp[6 * Kp2] + hp[7 * Kp2]));
                 } else {
-                    sres = 0.0;
-                    for (int c = 0; c < C; ++c) sres += hp[c * Kp2];
+                    // any other cluster size: four chains in a fixed order (same bits in every CTA)
+                    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+                    int c = 0;
+                    for (; c + 3 < C; c += 4) { s0 += hp[c * Kp2]; s1 += hp[(c + 1) * Kp2]; s2 += hp[(c + 2) * Kp2]; s3 += hp[(c + 3) * Kp2]; }
+                    for (; c < C; ++c) s0 += hp[c * Kp2];
+                    sres = (s0 + s1) + (s2 + s3);
                 }
                 SMD(hred)[q] = sres;
             }
@@ -1091,7 +1136,7 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) k_lanczos_cl3(const __grid_cons
         }
         if (tid == 0) mbar_expect_tx(&s_mbar[1], (unsigned int)(n * 8));      // every row of v_{j+1}, from whichever peer owns it
         LZ3_TICK(6);
-        if (!mbar_wait(&s_mbar[1], (gsync + 1) & 1)) s_ok = 0;
+        if (!mbar_wait(&s_mbar[1], (gsync + 1) & 1, a.spin_limit)) s_ok = 0;
         LZ3_TICK(4);
 
         // ================= Ritz analysis (redundant in every CTA; out of line) =================

@@ -18,7 +18,7 @@
 
 namespace pb {
 
-constexpr int RITZ_BI_MAXM = 15;      // pairs computed at most (one warp each; warp m computes one extra value)
+constexpr int RITZ_BI_MAXM = 16;      // pairs computed at most (one warp each; with fewer than 16 pairs warp m computes one extra value)
 constexpr int RITZ_BI_PAD = 16;       // padding rows behind the k real ones (the Sturm chain runs in blocks of 8 rows)
 
 struct RitzBiScratch {
@@ -27,11 +27,12 @@ struct RitzBiScratch {
     double* dxs;     // K + PAD  d[j] 2^-s
     double* zf;      // 16 * K   leading principal minors, one row per warp
     double* zb;      // 16 * K   trailing principal minors
-    double* lam;     // 16       eigenvalues (descending)
+    double* lam;     // 18       eigenvalues (descending)
+    double* rn;      // 16       residual || T u - lam u ||_inf of every vector
     int* fail;       // 1
 };
 
-__host__ __device__ inline size_t ritz_bi_scratch_doubles(int K) { return 3 * (size_t)K + 2 * RITZ_BI_PAD + 32 * (size_t)K + 16 + 2; }
+__host__ __device__ inline size_t ritz_bi_scratch_doubles(int K) { return 3 * (size_t)K + 2 * RITZ_BI_PAD + 32 * (size_t)K + 18 + 16 + 2; }
 
 __device__ inline RitzBiScratch ritz_bi_carve(double* base, int K) {
     RitzBiScratch s;
@@ -40,7 +41,8 @@ __device__ inline RitzBiScratch ritz_bi_carve(double* base, int K) {
     s.dxs = base; base += K + RITZ_BI_PAD;
     s.zf = base; base += 16 * (size_t)K;
     s.zb = base; base += 16 * (size_t)K;
-    s.lam = base; base += 16;
+    s.lam = base; base += 18;
+    s.rn = base; base += 16;
     s.fail = reinterpret_cast<int*>(base);
     return s;
 }
@@ -223,15 +225,24 @@ __device__ inline int ritz_top_bi(int k, const double* d, const double* e, int m
     RITZ_TICK(11);
 
     // ---- eigenvalue `warp` (0-based from the top) ----
-    const bool mine = (have == 0) ? (warp <= m) : (warp > have && warp <= m);      // value number `have` is already there
+    // values 0 .. min(m, 15): one more than the pairs (the gap below the last pair is checked on it), except with 16 pairs,
+    // where that gap is checked by a Sturm count instead
+    const int nval = min(m + 1, 16);
+    const bool mine = (have == 0) ? (warp < nval) : (warp > have && warp < nval);      // value number `have` is already there
     double lam_s = 0.0;
     if (mine) {
         const double wdt = (gu - gl) * inv_t;
         lam_s = ritz_value_warp(k, sc.dxs, sc.e2s, k - 1 - warp, gl * inv_t - 1e-3 * wdt, gu * inv_t + 1e-3 * wdt, tnorm * inv_t,
                                 (prof && warp == 0) ? prof + 18 : nullptr);
         if (lane == 0) sc.lam[warp] = lam_s * tscale;
-    } else if (warp <= m) {
+    } else if (warp < nval) {
         lam_s = sc.lam[warp] * inv_t;
+    }
+    if (m == 16 && warp == 15) {
+        // no warp is left for value 16: the gap below pair 15 holds iff exactly 16 eigenvalues are >= lam_15 - gap
+        double pdummy; int edummy;
+        const int c = sturm_count(k, sc.dxs, sc.e2s, lam_s - 1e-7 * (tnorm * inv_t), pdummy, edummy);
+        if (lane == 0 && k - c != 16) *sc.fail = 1;
     }
     RITZ_TICK(12);
 
@@ -303,24 +314,32 @@ __device__ inline int ritz_top_bi(int k, const double* d, const double* e, int m
         const double inrm = rsqrt(nrm2);
         for (int j = lane; j < k; j += 32) u[j] *= inrm;
         __syncwarp();
-        // residual check || T u - lam u ||_inf <= 1e-13 ||T||  (a vote, not a reduction: only the verdict matters)
+        // residual || T u - lam u ||_inf: must be <= 1e-13 ||T||; its value also decides below which pairs of vectors need
+        // their inner product checked at all
         const double lam = lam_s * tscale;
-        bool bad = !(nrm2 < 1e300) || !(nrm2 > 0.0);
+        double res = (nrm2 < 1e300 && nrm2 > 0.0) ? 0.0 : 1e300;
         for (int j = lane; j < k; j += 32) {
             double t = (d[j] - lam) * u[j];
             if (j > 0) t = fma(e[j - 1], u[j - 1], t);
             if (j < k - 1) t = fma(e[j], u[j + 1], t);
-            bad = bad || !(fabs(t) <= 1e-13 * tnorm);
+            res = fmax(res, fabs(t));
+            if (!(fabs(t) <= 1e300)) res = 1e300;           // NaN
         }
-        if (__any_sync(0xffffffffu, bad) && lane == 0) *sc.fail = 1;
+        for (int o = 16; o > 0; o >>= 1) res = fmax(res, __shfl_xor_sync(0xffffffffu, res, o));
+        if (lane == 0) { sc.rn[warp] = res; if (!(res <= 1e-13 * tnorm)) *sc.fail = 1; }
     }
     __syncthreads();
     RITZ_TICK(13);
     // ---- gaps and mutual orthogonality (one warp per pair of vectors: measured inside the eigsolve kernel, where this
     // code runs once per launch from a cold instruction cache, the compact warp-cooperative loop beats one thread per pair) ----
-    if (tid < m) {
+    if (tid < m && tid + 1 < nval) {
         if (!(sc.lam[tid] - sc.lam[tid + 1] >= 1e-7 * tnorm)) *sc.fail = 1;
     }
+    // Two unit vectors with residuals r_a, r_b for eigenvalues lam_a != lam_b satisfy
+    //     |u_a . u_b| <= (||r_a||_2 + ||r_b||_2) / |lam_a - lam_b|
+    // ((lam_a - lam_b) u_a.u_b = u_a.r_b - u_b.r_a for symmetric T): pairs whose bound is already below the 1e-12 bar need no
+    // inner product — with residuals of a few eps ||T|| that is every pair whose eigenvalues are not nearly degenerate.
+    const double sqk = sqrt((double)k);
     const int npairs = m * (m - 1) / 2;
 #pragma unroll 1
     for (int pidx = warp; pidx < npairs; pidx += (int)(blockDim.x >> 5)) {
@@ -329,6 +348,7 @@ __device__ inline int ritz_top_bi(int k, const double* d, const double* e, int m
         while ((b + 1) * b / 2 <= pidx) ++b;
         const int a_ = pidx - b * (b - 1) / 2;             // a_ < b
         if (b < have) continue;                            // both vectors were checked by the previous call
+        if ((sc.rn[a_] + sc.rn[b]) * sqk <= 1e-12 * fabs(sc.lam[a_] - sc.lam[b])) continue;
         const double* ua = U + (size_t)a_ * ldu;
         const double* ub = U + (size_t)b * ldu;
         double s = 0.0;

@@ -181,6 +181,7 @@ struct ConeDev {
     bool imp_tried = false, imp_ready = false;
     bool lowrank_valid = false; // x holds svec(Y diag(lam) Y') of the previous Krylov projection (Y, kept_* still on the device)
     bool used_implicit = false; // this iteration's eigsolve ran on the implicit operator (X was not formed)
+    bool announced_resident = false;
     bool have_V = false;        // Vfull holds the eigenvectors of this cone's previous full projection
     long long full_calls = 0;
     DBuf<double> Y;             // ld x (Kmax)
@@ -237,6 +238,7 @@ class Solver {
     bool lanczos_launch_cluster(ConeDev& cd, int cone_idx, int nev, int K, int maxiter, double tol);
     bool lanczos_launch_cluster3(ConeDev& cd, int cone_idx, int nev, int K, int maxiter, double tol);
     bool lanczos_launch_implicit(ConeDev& cd, int cone_idx, int nev, int K, int maxiter, double tol, double tau);
+    bool lanczos_launch_resident(ConeDev& cd, int cone_idx, int nev, int K, int maxiter, double tol);
     bool implicit_pattern(ConeDev& cd);
     double last_tau_ = 0.0;
     long long implicit_calls = 0;
@@ -250,6 +252,12 @@ class Solver {
     bool lz_demoted_ = false;
     int lz_arrow_ = 0;         // cl3 kernel: 1 = arrowhead thick restart + dense Ritz solves (first-round behaviour)
     int lz_poll_ns_ = 0;       // cl3 kernel: nanoseconds of back-off between polls of the exchange words
+    int lz_resident_ = 1;      // mid-size cones: single-cluster kernel with X resident in distributed shared memory (PROXSDP_B200_LZ_RESIDENT=0: off)
+    int lz_resident16_ = 1;    // ... also with the non-portable cluster size 16 (PROXSDP_B200_LZ_RESIDENT=8: portable size only, =16: that size only)
+    int lz_resident8_ = 1;
+    int lz_resident_ok_[2] = {0, 0};
+    long long resident_calls = 0;
+    long long lz_spin_limit_ = 4000000000LL;   // cycles (~2 s) a spin loop of the cluster kernels waits for a peer
     int lz_pf_ = -1;           // cl3 kernel: slab rows prefetched into L2 ahead of the loads (-1: 8 rows when the matrix exceeds L2)
     int lz_strict_ = 0;        // cl3 kernel: FP64 alpha + two Gram-Schmidt passes on every step (PROXSDP_B200_LZ_STRICT=1)
     int lz_xres_ = 0;          // >= 1: cap the resident slab rows of the cl3 symv at lz_xres_ - 1 (experiments / tests)
@@ -421,6 +429,8 @@ Solver::Solver(const proxsdp_problem_t* prob, const proxsdp_options_t* opt_in, b
     if (const char* e = getenv("PROXSDP_B200_LZ_STRICT")) lz_strict_ = atoi(e) != 0 ? 1 : 0;
     if (const char* e = getenv("PROXSDP_B200_LZ_POLL_NS")) lz_poll_ns_ = std::max(0, atoi(e));
     if (const char* e = getenv("PROXSDP_B200_LZ_PF")) lz_pf_ = std::max(0, atoi(e));
+    if (const char* e = getenv("PROXSDP_B200_LZ_SPIN_S")) lz_spin_limit_ = (long long)(std::max(1.0, atof(e)) * 2.0e9);
+    if (const char* e = getenv("PROXSDP_B200_LZ_RESIDENT")) { const int v = atoi(e); lz_resident_ = v != 0; lz_resident16_ = (v != 8); lz_resident8_ = (v != 16); }
     if (const char* e = getenv("PROXSDP_B200_LZ_ARROW")) lz_arrow_ = atoi(e) != 0 ? 1 : 0;
     // Nsight Compute cannot replay a launch that carries the cooperative attribute together with a cluster dimension
     // (it reports LaunchFailed and tears the process down): under an injected profiler the launch is a plain cluster
@@ -630,7 +640,8 @@ void Solver::setup_host(const proxsdp_problem_t* prob) {
             size_t mx = smem_optin_;
             std::vector<const void*> fns;
             for (int cpw = 1; cpw <= 8; ++cpw) if (const void* fn = lanczos_cl3_kernel(cpw)) fns.push_back(fn);
-            fns.push_back((const void*)k_lanczos_cl3<1, 1, 1, true>);
+            fns.push_back((const void*)k_lanczos_cl3<1, 1, 1, 1>);
+            fns.push_back((const void*)k_lanczos_cl3<1, 1, 1, 2>);
             for (const void* fn : fns) {
                 cudaFuncAttributes fa{};
                 PB_CUDA(cudaFuncGetAttributes(&fa, fn));
@@ -640,6 +651,8 @@ void Solver::setup_host(const proxsdp_problem_t* prob) {
                 PB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mx));
                 if (lz_cluster_ > 8) PB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
             }
+            // the resident single-cluster variant may use a cluster of 16 CTAs
+            if (cudaFuncSetAttribute((const void*)k_lanczos_cl3<1, 1, 1, 2>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) cudaGetLastError();
             attr_dev = dev_; attr_smem_max = mx; attr_nonportable = lz_cluster_ > 8;
         }
         lz_cl3_smem_max_ = attr_smem_max;
@@ -831,7 +844,7 @@ bool Solver::lanczos_launch_cluster3(ConeDev& cd, int cone_idx, int nev, int K, 
     a.vn_max = vn_max; a.use_bi = lz_bi_; a.stop_above = lz_stop_above_; a.strict = lz_strict_; a.poll_ns = lz_poll_ns_; a.arrow_restart = lz_arrow_; a.debug = getenv("PROXSDP_B200_LZ_DEBUG") ? 1 : 0;
     a.rbase = nside / G; a.rrem = nside % G; a.vbase = nside / C; a.vrem = nside % C;
     a.vals = cd.vals.p; a.info = cd.info.p; a.scal = scal_target_; a.cone = cone_idx;
-    a.L = L;
+    a.L = L; a.spin_limit = lz_spin_limit_;
     // a matrix that does not stay in L2 between two mat-vecs is pulled in by the TMA engine a few rows ahead of the loads
     {
         // whole slab when the matrix fits L2 (the loads then hit the near L2 partition); a window of ~16 MB over the grid otherwise
@@ -954,11 +967,11 @@ bool Solver::lanczos_launch_implicit(ConeDev& cd, int cone_idx, int nev, int K, 
     a.vn_max = vn_max; a.use_bi = lz_bi_; a.stop_above = 1e300; a.strict = lz_strict_; a.poll_ns = 0; a.arrow_restart = lz_arrow_; a.debug = 0;
     a.rbase = nside / C; a.rrem = nside % C; a.vbase = nside / C; a.vrem = nside % C;
     a.vals = cd.vals.p; a.info = cd.info.p; a.scal = scal_target_; a.cone = cone_idx;
-    a.L = L;
+    a.L = L; a.spin_limit = lz_spin_limit_;
     a.imp_Y = cd.Y.p; a.imp_kept_idx = cd.kept_idx.p; a.imp_kept_lam = cd.kept_lam.p; a.imp_nkept = cd.nkept.p;
     a.imp_rowptr = cd.imp_rowptr.p; a.imp_col = cd.imp_col.p; a.imp_pos = cd.imp_pos.p; a.imp_coef = cd.imp_coef.p;
     a.imp_Mty = Mty_[cur_].p + cd.off; a.imp_c = c_.p + cd.off; a.imp_tau = tau;
-    const void* kfn = (const void*)k_lanczos_cl3<1, 1, 1, true>;
+    const void* kfn = (const void*)k_lanczos_cl3<1, 1, 1, 1>;
     void* kargs[] = {&a};
     cudaError_t e = cudaLaunchKernelExC(&cfg, kfn, kargs);
     if (e != cudaSuccess && lz_coop_ && (e == cudaErrorNotSupported || e == cudaErrorInvalidValue)) {
@@ -978,7 +991,83 @@ bool Solver::lanczos_launch_implicit(ConeDev& cd, int cone_idx, int nev, int K, 
     return true;
 }
 
+// Mid-size cones: the whole matrix fits the distributed shared memory of ONE cluster — CTA rank c keeps
+// rows [c n/C, (c+1) n/C) of X next to its slice of the Krylov basis for the whole eigsolve (staged once by the TMA
+// engine), so a mat-vec is a shared-memory GEMV and every exchange of the step stays inside the cluster (DSMEM): no
+// grid-wide exchange through L2 at all.  Cluster size 8 up to side ~420, 16 (non-portable) up to side ~580 in FP64.
+bool Solver::lanczos_launch_resident(ConeDev& cd, int cone_idx, int nev, int K, int maxiter, double tol) {
+    if (!lz_resident_ || lz_mode_ == 1 || lz_kernel_ != 3 || K > LZC_KMAX || cd.side < 64) return false;
+    const int nside = cd.side;
+    const void* kfn = (const void*)k_lanczos_cl3<1, 1, 1, 2>;
+    const int cpr = lanczos_cpr(nside);
+    for (int C : {8, 16}) {
+        if (C == 16 && !lz_resident16_) break;
+        if (C == 8 && !lz_resident8_) continue;
+        const int vn_max = (nside + C - 1) / C;
+        if (vn_max > 4 * LZ_NW) continue;                 // the resident GEMV keeps at most 4 rows per warp
+        Lz3Layout L = lanczos_cl3_layout(K, vn_max, vn_max, nside, C, 0, 1);
+        const size_t smem = (size_t)L.total * sizeof(double);
+        if (smem > lz_cl3_smem_max_) continue;
+        cudaLaunchConfig_t cfg{};
+        cudaLaunchAttribute attr[2];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = (unsigned)C; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        attr[1].id = cudaLaunchAttributeCooperative;
+        attr[1].val.cooperative = 1;
+        cfg.blockDim = dim3(LZ_THREADS); cfg.stream = stream; cfg.attrs = attr; cfg.numAttrs = lz_coop_ ? 2 : 1;
+        cfg.gridDim = dim3((unsigned)C); cfg.dynamicSmemBytes = smem;
+        if (lz_resident_ok_[C == 16] == 0) {              // first use of this cluster size: can one such cluster be resident at all?
+            int max_clusters = 0;
+            if (cudaOccupancyMaxActiveClusters(&max_clusters, kfn, &cfg) != cudaSuccess || max_clusters < 1) { cudaGetLastError(); lz_resident_ok_[C == 16] = -1; }
+            else lz_resident_ok_[C == 16] = 1;
+        }
+        if (lz_resident_ok_[C == 16] < 0) continue;
+        if ((size_t)cd.ld * (size_t)(K + 1) > cd.Y.n) cd.Y.alloc((size_t)cd.ld * (size_t)(K + 1));
+        const size_t ws_len = 1 + (size_t)lanczos_kp(Kmax_ > K ? Kmax_ : K) * (size_t)lanczos_kp(Kmax_ > K ? Kmax_ : K);
+        for (int q = 0; q < 2; ++q) if (cd.ritz_ws[q].n < ws_len) { cd.ritz_ws[q].alloc(ws_len); cd.ritz_launches = 0; }
+        LanczosCl3Args a{};
+        a.X = cd.X.p; a.n = nside; a.ld = cd.ld; a.x0 = cd.resid.p; a.Y = cd.Y.p;
+        a.wg = nullptr; a.apart = nullptr; a.epoch_base = 0; a.res_begin_off = 0;
+        const int flip = (int)(cd.ritz_launches & 1);
+        a.ritz_rd = (lz_warm_ && cd.ritz_launches > 0 && (cd.ritz_launches % 32) != 0) ? cd.ritz_ws[flip].p : nullptr;
+        a.ritz_wr = lz_warm_ ? cd.ritz_ws[1 - flip].p : nullptr;
+        a.nev = nev; a.K = K; a.maxiter = maxiter; a.tol = tol;
+        a.vn_max = vn_max; a.use_bi = lz_bi_; a.stop_above = lz_stop_above_; a.strict = lz_strict_; a.poll_ns = 0; a.arrow_restart = lz_arrow_;
+        a.debug = getenv("PROXSDP_B200_LZ_DEBUG") ? 1 : 0;
+        a.rbase = nside / C; a.rrem = nside % C; a.vbase = nside / C; a.vrem = nside % C;
+        a.vals = cd.vals.p; a.info = cd.info.p; a.scal = scal_target_; a.cone = cone_idx;
+        a.L = L; a.spin_limit = lz_spin_limit_;
+        if (getenv("PROXSDP_B200_LZ_PROF")) { if (lz_prof_.n == 0) lz_prof_.alloc(8 + 8 * 256); a.prof = lz_prof_.p; }
+        void* kargs[] = {&a};
+        cudaError_t e = cudaLaunchKernelExC(&cfg, kfn, kargs);
+        if (e != cudaSuccess && lz_coop_ && (e == cudaErrorNotSupported || e == cudaErrorInvalidValue)) {
+            cudaGetLastError();
+            cfg.numAttrs = 1;
+            e = cudaLaunchKernelExC(&cfg, kfn, kargs);
+        }
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            lz_resident_ok_[C == 16] = -1;
+            if (getenv("PROXSDP_B200_DEBUG")) fprintf(stderr, "[lanczos] resident single-cluster kernel, cluster size %d: launch failed (%s)\n", C, cudaGetErrorString(e));
+            continue;
+        }
+        if (getenv("PROXSDP_B200_DEBUG") && !cd.announced_resident) {
+            cd.announced_resident = true;
+            fprintf(stderr, "[lanczos] cl3 resident kernel: side %d, K %d, ONE cluster of %d CTAs, %d rows of X per CTA in shared memory, %zu KB shared memory\n",
+                    nside, K, C, vn_max, smem >> 10);
+        }
+        (void)cpr;
+        cd.ritz_launches++;
+        launches += 1;
+        lz_cluster_launches_++;
+        resident_calls++;
+        return true;
+    }
+    return false;
+}
+
 void Solver::lanczos_launch(ConeDev& cd, int cone_idx, int nev, int K, int maxiter, double tol) {
+    if (lanczos_launch_resident(cd, cone_idx, nev, K, maxiter, tol)) return;
     if (lanczos_launch_cluster3(cd, cone_idx, nev, K, maxiter, tol)) return;
     if (lanczos_launch_cluster(cd, cone_idx, nev, K, maxiter, tol)) return;
     const int nside = cd.side;

@@ -341,6 +341,23 @@ def test_lanczos_kernel_variants_agree(gpu, oracle_mod, monkeypatch):
         assert np.abs(vg - vo).max() <= 1e-10 * np.abs(vo).max(), tag
         assert np.abs(A @ Vg - Vg * vg).max() <= 1e-9 * np.abs(vo).max(), tag
         assert np.abs(Vg.T @ Vg - np.eye(len(vg))).max() <= 1e-10, tag
+    # mid-size cones: the single-cluster kernel with X resident in distributed shared memory (cluster of 8, cluster of 16)
+    # against the grid-wide kernel
+    for n, nev, K in ((200, 3, 25), (400, 6, 25), (520, 4, 25)):
+        A = _lowrank_plus_noise(n, 7, 300 + n)
+        x0 = oracle_mod.eig_resid(n)
+        vo, _, io = oracle_mod.lanczos(np.triu(A), x0, nev, K)
+        for tag, env in (("resident", {}), ("resident, cluster of 8 only", {"PROXSDP_B200_LZ_RESIDENT": "8"}),
+                         ("resident, cluster of 16 only", {"PROXSDP_B200_LZ_RESIDENT": "16"}),
+                         ("grid-wide", {"PROXSDP_B200_LZ_RESIDENT": "0"})):
+            monkeypatch.delenv("PROXSDP_B200_LZ_RESIDENT", raising=False)
+            for k_, v_ in env.items():
+                monkeypatch.setenv(k_, v_)
+            vg, Vg, ig = gpu.lanczos(A, x0, nev, K, repeat=2)
+            assert (ig["converged"], ig["numops"], ig["numiter"]) == (io["converged"], io["numops"], io["numiter"]), (n, tag)
+            assert np.abs(vg - vo).max() <= 1e-10 * np.abs(vo).max(), (n, tag)
+            assert np.abs(A @ Vg - Vg * vg).max() <= 1e-9 * np.abs(vo).max(), (n, tag)
+    monkeypatch.delenv("PROXSDP_B200_LZ_RESIDENT", raising=False)
 
 
 def test_rank_sweep_large_krylov_dim(gpu, oracle_mod, golden_dir):
