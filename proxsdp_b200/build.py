@@ -60,7 +60,7 @@ def build_extension(force: bool = False, verbose: bool = False) -> str:
         obj = os.path.join(OBJDIR, src.replace(".cu", ".o"))
         if not force and not _obj_stale(os.path.join(CSRC, src), obj):
             return obj, ""
-        cmd = [nvcc] + NVCC_FLAGS + ["-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [nvcc] + NVCC_FLAGS + os.environ.get("PROXSDP_B200_NVCC_EXTRA", "").split() + ["-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd += ["-Xptxas", "-v"]
         res = subprocess.run(cmd, capture_output=True, text=True)

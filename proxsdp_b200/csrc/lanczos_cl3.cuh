@@ -395,6 +395,11 @@ __device__ __forceinline__ void symv_slab(const double* __restrict__ X, const in
     if (prof && tid == 0) { const long long tn = clock64(); prof[17] += tn - tp; tp = tn; }              // row totals + publish
 }
 
+// scratch of the re-tridiagonalising restart inside JB (lda x lda doubles): m2 Lanczos vectors of pitch m2 | 1, T~, two work vectors
+__device__ __forceinline__ bool lz3_restart_fits(const int m2, const int lda) {
+    return m2 >= 1 && m2 <= 31 && m2 * (m2 | 1) + 2 * m2 + 64 <= lda * lda;
+}
+
 // Ritz analysis + thick restart, out of line: it runs once or twice per launch, and keeping its ~100 KB of code
 // out of the per-step loop keeps the loop inside the instruction cache.  State in/out through st[] (shared memory):
 //   st[0] k, st[2] arrow, st[3] howmany, st[4] numiter, st[5] first_analysis, st[6] converged, st[7] finished.
@@ -415,7 +420,7 @@ __device__ __noinline__ void lz3_ritz(const LanczosCl3Args& a, double* sbase, in
     // Thick restart as KrylovKit does it: keep the `keep` leading Ritz pairs (theta_t, y_t = V u_t) and the residual
     // vector r.  In the basis [y_0 .. y_keep-1, r] the Rayleigh quotient is diag(theta) bordered by the row
     // f_t = beta u_t[K-1]; an orthogonal change of basis inside span(y) turns it back into a TRIDIAGONAL matrix:
-    // Lanczos on diag(theta) started from f / ||f|| (full re-orthogonalisation, keep <= 16 steps on vectors of length
+    // Lanczos on diag(theta) started from f / ||f|| (full re-orthogonalisation, at most 31 steps on vectors of length
     // keep: one warp, lane <-> component) gives Q~ with Q~' diag(theta) Q~ = T~ and Q~' f = ||f|| e_0; taken in
     // reverse order the coupling to r sits in the last row, as the three-term recurrence expects.  The basis is
     // rotated once by U Q~, the recurrence carries on with a plain tridiagonal (so every later Ritz analysis takes the
@@ -431,12 +436,12 @@ __device__ __noinline__ void lz3_ritz(const LanczosCl3Args& a, double* sbase, in
         const int* order = reinterpret_cast<const int*>(SMD(order));
         double* Wc = SMD(JA);                    // K x keep coefficients of the new basis vectors in the old Lanczos basis
         double* Qs = SMD(JB);                    // m2 x MP: Qs[j * MP + c] = component c of Lanczos vector j
-        const int MP = 17;
-        double* ta = Qs + 16 * MP;               // diagonal of T~
-        double* tb = ta + 16;                    // off-diagonal of T~
-        double* ws = tb + 16;                    // work vector
+        const int m2 = keep - nlock;             // pairs that take part in the re-tridiagonalisation (1 <= m2 <= 31)
+        const int MP = m2 | 1;                   // odd row pitch: conflict-free columns
+        double* ta = Qs + m2 * MP;               // diagonal of T~
+        double* tb = ta + m2;                    // off-diagonal of T~
+        double* ws = tb + m2;                    // work vector
         double* hs = ws + 32;                    // re-orthogonalisation coefficients
-        const int m2 = keep - nlock;             // pairs that take part in the re-tridiagonalisation (>= 1)
         __syncthreads();                         // D, f, order, JU are final; the bisection / Jacobi scratch in JA, JB is dead
         if (tid < 32) {
             const int c = tid;                   // component c <-> kept pair nlock + c
@@ -532,7 +537,7 @@ __device__ __noinline__ void lz3_ritz(const LanczosCl3Args& a, double* sbase, in
         k = keep;                       // the caller's k++ makes it keep + 1
         numiter++;
     };
-    // restart that keeps the arrowhead form (large Krylov dimensions: keep > 16 does not fit the one-warp reduction above;
+    // restart that keeps the arrowhead form (large Krylov dimensions: more than 31 unlocked pairs do not fit the one-warp reduction above;
     // the dense Jacobi solver diagonalises arrow + tridiagonal tail directly, which is the same Krylov space)
     auto thick_restart_arrow = [&](const int keep) {
         double* Vs = SMD(Vs);
@@ -585,7 +590,7 @@ __device__ __noinline__ void lz3_ritz(const LanczosCl3Args& a, double* sbase, in
             else if (cv < howmany && k == K && numiter < a.maxiter) {
                 // not converged at the end of a Krylov cycle: the restart needs the `keep` leading pairs — one warp each
                 const int keep = (3 * K + 2 * cv) / 5;
-                if (keep <= RITZ_BI_MAXM && keep < k && !a.arrow_restart) {
+                if (keep <= RITZ_BI_MAXM && keep < k && !a.arrow_restart && lz3_restart_fits(keep - cv, lda)) {
                     __syncthreads();
                     if (mb < keep) mb = solve(keep, mb);      // the pairs of the first call stay
                     int cv2 = 0;
@@ -658,7 +663,9 @@ __device__ __noinline__ void lz3_ritz(const LanczosCl3Args& a, double* sbase, in
                 finished = 1;
             } else {
                 const int keep = (3 * K + 2 * converged) / 5;
-                if (keep <= 16 && arrow < 0 && !a.arrow_restart) thick_restart_tridiag(keep, min(converged, keep - 1)); else thick_restart_arrow(keep);
+                const int nlk = min(converged, keep - 1);
+                if (keep - nlk <= 31 && arrow < 0 && !a.arrow_restart && lz3_restart_fits(keep - nlk, lda)) thick_restart_tridiag(keep, nlk);
+                else thick_restart_arrow(keep);
             }
         }
     }
@@ -1005,7 +1012,7 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) k_lanczos_cl3(const __grid_cons
 
         // ================= one Gram-Schmidt pass inside the cluster (a second one only on breakdown) =================
         double wn2 = 0.0, hn2 = 0.0;
-        for (int pass = 0; pass < 2; ++pass) {
+        for (int pass = 0; pass < 3; ++pass) {
             // partial dots: lane <-> q (q == j+1: ||w||^2), warp <-> my RW rows; no cross-lane reduction at all
             {
                 const double* Vs = SMD(Vs);
@@ -1033,7 +1040,7 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) k_lanczos_cl3(const __grid_cons
 #pragma unroll
                 for (int w = 0; w < LZ_NW; w += 4) { s0 += dp[w * Kp2]; s1 += dp[(w + 1) * Kp2]; s2 += dp[(w + 2) * Kp2]; s3 += dp[(w + 3) * Kp2]; }
                 const double sres = (s0 + s1) + (s2 + s3);
-                const unsigned int dst = smem_u32(SMD(hpart) + pass * C * Kp2 + crank * Kp2 + q), mb = smem_u32(&s_mbar[0]);
+                const unsigned int dst = smem_u32(SMD(hpart) + (pass & 1) * C * Kp2 + crank * Kp2 + q), mb = smem_u32(&s_mbar[0]);
                 for (int c = 0; c < C; ++c) st_async_f64(mapa_u32(dst, c), sres, mapa_u32(mb, c));
             }
             if (tid == 0) mbar_expect_tx(&s_mbar[0], (unsigned int)(C * (j + 2) * 8));      // j + 2 dots from each of the C peers (me included)
@@ -1043,7 +1050,7 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) k_lanczos_cl3(const __grid_cons
             LZ3_TICK(3);
             // h[q] = sum over the C peers in rank order (fixed tree)
             for (int q = tid; q <= j + 1; q += LZ_THREADS) {
-                const double* hp = SMD(hpart) + pass * C * Kp2 + q;
+                const double* hp = SMD(hpart) + (pass & 1) * C * Kp2 + q;
                 double sres;
                 if (C == 8) {
                     sres = ((hp[0] + hp[Kp2]) + (hp[2 * Kp2] + hp[3 * Kp2])) + ((hp[4 * Kp2] + hp[5 * Kp2]) + (hp[6 * Kp2] + hp[7 * Kp2]));
@@ -1098,7 +1105,15 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) k_lanczos_cl3(const __grid_cons
                     }
                 }
             }
-            if (pass == 1 || (!a.strict && hn2 <= 0.25 * wn2)) break;      // DGKS: the pass shrank w by less than 1/sqrt(2)... (margin 2x): one pass is enough
+            // DGKS: the pass shrank w by less than 1/sqrt(2) (margin 2x): one pass is enough.  After a second pass the norm
+            // below, ||w||^2 - ||h||^2, is only trusted when that pass removed next to nothing; otherwise (w lies in the span
+            // of the basis to working precision: an invariant subspace, e.g. a multiple eigenvalue whose copies are exhausted)
+            // a third pass measures the norm of what is left directly — its ||h||^2 is then pure rounding.  Without it the
+            // difference cancels, beta comes out wrong by a large factor, the next "unit" vector has norm 60 and its alpha
+            // pollutes the Rayleigh quotient (seen on mcp500-1 at a 3-fold eigenvalue: a Ritz value of 142 933 for ||A|| = 38).
+            if (pass == 2) break;
+            if (pass == 1 && hn2 <= 1e-4 * wn2) break;
+            if (pass == 0 && !a.strict && hn2 <= 0.25 * wn2) break;
             // second pass (breakdown only).  Its dots read the updated wv of every warp (block barrier), and they travel
             // through the SAME mbarrier as the first pass: a peer that is already in its second pass must not credit
             // bytes to my barrier while my first-pass phase is still open (I may be waiting for a third CTA), hence a

@@ -18,21 +18,21 @@
 
 namespace pb {
 
-constexpr int RITZ_BI_MAXM = 16;      // pairs computed at most (one warp each; with fewer than 16 pairs warp m computes one extra value)
+constexpr int RITZ_BI_MAXM = 31;      // pairs computed at most: warp w takes pairs w, w + 16 (one extra VALUE is computed after the last pair)
 constexpr int RITZ_BI_PAD = 16;       // padding rows behind the k real ones (the Sturm chain runs in blocks of 8 rows)
 
 struct RitzBiScratch {
     double* es;      // K        e[j] 2^-s                      (s: the power-of-two scale, entries of T 2^-s are <= 1)
     double* e2s;     // K + PAD  (e[j] 2^-s)^2, zero from row k - 1 on
     double* dxs;     // K + PAD  d[j] 2^-s
-    double* zf;      // 16 * K   leading principal minors, one row per warp
+    double* zf;      // 16 * K   leading principal minors, one row per warp (re-used when a warp takes a second pair)
     double* zb;      // 16 * K   trailing principal minors
-    double* lam;     // 18       eigenvalues (descending)
-    double* rn;      // 16       residual || T u - lam u ||_inf of every vector
+    double* lam;     // 32       eigenvalues (descending)
+    double* rn;      // 32       residual || T u - lam u ||_inf of every vector
     int* fail;       // 1
 };
 
-__host__ __device__ inline size_t ritz_bi_scratch_doubles(int K) { return 3 * (size_t)K + 2 * RITZ_BI_PAD + 32 * (size_t)K + 18 + 16 + 2; }
+__host__ __device__ inline size_t ritz_bi_scratch_doubles(int K) { return 3 * (size_t)K + 2 * RITZ_BI_PAD + 32 * (size_t)K + 32 + 32 + 2; }
 
 __device__ inline RitzBiScratch ritz_bi_carve(double* base, int K) {
     RitzBiScratch s;
@@ -41,8 +41,8 @@ __device__ inline RitzBiScratch ritz_bi_carve(double* base, int K) {
     s.dxs = base; base += K + RITZ_BI_PAD;
     s.zf = base; base += 16 * (size_t)K;
     s.zb = base; base += 16 * (size_t)K;
-    s.lam = base; base += 18;
-    s.rn = base; base += 16;
+    s.lam = base; base += 32;
+    s.rn = base; base += 32;
     s.fail = reinterpret_cast<int*>(base);
     return s;
 }
@@ -224,26 +224,18 @@ __device__ inline int ritz_top_bi(int k, const double* d, const double* e, int m
     }
     RITZ_TICK(11);
 
-    // ---- eigenvalue `warp` (0-based from the top) ----
-    // values 0 .. min(m, 15): one more than the pairs (the gap below the last pair is checked on it), except with 16 pairs,
-    // where that gap is checked by a Sturm count instead
-    const int nval = min(m + 1, 16);
-    const bool mine = (have == 0) ? (warp < nval) : (warp > have && warp < nval);      // value number `have` is already there
-    double lam_s = 0.0;
-    if (mine) {
+    // ---- eigenvalues 0 .. m (0-based from the top; one more than the pairs: the gap below the last pair is checked on it),
+    // warp w takes the values w, w + 16 ----
+    const int nwarps = (int)(blockDim.x >> 5);
+    const int nval = m + 1;
+    for (int idx = warp; idx < nval; idx += nwarps) {
+        if (idx <= have && have > 0) continue;          // values 0 .. have are still there from the previous call
         const double wdt = (gu - gl) * inv_t;
-        lam_s = ritz_value_warp(k, sc.dxs, sc.e2s, k - 1 - warp, gl * inv_t - 1e-3 * wdt, gu * inv_t + 1e-3 * wdt, tnorm * inv_t,
-                                (prof && warp == 0) ? prof + 18 : nullptr);
-        if (lane == 0) sc.lam[warp] = lam_s * tscale;
-    } else if (warp < nval) {
-        lam_s = sc.lam[warp] * inv_t;
+        const double lam_s = ritz_value_warp(k, sc.dxs, sc.e2s, k - 1 - idx, gl * inv_t - 1e-3 * wdt, gu * inv_t + 1e-3 * wdt, tnorm * inv_t,
+                                             (prof && idx == 0) ? prof + 18 : nullptr);
+        if (lane == 0) sc.lam[idx] = lam_s * tscale;
     }
-    if (m == 16 && warp == 15) {
-        // no warp is left for value 16: the gap below pair 15 holds iff exactly 16 eigenvalues are >= lam_15 - gap
-        double pdummy; int edummy;
-        const int c = sturm_count(k, sc.dxs, sc.e2s, lam_s - 1e-7 * (tnorm * inv_t), pdummy, edummy);
-        if (lane == 0 && k - c != 16) *sc.fail = 1;
-    }
+    __syncwarp();
     RITZ_TICK(12);
 
     // ---- eigenvector `warp` by the twisted factorisation (Parlett & Dhillon), written on the leading / trailing
@@ -255,9 +247,12 @@ __device__ inline int ritz_top_bi(int k, const double* d, const double* e, int m
     // Nothing is ever divided by an off-diagonal entry: a (nearly) decoupled tridiagonal — the Rayleigh quotient right
     // after a thick restart with converged Ritz pairs has couplings of 1e-13 — is handled like any other (entries of
     // the scaled matrix are <= 2 in modulus and k <= 101, so the minors stay far from the overflow threshold).
-    if (warp < m && warp >= have) {
+    for (int idx = warp; idx < m; idx += nwarps) {
+        if (idx < have) continue;
+        const double lam_s = sc.lam[idx] * inv_t;   // (written by this very warp, or by the previous call)
         double* pf = sc.zf + (size_t)warp * k;      // pf[j] = p_j   (p_{-1} = 1)
         double* pb = sc.zb + (size_t)warp * k;      // pb[j] = q_j   (q_k = 1)
+        __syncwarp();                               // (second pair of this warp: the minors of the first one are dead)
         if (lane < 2) minor_chain(k, lane, sc.dxs, sc.e2s, lam_s, lane ? pb : pf);
         __syncwarp();
         double best = 1e300; int bestr = 0;
@@ -273,7 +268,7 @@ __device__ inline int ritz_top_bi(int k, const double* d, const double* e, int m
             const int orr = __shfl_xor_sync(0xffffffffu, bestr, o);
             if (ob < best || (ob == best && orr < bestr)) { best = ob; bestr = orr; }
         }
-        double* u = U + (size_t)warp * ldu;
+        double* u = U + (size_t)idx * ldu;
         {
             const double pm = (bestr > 0) ? pf[bestr - 1] : 1.0, qp = (bestr < k - 1) ? pb[bestr + 1] : 1.0;
             const double* __restrict__ es = sc.es;
@@ -326,13 +321,13 @@ __device__ inline int ritz_top_bi(int k, const double* d, const double* e, int m
             if (!(fabs(t) <= 1e300)) res = 1e300;           // NaN
         }
         for (int o = 16; o > 0; o >>= 1) res = fmax(res, __shfl_xor_sync(0xffffffffu, res, o));
-        if (lane == 0) { sc.rn[warp] = res; if (!(res <= 1e-13 * tnorm)) *sc.fail = 1; }
+        if (lane == 0) { sc.rn[idx] = res; if (!(res <= 1e-13 * tnorm)) *sc.fail = 1; }
     }
     __syncthreads();
     RITZ_TICK(13);
     // ---- gaps and mutual orthogonality (one warp per pair of vectors: measured inside the eigsolve kernel, where this
     // code runs once per launch from a cold instruction cache, the compact warp-cooperative loop beats one thread per pair) ----
-    if (tid < m && tid + 1 < nval) {
+    if (tid < m) {
         if (!(sc.lam[tid] - sc.lam[tid + 1] >= 1e-7 * tnorm)) *sc.fail = 1;
     }
     // Two unit vectors with residuals r_a, r_b for eigenvalues lam_a != lam_b satisfy

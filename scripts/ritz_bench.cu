@@ -72,7 +72,7 @@ int main(int argc, char** argv) {
     const size_t smem = (3 * 128 + (size_t)((K + 1) | 1) * 128 + pb::ritz_bi_scratch_doubles(K) + 64) * 8;
     cudaFuncSetAttribute(k_bench, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     for (int reps : {20, 1})
-    for (int want : {3, 6, 10, 15, 16}) {
+    for (int want : {3, 6, 10, 16, 20, 24}) {
         for (int rep = 0; rep < 1; ++rep) {
             k_bench<<<1, 512, smem>>>(K, dd, de, want, reps, dl, dU, dp, dg);
             cudaError_t err = cudaDeviceSynchronize();
