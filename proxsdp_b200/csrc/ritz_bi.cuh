@@ -18,7 +18,7 @@
 
 namespace pb {
 
-constexpr int RITZ_BI_MAXM = 31;      // pairs computed at most: warp w takes pairs w, w + 16 (one extra VALUE is computed after the last pair)
+constexpr int RITZ_BI_MAXM = 47;      // pairs computed at most: warp w takes pairs w, w + 16, w + 32 (one extra VALUE is computed after the last pair)
 constexpr int RITZ_BI_PAD = 16;       // padding rows behind the k real ones (the Sturm chain runs in blocks of 8 rows)
 
 struct RitzBiScratch {
@@ -27,12 +27,12 @@ struct RitzBiScratch {
     double* dxs;     // K + PAD  d[j] 2^-s
     double* zf;      // 16 * K   leading principal minors, one row per warp (re-used when a warp takes a second pair)
     double* zb;      // 16 * K   trailing principal minors
-    double* lam;     // 32       eigenvalues (descending)
-    double* rn;      // 32       residual || T u - lam u ||_inf of every vector
+    double* lam;     // 48       eigenvalues (descending)
+    double* rn;      // 48       residual || T u - lam u ||_inf of every vector
     int* fail;       // 1
 };
 
-__host__ __device__ inline size_t ritz_bi_scratch_doubles(int K) { return 3 * (size_t)K + 2 * RITZ_BI_PAD + 32 * (size_t)K + 32 + 32 + 2; }
+__host__ __device__ inline size_t ritz_bi_scratch_doubles(int K) { return 3 * (size_t)K + 2 * RITZ_BI_PAD + 32 * (size_t)K + 48 + 48 + 2; }
 
 __device__ inline RitzBiScratch ritz_bi_carve(double* base, int K) {
     RitzBiScratch s;
@@ -41,8 +41,8 @@ __device__ inline RitzBiScratch ritz_bi_carve(double* base, int K) {
     s.dxs = base; base += K + RITZ_BI_PAD;
     s.zf = base; base += 16 * (size_t)K;
     s.zb = base; base += 16 * (size_t)K;
-    s.lam = base; base += 32;
-    s.rn = base; base += 32;
+    s.lam = base; base += 48;
+    s.rn = base; base += 48;
     s.fail = reinterpret_cast<int*>(base);
     return s;
 }
