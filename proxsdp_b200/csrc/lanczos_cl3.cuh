@@ -152,6 +152,7 @@ struct LanczosCl3Args {
     int arrow_restart;         // 1: keep the arrowhead form after a thick restart (dense Jacobi Ritz solves; PROXSDP_B200_LZ_ARROW=1)
     long long spin_limit;      // cycles a spin loop waits for a peer before the launch gives up (~2 s; PROXSDP_B200_LZ_SPIN_S
                                // stretches it for runs under compute-sanitizer, where a peer can be 100x slower)
+    int bi_memory;             // 1: a declined bisection Ritz solve sends the later analyses of the launch straight to the dense solver
     int pf_rows;               // > 0: slab rows prefetched into L2 ahead of the register loads (matrices larger than L2;
                                // PROXSDP_B200_LZ_PF overrides the host's choice)
     int poll_ns;               // back-off between two polls of the flagged exchange words (PROXSDP_B200_LZ_POLL_NS)
@@ -402,7 +403,9 @@ __device__ __forceinline__ bool lz3_restart_fits(const int m2, const int lda) {
 
 // Ritz analysis + thick restart, out of line: it runs once or twice per launch, and keeping its ~100 KB of code
 // out of the per-step loop keeps the loop inside the instruction cache.  State in/out through st[] (shared memory):
-//   st[0] k, st[2] arrow, st[3] howmany, st[4] numiter, st[5] first_analysis, st[6] converged, st[7] finished.
+//   st[0] k, st[2] arrow, st[3] howmany, st[4] numiter, st[5] first_analysis, st[6] converged, st[7] finished,
+//   st[9] bisection verdicts of this launch: bit 0 = the leading pairs were declined once, bit 1 = the `keep` pairs were
+//   (a near-multiple eigenvalue stays one for the rest of the eigsolve: later analyses go straight to the dense solver).
 // All threads of the CTA call it; every CTA of the grid computes the same result from bitwise identical data.
 __device__ __noinline__ void lz3_ritz(const LanczosCl3Args& a, double* sbase, int* st, const double beta, const int vn, const int cta,
                                       long long* prof) {
@@ -411,6 +414,7 @@ __device__ __noinline__ void lz3_ritz(const LanczosCl3Args& a, double* sbase, in
     const int K = a.K, VNp = lanczos_cl_vnp(a.vn_max);
     int k = st[0], arrow = st[2], howmany = st[3], numiter = st[4];
     const bool first_analysis = st[5] != 0;
+    int bi_bad = a.bi_memory ? st[9] : 0;
     int converged = 0, finished = 0;
     __syncthreads();                              // everybody has read the state before thread 0 rewrites it
     const int lda = lanczos_kp(K);
@@ -565,7 +569,7 @@ __device__ __noinline__ void lz3_ritz(const LanczosCl3Args& a, double* sbase, in
     };
     // ---- fast path: the leading pairs of the tridiagonal Rayleigh quotient by bisection + twisted vectors ----
     bool done_bi = false;
-    if (a.use_bi && arrow < 0 && 2 * (size_t)lda * lda >= ritz_bi_scratch_doubles(K)) {
+    if (a.use_bi && arrow < 0 && !(bi_bad & 1) && 2 * (size_t)lda * lda >= ritz_bi_scratch_doubles(K)) {
         RitzBiScratch bs = ritz_bi_carve(SMD(JA), K);          // JA and JB are contiguous and unused here
         auto solve = [&](const int want, const int have) -> int {
             const int got = ritz_top_bi(k, SMD(Hd), SMD(He), want, SMD(D), SMD(JU), lda, bs, prof, have);
@@ -577,6 +581,7 @@ __device__ __noinline__ void lz3_ritz(const LanczosCl3Args& a, double* sbase, in
             return got;
         };
         int mb = solve(howmany + 4, 0);
+        if (mb == 0) bi_bad |= 1;
         if (mb > 0) {
             int cv = 0;
             while (cv < mb && fabs(SMD(f)[cv]) <= a.tol) cv++;
@@ -590,9 +595,10 @@ __device__ __noinline__ void lz3_ritz(const LanczosCl3Args& a, double* sbase, in
             else if (cv < howmany && k == K && numiter < a.maxiter) {
                 // not converged at the end of a Krylov cycle: the restart needs the `keep` leading pairs — one warp each
                 const int keep = (3 * K + 2 * cv) / 5;
-                if (keep <= RITZ_BI_MAXM && keep < k && !a.arrow_restart && lz3_restart_fits(keep - cv, lda)) {
+                if (keep <= RITZ_BI_MAXM && keep < k && !a.arrow_restart && !(bi_bad & 2) && lz3_restart_fits(keep - cv, lda)) {
                     __syncthreads();
                     if (mb < keep) mb = solve(keep, mb);      // the pairs of the first call stay
+                    if (mb < keep) bi_bad |= 2;
                     int cv2 = 0;
                     while (cv2 < mb && fabs(SMD(f)[cv2]) <= a.tol) cv2++;
                     if (mb >= keep && cv2 == cv) {
@@ -671,6 +677,7 @@ __device__ __noinline__ void lz3_ritz(const LanczosCl3Args& a, double* sbase, in
     }
     if (tid == 0) {
         st[0] = k; st[2] = arrow; st[3] = howmany; st[4] = numiter; st[5] = first_out ? 1 : 0; st[6] = converged; st[7] = finished;
+        st[9] = bi_bad;
     }
     __syncthreads();
 #undef SMD
@@ -724,7 +731,7 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) k_lanczos_cl3(const __grid_cons
     const int prow = (cta == 0) ? 0 : (cta == C - 1) ? 1 : (cta == G / 2) ? 2 : (cta == G - 1) ? 3 : -1;
     const bool profiling = (a.prof != nullptr) && prow >= 0;
     if (tid < 32) s_prof[tid] = 0;
-    if (tid == 0) s_ok = 1;
+    if (tid == 0) { s_ok = 1; s_state[9] = 0; }
     // (the running clock sits in s_prof[31], not in a register that would have to live across the symv)
 #define tprev s_prof[31]
 #define LZ3_TICK(slot) do { if (profiling && tid == 0) { long long tn = clock64(); s_prof[slot] += tn - tprev; tprev = tn; } } while (0)

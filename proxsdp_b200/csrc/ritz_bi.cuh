@@ -235,7 +235,12 @@ __device__ inline int ritz_top_bi(int k, const double* d, const double* e, int m
                                              (prof && idx == 0) ? prof + 18 : nullptr);
         if (lane == 0) sc.lam[idx] = lam_s * tscale;
     }
-    __syncwarp();
+    // a (nearly) multiple eigenvalue makes the routine decline: find that out now, before the vectors are computed
+    __syncthreads();
+    {
+        const bool close = (tid < m) && !(sc.lam[tid] - sc.lam[tid + 1] >= 1e-7 * tnorm);
+        if (__syncthreads_or(close ? 1 : 0)) return 0;
+    }
     RITZ_TICK(12);
 
     // ---- eigenvector `warp` by the twisted factorisation (Parlett & Dhillon), written on the leading / trailing
@@ -327,9 +332,7 @@ __device__ inline int ritz_top_bi(int k, const double* d, const double* e, int m
     RITZ_TICK(13);
     // ---- gaps and mutual orthogonality (one warp per pair of vectors: measured inside the eigsolve kernel, where this
     // code runs once per launch from a cold instruction cache, the compact warp-cooperative loop beats one thread per pair) ----
-    if (tid < m) {
-        if (!(sc.lam[tid] - sc.lam[tid + 1] >= 1e-7 * tnorm)) *sc.fail = 1;
-    }
+    // (the gaps were checked right after the values)
     // Two unit vectors with residuals r_a, r_b for eigenvalues lam_a != lam_b satisfy
     //     |u_a . u_b| <= (||r_a||_2 + ||r_b||_2) / |lam_a - lam_b|
     // ((lam_a - lam_b) u_a.u_b = u_a.r_b - u_b.r_a for symmetric T): pairs whose bound is already below the 1e-12 bar need no

@@ -258,6 +258,8 @@ class Solver {
     int lz_resident_ok_[2] = {0, 0};
     long long resident_calls = 0;
     long long lz_spin_limit_ = 4000000000LL;   // cycles (~2 s) a spin loop of the cluster kernels waits for a peer
+    int lz_bi_memory_ = 0;     // PROXSDP_B200_RITZ_MEM=1: once a bisection Ritz solve has declined, the later analyses of that launch go straight
+                               // to the dense solver (experiment; off: on gpp500-1 it changes which copies of multiple eigenvalues are found)
     int lz_pf_ = -1;           // cl3 kernel: slab rows prefetched into L2 ahead of the loads (-1: 8 rows when the matrix exceeds L2)
     int lz_strict_ = 0;        // cl3 kernel: FP64 alpha + two Gram-Schmidt passes on every step (PROXSDP_B200_LZ_STRICT=1)
     int lz_xres_ = 0;          // >= 1: cap the resident slab rows of the cl3 symv at lz_xres_ - 1 (experiments / tests)
@@ -429,6 +431,7 @@ Solver::Solver(const proxsdp_problem_t* prob, const proxsdp_options_t* opt_in, b
     if (const char* e = getenv("PROXSDP_B200_LZ_STRICT")) lz_strict_ = atoi(e) != 0 ? 1 : 0;
     if (const char* e = getenv("PROXSDP_B200_LZ_POLL_NS")) lz_poll_ns_ = std::max(0, atoi(e));
     if (const char* e = getenv("PROXSDP_B200_LZ_PF")) lz_pf_ = std::max(0, atoi(e));
+    if (const char* e = getenv("PROXSDP_B200_RITZ_MEM")) lz_bi_memory_ = atoi(e);
     if (const char* e = getenv("PROXSDP_B200_LZ_SPIN_S")) lz_spin_limit_ = (long long)(std::max(1.0, atof(e)) * 2.0e9);
     if (const char* e = getenv("PROXSDP_B200_LZ_RESIDENT")) { const int v = atoi(e); lz_resident_ = v != 0; lz_resident16_ = (v != 8); lz_resident8_ = (v != 16); }
     if (const char* e = getenv("PROXSDP_B200_LZ_ARROW")) lz_arrow_ = atoi(e) != 0 ? 1 : 0;
@@ -844,7 +847,7 @@ bool Solver::lanczos_launch_cluster3(ConeDev& cd, int cone_idx, int nev, int K, 
     a.vn_max = vn_max; a.use_bi = lz_bi_; a.stop_above = lz_stop_above_; a.strict = lz_strict_; a.poll_ns = lz_poll_ns_; a.arrow_restart = lz_arrow_; a.debug = getenv("PROXSDP_B200_LZ_DEBUG") ? 1 : 0;
     a.rbase = nside / G; a.rrem = nside % G; a.vbase = nside / C; a.vrem = nside % C;
     a.vals = cd.vals.p; a.info = cd.info.p; a.scal = scal_target_; a.cone = cone_idx;
-    a.L = L; a.spin_limit = lz_spin_limit_;
+    a.L = L; a.spin_limit = lz_spin_limit_; a.bi_memory = lz_bi_memory_;
     // a matrix that does not stay in L2 between two mat-vecs is pulled in by the TMA engine a few rows ahead of the loads
     {
         // whole slab when the matrix fits L2 (the loads then hit the near L2 partition); a window of ~16 MB over the grid otherwise
@@ -967,7 +970,7 @@ bool Solver::lanczos_launch_implicit(ConeDev& cd, int cone_idx, int nev, int K, 
     a.vn_max = vn_max; a.use_bi = lz_bi_; a.stop_above = 1e300; a.strict = lz_strict_; a.poll_ns = 0; a.arrow_restart = lz_arrow_; a.debug = 0;
     a.rbase = nside / C; a.rrem = nside % C; a.vbase = nside / C; a.vrem = nside % C;
     a.vals = cd.vals.p; a.info = cd.info.p; a.scal = scal_target_; a.cone = cone_idx;
-    a.L = L; a.spin_limit = lz_spin_limit_;
+    a.L = L; a.spin_limit = lz_spin_limit_; a.bi_memory = lz_bi_memory_;
     a.imp_Y = cd.Y.p; a.imp_kept_idx = cd.kept_idx.p; a.imp_kept_lam = cd.kept_lam.p; a.imp_nkept = cd.nkept.p;
     a.imp_rowptr = cd.imp_rowptr.p; a.imp_col = cd.imp_col.p; a.imp_pos = cd.imp_pos.p; a.imp_coef = cd.imp_coef.p;
     a.imp_Mty = Mty_[cur_].p + cd.off; a.imp_c = c_.p + cd.off; a.imp_tau = tau;
@@ -1036,7 +1039,7 @@ bool Solver::lanczos_launch_resident(ConeDev& cd, int cone_idx, int nev, int K, 
         a.debug = getenv("PROXSDP_B200_LZ_DEBUG") ? 1 : 0;
         a.rbase = nside / C; a.rrem = nside % C; a.vbase = nside / C; a.vrem = nside % C;
         a.vals = cd.vals.p; a.info = cd.info.p; a.scal = scal_target_; a.cone = cone_idx;
-        a.L = L; a.spin_limit = lz_spin_limit_;
+        a.L = L; a.spin_limit = lz_spin_limit_; a.bi_memory = lz_bi_memory_;
         if (getenv("PROXSDP_B200_LZ_PROF")) { if (lz_prof_.n == 0) lz_prof_.alloc(8 + 8 * 256); a.prof = lz_prof_.p; }
         void* kargs[] = {&a};
         cudaError_t e = cudaLaunchKernelExC(&cfg, kfn, kargs);

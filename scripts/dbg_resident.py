@@ -5,7 +5,7 @@ ROOT = os.environ.get("GRAFT_REPO_ROOT", os.path.dirname(os.path.dirname(os.path
 sys.path.insert(0, ROOT)
 from proxsdp_b200 import Options, solver
 from proxsdp_b200.problems import load_problem
-aff, con = load_problem(os.path.join(ROOT, "tests", "golden", "sdplib_mcp500-1.npz"))
+aff, con = load_problem(os.path.join(ROOT, "tests", "golden", "sdplib_" + os.environ.get("PROBLEM", "mcp500-1") + ".npz"))
 mode = sys.argv[1] if len(sys.argv) > 1 else "full"
 if mode == "full":
     solver.chambolle_pock(aff, con, Options(max_iter=5))

@@ -2,7 +2,7 @@
 
     python scripts/ncu_summarise.py r2x
 
-reads  gpurun_out/launches_<tag>.csv, gpurun_out/prof_step_<tag>.ncu-rep, gpurun_out/prof_lanczos5000_<tag>.ncu-rep
+reads  gpurun_out/launches_<tag>.csv, gpurun_out/prof_step_<tag>.ncu-rep (or its _raw.csv export), gpurun_out/prof_lanczos5000_<tag>.ncu-rep
 writes profiles/<tag>_launches.csv, profiles/<tag>_launches_summary.md, profiles/<tag>_step_ncu_full.md,
        profiles/<tag>_lanczos5000_ncu_full.md, profiles/lanczos_traffic.json
 (`ncu -i ... --page raw --csv` runs here: reading a report needs no GPU).
@@ -31,7 +31,11 @@ def short(name):
 
 
 def raw_page(rep):
-    txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    csv_path = rep.replace(".ncu-rep", "_raw.csv")
+    if not os.path.exists(rep) and os.path.exists(csv_path):      # the GPU job already exported the raw page
+        txt = open(csv_path).read()
+    else:
+        txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(txt)))
     start = next(i for i, r in enumerate(rows) if r and r[0] == "ID")
     return rows[start], rows[start + 1], rows[start + 2:]

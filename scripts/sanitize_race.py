@@ -1,6 +1,7 @@
 """Reduced driver for `compute-sanitizer --tool racecheck` (shared-memory hazards; ~100x slower than a plain run on the
-spin-waiting cluster kernel): one Krylov projection of a side-96 cone through k_lanczos_cl3 (all rows resident in shared
-memory, TMA staging, DSMEM exchanges, Ritz bisection), one exact projection of a side-130 cone (block-Jacobi), a batch of
+spin-waiting cluster kernel): one Krylov projection of a side-128 cone (sides <= 100 = min_size_krylov_eigs take the full
+eigendecomposition) through the single-cluster resident variant of k_lanczos_cl3 and one through the grid-wide variant
+(TMA staging, DSMEM exchanges, flagged grid exchange, Ritz bisection), one exact projection of a side-130 cone (block-Jacobi), a batch of
 four small cones, and 12 iterations of the README Max-Cut solve (fused line-search ladder, residual kernels, record)."""
 import os, sys
 import numpy as np
@@ -9,9 +10,13 @@ from proxsdp_b200 import Options, solver
 from proxsdp_b200.problems import README_W, maxcut_problem, mimo_problem, stack_problems
 
 rng = np.random.default_rng(0)
-x = rng.standard_normal(96 * 97 // 2)
-xg, cg, mg, cvg, ng, ms = solver.psd_project([96], x, [2], Options())
-print("krylov projection side 96: rank", cg, "converged", cvg, "matvecs", ng, flush=True)
+x = rng.standard_normal(128 * 129 // 2)
+xg, cg, mg, cvg, ng, ms = solver.psd_project([128], x, [2], Options())
+print("krylov projection side 128, resident single-cluster kernel: rank", cg, "converged", cvg, "matvecs", ng, flush=True)
+os.environ["PROXSDP_B200_LZ_RESIDENT"] = "0"
+xg, cg, mg, cvg, ng, ms = solver.psd_project([128], x, [2], Options())
+print("krylov projection side 128, grid-wide kernel: rank", cg, "converged", cvg, "matvecs", ng, flush=True)
+os.environ.pop("PROXSDP_B200_LZ_RESIDENT")
 x = rng.standard_normal(130 * 131 // 2)
 xg, cg, mg, cvg, ng, ms = solver.psd_project([130], x, [2], Options(full_eig_decomp=True))
 print("exact projection side 130: rank", cg, flush=True)
