@@ -452,6 +452,9 @@ __device__ __noinline__ void lz3_ritz(const LanczosCl3Args& a, double* sbase, in
             const double th = (c < m2) ? SMD(D)[nlock + c] : 0.0;
             const double fc = (c < m2) ? SMD(f)[nlock + c] : 0.0;
             const double nf = sqrt(warp_sum(fc * fc));
+            double thmax = fabs(th);
+            for (int o = 16; o > 0; o >>= 1) thmax = fmax(thmax, __shfl_xor_sync(0xffffffffu, thmax, o));
+            thmax = fmax(thmax, 1e-300);
             double qprev = 0.0, qcur = (nf > 0.0) ? fc / nf : ((c == 0) ? 1.0 : 0.0);
             double bprev = 0.0;
             for (int j = 0; j < m2; ++j) {
@@ -461,9 +464,14 @@ __device__ __noinline__ void lz3_ritz(const LanczosCl3Args& a, double* sbase, in
                 w -= aj * qcur + bprev * qprev;
                 if (c == 0) ta[j] = aj;
                 if (j == m2 - 1) break;
-                // two classical Gram-Schmidt passes of w against q_0 .. q_j: lane i <-> coefficient of q_i
-                auto reorth = [&]() {
-                    for (int pass = 0; pass < 2; ++pass) {
+                // Gram-Schmidt passes of w against q_0 .. q_j (lane i <-> coefficient of q_i), repeated until a pass no longer
+                // shrinks the vector (DGKS): with components of f that are tiny or exactly zero — multiple eigenvalues, pairs
+                // that have all but converged — w is annihilated down to rounding noise, and a fixed number of passes then
+                // leaves a "unit" vector that is not orthogonal to its predecessors at all (seen: a rotated basis with
+                // || V'V - I || = 1 and Ritz residuals of 1e4 on matrices with 3-fold eigenvalues)
+                auto reorth = [&]() -> double {
+                    double nprev = sqrt(warp_sum((c < m2) ? w * w : 0.0)), ncur = nprev;
+                    for (int pass = 0; pass < 6; ++pass) {
                         __syncwarp();
                         ws[c] = (c < m2) ? w : 0.0;
                         __syncwarp();
@@ -472,19 +480,28 @@ __device__ __noinline__ void lz3_ritz(const LanczosCl3Args& a, double* sbase, in
                         hs[c] = (c <= j) ? h : 0.0;
                         __syncwarp();
                         if (c < m2) for (int i = 0; i <= j; ++i) w = fma(-hs[i], Qs[i * MP + c], w);
+                        ncur = sqrt(warp_sum((c < m2) ? w * w : 0.0));
+                        if (!(ncur < 0.7 * nprev)) break;
+                        nprev = ncur;
                     }
-                    return sqrt(warp_sum((c < m2) ? w * w : 0.0));
+                    return ncur;
                 };
                 double nb = reorth();
                 double bj = nb;
-                if (!(nb > 1e-200)) {
-                    // exact breakdown (an f_t that is exactly zero, or a repeated theta): carry on with any direction
-                    // orthogonal to the q's — T~ decouples there (off-diagonal 0)
-                    for (int t0 = 0; t0 < m2; ++t0) {
-                        w = (c == t0) ? 1.0 : 0.0;
-                        nb = reorth();
-                        if (nb > 0.5) break;
+                if (!(nb > 1e-14 * thmax)) {
+                    // breakdown (an f_t that is zero or negligible, a repeated theta): what is left of w is rounding noise.
+                    // T~ decouples here (off-diagonal 0: the coupling dropped is below 1e-14 ||Theta||) and the run carries on
+                    // with the coordinate vector that has the largest component outside span(q_0 .. q_j), which is >= 1/sqrt(m2)
+                    double g = (c < m2) ? 1.0 : -1.0;
+                    if (c < m2) for (int i = 0; i <= j; ++i) { const double qi = Qs[i * MP + c]; g = fma(-qi, qi, g); }
+                    int t0 = c;
+                    for (int o = 16; o > 0; o >>= 1) {
+                        const double og = __shfl_xor_sync(0xffffffffu, g, o);
+                        const int ot = __shfl_xor_sync(0xffffffffu, t0, o);
+                        if (og > g || (og == g && ot < t0)) { g = og; t0 = ot; }
                     }
+                    w = (c == t0) ? 1.0 : 0.0;
+                    nb = reorth();
                     bj = 0.0;
                 }
                 if (c == 0) tb[j] = bj;

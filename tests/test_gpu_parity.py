@@ -360,6 +360,37 @@ def test_lanczos_kernel_variants_agree(gpu, oracle_mod, monkeypatch):
     monkeypatch.delenv("PROXSDP_B200_LZ_RESIDENT", raising=False)
 
 
+@pytest.mark.parametrize("n,nev", [(300, 6), (520, 10), (900, 8)])
+def test_lanczos_multiple_eigenvalues(gpu, oracle_mod, monkeypatch, n, nev):
+    """Multiple eigenvalues (gpp500-1 has them): a single-vector Krylov method sees the copies of a multiple eigenvalue only
+    through rounding, so WHICH copies come back is not pinned — but whatever comes back must be eigenpairs: unit, mutually
+    orthogonal Ritz vectors with residuals at the eigsolve's tolerance and Ritz values inside the spectrum, on every Ritz /
+    restart path (this is the case where a cancelled residual norm once put a Ritz value of 142 933 into a matrix of norm 38)."""
+    rng = np.random.default_rng(n)
+    Q, _ = np.linalg.qr(rng.standard_normal((n, n)))
+    lam = np.concatenate([[10.0] * 3, [8.0] * 4, [7.5, 7.5], [6.0] * 3, rng.uniform(-3.0, 3.0, n - 12)])
+    A = (Q * lam) @ Q.T
+    A = 0.5 * (A + A.T)
+    x0 = oracle_mod.eig_resid(n)
+    for tag, env in (("default", {}), ("dense Ritz solver", {"PROXSDP_B200_RITZ_BI": "0"}), ("arrow restarts", {"PROXSDP_B200_LZ_ARROW": "1"}),
+                     ("strict arithmetic", {"PROXSDP_B200_LZ_STRICT": "1"}), ("grid-wide kernel", {"PROXSDP_B200_LZ_RESIDENT": "0"}),
+                     ("grid-wide, dense Ritz solver", {"PROXSDP_B200_LZ_RESIDENT": "0", "PROXSDP_B200_RITZ_BI": "0"})):
+        for k_ in ("PROXSDP_B200_RITZ_BI", "PROXSDP_B200_LZ_ARROW", "PROXSDP_B200_LZ_STRICT", "PROXSDP_B200_LZ_RESIDENT"):
+            monkeypatch.delenv(k_, raising=False)
+        for k_, v_ in env.items():
+            monkeypatch.setenv(k_, v_)
+        vg, Vg, ig = gpu.lanczos(A, x0, nev, 25)
+        m = len(vg)
+        assert m >= 1 and ig["converged"] >= min(nev, m) - 0, (tag, ig)
+        c = min(ig["converged"], m)
+        assert np.abs(A @ Vg[:, :c] - Vg[:, :c] * vg[:c]).max() <= 1e-9 * 10.0, (tag, ig)
+        assert np.abs(Vg.T @ Vg - np.eye(m)).max() <= 1e-9, (tag, ig)
+        assert vg.max() <= 10.0 + 1e-9 and vg.min() >= -3.0 - 1e-9, (tag, vg)
+        assert abs(vg[0] - 10.0) <= 1e-9, (tag, vg)
+    for k_ in ("PROXSDP_B200_RITZ_BI", "PROXSDP_B200_LZ_ARROW", "PROXSDP_B200_LZ_STRICT", "PROXSDP_B200_LZ_RESIDENT"):
+        monkeypatch.delenv(k_, raising=False)
+
+
 def test_rank_sweep_large_krylov_dim(gpu, oracle_mod, golden_dir):
     """Config C3: target rank above the reference's default Krylov cap (K = 2r+1 = 51) on mcp250-1."""
     aff, con = load_problem(f"{golden_dir}/sdplib_mcp250-1.npz")
