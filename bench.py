@@ -285,6 +285,15 @@ def run_b200(args):
                          "(use --impl reference for the CPU restatement)")
     torch.cuda.set_device(local_rank)
     if world > 1:
+        # one process per GPU: every rank's host thread launches ~10 kernels per iteration and spins on the iteration record,
+        # so two ranks must not end up time-sharing one core — give each rank its own slice of the allowed CPUs
+        try:
+            cpus = sorted(os.sched_getaffinity(0))
+            per = len(cpus) // world
+            if per >= 1:
+                os.sched_setaffinity(0, cpus[local_rank * per:(local_rank + 1) * per])
+        except (AttributeError, OSError):
+            pass
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     from proxsdp_b200 import Options, solver
