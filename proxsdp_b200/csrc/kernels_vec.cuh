@@ -53,6 +53,25 @@ __device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(
 __device__ __forceinline__ double sub_rn(double a, double b) { return __dsub_rn(a, b); }
 
 // ---------------------------------------------------------------------------
+// Structural-nonzero bitmap of (M'y, c): bit k set iff M' has a non-empty row k or c[k] != 0.  On Max-Cut n = 2000 that is
+// 24 000 of 2 001 000 entries: the streaming kernels below skip the loads of Mty / Mty_old / c where the bit is clear
+// (x - tau (0 + 0) == x to the last bit), i.e. 32 - 48 MB of zeros per iteration are not read.
+// ---------------------------------------------------------------------------
+__global__ void k_mask_from_c(const double* __restrict__ c, long long N, unsigned int* __restrict__ mask) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < N; i += stride)
+        if (c[i] != 0.0) atomicOr(mask + (i >> 5), 1u << (i & 31));
+}
+__global__ void k_mask_from_rows(const int* __restrict__ rows, int n_rows, unsigned int* __restrict__ mask) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q < n_rows) { const int r = rows[q]; atomicOr(mask + (r >> 5), 1u << (r & 31)); }
+}
+__device__ __forceinline__ bool mask_bit(const unsigned int* __restrict__ mask, const long long k) {
+    return mask == nullptr || ((mask[k >> 5] >> (k & 31)) & 1u) != 0u;
+}
+
+// ---------------------------------------------------------------------------
 // K1+K2: X = mat(x - tau*(Mty + c)) for one PSD cone, full n x n (both triangles).
 // 32x32 tiles of the upper triangle; the mirrored tile goes through shared memory so
 // that both global writes are coalesced.  svec order: k(i,j) = j(j+1)/2 + i, i <= j.
@@ -61,7 +80,8 @@ __device__ __forceinline__ double sub_rn(double a, double b) { return __dsub_rn(
 template <bool PRIMAL>
 __global__ void __launch_bounds__(256)
 k_svec_to_mat(const double* __restrict__ x, const double* __restrict__ Mty, const double* __restrict__ c,
-              double tau, double scale, int n, int ld, double* __restrict__ X) {
+              double tau, double scale, int n, int ld, double* __restrict__ X,
+              const unsigned int* __restrict__ mask = nullptr, long long mask_off = 0) {
     __shared__ double tile[32][33];
     // decode tile pair index t -> (bi, bj), bi <= bj, column-major over the upper triangle of tiles
     int t = blockIdx.x;
@@ -78,7 +98,10 @@ k_svec_to_mat(const double* __restrict__ x, const double* __restrict__ Mty, cons
         if (i < n && j < n && i <= j) {
             size_t k = (size_t)j * (size_t)(j + 1) / 2 + (size_t)i;
             double u;
-            if (PRIMAL) u = sub_rn(x[k], mul_rn(tau, add_rn(Mty[k], c[k])));   // x .-= tau .* (Mty .+ c)
+            if (PRIMAL) {                                                      // x .-= tau .* (Mty .+ c)
+                const double mc = mask_bit(mask, mask_off + (long long)k) ? add_rn(Mty[k], c[k]) : 0.0;
+                u = sub_rn(x[k], mul_rn(tau, mc));
+            }
             else u = x[k] * scale;
             v = (i != j) ? u / sqrt2 : u;                                      // off-diagonals / sqrt(2)
             X[(size_t)i + (size_t)j * ld] = v;
@@ -515,7 +538,8 @@ __global__ void __launch_bounds__(256) k_ls_apply(LadderArgs a, const double* __
 __global__ void __launch_bounds__(256, 4)      // 4 CTAs per SM = the whole grid in one resident wave (solver.cu: blocksN)
 k_residual_primal(long long N, const double* __restrict__ x, const double* __restrict__ x_old,
                   const double* __restrict__ Mty, const double* __restrict__ Mty_old,
-                  const double* __restrict__ c, double* __restrict__ scal, ReduceWs ws) {
+                  const double* __restrict__ c, double* __restrict__ scal, ReduceWs ws,
+                  const unsigned int* __restrict__ mask = nullptr) {
     __shared__ double red[40];
     __shared__ int s_last;
     if (scal[S_POISON] != 0.0 || scal[S_LS_ACCEPTED] == 0.0) return;
@@ -537,15 +561,23 @@ k_residual_primal(long long N, const double* __restrict__ x, const double* __res
         den = nanmax(den, fabs(pold));
         ob = fma(cc, xn, ob);
     };
+    // pair i = entries 2i, 2i + 1: both bits sit in one mask word; where they are clear Mty, Mty_old and c are exact zeros
+    auto live = [&](const long long i) -> bool { return mask == nullptr || ((mask[i >> 4] >> ((2 * i) & 31)) & 3u) != 0u; };
+    const double2 z2 = make_double2(0.0, 0.0);
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     for (; i + stride < npair; i += 2 * stride) {
-        const double2 a0 = x2[i], b0 = xo2[i], d0 = m2[i], e0 = mo2[i], f0 = c2[i];
-        const double2 a1 = x2[i + stride], b1 = xo2[i + stride], d1 = m2[i + stride], e1 = mo2[i + stride], f1 = c2[i + stride];
+        const bool l0 = live(i), l1 = live(i + stride);
+        const double2 a0 = x2[i], b0 = xo2[i];
+        const double2 a1 = x2[i + stride], b1 = xo2[i + stride];
+        const double2 d0 = l0 ? m2[i] : z2, e0 = l0 ? mo2[i] : z2, f0 = l0 ? c2[i] : z2;
+        const double2 d1 = l1 ? m2[i + stride] : z2, e1 = l1 ? mo2[i + stride] : z2, f1 = l1 ? c2[i + stride] : z2;
         one(a0.x, b0.x, d0.x, e0.x, f0.x, obj); one(a0.y, b0.y, d0.y, e0.y, f0.y, obj1);
         one(a1.x, b1.x, d1.x, e1.x, f1.x, obj); one(a1.y, b1.y, d1.y, e1.y, f1.y, obj1);
     }
     for (; i < npair; i += stride) {
-        const double2 a0 = x2[i], b0 = xo2[i], d0 = m2[i], e0 = mo2[i], f0 = c2[i];
+        const bool l0 = live(i);
+        const double2 a0 = x2[i], b0 = xo2[i];
+        const double2 d0 = l0 ? m2[i] : z2, e0 = l0 ? mo2[i] : z2, f0 = l0 ? c2[i] : z2;
         one(a0.x, b0.x, d0.x, e0.x, f0.x, obj); one(a0.y, b0.y, d0.y, e0.y, f0.y, obj1);
     }
     if ((N & 1) && blockIdx.x == 0 && threadIdx.x == 0) one(x[N - 1], x_old[N - 1], Mty[N - 1], Mty_old[N - 1], c[N - 1], obj);

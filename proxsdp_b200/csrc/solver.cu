@@ -260,6 +260,7 @@ class Solver {
     long long lz_spin_limit_ = 4000000000LL;   // cycles (~2 s) a spin loop of the cluster kernels waits for a peer
     int lz_bi_memory_ = 0;     // PROXSDP_B200_RITZ_MEM=1: once a bisection Ritz solve has declined, the later analyses of that launch go straight
                                // to the dense solver (experiment; off: on gpp500-1 it changes which copies of multiple eigenvalues are found)
+    DBuf<unsigned int> nzmask_;   // structural-nonzero bitmap of (M'y, c): the streaming kernels skip the zeros (kernels_vec.cuh)
     int lz_pf_ = -1;           // cl3 kernel: slab rows prefetched into L2 ahead of the loads (-1: 8 rows when the matrix exceeds L2)
     int lz_strict_ = 0;        // cl3 kernel: FP64 alpha + two Gram-Schmidt passes on every step (PROXSDP_B200_LZ_STRICT=1)
     int lz_xres_ = 0;          // >= 1: cap the resident slab rows of the cl3 symv at lz_xres_ - 1 (experiments / tests)
@@ -557,6 +558,13 @@ void Solver::setup_host(const proxsdp_problem_t* prob) {
     b_.upload(b_host_); h_.upload(h_host_);
     b_orig_d_.upload(b_host_); h_orig_d_.upload(h_host_);
     for (int q = 0; q < 2; ++q) { x_[q].alloc((size_t)n); Mty_[q].alloc((size_t)n); y_[q].alloc((size_t)R); Mx_[q].alloc((size_t)R); }
+    if (n > 0 && !getenv("PROXSDP_B200_NO_NZMASK")) {
+        // (Mty is only ever written at the non-empty rows of M', c is fixed: the bitmap is built once)
+        nzmask_.alloc((size_t)((n + 31) / 32 + 1));
+        k_mask_from_c<<<std::max(1, std::min(num_sms_ * 8, ceil_div(n, 256))), 256, 0, stream>>>(c_.p, n, nzmask_.p);
+        launches++;
+        if (Mt_.n_nz > 0) { k_mask_from_rows<<<ceil_div(Mt_.n_nz, 256), 256, 0, stream>>>(Mt_.nz_rows.p, Mt_.n_nz, nzmask_.p); launches++; }
+    }
     st.lap("setup: cones");
 
     // cones
@@ -1238,7 +1246,7 @@ void Solver::psd_projection_launch(long long iter, double tau, bool force_full) 
         }
         if (!cd.used_implicit) {
             k_svec_to_mat<true><<<tiles, dim3(32, 8), 0, stream>>>(x + cd.off, Mty + cd.off, c_.p + cd.off, tau, 1.0,
-                                                                   cd.side, cd.ld, cd.X.p);
+                                                                   cd.side, cd.ld, cd.X.p, nzmask_.p, (long long)cd.off);
             launches++;
         }
         if (krylov) {
@@ -1352,7 +1360,7 @@ void Solver::launch_post_eig(double tau0, bool first_pass) {
     if (fused_ladder_) launch_ladder(0, ntr, tau0);
     else for (int t = 0; t < ntr; ++t) launch_dual_trial(t, tau0);
     int blocksN = std::max(1, std::min(std::min(reduce_blocks_, 4 * num_sms_), ceil_div(n, 512)));      // one resident wave
-    k_residual_primal<<<blocksN, 256, 0, stream>>>(n, xn, x_[cur_].p, Mty_[1 - cur_].p, Mty_[cur_].p, c_.p, scal_d_.p, ws_);
+    k_residual_primal<<<blocksN, 256, 0, stream>>>(n, xn, x_[cur_].p, Mty_[1 - cur_].p, Mty_[cur_].p, c_.p, scal_d_.p, ws_, nzmask_.p);
     int blocksR = std::max(1, std::min(reduce_blocks_, ceil_div(R, 256)));
     k_residual_dual<<<blocksR, 256, 0, stream>>>((int)p, (int)m, beta_, opt.line_search_flag ? 1 : 0, dual_step_,
                                                  y_[1 - cur_].p, y_[cur_].p, Mx_[1 - cur_].p, Mx_[cur_].p, b_.p, h_.p,
@@ -1861,7 +1869,7 @@ bool Solver::run(long long max_steps, bool flush_l2) {
             const double keep_ops = scal_host[S_NUMOPS];
             evals = linesearch_continue(tau0, ls_exhausted, ls_last_tau);
             int blocksN = std::max(1, std::min(std::min(reduce_blocks_, 4 * num_sms_), ceil_div(n, 512)));      // one resident wave
-            k_residual_primal<<<blocksN, 256, 0, stream>>>(n, x_[1 - cur_].p, x_[cur_].p, Mty_[1 - cur_].p, Mty_[cur_].p, c_.p, scal_d_.p, ws_);
+            k_residual_primal<<<blocksN, 256, 0, stream>>>(n, x_[1 - cur_].p, x_[cur_].p, Mty_[1 - cur_].p, Mty_[cur_].p, c_.p, scal_d_.p, ws_, nzmask_.p);
             int blocksR = std::max(1, std::min(reduce_blocks_, ceil_div(R, 256)));
             k_residual_dual<<<blocksR, 256, 0, stream>>>((int)p, (int)m, beta_, 1, dual_step_, y_[1 - cur_].p, y_[cur_].p,
                                                          Mx_[1 - cur_].p, Mx_[cur_].p, b_.p, h_.p, scal_d_.p, ws_);
