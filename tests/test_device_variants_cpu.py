@@ -6,6 +6,10 @@ restatement (both scripts restate the device arithmetic in numpy / Python floats
   converged counts, Ritz values and basis orthogonality with the C oracle on 13 matrix families.
 * ritz_bi.cuh counts eigenvalues with a pre-scaled, division-free Sturm recurrence rescaled every 8 rows
   -> scripts/sturm_check.py compares the counts with LAPACK on random / graded / clustered tridiagonals.
+* ritz_bi.cuh finds Ritz values by secant-steered clustered multisection, and lanczos_cl3.cuh turns the bordered Rayleigh
+  quotient of a thick restart back into a tridiagonal by a small Lanczos run with a DGKS loop and a relative breakdown test
+  (KrylovKit: dense `tridiageigh!` and a Householder reduction) -> scripts/ritz_restart_check.py checks both against LAPACK,
+  the restart on repeated values and on zero / negligible / graded couplings.
 """
 import importlib.util
 import os
@@ -26,3 +30,7 @@ def test_one_pass_reorthogonalisation_matches_oracle_counts():
 
 def test_scaled_sturm_count_matches_lapack():
     assert _load("sturm_check").main() == 0
+
+
+def test_ritz_values_and_retridiagonalising_restart_match_lapack():
+    assert _load("ritz_restart_check").main() == 0
