@@ -438,3 +438,31 @@ def test_implicit_operator_equals_dense_path(gpu, oracle_mod):
     aff, con = _load(f"{conftest.GOLDEN}/sdplib_mcp124-1.npz")
     ri = gpu.chambolle_pock(aff, con, Options(implicit_psd_operator=True))
     assert ri.status == 1 and abs(ri.objval - (-141.9905)) <= 5e-3 * 141.9905 and ri.implicit_calls > 0
+
+
+@pytest.mark.parametrize("which", ["mcp124-1", "mcp250-1", "er300", "mimo16"])
+def test_full_solves_end_at_certified_optima(gpu, golden_dir, which):
+    """No oracle here: the device's primal-dual pair is checked against a weak-duality certificate recomputed in
+    numpy / LAPACK (tests/certificates.py) — feasibility of X, PSD-ness of X and of the dual slack C + A'y + G'y_in,
+    and the bracket [dual objective + lambda_min(S) trace(X), primal objective] around the optimum."""
+    from certificates import certificate
+    if which == "er300":
+        aff, con = maxcut_er_problem(300, 0.05, seed=0)
+        opt = Options(tol_gap=1e-5, tol_feasibility=1e-5)
+    elif which == "mimo16":
+        aff, con = mimo_problem(5, 16)
+        opt = Options(tol_gap=1e-6, tol_feasibility=1e-6)
+    else:
+        aff, con = load_problem(f"{golden_dir}/sdplib_{which}.npz")
+        opt = Options(tol_gap=1e-5, tol_feasibility=1e-5)
+    r = gpu.chambolle_pock(aff, con, opt)
+    assert r.status == 1
+    k = certificate(aff, con, r)
+    side = con.sdpcone[0].sq_side
+    assert k["eq"] <= 1e-4 and k["ineq"] <= 1e-4 and k["lam_x"] >= -1e-6 and k["y_in_min"] >= -1e-9
+    assert abs(k["trace"] - side) <= 1e-2                    # diag(X) = 1 in all four families
+    lower = k["dual"] + min(k["lam_s"], 0.0) * side
+    scale = 1.0 + abs(k["primal"])
+    assert lower <= k["primal"] + 1e-5 * scale, k            # X is feasible to 1e-5 only
+    assert k["primal"] - lower <= 2e-3 * scale, k
+    assert abs(r.objval - k["primal"]) <= 1e-9 * scale and abs(r.dual_objval - k["dual"]) <= 1e-6 * scale
