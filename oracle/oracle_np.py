@@ -29,6 +29,25 @@ def _svec_maps(side):
     return np.array(ii), np.array(jj)
 
 
+def equilibrate(M: sp.spmatrix, opt: Options):
+    """equilibration.jl:1-71 with scipy sparse products in place of the reference's loops over nzrange."""
+    R, n = M.shape
+    alpha2, beta2, gamma = np.sqrt(n / R), np.sqrt(R / n), 0.1
+    u, v, u_, v_ = np.zeros(R), np.zeros(n), np.zeros(R), np.zeros(n)
+    M = sp.csr_matrix(M)
+    for it in range(1, int(opt.equilibration_iters) + 1):
+        M_ = sp.diags(np.exp(u)) @ (M @ sp.diags(np.exp(v)))
+        sq = M_.multiply(M_)
+        row_norms, col_norms = np.asarray(sq.sum(axis=1)).ravel(), np.asarray(sq.sum(axis=0)).ravel()
+        step = 2.0 / (gamma * (it + 1.0))
+        u = np.clip(u - step * (row_norms - alpha2 + gamma * u), opt.equilibration_lb, opt.equilibration_ub)
+        v = v - step * (col_norms - beta2 + gamma * v)
+        v = np.clip(np.full(n, v.sum() / n), 0.0, opt.equilibration_ub)
+        u_ = 2.0 * u / (it + 2.0) + it * u_ / (it + 2.0)
+        v_ = 2.0 * v / (it + 2.0) + it * v_ / (it + 2.0)
+    return np.exp(u_), np.exp(v_)
+
+
 def solve_exact(aff: AffineSets, con: ConicSets, opt: Options, max_iter: int):
     n, p, m = aff.n, aff.p, aff.m
     norm_b, norm_h, norm_c = np.linalg.norm(aff.b), np.linalg.norm(aff.h), np.linalg.norm(aff.c)
@@ -39,6 +58,24 @@ def solve_exact(aff: AffineSets, con: ConicSets, opt: Options, max_iter: int):
     A = sp.csc_matrix(aff.A)[:, ord_] if p else sp.csc_matrix((0, n))
     G = sp.csc_matrix(aff.G)[:, ord_] if m else sp.csc_matrix((0, n))
     c = np.asarray(aff.c, dtype=float)[ord_].copy()
+    b, h = np.asarray(aff.b, float).copy(), np.asarray(aff.h, float).copy()
+    # diagonal preconditioning (pdhg.jl:64-93)
+    use_eq = bool(opt.equilibration)
+    M0 = sp.vstack([A, G]).tocsc()
+    if use_eq:
+        dense_min = min(M0.data.min(initial=np.inf), 0.0 if M0.nnz < M0.shape[0] * M0.shape[1] else np.inf)
+        dense_max = max(M0.data.max(initial=-np.inf), 0.0 if M0.nnz < M0.shape[0] * M0.shape[1] else -np.inf)
+        if dense_min / dense_max <= opt.equilibration_limit:
+            use_eq = False
+    if opt.equilibration_force:
+        use_eq = True
+    E_eq = D_eq = None
+    if use_eq:
+        E_eq, D_eq = equilibrate(M0, opt)
+        Ms = sp.diags(E_eq) @ M0 @ sp.diags(D_eq)
+        A, G = sp.csc_matrix(Ms[:p]), sp.csc_matrix(Ms[p:])
+        b, h = E_eq[:p] * b, E_eq[p:] * h
+        c = D_eq * c
     # norm_scaling (scaling.jl:28-58)
     scale = np.ones(n)
     off = 0
@@ -56,7 +93,6 @@ def solve_exact(aff: AffineSets, con: ConicSets, opt: Options, max_iter: int):
     M = sp.vstack([A @ D, G @ D]).tocsr()
     Mt = M.T.tocsr()
     c = c * scale
-    b, h = np.asarray(aff.b, float), np.asarray(aff.h, float)
     fro = np.sqrt((M.data ** 2).sum())
     tau = 1.0 / (fro if fro >= 1e-10 else 1.0)
     tau_old, sigma, theta, beta, adapt = tau, tau, opt.initial_theta, opt.initial_beta, opt.initial_adapt_level
@@ -200,6 +236,9 @@ def solve_exact(aff: AffineSets, con: ConicSets, opt: Options, max_iter: int):
     for (o, side, ii, jj) in blocks:
         seg = xs[o:o + len(ii)]
         xs[o:o + len(ii)] = np.where(ii != jj, seg / sqrt2, seg)
+    if use_eq:                                   # pdhg.jl:751-755
+        xs = D_eq * xs
+        y = E_eq * y
     primal = np.zeros(n)
     primal[ord_] = xs
     return dict(status=status, iter=k, primal=primal, y=y, trace=np.array(trace))

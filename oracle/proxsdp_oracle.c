@@ -228,6 +228,7 @@ typedef struct {
     int64_t n, p, m, R;
     csc_t A, G, A_orig, G_orig, M, Mt;
     double *b, *h, *c, *b_orig, *h_orig, *c_orig;
+    double *eq_E, *eq_D;    /* diagonal preconditioners of equilibrate! (NULL when equilibration is off) */
     int64_t n_sdp, n_soc;
     int64_t* sdp_side;
     int64_t* sdp_off;       /* offset of cone k's svec block in x */
@@ -639,6 +640,10 @@ static double dual_feas_y(state_t* s, const double* y, const double* c) {
 static void cache_solution(state_t* s, const opts_t* opt, const double* c, proxsdp_result_t* out) {
     fix_diag_scaling(s, s->x, sqrt(2.0));
     int64_t n = s->n, p = s->p, m = s->m;
+    if (opt->equilibration && s->eq_E) {          /* remove equilibrating (pdhg.jl:751-755) */
+        for (int64_t j = 0; j < n; ++j) s->x[j] = s->eq_D[j] * s->x[j];
+        for (int64_t i = 0; i < p + m; ++i) s->y[i] = s->eq_E[i] * s->y[i];
+    }
     double* slack_eq = (double*)calloc((size_t)(p > 0 ? p : 1), sizeof(double));
     double* slack_in = (double*)calloc((size_t)(m > 0 ? m : 1), sizeof(double));
     double* dual_cone = (double*)calloc((size_t)(n > 0 ? n : 1), sizeof(double));
@@ -674,6 +679,50 @@ static void cache_solution(state_t* s, const opts_t* opt, const double* c, proxs
     out->final_primal_res = circ_get(&s->primal_residual, s->iter);
     out->final_dual_res = circ_get(&s->dual_residual, s->iter);
     free(slack_eq); free(slack_in); free(dual_cone);
+}
+
+/* equilibrate! (equilibration.jl:1-71): Ruiz-like diagonal scaling by projected gradient steps on
+   sum_ij (E_i M_ij D_j)^2 with averaged iterates; the column scaling is re-set to its mean in every step */
+static void eq_box_project(double* y, int64_t len, double lb, double ub) {
+    for (int64_t i = 0; i < len; ++i) y[i] = fmin(ub, fmax(y[i], lb));
+}
+static void equilibrate(const csc_t* M, int64_t n, int64_t R, const opts_t* opt, double* E, double* D) {
+    int64_t max_iters = opt->equilibration_iters;
+    double lb = opt->equilibration_lb, ub = opt->equilibration_ub;
+    double alpha = pow((double)n / (double)R, 0.25), beta = pow((double)R / (double)n, 0.25);
+    double alpha2 = alpha * alpha, beta2 = beta * beta, gamma = 0.1;
+    double* u = (double*)calloc((size_t)R + 1, sizeof(double));
+    double* v = (double*)calloc((size_t)n + 1, sizeof(double));
+    double* u_ = (double*)calloc((size_t)R + 1, sizeof(double));
+    double* v_ = (double*)calloc((size_t)n + 1, sizeof(double));
+    double* row_norms = (double*)calloc((size_t)R + 1, sizeof(double));
+    double* col_norms = (double*)calloc((size_t)n + 1, sizeof(double));
+    for (int64_t iter = 1; iter <= max_iters; ++iter) {
+        for (int64_t i = 0; i < R; ++i) E[i] = exp(u[i]);
+        for (int64_t j = 0; j < n; ++j) D[j] = exp(v[j]);
+        double step_size = 2.0 / (gamma * ((double)iter + 1.0));
+        for (int64_t i = 0; i < R; ++i) row_norms[i] = 0.0;
+        for (int64_t j = 0; j < n; ++j) {
+            double cn = 0.0;
+            for (int64_t q = M->colptr[j]; q < M->colptr[j + 1]; ++q) {
+                double w = E[M->rowidx[q]] * (M->val[q] * D[j]);      /* mul!(M_, M, D); mul!(M_, E, M_) */
+                row_norms[M->rowidx[q]] += w * w;
+                cn += w * w;
+            }
+            col_norms[j] = cn;
+        }
+        for (int64_t i = 0; i < R; ++i) u[i] -= step_size * (row_norms[i] - alpha2 + gamma * u[i]);
+        eq_box_project(u, R, lb, ub);
+        double sum_v = 0.0;
+        for (int64_t j = 0; j < n; ++j) { v[j] -= step_size * (col_norms[j] - beta2 + gamma * v[j]); sum_v += v[j]; }
+        for (int64_t j = 0; j < n; ++j) v[j] = sum_v / (double)n;
+        eq_box_project(v, n, 0.0, ub);
+        for (int64_t i = 0; i < R; ++i) u_[i] = 2.0 * u[i] / ((double)iter + 2.0) + (double)iter * u_[i] / ((double)iter + 2.0);
+        for (int64_t j = 0; j < n; ++j) v_[j] = 2.0 * v[j] / ((double)iter + 2.0) + (double)iter * v_[j] / ((double)iter + 2.0);
+    }
+    for (int64_t i = 0; i < R; ++i) E[i] = exp(u_[i]);
+    for (int64_t j = 0; j < n; ++j) D[j] = exp(v_[j]);
+    free(u); free(v); free(u_); free(v_); free(row_norms); free(col_norms);
 }
 
 /* certificate_parameters (pdhg.jl:670-676) */
@@ -762,7 +811,7 @@ static int oracle_solve_impl(const proxsdp_problem_t* prob, const proxsdp_option
     int64_t R = s->R;
     s->shard = shard;
     if (shard) { s->global_n = shard->global_n; s->global_R = shard->global_p + shard->global_m; }
-    if (opt->equilibration || opt->equilibration_force) return -2;   /* out of scope */
+    if ((opt->equilibration || opt->equilibration_force) && shard) return -2;   /* row / column norms of the whole M needed */
 
     /* Params (pdhg.jl:7-31) */
     s->theta = opt->initial_theta;
@@ -855,6 +904,40 @@ static int oracle_solve_impl(const proxsdp_problem_t* prob, const proxsdp_option
     /* copies before scaling (pdhg.jl:59-61) */
     s->A_orig = csc_copy(&s->A);
     s->G_orig = csc_copy(&s->G);
+
+    /* diagonal preconditioning (pdhg.jl:64-93) */
+    if (opt->equilibration) {
+        csc_t M0 = csc_vstack(&s->A, &s->G);
+        /* maximum(M) / minimum(M) of a SparseMatrixCSC run over the structural zeros as well */
+        double UB = 0.0, LB = 0.0;
+        int have = 0;
+        for (int64_t q = 0; q < M0.nnz; ++q) {
+            if (!have || M0.val[q] > UB) UB = M0.val[q];
+            if (!have || M0.val[q] < LB) LB = M0.val[q];
+            have = 1;
+        }
+        if ((double)M0.nnz < (double)R * (double)n) { if (!have || 0.0 > UB) UB = 0.0; if (!have || 0.0 < LB) LB = 0.0; }
+        if (LB / UB <= opt->equilibration_limit) opt->equilibration = 0;
+        csc_free(&M0);
+    }
+    /* (with equilibration_force alone the reference reaches equilibrate! with M undefined, pdhg.jl:74-78: an
+       UndefVarError.  Here the forced case runs on M = [A; G] like the unforced one — what the author meant.) */
+    if (opt->equilibration_force) opt->equilibration = 1;
+    if (opt->equilibration) {
+        csc_t M0 = csc_vstack(&s->A, &s->G);
+        s->eq_E = (double*)calloc((size_t)R + 1, sizeof(double));
+        s->eq_D = (double*)calloc((size_t)n + 1, sizeof(double));
+        equilibrate(&M0, n, R, opt, s->eq_E, s->eq_D);
+        /* M = E * M * D (left to right), A / G = its row blocks, rhs = E * rhs, c = D * c */
+        for (int64_t j = 0; j < n; ++j) {
+            for (int64_t q = s->A.colptr[j]; q < s->A.colptr[j + 1]; ++q) s->A.val[q] = (s->eq_E[s->A.rowidx[q]] * s->A.val[q]) * s->eq_D[j];
+            for (int64_t q = s->G.colptr[j]; q < s->G.colptr[j + 1]; ++q) s->G.val[q] = (s->eq_E[p + s->G.rowidx[q]] * s->G.val[q]) * s->eq_D[j];
+            s->c[j] = s->eq_D[j] * s->c[j];
+        }
+        for (int64_t i = 0; i < p; ++i) s->b[i] = s->eq_E[i] * s->b_orig[i];
+        for (int64_t i = 0; i < m; ++i) s->h[i] = s->eq_E[p + i] * s->h_orig[i];
+        csc_free(&M0);
+    }
 
     /* norm_scaling (scaling.jl:28-58) */
     {
@@ -1191,7 +1274,7 @@ static int oracle_solve_impl(const proxsdp_problem_t* prob, const proxsdp_option
 
     /* free */
     csc_free(&s->A); csc_free(&s->G); csc_free(&s->A_orig); csc_free(&s->G_orig); csc_free(&s->M); csc_free(&s->Mt);
-    free(s->b); free(s->h); free(s->c); free(s->b_orig); free(s->h_orig); free(s->c_orig);
+    free(s->b); free(s->h); free(s->c); free(s->b_orig); free(s->h_orig); free(s->c_orig); free(s->eq_E); free(s->eq_D);
     free(s->sdp_side); free(s->sdp_off); free(s->soc_off); free(s->soc_len); free(s->var_ordering);
     free(s->x); free(s->x_old); free(s->y); free(s->y_old); free(s->Mty); free(s->Mty_old);
     free(s->Mx); free(s->Mx_old); free(s->y_half); free(s->y_temp);

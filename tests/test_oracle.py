@@ -250,3 +250,42 @@ def test_step_seams_against_numpy_restatement(oracle_mod):
         t *= opt.linsearch_decay
     assert trials == it + 1 and abs(sc["primal_step"] - t) <= 1e-15 and abs(sc["theta"] - theta) <= 1e-15
     assert np.abs(yn - yt).max() <= 1e-13 and np.abs(Mn - Mt).max() <= 1e-13
+
+
+@pytest.mark.parametrize("which", ["C1", "mimo8", "sdp_badly_scaled"])
+def test_equilibration_vs_numpy_mirror(oracle_mod, which):
+    """equilibrate! (reference src/equilibration.jl:1-71) and its use in setup / result assembly (src/pdhg.jl:64-93,
+    751-755): the C oracle against the numpy mirror, exact-projection mode, forced equilibration."""
+    from oracle import oracle_np
+    if which == "C1":
+        aff, con = maxcut_problem(README_W)[:2]
+    elif which == "mimo8":
+        aff, con = mimo_problem(1, 8)
+    else:
+        # rows of very different magnitude: the case the preconditioner is for
+        aff, con = mimo_problem(2, 6)
+        scale = np.logspace(-2, 2, aff.p)
+        import scipy.sparse as sp
+        aff.A = sp.csc_matrix(sp.diags(scale) @ aff.A)
+        aff.b = scale * aff.b
+    opt = Options(full_eig_decomp=True, trace_cap=300, max_iter=300, equilibration_force=True, equilibration_iters=200)
+    ro = oracle_mod.chambolle_pock(aff, con, opt)
+    rn = oracle_np.solve_exact(aff, con, opt, 300)
+    plain = oracle_mod.chambolle_pock(aff, con, Options(full_eig_decomp=True, trace_cap=300, max_iter=300))
+    assert ro.iter == rn["iter"]
+    k = len(rn["trace"])
+    a, b = ro.trace[:k, 1:9], rn["trace"][:k, 1:9]
+    assert np.abs(a - b).max() <= 1e-6 * max(1.0, np.abs(b).max())
+    assert np.abs(ro.primal - rn["primal"]).max() < 1e-8 * max(1.0, np.abs(rn["primal"]).max())
+    assert np.abs(np.concatenate([ro.dual_eq, ro.dual_in]) - rn["y"]).max() < 1e-8 * max(1.0, np.abs(rn["y"]).max())
+    # the preconditioner changed the trajectory (the test would be vacuous otherwise)
+    kk = min(len(plain.trace), k)
+    assert np.abs(plain.trace[:kk, 1:9] - ro.trace[:kk, 1:9]).max() > 1e-6
+
+
+def test_equilibration_switches_itself_off(oracle_mod):
+    """pdhg.jl:66-73: with min(M) / max(M) <= equilibration_limit (any sparse M: min = 0) the option is dropped."""
+    aff, con = mimo_problem(1, 6)
+    a = oracle_mod.chambolle_pock(aff, con, Options(equilibration=True, max_iter=50, trace_cap=50))
+    b = oracle_mod.chambolle_pock(aff, con, Options(max_iter=50, trace_cap=50))
+    assert np.array_equal(a.trace[:, 1:9], b.trace[:, 1:9]) and np.array_equal(a.primal, b.primal)
