@@ -339,7 +339,147 @@ void upload_async(DBuf<T>& d, const T* h, size_t count, cudaStream_t s) {
     g_h2d_bytes += (long long)(count * sizeof(T));
 }
 
+// ---------------------------------------------------------------------------
+// equilibrate! (reference src/equilibration.jl:1-71) on the device
+// ---------------------------------------------------------------------------
+// The reference re-sets the column scaling v to its mean in every step (equilibration.jl:56-58), so v is one number and
+// D = exp(v) I.  With that the step only sees M through the row sums r_i = sum_j M_ij^2:
+//   row_norms_i = (exp(u_i) exp(v))^2 r_i,      sum_j col_norms_j = sum_i row_norms_i,
+// and the whole iteration is R independent scalar recurrences coupled by one sum per step.  One CTA walks all steps
+// (rows strided over its 1024 threads, the sum folded in a fixed order: bit-reproducible); u and its running average
+// live in global memory.  out[0] = 1 if the preconditioner is applied, out[1] = d = exp(mean-averaged v).
+struct EqArgs {
+    const int* rowptr; const double* val_o; long long R, n, nnz;
+    double lb, ub, limit; long long iters; int enabled, force;
+    double* u; double* ubar; double* r; double* E; double* out;
+};
+__global__ void __launch_bounds__(1024) k_equilibrate(EqArgs a) {
+    __shared__ double red[40];
+    __shared__ double s_min[32], s_max[32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // ---- pdhg.jl:66-73: maximum(M) / minimum(M) run over the structural zeros of the sparse matrix as well
+    int on = a.enabled;
+    if (on) {
+        double mn = INFINITY, mx = -INFINITY;
+        for (long long k = tid; k < a.nnz; k += blockDim.x) { const double v = a.val_o[k]; mn = fmin(mn, v); mx = fmax(mx, v); }
+        for (int o = 16; o; o >>= 1) { mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o)); mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o)); }
+        if (lane == 0) { s_min[warp] = mn; s_max[warp] = mx; }
+        __syncthreads();
+        mn = s_min[0]; mx = s_max[0];
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) { mn = fmin(mn, s_min[w]); mx = fmax(mx, s_max[w]); }
+        if ((double)a.nnz < (double)a.R * (double)a.n) { mn = fmin(mn, 0.0); mx = fmax(mx, 0.0); }
+        if (mn / mx <= a.limit) on = 0;
+    }
+    if (a.force) on = 1;
+    if (tid == 0) { a.out[0] = on ? 1.0 : 0.0; a.out[1] = 1.0; }
+    if (!on) return;
+    // ---- r_i, u = ubar = 0
+    for (long long i = tid; i < a.R; i += blockDim.x) {
+        double s0 = 0.0;
+        for (int k = a.rowptr[i]; k < a.rowptr[i + 1]; ++k) { const double v = a.val_o[k]; s0 = fma(v, v, s0); }
+        a.r[i] = s0; a.u[i] = 0.0; a.ubar[i] = 0.0;
+    }
+    const double alpha2 = sqrt((double)a.n / (double)a.R), beta2 = sqrt((double)a.R / (double)a.n), gamma = 0.1;
+    double v = 0.0, vbar = 0.0;
+    for (long long it = 1; it <= a.iters; ++it) {
+        const double step = 2.0 / (gamma * ((double)it + 1.0));
+        const double dv = exp(v);
+        const double w2 = 2.0 / ((double)it + 2.0), w1 = (double)it / ((double)it + 2.0);
+        double S = 0.0;
+        for (long long i = tid; i < a.R; i += blockDim.x) {
+            double u = a.u[i];
+            const double e = exp(u) * dv;
+            const double rn = e * e * a.r[i];
+            S += rn;
+            u -= step * (rn - alpha2 + gamma * u);
+            u = fmin(a.ub, fmax(u, a.lb));
+            a.u[i] = u;
+            a.ubar[i] = w2 * u + w1 * a.ubar[i];
+        }
+        S = block_sum(S, red);
+        // mean over the columns of  v_j - step (col_norms_j - beta2 + gamma v_j)
+        v = v - step * (S / (double)a.n - beta2 + gamma * v);
+        v = fmin(a.ub, fmax(v, 0.0));
+        vbar = w2 * v + w1 * vbar;
+    }
+    for (long long i = tid; i < a.R; i += blockDim.x) a.E[i] = exp(a.ubar[i]);
+    if (tid == 0) a.out[1] = exp(vbar);
+}
+
+// working values of M (transposed == 0: row = constraint, colidx = position) or M' (transposed == 1: compact row =
+// position nz_rows[q], colidx = constraint) from the caller's values: ((E_i v) d), then norm_scaling's sqrt(2)/2 on
+// the off-diagonal positions — the order of pdhg.jl:80 (E * M * D) and scaling.jl:28-58.  One warp per row.
+__global__ void k_eq_apply(const int* __restrict__ rowptr, int nrows, const int* __restrict__ nz_rows,
+                           const int* __restrict__ colidx, const double* __restrict__ val_o, double* __restrict__ val,
+                           const double* __restrict__ E, const double* __restrict__ dptr, int transposed, long long psd_end,
+                           const long long* __restrict__ cone_off, int n_sdp) {
+    const long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (wid >= nrows) return;
+    const int rowid = nz_rows ? nz_rows[wid] : (int)wid;
+    const double d = *dptr;
+    for (int k = rowptr[wid] + lane; k < rowptr[wid + 1]; k += 32) {
+        const int i = transposed ? colidx[k] : rowid;
+        const long long pos = transposed ? rowid : colidx[k];
+        const double w = __dmul_rn(__dmul_rn(E[i], val_o[k]), d);
+        val[k] = offdiag_position(pos, psd_end, cone_off, n_sdp) ? __dmul_rn(w, 0.70710678118654752440) : w;
+    }
+}
+__global__ void k_eq_mul(const double* __restrict__ src, const double* __restrict__ E, long long len, double* __restrict__ dst) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += stride) dst[i] = __dmul_rn(E[i], src[i]);
+}
+__global__ void k_eq_mul_scalar(const double* __restrict__ src, const double* __restrict__ dptr, long long len, double* __restrict__ dst) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const double d = *dptr;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += stride) dst[i] = __dmul_rn(d, src[i]);
+}
+
 }  // namespace
+
+void launch_eq_mul(const double* src, const double* E, long long len, double* dst, cudaStream_t stream) {
+    if (len > 0) k_eq_mul<<<(int)std::min<long long>((len + 255) / 256, 148 * 8), 256, 0, stream>>>(src, E, len, dst);
+}
+void launch_eq_mul_scalar(const double* src, const double* dptr, long long len, double* dst, cudaStream_t stream) {
+    if (len > 0) k_eq_mul_scalar<<<(int)std::min<long long>((len + 255) / 256, 148 * 8), 256, 0, stream>>>(src, dptr, len, dst);
+}
+
+bool equilibrate_device(CsrDev& M, CsrDev& Mt, long long n, long long R, const proxsdp_options_t& opt,
+                        const long long* cone_off_d, int n_sdp, long long psd_end, cudaStream_t stream, EquilibrateOut& out) {
+    out.applied = false;
+    if (n <= 0 || R <= 0 || M.nnz <= 0) return false;       // nothing to scale
+    DBuf<double> u, ubar, r, partials;
+    u.alloc_raw((size_t)R); ubar.alloc_raw((size_t)R); r.alloc_raw((size_t)R);
+    out.E.alloc_raw((size_t)R); out.d.alloc_raw(4);
+    EqArgs a{};
+    a.rowptr = M.rowptr.p; a.val_o = M.val_orig.p; a.R = R; a.n = n; a.nnz = M.nnz;
+    a.lb = opt.equilibration_lb; a.ub = opt.equilibration_ub; a.limit = opt.equilibration_limit;
+    a.iters = opt.equilibration_iters; a.enabled = opt.equilibration ? 1 : 0; a.force = opt.equilibration_force ? 1 : 0;
+    a.u = u.p; a.ubar = ubar.p; a.r = r.p; a.E = out.E.p; a.out = out.d.p + 2;
+    k_equilibrate<<<1, 1024, 0, stream>>>(a);
+    out.launches++;
+    double h[2] = {0.0, 1.0};
+    PB_CUDA(cudaMemcpyAsync(h, out.d.p + 2, sizeof(double) * 2, cudaMemcpyDeviceToHost, stream));
+    PB_CUDA(cudaStreamSynchronize(stream));
+    g_d2h_bytes += 16;
+    if (h[0] == 0.0) { out.E.release(); out.d.release(); return false; }
+    out.applied = true;
+    out.d_host = h[1];
+    PB_CUDA(cudaMemcpyAsync(out.d.p, out.d.p + 3, sizeof(double), cudaMemcpyDeviceToDevice, stream));    // d at slot 0
+    k_eq_apply<<<ceil_div((long long)M.nrows * 32, 256), 256, 0, stream>>>(M.rowptr.p, M.nrows, nullptr, M.colidx.p, M.val_orig.p,
+                                                                           M.val.p, out.E.p, out.d.p, 0, psd_end, cone_off_d, n_sdp);
+    k_eq_apply<<<ceil_div((long long)Mt.n_nz * 32, 256), 256, 0, stream>>>(Mt.rowptr.p, Mt.n_nz, Mt.nz_rows.p, Mt.colidx.p, Mt.val_orig.p,
+                                                                           Mt.val.p, out.E.p, out.d.p, 1, psd_end, cone_off_d, n_sdp);
+    const int red_blocks = 148 * 4;
+    partials.alloc_raw((size_t)red_blocks + 1);
+    k_sumsq_partial<<<red_blocks, 256, 0, stream>>>(Mt.val.p, Mt.nnz, partials.p);
+    k_sum_fold<<<1, 256, 0, stream>>>(partials.p, red_blocks, partials.p + red_blocks);
+    out.launches += 4;
+    PB_CUDA(cudaMemcpyAsync(&out.fro2, partials.p + red_blocks, sizeof(double), cudaMemcpyDeviceToHost, stream));
+    PB_CUDA(cudaStreamSynchronize(stream));      // also keeps u / ubar / r alive until the kernel is done
+    g_d2h_bytes += 8;
+    return true;
+}
 
 void launch_gather(const double* src, const int* perm, long long n, double* out, cudaStream_t stream) {
     if (n <= 0) return;

@@ -104,6 +104,25 @@ struct ConeTable {
 void ingest_problem(const proxsdp_problem_t* prob, const ConeTable& cones, const int* cone_side_d,
                     const long long* cone_off_d, bool want_matrices, cudaStream_t stream, IngestOut& out);
 
+// equilibrate! (reference src/equilibration.jl:1-71) and the scaling M <- E M D of src/pdhg.jl:64-93 on the device.
+// Decides like the reference (option, min(M) / max(M) against equilibration_limit, equilibration_force); when the
+// preconditioner is applied the working values of M and M' are rebuilt from the caller's values, fro2 = ||M||_F^2 of
+// the new working matrix.  D is a multiple of the identity by construction (the reference re-sets the column scaling to
+// its mean in every step), so it is kept as one number: d[0] on the device, d_host on the host.
+struct EquilibrateOut {
+    bool applied = false;
+    DBuf<double> E;                   // R row scalings
+    DBuf<double> d;                   // d[0] = the column scaling
+    double d_host = 1.0;
+    double fro2 = 0.0;
+    long long launches = 0;
+};
+bool equilibrate_device(CsrDev& M, CsrDev& Mt, long long n, long long R, const proxsdp_options_t& opt,
+                        const long long* cone_off_d, int n_sdp, long long psd_end, cudaStream_t stream, EquilibrateOut& out);
+// dst[i] = E[i] * src[i] ; dst[i] = d[0] * src[i]   (src == dst allowed)
+void launch_eq_mul(const double* src, const double* E, long long len, double* dst, cudaStream_t stream);
+void launch_eq_mul_scalar(const double* src, const double* dptr, long long len, double* dst, cudaStream_t stream);
+
 // out[i] = src[perm ? perm[i] : i]
 void launch_gather(const double* src, const int* perm, long long n, double* out, cudaStream_t stream);
 

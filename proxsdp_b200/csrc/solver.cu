@@ -312,6 +312,7 @@ class Solver {
     CsrDev M_, Mt_;
     DBuf<int> ord_d_, var_ordering_d_;             // empty when identity_
     DBuf<double> c_orig_d_, b_orig_d_, h_orig_d_;  // un-scaled objective (position order) and right-hand sides
+    DBuf<double> eq_E_d_, eq_d_d_;                 // equilibrate!: row scalings E (R), column scaling d[0] (D = d I)
     DBuf<double> res_x_d_, res_dc_d_, res_user_d_, res_slack_d_, feas_d_, scal_scratch_d_;
     double* scal_target_ = nullptr;                // scalar record the eigen kernels write to (scal_d_ inside the loop)
     // the iteration record reaches the host through mapped page-locked memory (scal_host) + a sequence word
@@ -467,8 +468,8 @@ void Solver::setup_host(const proxsdp_problem_t* prob) {
     const long long base = prob->index_base;
     n_sdp = (int)prob->n_sdp; n_soc = (int)prob->n_soc;
     if (n < 0 || p < 0 || m < 0 || (base != 0 && base != 1)) throw CudaError(-1, "invalid problem sizes");
-    if (opt.equilibration || opt.equilibration_force)
-        throw CudaError(-2, "equilibration is not supported by the B200 path (off by default in the reference)");
+    if ((opt.equilibration || opt.equilibration_force) && sharded())
+        throw CudaError(-2, "equilibration needs the row norms of the whole constraint matrix: not available on the sharded path");
     if (!opt.approx_norm) throw CudaError(-2, "approx_norm=false (exact spectral norm) is not supported");
     if (n >= (1LL << 31) - 64 || R >= (1LL << 31) - 64) throw CudaError(-1, "problem too large for 32-bit indices");
 
@@ -518,6 +519,17 @@ void Solver::setup_host(const proxsdp_problem_t* prob) {
     b_host_.assign(prob->b, prob->b + p); h_host_.assign(prob->h, prob->h + m);
     st.lap("setup: params + vectors");
 
+    // diagonal preconditioning (pdhg.jl:64-93, equilibration.jl); like the reference this mutates opt.equilibration
+    if ((opt.equilibration || opt.equilibration_force) && !cones_only_) {
+        EquilibrateOut eq;
+        opt.equilibration = equilibrate_device(M_, Mt_, n, R, opt, cone_off_d_.p, n_sdp, psd_end_, stream, eq) ? 1 : 0;
+        launches += eq.launches;
+        if (opt.equilibration) { eq_E_d_ = std::move(eq.E); eq_d_d_ = std::move(eq.d); ing.fro2 = eq.fro2; }
+    } else {
+        opt.equilibration = 0;
+    }
+    const bool equilibrated = opt.equilibration != 0;
+
     // step size: 1 / ||M||_F (pdhg.jl:121-133)
     double fro = ing.fro2;
     double any_cone = (n_soc > 0 || n_sdp > 0) ? 1.0 : 0.0, any_soc = n_soc > 0 ? 1.0 : 0.0;
@@ -551,12 +563,19 @@ void Solver::setup_host(const proxsdp_problem_t* prob) {
     // *= sqrt(2)/2); the un-scaled copy stays for the dual cone of the result (pdhg.jl:701-710)
     c_.alloc_raw((size_t)n);
     if (n > 0) {
+        const double* c_src = c_orig_d_.p;
+        if (equilibrated) { launch_eq_mul_scalar(c_orig_d_.p, eq_d_d_.p, n, c_.p, stream); launches++; c_src = c_.p; }    // c = D c (pdhg.jl:86)
         k_scale_offdiag_copy<<<std::max(1, std::min(num_sms_ * 8, ceil_div(n, 256))), 256, 0, stream>>>(
-            c_orig_d_.p, n, psd_end_, cone_off_d_.p, n_sdp, cte, 0, c_.p);
+            c_src, n, psd_end_, cone_off_d_.p, n_sdp, cte, 0, c_.p);
         launches++;
     }
     b_.upload(b_host_); h_.upload(h_host_);
     b_orig_d_.upload(b_host_); h_orig_d_.upload(h_host_);
+    if (equilibrated) {      // rhs = E rhs (pdhg.jl:83-85); the uploads above went through the legacy stream: ordered
+        launch_eq_mul(b_.p, eq_E_d_.p, p, b_.p, stream);
+        launch_eq_mul(h_.p, eq_E_d_.p + p, m, h_.p, stream);
+        launches += (p > 0) + (m > 0);
+    }
     for (int q = 0; q < 2; ++q) { x_[q].alloc((size_t)n); Mty_[q].alloc((size_t)n); y_[q].alloc((size_t)R); Mx_[q].alloc((size_t)R); }
     if (n > 0 && !getenv("PROXSDP_B200_NO_NZMASK")) {
         // (Mty is only ever written at the non-empty rows of M', c is fixed: the bitmap is built once)
@@ -1602,6 +1621,11 @@ void Solver::cache_solution(double c_factor, proxsdp_result_t* out) {
     if (n_sdp > 0 && n > 0) {
         k_scale_offdiag_copy<<<blocks_n, 256, 0, stream>>>(x_[cur_].p, n, psd_end_, cone_off_d_.p, n_sdp, std::sqrt(2.0), 1, x_[cur_].p);
         launches++;
+    }
+    if (opt.equilibration && eq_E_d_.p) {        // remove equilibrating (pdhg.jl:751-755), in place like the reference
+        launch_eq_mul_scalar(x_[cur_].p, eq_d_d_.p, n, x_[cur_].p, stream);
+        launch_eq_mul(y_[cur_].p, eq_E_d_.p, R, y_[cur_].p, stream);
+        launches += (n > 0) + (R > 0);
     }
     const double* xw = x_[cur_].p;
     const double* yw = y_[cur_].p;

@@ -10,6 +10,9 @@ restatement (both scripts restate the device arithmetic in numpy / Python floats
   quotient of a thick restart back into a tridiagonal by a small Lanczos run with a DGKS loop and a relative breakdown test
   (KrylovKit: dense `tridiageigh!` and a Householder reduction) -> scripts/ritz_restart_check.py checks both against LAPACK,
   the restart on repeated values and on zero / negligible / graded couplings.
+* runtime.cu `k_equilibrate` walks equilibrate! as R scalar recurrences coupled by one sum (the reference's column
+  scaling is a multiple of the identity by construction) -> scripts/equilibrate_check.py compares E and D with the literal
+  restatement (oracle/oracle_np.py) on sparse matrices with badly scaled rows.
 """
 import importlib.util
 import os
@@ -34,3 +37,7 @@ def test_scaled_sturm_count_matches_lapack():
 
 def test_ritz_values_and_retridiagonalising_restart_match_lapack():
     assert _load("ritz_restart_check").main() == 0
+
+
+def test_collapsed_equilibration_matches_literal_restatement():
+    assert _load("equilibrate_check").main() == 0

@@ -459,10 +459,61 @@ def test_full_solves_end_at_certified_optima(gpu, golden_dir, which):
     assert r.status == 1
     k = certificate(aff, con, r)
     side = con.sdpcone[0].sq_side
-    assert k["eq"] <= 1e-4 and k["ineq"] <= 1e-4 and k["lam_x"] >= -1e-6 and k["y_in_min"] >= -1e-9
-    assert abs(k["trace"] - side) <= 1e-2                    # diag(X) = 1 in all four families
+    # the solver's feasibility measure is relative to 1 + ||b|| (reference src/residuals.jl:2-35)
+    tol_eq = 2.0 * opt.tol_feasibility * (1.0 + np.linalg.norm(aff.b))
+    tol_in = 2.0 * opt.tol_feasibility * (1.0 + np.linalg.norm(aff.h))
+    assert k["eq"] <= tol_eq and k["ineq"] <= tol_in and k["lam_x"] >= -1e-6 and k["y_in_min"] >= -1e-9
+    assert abs(k["trace"] - side) <= side * tol_eq           # diag(X) = 1 in all four families
     lower = k["dual"] + min(k["lam_s"], 0.0) * side
     scale = 1.0 + abs(k["primal"])
-    assert lower <= k["primal"] + 1e-5 * scale, k            # X is feasible to 1e-5 only
+    assert lower <= k["primal"] + 1e-4 * scale, k            # X is feasible to tol_eq only: it may undercut the bound by |y|_1 tol_eq
     assert k["primal"] - lower <= 2e-3 * scale, k
     assert abs(r.objval - k["primal"]) <= 1e-9 * scale and abs(r.dual_objval - k["dual"]) <= 1e-6 * scale
+
+
+@pytest.mark.parametrize("which", ["C1", "mimo8", "badly_scaled_rows", "mcp124-1-krylov", "permuted"])
+def test_equilibration_vs_oracle(gpu, oracle_mod, golden_dir, which):
+    """`equilibrate!` on the device (reference src/equilibration.jl:1-71) and the scaled setup / un-scaled result of
+    src/pdhg.jl:64-93, 751-755: traces, primal, duals, slacks and dual cone against the oracle."""
+    from proxsdp_b200.problems import README_W, maxcut_problem
+    kw = dict(full_eig_decomp=True)
+    if which == "C1":
+        aff, con = maxcut_problem(README_W)[:2]
+    elif which == "mimo8":
+        aff, con = mimo_problem(1, 8)
+    elif which == "badly_scaled_rows":
+        aff, con = mimo_problem(2, 6)
+        scale = np.logspace(-2, 2, aff.p)
+        aff.A = sp.csc_matrix(sp.diags(scale) @ aff.A)
+        aff.b = scale * aff.b
+    elif which == "permuted":
+        aff, con = sensorloc_problem(1, 8, soc_variant=True)
+        aff, con, _ = _scrambled(aff, con, 5)
+    else:
+        aff, con = load_problem(f"{golden_dir}/sdplib_mcp124-1.npz")
+        kw = dict()
+    # equilibrate! itself is ill-conditioned on mcp124-1 (n / (p + m) = 62): its first steps (step sizes 10, 6.7, 5 ...)
+    # throw u between the two ends of its box, and a one-ulp difference between two exp() implementations comes out as
+    # 1e-6 ... 1e-5 relative in E (measured on the CPU by perturbing the restated iteration; device vs glibc: 1.2e-5).
+    # The reference has the same sensitivity to its libm.  Everything downstream is compared at that level.
+    rtol = 1e-6 if kw else 1e-3
+    iters = 200 if kw else 30      # truncated projections: trajectories are compared while rounding has not separated them
+    opt = Options(max_iter=iters, trace_cap=iters, equilibration_force=True, equilibration_iters=300, **kw)
+    rg = gpu.chambolle_pock(aff, con, opt)
+    ro = oracle_mod.chambolle_pock(aff, con, opt)
+    k = min(len(rg.trace), len(ro.trace))
+    assert k > 0 and len(rg.trace) == len(ro.trace)
+    assert np.abs(rg.trace[:k, 1:9] - ro.trace[:k, 1:9]).max() <= rtol * max(1.0, np.abs(ro.trace[:k, 1:9]).max())
+    _same_solution(rg, ro, rtol=rtol)
+    # not vacuous: the plain run differs
+    rp = gpu.chambolle_pock(aff, con, Options(max_iter=iters, trace_cap=iters, **kw))
+    kk = min(len(rp.trace), k)
+    assert np.abs(rp.trace[:kk, 1:9] - rg.trace[:kk, 1:9]).max() > 1e-2
+
+
+def test_equilibration_switches_itself_off(gpu):
+    """pdhg.jl:66-73: min(M) / max(M) <= equilibration_limit (every sparse M) drops the option: bit-identical to a plain run."""
+    aff, con = mimo_problem(1, 6)
+    a = gpu.chambolle_pock(aff, con, Options(equilibration=True, max_iter=50, trace_cap=50))
+    b = gpu.chambolle_pock(aff, con, Options(max_iter=50, trace_cap=50))
+    assert np.array_equal(a.trace[:, 1:9], b.trace[:, 1:9]) and np.array_equal(a.primal, b.primal)

@@ -104,7 +104,7 @@ def test_maxcut_full_solve_certified_optimum(oracle_mod, golden_dir, name, n):
     r = oracle_mod.chambolle_pock(aff, con, Options(tol_gap=1e-5, tol_feasibility=1e-5))
     assert r.status == 1 and r.lanczos_calls > 0
     k = _certificate(aff, con, r)
-    assert k["eq"] <= 1e-4 and k["lam_x"] >= -1e-6
+    assert k["eq"] <= 2e-5 * (1.0 + np.sqrt(n)) and k["lam_x"] >= -1e-6
     assert abs(k["trace"] - n) <= 1e-2
     lower = k["dual"] + min(k["lam_s"], 0.0) * n            # certified lower bound on the optimum
     assert lower <= k["primal"] + 1e-5 * abs(k["primal"])   # X is feasible to 1e-5 only, so it may undercut the bound by that
