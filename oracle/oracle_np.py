@@ -94,6 +94,12 @@ def solve_exact(aff: AffineSets, con: ConicSets, opt: Options, max_iter: int):
     Mt = M.T.tocsr()
     c = c * scale
     fro = np.sqrt((M.data ** 2).sum())
+    if not opt.approx_norm:                      # pdhg.jl:107-118: Arpack.svds(M, nsv = 1), dense svd below two rows / columns
+        import scipy.sparse.linalg as spla
+        if min(M.shape) >= 2:
+            fro = float(spla.svds(M.tocsc(), k=1, tol=0, return_singular_vectors=False)[0])
+        else:
+            fro = float(np.linalg.svd(M.toarray(), compute_uv=False).max(initial=0.0))
     tau = 1.0 / (fro if fro >= 1e-10 else 1.0)
     tau_old, sigma, theta, beta, adapt = tau, tau, opt.initial_theta, opt.initial_beta, opt.initial_adapt_level
     R = p + m

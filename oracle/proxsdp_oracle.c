@@ -725,6 +725,51 @@ static void equilibrate(const csc_t* M, int64_t n, int64_t R, const opts_t* opt,
     free(u); free(v); free(u_); free(v_); free(row_norms); free(col_norms);
 }
 
+/* sigma_max(M) = sqrt(lambda_max of the smaller Gram matrix), by the dense symmetric eigensolver below a side of 4000,
+   by power iteration on M M' beyond that (the reference: ARPACK svds; any converged method returns the same number) */
+static double exact_spectral_norm(const csc_t* M, const csc_t* Mt) {
+    int64_t R = M->nr, n = M->nc;
+    if (R == 0 || n == 0 || M->nnz == 0) return 0.0;
+    int64_t d = (R <= n) ? R : n;                /* side of the smaller Gram matrix: M M' or M' M */
+    if (d <= 4000) {
+        double* Gm = (double*)calloc((size_t)d * (size_t)d, sizeof(double));
+        double* w = (double*)calloc((size_t)d, sizeof(double));
+        double* Z = (double*)calloc((size_t)d * (size_t)d, sizeof(double));
+        /* Gram[i][j] = sum_c T[i][c] T[j][c]: T = M (columns = variables) for M M', T = M' (columns = constraints) for M' M */
+        const csc_t* T = (R <= n) ? M : Mt;
+        for (int64_t c = 0; c < T->nc; ++c)
+            for (int64_t q1 = T->colptr[c]; q1 < T->colptr[c + 1]; ++q1)
+                for (int64_t q2 = T->colptr[c]; q2 < T->colptr[c + 1]; ++q2) {
+                    int64_t i = T->rowidx[q1], j = T->rowidx[q2];
+                    if (i <= j) Gm[i + j * d] += T->val[q1] * T->val[q2];
+                }
+        int rc = oracle_eigh(d, Gm, w, Z);
+        double lam = rc == 0 ? w[d - 1] : -1.0;
+        free(Gm); free(w); free(Z);
+        return lam >= 0.0 ? sqrt(lam) : (rc == 0 ? 0.0 : -1.0);
+    }
+    double* v = (double*)calloc((size_t)R, sizeof(double));
+    double* t = (double*)calloc((size_t)n, sizeof(double));
+    double* w = (double*)calloc((size_t)R, sizeof(double));
+    uint64_t seed = 1234;
+    for (int64_t i = 0; i < R; ++i) v[i] = 0.5 + sm_uniform(&seed);
+    double nv = vnorm2(R, v), lam = 0.0, lam_old = -1.0;
+    for (int64_t i = 0; i < R; ++i) v[i] /= nv;
+    int ok = 0;
+    for (int it = 0; it < 200000; ++it) {
+        csc_mul(Mt, v, t);
+        csc_mul(M, t, w);
+        lam = vdot(R, v, w);
+        nv = vnorm2(R, w);
+        if (nv == 0.0) { lam = 0.0; ok = 1; break; }
+        for (int64_t i = 0; i < R; ++i) v[i] = w[i] / nv;
+        if (fabs(lam - lam_old) <= 1e-15 * fabs(lam)) { ok = 1; break; }
+        lam_old = lam;
+    }
+    free(v); free(t); free(w);
+    return ok ? sqrt(fmax(lam, 0.0)) : -1.0;
+}
+
 /* certificate_parameters (pdhg.jl:670-676) */
 static void certificate_parameters(state_t* s, opts_t* opt) {
     s->certificate_search_min_iter = s->iter + 2 * opt->convergence_window + s->iter / 5 + 1000;
@@ -1001,6 +1046,14 @@ static int oracle_solve_impl(const proxsdp_problem_t* prob, const proxsdp_option
     s->Mt = csc_transpose(&s->M);
     double spectral_norm = vnorm2(s->M.nnz, s->M.val);       /* approx_norm = true: Frobenius */
     if (shard) { double v = spectral_norm * spectral_norm; red(s, &v, 1, 0); spectral_norm = sqrt(v); }
+    if (!opt->approx_norm) {
+        /* pdhg.jl:107-118: the largest singular value of M (Arpack.svds, or a dense svd for fewer than two rows /
+           columns; the Frobenius norm stays when that fails) */
+        if (shard) return -2;
+        double sv = exact_spectral_norm(&s->M, &s->Mt);
+        if (sv >= 0.0) spectral_norm = sv;
+        else fprintf(stderr, "    WARNING: Failed to compute spectral norm of M, shifting to Frobenius norm\n");
+    }
     if (spectral_norm < 1e-10) spectral_norm = 1.0;
     s->primal_step = 1.0 / spectral_norm;
     s->primal_step_old = s->primal_step;

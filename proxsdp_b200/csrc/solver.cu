@@ -275,6 +275,7 @@ class Solver {
 
   private:
     void setup_host(const proxsdp_problem_t* prob);
+    double spectral_norm_device();
     void launch_spmv(const CsrDev& A, const double* x, double* y);
     void launch_full_projection_large(int k);
     void launch_reconstruct(ConeDev& cd, double* x_out);
@@ -462,6 +463,121 @@ Solver::~Solver() {
     if (stream) cudaStreamDestroy(stream);
 }
 
+// ---------------------------------------------------------------------------
+// approx_norm = false: sigma_max(M) (reference src/pdhg.jl:107-118, Arpack.svds(M, nsv = 1))
+// ---------------------------------------------------------------------------
+// y[row_ids ? row_ids[w] : w] = sum_k val[k] x[colidx[k]] over the entries of (compact) row w; one warp per row
+__global__ void k_spmv_warp_rows(const int* __restrict__ rowptr, int nrows, const int* __restrict__ row_ids,
+                                 const int* __restrict__ colidx, const double* __restrict__ val,
+                                 const double* __restrict__ x, double* __restrict__ y) {
+    const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (w >= nrows) return;
+    const int lane = threadIdx.x & 31;
+    double s0 = 0.0;
+    for (int k = rowptr[w] + lane; k < rowptr[w + 1]; k += 32) s0 = fma(val[k], x[colidx[k]], s0);
+    s0 = warp_sum(s0);
+    if (lane == 0) y[row_ids ? row_ids[w] : (int)w] = s0;
+}
+
+// cyclic Jacobi on a small dense symmetric matrix (host; k <= 48): A -> eigenvalues on the diagonal, Z = eigenvectors
+static void host_jacobi_eigh(int k, std::vector<double>& A, std::vector<double>& Z) {
+    Z.assign((size_t)k * k, 0.0);
+    for (int i = 0; i < k; ++i) Z[(size_t)i * k + i] = 1.0;
+    for (int sweep = 0; sweep < 60; ++sweep) {
+        double off = 0.0, dia = 0.0;
+        for (int i = 0; i < k; ++i) for (int j = 0; j < k; ++j) { const double a = A[(size_t)i * k + j]; if (i == j) dia += a * a; else off += a * a; }
+        if (off <= 1e-32 * (dia + off)) break;
+        for (int pp = 0; pp < k - 1; ++pp)
+            for (int q = pp + 1; q < k; ++q) {
+                const double apq = A[(size_t)pp * k + q];
+                if (apq == 0.0) continue;
+                const double theta = (A[(size_t)q * k + q] - A[(size_t)pp * k + pp]) / (2.0 * apq);
+                const double t = (theta >= 0.0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1.0));
+                const double c = 1.0 / std::sqrt(t * t + 1.0), sn = t * c;
+                for (int r = 0; r < k; ++r) {       // columns pp, q
+                    const double arp = A[(size_t)r * k + pp], arq = A[(size_t)r * k + q];
+                    A[(size_t)r * k + pp] = c * arp - sn * arq; A[(size_t)r * k + q] = sn * arp + c * arq;
+                }
+                for (int r = 0; r < k; ++r) {       // rows pp, q
+                    const double apr = A[(size_t)pp * k + r], aqr = A[(size_t)q * k + r];
+                    A[(size_t)pp * k + r] = c * apr - sn * aqr; A[(size_t)q * k + r] = sn * apr + c * aqr;
+                }
+                for (int r = 0; r < k; ++r) {
+                    const double zrp = Z[(size_t)r * k + pp], zrq = Z[(size_t)r * k + q];
+                    Z[(size_t)r * k + pp] = c * zrp - sn * zrq; Z[(size_t)r * k + q] = sn * zrp + c * zrq;
+                }
+            }
+    }
+}
+
+// Largest singular value of the working M = sqrt(lambda_max(M M')): restarted Lanczos with full re-orthogonalisation on
+// vectors of length R.  The two sparse products of every step run on the device (M' as DCSR into a zero-initialised
+// n-vector, then M); the R-vectors, the small Rayleigh quotient and the restart live on the host — this is setup code
+// (a few dozen products of 20 nnz bytes each), the reference spends it inside ARPACK.  Returns -1 when 60 restarts do
+// not bring the residual below 1e-11 lambda (the caller keeps the Frobenius norm, like the reference's `catch`).
+double Solver::spectral_norm_device() {
+    if (R <= 0 || n <= 0 || M_.nnz <= 0) return 0.0;
+    const int K = (int)std::min<long long>(R, 40);
+    DBuf<double> v_d, t_d, w_d;
+    v_d.alloc_raw((size_t)R); w_d.alloc_raw((size_t)R); t_d.alloc((size_t)n);
+    std::vector<double> V((size_t)R * (size_t)(K + 1)), w((size_t)R), alpha((size_t)K), beta((size_t)K + 1, 0.0);
+    eig_resid_default(R, 1234, 3, V.data());
+    auto dot = [&](const double* a, const double* b) { double s0 = 0.0; for (long long i = 0; i < R; ++i) s0 += a[i] * b[i]; return s0; };
+    auto matvec = [&](const double* vin, double* wout) {
+        PB_CUDA(cudaMemcpyAsync(v_d.p, vin, sizeof(double) * (size_t)R, cudaMemcpyHostToDevice, stream));
+        if (Mt_.n_nz > 0)
+            k_spmv_warp_rows<<<ceil_div((long long)Mt_.n_nz * 32, 256), 256, 0, stream>>>(Mt_.rowptr.p, Mt_.n_nz, Mt_.nz_rows.p, Mt_.colidx.p,
+                                                                                     Mt_.val.p, v_d.p, t_d.p);
+        k_spmv_warp_rows<<<ceil_div((long long)R * 32, 256), 256, 0, stream>>>(M_.rowptr.p, (int)R, nullptr, M_.colidx.p, M_.val.p, t_d.p, w_d.p);
+        launches += 2;
+        PB_CUDA(cudaMemcpyAsync(wout, w_d.p, sizeof(double) * (size_t)R, cudaMemcpyDeviceToHost, stream));
+        PB_CUDA(cudaStreamSynchronize(stream));
+        g_h2d_bytes += 8 * R; g_d2h_bytes += 8 * R;
+    };
+    for (int restart = 0; restart < 60; ++restart) {
+        int k = 0;
+        bool invariant = false;
+        for (int j = 0; j < K; ++j) {
+            double* vj = V.data() + (size_t)j * R;
+            matvec(vj, w.data());
+            alpha[(size_t)j] = dot(w.data(), vj);
+            for (int pass = 0; pass < 2; ++pass)
+                for (int q = 0; q <= j; ++q) {
+                    const double* vq = V.data() + (size_t)q * R;
+                    const double h = dot(vq, w.data());
+                    for (long long i = 0; i < R; ++i) w[(size_t)i] -= h * vq[i];
+                }
+            const double bn = std::sqrt(dot(w.data(), w.data()));
+            beta[(size_t)j + 1] = bn;
+            k = j + 1;
+            if (bn <= 1e-14 * std::fabs(alpha[0]) || bn == 0.0) { invariant = true; break; }
+            double* vn = V.data() + (size_t)(j + 1) * R;
+            for (long long i = 0; i < R; ++i) vn[i] = w[(size_t)i] / bn;
+        }
+        std::vector<double> T((size_t)k * k, 0.0), Z;
+        for (int i = 0; i < k; ++i) {
+            T[(size_t)i * k + i] = alpha[(size_t)i];
+            if (i + 1 < k) { T[(size_t)i * k + i + 1] = beta[(size_t)i + 1]; T[(size_t)(i + 1) * k + i] = beta[(size_t)i + 1]; }
+        }
+        host_jacobi_eigh(k, T, Z);
+        int best = 0;
+        for (int i = 1; i < k; ++i) if (T[(size_t)i * k + i] > T[(size_t)best * k + best]) best = i;
+        const double lam = T[(size_t)best * k + best];
+        const double resid = std::fabs(beta[(size_t)k] * Z[(size_t)(k - 1) * k + best]);
+        if (invariant || k == R || resid <= 1e-11 * std::fabs(lam)) return std::sqrt(std::max(lam, 0.0));
+        // restart from the Ritz vector
+        std::fill(w.begin(), w.end(), 0.0);
+        for (int q = 0; q < k; ++q) {
+            const double zq = Z[(size_t)q * k + best];
+            const double* vq = V.data() + (size_t)q * R;
+            for (long long i = 0; i < R; ++i) w[(size_t)i] += zq * vq[i];
+        }
+        const double nw = std::sqrt(dot(w.data(), w.data()));
+        for (long long i = 0; i < R; ++i) V[(size_t)i] = w[(size_t)i] / nw;
+    }
+    return -1.0;
+}
+
 void Solver::setup_host(const proxsdp_problem_t* prob) {
     StageTimer st("setup: cone table + ingest");
     n = prob->n; p = prob->p; m = prob->m; R = p + m;
@@ -470,7 +586,8 @@ void Solver::setup_host(const proxsdp_problem_t* prob) {
     if (n < 0 || p < 0 || m < 0 || (base != 0 && base != 1)) throw CudaError(-1, "invalid problem sizes");
     if ((opt.equilibration || opt.equilibration_force) && sharded())
         throw CudaError(-2, "equilibration needs the row norms of the whole constraint matrix: not available on the sharded path");
-    if (!opt.approx_norm) throw CudaError(-2, "approx_norm=false (exact spectral norm) is not supported");
+    if (!opt.approx_norm && sharded())
+        throw CudaError(-2, "approx_norm=false needs the singular values of the whole constraint matrix: not available on the sharded path");
     if (n >= (1LL << 31) - 64 || R >= (1LL << 31) - 64) throw CudaError(-1, "problem too large for 32-bit indices");
 
     // norms of the right-hand sides before any scaling (pdhg.jl:14-15); ||c|| comes back from the device ingest
@@ -544,6 +661,11 @@ void Solver::setup_host(const proxsdp_problem_t* prob) {
     }
     global_has_soc_ = any_soc != 0.0;
     fro = std::sqrt(fro);
+    if (!opt.approx_norm && !cones_only_) {
+        const double sv = spectral_norm_device();
+        if (sv >= 0.0) fro = sv;
+        else fprintf(stderr, "    WARNING: Failed to compute spectral norm of M, shifting to Frobenius norm\n");
+    }
     if (fro < 1e-10) fro = 1.0;
     primal_step_ = 1.0 / fro; primal_step_old_ = primal_step_; dual_step_ = primal_step_;
     const double cte = std::sqrt(2.0) / 2.0;

@@ -517,3 +517,32 @@ def test_equilibration_switches_itself_off(gpu):
     a = gpu.chambolle_pock(aff, con, Options(equilibration=True, max_iter=50, trace_cap=50))
     b = gpu.chambolle_pock(aff, con, Options(max_iter=50, trace_cap=50))
     assert np.array_equal(a.trace[:, 1:9], b.trace[:, 1:9]) and np.array_equal(a.primal, b.primal)
+
+
+@pytest.mark.parametrize("which", ["C1", "mimo8", "sensorloc", "mcp124-1-krylov", "permuted"])
+def test_exact_spectral_norm_vs_oracle(gpu, oracle_mod, golden_dir, which):
+    """approx_norm = false (reference src/pdhg.jl:107-118): the initial step sizes come from sigma_max(M), computed on
+    the device by a restarted Lanczos run on M M' (the oracle: dense Gram matrix + eigendecomposition, itself pinned to
+    ARPACK svds by tests/test_oracle.py)."""
+    from proxsdp_b200.problems import README_W, maxcut_problem
+    kw = dict(full_eig_decomp=True)
+    if which == "C1":
+        aff, con = maxcut_problem(README_W)[:2]
+    elif which == "mimo8":
+        aff, con = mimo_problem(1, 8)
+    elif which == "sensorloc":
+        aff, con = sensorloc_problem(0, 10)
+    elif which == "permuted":
+        aff, con = sensorloc_problem(1, 8, soc_variant=True)
+        aff, con, _ = _scrambled(aff, con, 5)
+    else:
+        aff, con = load_problem(f"{golden_dir}/sdplib_mcp124-1.npz")
+        kw = dict()
+    iters = 200 if kw else 40
+    opt = Options(max_iter=iters, trace_cap=iters, approx_norm=False, **kw)
+    rg = gpu.chambolle_pock(aff, con, opt)
+    ro = oracle_mod.chambolle_pock(aff, con, opt)
+    assert len(rg.trace) == len(ro.trace) and len(ro.trace) > 0
+    assert abs(rg.trace[0, 7] - ro.trace[0, 7]) <= 1e-10 * abs(ro.trace[0, 7])      # the first primal step: sqrt(1 + theta) / sigma_max
+    assert np.abs(rg.trace[:, 1:9] - ro.trace[:, 1:9]).max() <= 1e-6 * max(1.0, np.abs(ro.trace[:, 1:9]).max())
+    _same_solution(rg, ro)

@@ -289,3 +289,27 @@ def test_equilibration_switches_itself_off(oracle_mod):
     a = oracle_mod.chambolle_pock(aff, con, Options(equilibration=True, max_iter=50, trace_cap=50))
     b = oracle_mod.chambolle_pock(aff, con, Options(max_iter=50, trace_cap=50))
     assert np.array_equal(a.trace[:, 1:9], b.trace[:, 1:9]) and np.array_equal(a.primal, b.primal)
+
+
+@pytest.mark.parametrize("which", ["C1", "mimo8", "sensorloc"])
+def test_exact_spectral_norm_vs_arpack_svds(oracle_mod, which):
+    """approx_norm = false (reference src/pdhg.jl:107-118): the step sizes start from 1 / sigma_max(M) — the numpy mirror
+    calls ARPACK svds like the reference does; exact-projection mode."""
+    from oracle import oracle_np
+    if which == "C1":
+        aff, con = maxcut_problem(README_W)[:2]
+    elif which == "mimo8":
+        aff, con = mimo_problem(1, 8)
+    else:
+        aff, con = sensorloc_problem(0, 10)
+    opt = Options(full_eig_decomp=True, trace_cap=200, max_iter=200, approx_norm=False)
+    ro = oracle_mod.chambolle_pock(aff, con, opt)
+    rn = oracle_np.solve_exact(aff, con, opt, 200)
+    assert ro.iter == rn["iter"]
+    k = len(rn["trace"])
+    a, b = ro.trace[:k, 1:9], rn["trace"][:k, 1:9]
+    assert np.abs(a - b).max() <= 1e-6 * max(1.0, np.abs(b).max())
+    assert np.abs(ro.primal - rn["primal"]).max() < 1e-8 * max(1.0, np.abs(rn["primal"]).max())
+    plain = oracle_mod.chambolle_pock(aff, con, Options(full_eig_decomp=True, trace_cap=200, max_iter=200))
+    if which != "C1":        # C1: M = 4 unit rows, sigma_max = 1 but ||M||_F = 2
+        assert plain.trace[0, 7] != ro.trace[0, 7]
