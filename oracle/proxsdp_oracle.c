@@ -1079,7 +1079,9 @@ static int oracle_solve_impl(const proxsdp_problem_t* prob, const proxsdp_option
         compute_residual(s);
         compute_gap(s);
 
-        if (opt->check_dual_feas && (k % opt->check_dual_feas_freq) == 0) {       /* pdhg.jl:166-173 */
+        /* (the log itself, printing.jl, is not restated here: only its effect on dual_feasibility_check) */
+        if ((opt->check_dual_feas && (k % opt->check_dual_feas_freq) == 0) ||
+            (opt->log_verbose && opt->log_freq > 0 && (k % opt->log_freq) == 0 && opt->extended_log2)) {       /* pdhg.jl:166-173 */
             double f = s->stop_reason == 6 ? 0.0 : 1.0;
             double* cc = (double*)malloc(sizeof(double) * ((size_t)n + 1));
             for (int64_t i = 0; i < n; ++i) cc[i] = f * s->c_orig[i];

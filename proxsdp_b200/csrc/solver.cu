@@ -19,6 +19,7 @@
 #include "../../include/proxsdp_b200.h"
 #include "common.cuh"
 #include "runtime.cuh"
+#include "printing.hpp"
 #include "fulleig.cuh"
 #include "jacobi.cuh"
 #include "kernels_vec.cuh"
@@ -276,6 +277,8 @@ class Solver {
   private:
     void setup_host(const proxsdp_problem_t* prob);
     double spectral_norm_device();
+    bool logging() const { return opt.log_verbose && rank_ == 0; }     // sharded runs: rank 0 writes the log
+    void log_progress(double dual_feas_val);
     void launch_spmv(const CsrDev& A, const double* x, double* y);
     void launch_full_projection_large(int k);
     void launch_reconstruct(ConeDev& cd, double* x_out);
@@ -1930,6 +1933,14 @@ void Solver::host_residuals(long long k) {
 // ---------------------------------------------------------------------------
 // chambolle_pock main loop (pdhg.jl:145-530)
 // ---------------------------------------------------------------------------
+void Solver::log_progress(double dual_feas_val) {      // print_progress (printing.jl:99-151)
+    long long tr = 0;
+    for (long long r : target_rank) tr += r;
+    plog::emit(plog::progress(iter_, prim_obj_.get(iter_), dual_gap_.get(iter_), feasibility_.get(iter_), primal_residual_.get(iter_),
+                            dual_residual_.get(iter_), tr, now_s() - time0_, dual_obj_.get(iter_), dual_feas_val,
+                            opt.extended_log != 0, opt.extended_log2 != 0, opt.log_repeat_header != 0));
+}
+
 void Solver::solve(proxsdp_result_t* out) {
     begin(out);
     run(-1, false);
@@ -1941,6 +1952,18 @@ void Solver::begin(proxsdp_result_t* out) {
     out_ = out;
     out->trace_len = 0;
     ada_count_ = 0; have_cached_ = false; loop_done_ = false; k_next_ = 1; t_loop_accum_ = 0;
+    if (logging()) {                              // pdhg.jl:43-52
+        std::vector<long long> sides, lens;
+        for (const ConeDev& cd : cones) sides.push_back(cd.side);
+        for (int l : soc_len_h_) lens.push_back(l);
+        std::string hdr = plog::header_1();
+        hdr += plog::parameters(opt.tol_gap, opt.tol_feasibility, opt.tol_primal, opt.tol_dual, opt.tol_soc, opt.tol_psd,
+                               n_soc >= 1, n_sdp >= 1, opt.max_iter_local, opt.time_limit);
+        hdr += plog::constraints(p, m);
+        if (n_soc + n_sdp > 0) hdr += plog::prob_data(lens, sides);
+        hdr += plog::header_2(opt.extended_log != 0, opt.extended_log2 != 0, true);
+        plog::emit(hdr);
+    }
 
     // advanced initialisation (pdhg.jl:138-142): x = tau*c ; Mx = M x ; Mx_old = M*0 = 0
     if (opt.advanced_initialization) {
@@ -2046,7 +2069,8 @@ bool Solver::run(long long max_steps, bool flush_l2) {
         host_residuals(k);
         cur_ = 1 - cur_;    // keep-old copies (residuals.jl:65-68) are a pointer swap
 
-        if (opt.check_dual_feas && (k % opt.check_dual_feas_freq) == 0) {     // pdhg.jl:166-173
+        if ((opt.check_dual_feas && (k % opt.check_dual_feas_freq) == 0) ||
+            (opt.log_verbose && opt.log_freq > 0 && (k % opt.log_freq) == 0 && opt.extended_log2)) {     // pdhg.jl:166-173
             double f = stop_reason_ == 6 ? 0.0 : 1.0;
             dual_feasibility_ = dual_feas_device(y_[cur_].p, f);
             host_reduce(&dual_feasibility_, 1, 1);
@@ -2054,6 +2078,7 @@ bool Solver::run(long long max_steps, bool flush_l2) {
         } else {
             dual_feasibility_check_ = false;
         }
+        if (logging() && opt.log_freq > 0 && (k % opt.log_freq) == 0) log_progress(dual_feasibility_);   // pdhg.jl:176-178
         record_trace(out);
 
         if (iter_ < certificate_search_min_iter_) continue;                   // pdhg.jl:180-182
@@ -2067,6 +2092,7 @@ bool Solver::run(long long max_steps, bool flush_l2) {
                     if (dual_feasibility_ < opt.tol_feasibility_dual) {
                         certificate_found_ = true;
                         append(" [Dual ray found]");
+                        if (logging()) plog::emit(plog::note("Dual ray found"));
                         break;
                     }
                 }
@@ -2075,6 +2101,7 @@ bool Solver::run(long long max_steps, bool flush_l2) {
                     if (feasibility_.get(iter_) < opt.tol_feasibility) {
                         certificate_found_ = true;
                         append(" [Primal ray found]");
+                        if (logging()) plog::emit(plog::note("Primal ray found"));
                         break;
                     }
                 }
@@ -2083,6 +2110,7 @@ bool Solver::run(long long max_steps, bool flush_l2) {
             if ((prim_obj_.get(k) < -opt.certificate_fail_tol && dual_obj_.get(k) < -opt.certificate_fail_tol &&
                  feasibility_.get(iter_) < -opt.certificate_fail_tol) || cr != cr) {
                 append(" [Failed to find certificate]");
+                if (logging()) plog::emit(plog::note("Failed to finds certificate"));
                 break;
             }
         }
@@ -2105,6 +2133,7 @@ bool Solver::run(long long max_steps, bool flush_l2) {
                     stop_reason_string_ = "Optimal solution found";
                 } else {
                     append(" [Failed to find certificate - type 2]");
+                    if (logging()) plog::emit(plog::note("Failed to find certificate - type 2"));
                     break;
                 }
                 break;
@@ -2145,6 +2174,7 @@ bool Solver::run(long long max_steps, bool flush_l2) {
         }
 
         auto start_cert_infeas = [&]() {       // certificate_infeasibility (pdhg.jl:655-676)
+            if (logging()) plog::emit(plog::note("Begin search for infeasibility certificate"));
             PB_CUDA(cudaMemsetAsync(c_.p, 0, sizeof(double) * (size_t)std::max<long long>(n, 1), stream));
             certificate_search_min_iter_ = iter_ + 2 * opt.convergence_window + iter_ / 5 + 1000;
             certificate_search_ = true;
@@ -2153,6 +2183,7 @@ bool Solver::run(long long max_steps, bool flush_l2) {
             cache_solution(1.0, out); have_cached = true;
         };
         auto start_cert_dual_infeas = [&]() {  // certificate_dual_infeasibility (pdhg.jl:639-653)
+            if (logging()) plog::emit(plog::note("Begin search for dual infeasibility certificate"));
             std::fill(b_host_.begin(), b_host_.end(), 0.0);
             std::fill(h_host_.begin(), h_host_.end(), 0.0);
             PB_CUDA(cudaMemsetAsync(b_.p, 0, sizeof(double) * (size_t)std::max<long long>(p, 1), stream));
@@ -2185,11 +2216,13 @@ bool Solver::run(long long max_steps, bool flush_l2) {
             } else if (iter_ >= opt.max_iter_local) {
                 stop_reason_ = 3;
                 stop_reason_string_ = "Iteration limit of " + std::to_string(opt.max_iter_local) + " was hit";
+                if (opt.warn_on_limit && rank_ == 0) fprintf(stderr, "Warning:     WARNING: Iteration limit hit.\n");   // @warn, pdhg.jl:369-371
             } else {
                 stop_reason_ = 2;
                 char buf[160];
                 snprintf(buf, sizeof(buf), "Time limit hit, limit: %g time: %g", opt.time_limit, now_s() - time0_);
                 stop_reason_string_ = buf;
+                if (opt.warn_on_limit && rank_ == 0) plog::emit("    WARNING: Time limit hit.\n");                          // pdhg.jl:375-377
             }
             if (iter_ >= opt.max_iter_local || elapsed_k >= opt.time_limit) break;
         }
@@ -2258,6 +2291,21 @@ void Solver::finish(proxsdp_result_t* out) {
         }
     }
     out->time_loop = t_loop_accum_;
+    if (opt.log_verbose) {                        // pdhg.jl:486-505
+        const double time_ = now_s() - time0_;
+        double val = -1.0;
+        if (opt.extended_log2) {
+            val = dual_feas_device(y_[cur_].p, stop_reason_ == 6 ? 0.0 : 1.0);
+            host_reduce(&val, 1, 1);
+        }
+        if (logging()) {
+            log_progress(val);
+            long long max_rank = 0;
+            for (long long r : current_rank) max_rank = std::max(max_rank, r);
+            plog::emit(plog::result(stop_reason_string_, time_, prim_obj_.get(iter_), dual_obj_.get(iter_), dual_gap_.get(iter_),
+                                  equa_feasibility_, ineq_feasibility_, max_rank));
+        }
+    }
     // results (pdhg.jl:486-529)
     if (opt.certificate_search && certificate_search_) {
         if (certificate_found_) {

@@ -546,3 +546,35 @@ def test_exact_spectral_norm_vs_oracle(gpu, oracle_mod, golden_dir, which):
     assert abs(rg.trace[0, 7] - ro.trace[0, 7]) <= 1e-10 * abs(ro.trace[0, 7])      # the first primal step: sqrt(1 + theta) / sigma_max
     assert np.abs(rg.trace[:, 1:9] - ro.trace[:, 1:9]).max() <= 1e-6 * max(1.0, np.abs(ro.trace[:, 1:9]).max())
     _same_solution(rg, ro)
+
+
+def test_log_verbose_output_and_extended_log_control_flow(gpu, oracle_mod, capfd):
+    """`log_verbose` (reference src/printing.jl, src/pdhg.jl:43-52, 176-178, 486-505): header, one progress line every
+    `log_freq` iterations, final line + result block, written by the library to stdout.  `extended_log2` also makes the
+    loop evaluate the dual feasibility at the logged iterations (src/pdhg.jl:166-173): same trajectory as the oracle."""
+    from proxsdp_b200.problems import README_W, maxcut_problem
+    aff, con = maxcut_problem(README_W)[:2]
+    opt = Options(tol_gap=1e-4, tol_feasibility=1e-4, log_verbose=True, log_freq=10, extended_log2=True, trace_cap=200)
+    r = gpu.chambolle_pock(aff, con, opt)
+    out = capfd.readouterr().out
+    ro = oracle_mod.chambolle_pock(aff, con, opt)
+    capfd.readouterr()
+    _same_solution(r, ro)
+    lines = out.splitlines()
+    assert "ProxSDP : Proximal Semidefinite Programming Solver" in out
+    assert "       tol_gap = 0.0001 tol_feasibility = 0.0001" in lines
+    assert "       4 linear equalities and " in lines
+    assert "       1 psd cone of size 4" in lines
+    assert "|  iter  | prim obj | rel. gap |  feasb.  | prim res | dual res | tg. rank |  time(s) | dual obj | d feasb. |" in lines
+    prog = [ln for ln in lines if ln.startswith("|") and not ln.startswith("|  iter")]
+    assert len(prog) == r.iter // 10 + 1                       # every 10th iteration + the final line
+    first = [c.strip() for c in prog[0].strip("|").split("|")]
+    assert first[0] == "10" and len(first) == 10
+    k = 9                                                      # trace row of iteration 10
+    assert first[1] == "%.2e" % r.trace[k, 1] and first[2] == "%.2e" % r.trace[k, 3] and first[8] == "%.3f" % r.trace[k, 2]
+    assert "       Optimal solution found" in lines
+    assert any(ln.startswith("       Primal objective = -17.99") for ln in lines)
+    assert "    Rank of p.s.d. variable is 1." in lines
+    # silent by default
+    gpu.chambolle_pock(aff, con, Options(tol_gap=1e-4, tol_feasibility=1e-4))
+    assert capfd.readouterr().out == ""
