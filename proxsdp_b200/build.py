@@ -26,7 +26,7 @@ def _nvcc() -> str:
 
 
 def _deps():
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh"))]
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".hpp"))]
     deps += [os.path.join(HERE, "..", "include", f) for f in ("proxsdp_b200.h", "proxsdp_b200_types.h")]
     return deps
 
