@@ -110,6 +110,13 @@ def test_full_solve_c2_headline(gpu, oracle_mod, golden_dir, lz_mode):
     assert np.abs(np.diag(X) - 1.0).max() <= 1e-4 * (1.0 + np.sqrt(2000.0))    # diag(X) = 1 to tol_feasibility (1 + ||b||)
     w = np.linalg.eigvalsh(X)
     assert w.min() >= -1e-4 * w.max()                                       # minus_rank == 0 (test/moi_sdplib.jl:53-56)
+    # the optimum of the headline instance, pinned without any solver: weak-duality bracket recomputed in LAPACK from the
+    # device's primal and dual vectors (the oracle's own solve closes it to 2.4e-4 relative: [-14214.24, -14210.76])
+    from certificates import maxcut_bracket
+    lower, primal, k = maxcut_bracket(aff, con, rg, 2000)
+    assert k["eq"] <= 2e-4 * (1.0 + np.sqrt(2000.0)) and k["lam_x"] >= -1e-6
+    assert lower <= primal + 1e-4 * abs(primal) and primal - lower <= 1e-3 * abs(primal), k
+    assert -14214.24 - 1.5 <= primal <= -14210.76 + 1.5      # inside the oracle's certified interval, widened by tol_gap
 
 
 def test_full_solve_maxG32(gpu, oracle_mod, golden_dir):
