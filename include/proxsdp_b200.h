@@ -8,7 +8,7 @@
  * ctypes (proxsdp_b200/solver.py).  Plain pointers and sizes only.
  *
  * Return value of every function: 0 on success, negative on failure
- *   -1  invalid argument            -2  unsupported on this path (equilibration / exact norm when sharded)
+ *   -1  invalid argument            -2  unsupported on this path (equilibration when sharded)
  *   -3  malformed cones             -4  out of device/host memory
  *   -5  no CUDA device / extension  <= -100  CUDA runtime error (-100 - cudaError_t)
  * The solver's own outcome (optimal, limits, infeasible, ...) is NOT an error: it is

@@ -1049,8 +1049,14 @@ static int oracle_solve_impl(const proxsdp_problem_t* prob, const proxsdp_option
     if (!opt->approx_norm) {
         /* pdhg.jl:107-118: the largest singular value of M (Arpack.svds, or a dense svd for fewer than two rows /
            columns; the Frobenius norm stays when that fails) */
-        if (shard) return -2;
         double sv = exact_spectral_norm(&s->M, &s->Mt);
+        if (shard) {
+            /* the shards are independent blocks (no row of one rank touches another rank's variables), so M is block
+               diagonal up to a permutation and sigma_max(M) = max over the ranks; a failure on any rank fails all */
+            double v[2] = {sv, sv < 0.0 ? 1.0 : 0.0};
+            red(s, v, 2, 1);
+            sv = v[1] != 0.0 ? -1.0 : v[0];
+        }
         if (sv >= 0.0) spectral_norm = sv;
         else fprintf(stderr, "    WARNING: Failed to compute spectral norm of M, shifting to Frobenius norm\n");
     }

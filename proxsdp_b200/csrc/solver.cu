@@ -589,8 +589,6 @@ void Solver::setup_host(const proxsdp_problem_t* prob) {
     if (n < 0 || p < 0 || m < 0 || (base != 0 && base != 1)) throw CudaError(-1, "invalid problem sizes");
     if ((opt.equilibration || opt.equilibration_force) && sharded())
         throw CudaError(-2, "equilibration needs the row norms of the whole constraint matrix: not available on the sharded path");
-    if (!opt.approx_norm && sharded())
-        throw CudaError(-2, "approx_norm=false needs the singular values of the whole constraint matrix: not available on the sharded path");
     if (n >= (1LL << 31) - 64 || R >= (1LL << 31) - 64) throw CudaError(-1, "problem too large for 32-bit indices");
 
     // norms of the right-hand sides before any scaling (pdhg.jl:14-15); ||c|| comes back from the device ingest
@@ -665,7 +663,14 @@ void Solver::setup_host(const proxsdp_problem_t* prob) {
     global_has_soc_ = any_soc != 0.0;
     fro = std::sqrt(fro);
     if (!opt.approx_norm && !cones_only_) {
-        const double sv = spectral_norm_device();
+        double sv = spectral_norm_device();
+        if (sharded()) {
+            // the shards are independent blocks (no row of one rank touches another rank's variables): M is block diagonal
+            // up to a permutation and sigma_max(M) = max over the ranks; a failure on any rank fails all
+            double v[2] = {sv, sv < 0.0 ? 1.0 : 0.0};
+            host_reduce(v, 2, 1);
+            sv = v[1] != 0.0 ? -1.0 : v[0];
+        }
         if (sv >= 0.0) fro = sv;
         else fprintf(stderr, "    WARNING: Failed to compute spectral norm of M, shifting to Frobenius norm\n");
     }

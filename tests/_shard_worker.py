@@ -24,6 +24,9 @@ def main():
     if case == "mimo":
         probs = [mimo_problem(200 + s, 6 + (s % 3)) for s in range(7)]          # ragged batch, 7 blocks on 2-3 ranks
         opt = Options(trace_cap=50)
+    elif case == "mimo_exact_norm":
+        probs = [mimo_problem(200 + s, 6 + (s % 3)) for s in range(5)]
+        opt = Options(trace_cap=50, approx_norm=False)          # sigma_max of the block-diagonal M = max over the ranks
     else:
         probs = [sensorloc_problem(3, 8, soc_variant=True), mimo_problem(11, 5), sensorloc_problem(4, 6)]   # SOC + PSD blocks
         opt = Options(max_iter=400, trace_cap=50)

@@ -60,7 +60,7 @@ def test_shard_and_merge_roundtrip():
     assert np.array_equal(merged.primal, x)
 
 
-@pytest.mark.parametrize("world,case", [(2, "mimo"), (3, "mimo"), (2, "mixed")])
+@pytest.mark.parametrize("world,case", [(2, "mimo"), (3, "mimo"), (2, "mixed"), (2, "mimo_exact_norm")])
 def test_sharded_oracle_equals_whole_solve(world, case):
     port = _free_port()
     procs = []
