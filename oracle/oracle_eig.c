@@ -266,6 +266,11 @@ typedef void (*oracle_matvec_fn)(int64_t n, const double* A, const double* x, do
  * *nvals_out = max(howmany', converged) as KrylovKit returns,
  * *converged_out = info.converged, *numops_out = info.numops, *numiter_out.
  * A: n x n column-major, upper triangle meaningful.  Returns 0. */
+/* Lanczos(...; eager = true): the Ritz analysis also runs after every expansion step once K >= howmany, and the
+ * eigsolve stops as soon as `howmany` pairs have converged (KrylovKit eigsolve, lanczos.jl).  Set by the caller
+ * (reference src/eigsolver.jl:809: opt.krylovkit_eager). */
+int oracle_lanczos_eager = 0;
+
 int oracle_lanczos(int64_t n, const double* A, const double* x0, int64_t howmany,
                    int64_t krylovdim, int64_t maxiter, double tol,
                    double* vals, double* vecs, int64_t* nvals_out,
@@ -313,7 +318,7 @@ int oracle_lanczos(int64_t n, const double* A, const double* x0, int64_t howmany
         beta = betas[k - 1];
         Kcur = k;
         if (beta <= tol && Kcur < howmany) howmany = Kcur;
-        if (Kcur == K || beta <= tol) {
+        if (Kcur == K || beta <= tol || (oracle_lanczos_eager && Kcur >= howmany)) {
             if (Kcur == 1) {
                 D[0] = alphas[0];
                 U[0] = 1.0;

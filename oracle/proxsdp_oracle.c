@@ -33,6 +33,7 @@
 #include "../include/proxsdp_b200_types.h"
 
 /* from oracle_eig.c */
+extern int oracle_lanczos_eager;
 int oracle_eigh(int64_t n, double* A, double* w, double* Z);
 int oracle_lanczos(int64_t n, const double* A, const double* x0, int64_t howmany,
                    int64_t krylovdim, int64_t maxiter, double tol,
@@ -337,8 +338,10 @@ static void krylov_eig(state_t* s, const opts_t* opt, int64_t idx) {
     if (ncv < opt->eigsolver_min_lanczos) ncv = opt->eigsolver_min_lanczos;   /* eigsolver.jl:794 */
     int64_t nvals = 0, conv = 0, numops = 0, numiter = 0;
     s->eig_converged[idx] = 1;
+    oracle_lanczos_eager = opt->krylovkit_eager != 0;                            /* eigsolver.jl:809 */
     oracle_lanczos(n, X, s->resid[idx], nev, ncv, opt->krylovkit_max_iter, opt->krylovkit_tol,
                    s->lan_vals, s->lan_vecs, &nvals, &conv, &numops, &numiter);
+    oracle_lanczos_eager = 0;
     s->lanczos_calls++;
     s->lanczos_matvecs += numops;
     s->eig_converged_eigs[idx] = conv;

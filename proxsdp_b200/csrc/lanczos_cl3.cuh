@@ -156,6 +156,8 @@ struct LanczosCl3Args {
     int pf_rows;               // > 0: slab rows prefetched into L2 ahead of the register loads (matrices larger than L2;
                                // PROXSDP_B200_LZ_PF overrides the host's choice)
     int poll_ns;               // back-off between two polls of the flagged exchange words (PROXSDP_B200_LZ_POLL_NS)
+    int eager;                 // 1: KrylovKit's `eager` schedule (opt.krylovkit_eager, reference src/eigsolver.jl:809): the Ritz
+                               // analysis also runs after every expansion step once k >= howmany
     int strict;                // 1: KrylovKit's arithmetic to the letter — alpha of the local step summed in FP64 and two
                                // Gram-Schmidt passes on every step (PROXSDP_B200_LZ_STRICT=1); 0: FP32 tree for the provisional
                                // alpha and a second pass only when the DGKS test asks for it (same counts)
@@ -598,7 +600,7 @@ __device__ __noinline__ void lz3_ritz(const LanczosCl3Args& a, double* sbase, in
             return got;
         };
         int mb = solve(howmany + 4, 0);
-        if (mb == 0) bi_bad |= 1;
+        if (mb == 0 && !(a.eager && k < 8)) bi_bad |= 1;     // (eager analyses of a basis younger than 8 vectors go to the dense solver without prejudice)
         if (mb > 0) {
             int cv = 0;
             while (cv < mb && fabs(SMD(f)[cv]) <= a.tol) cv++;
@@ -609,6 +611,7 @@ __device__ __noinline__ void lz3_ritz(const LanczosCl3Args& a, double* sbase, in
 #endif
             if (cv >= howmany && cv < mb) { converged = cv; finished = 1; done_bi = true; }
             else if (SMD(D)[0] > a.stop_above) { converged = max(cv, 1); finished = 1; done_bi = true; }      // bound certified
+            else if (a.eager && beta > a.tol && cv < howmany && k < K) { converged = cv; done_bi = true; }      // eager analysis, not there yet: expand further
             else if (cv < howmany && k == K && numiter < a.maxiter) {
                 // not converged at the end of a Krylov cycle: the restart needs the `keep` leading pairs — one warp each
                 const int keep = (3 * K + 2 * cv) / 5;
@@ -1180,7 +1183,7 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) k_lanczos_cl3(const __grid_cons
 
         // ================= Ritz analysis (redundant in every CTA; out of line) =================
         if (beta <= a.tol && k < howmany) howmany = k;
-        if (k == K || beta <= a.tol) {
+        if (k == K || beta <= a.tol || (a.eager && k >= howmany)) {
             if (tid == 0) {
                 s_state[0] = k; s_state[2] = arrow; s_state[3] = howmany; s_state[4] = numiter; s_state[5] = first_analysis ? 1 : 0;
             }

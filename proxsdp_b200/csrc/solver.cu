@@ -1001,7 +1001,7 @@ bool Solver::lanczos_launch_cluster3(ConeDev& cd, int cone_idx, int nev, int K, 
     a.ritz_rd = (lz_warm_ && cd.ritz_launches > 0 && (cd.ritz_launches % 32) != 0) ? cd.ritz_ws[flip].p : nullptr;
     a.ritz_wr = lz_warm_ ? cd.ritz_ws[1 - flip].p : nullptr;
     a.nev = nev; a.K = K; a.maxiter = maxiter; a.tol = tol;
-    a.vn_max = vn_max; a.use_bi = lz_bi_; a.stop_above = lz_stop_above_; a.strict = lz_strict_; a.poll_ns = lz_poll_ns_; a.arrow_restart = lz_arrow_; a.debug = getenv("PROXSDP_B200_LZ_DEBUG") ? 1 : 0;
+    a.vn_max = vn_max; a.use_bi = lz_bi_; a.stop_above = lz_stop_above_; a.strict = lz_strict_; a.eager = (opt.krylovkit_eager && lz_stop_above_ >= 1e300) ? 1 : 0; a.poll_ns = lz_poll_ns_; a.arrow_restart = lz_arrow_; a.debug = getenv("PROXSDP_B200_LZ_DEBUG") ? 1 : 0;
     a.rbase = nside / G; a.rrem = nside % G; a.vbase = nside / C; a.vrem = nside % C;
     a.vals = cd.vals.p; a.info = cd.info.p; a.scal = scal_target_; a.cone = cone_idx;
     a.L = L; a.spin_limit = lz_spin_limit_; a.bi_memory = lz_bi_memory_;
@@ -1124,7 +1124,7 @@ bool Solver::lanczos_launch_implicit(ConeDev& cd, int cone_idx, int nev, int K, 
     a.ritz_rd = (lz_warm_ && cd.ritz_launches > 0 && (cd.ritz_launches % 32) != 0) ? cd.ritz_ws[flip].p : nullptr;
     a.ritz_wr = lz_warm_ ? cd.ritz_ws[1 - flip].p : nullptr;
     a.nev = nev; a.K = K; a.maxiter = maxiter; a.tol = tol;
-    a.vn_max = vn_max; a.use_bi = lz_bi_; a.stop_above = 1e300; a.strict = lz_strict_; a.poll_ns = 0; a.arrow_restart = lz_arrow_; a.debug = 0;
+    a.vn_max = vn_max; a.use_bi = lz_bi_; a.stop_above = 1e300; a.strict = lz_strict_; a.eager = (opt.krylovkit_eager && lz_stop_above_ >= 1e300) ? 1 : 0; a.poll_ns = 0; a.arrow_restart = lz_arrow_; a.debug = 0;
     a.rbase = nside / C; a.rrem = nside % C; a.vbase = nside / C; a.vrem = nside % C;
     a.vals = cd.vals.p; a.info = cd.info.p; a.scal = scal_target_; a.cone = cone_idx;
     a.L = L; a.spin_limit = lz_spin_limit_; a.bi_memory = lz_bi_memory_;
@@ -1192,7 +1192,7 @@ bool Solver::lanczos_launch_resident(ConeDev& cd, int cone_idx, int nev, int K, 
         a.ritz_rd = (lz_warm_ && cd.ritz_launches > 0 && (cd.ritz_launches % 32) != 0) ? cd.ritz_ws[flip].p : nullptr;
         a.ritz_wr = lz_warm_ ? cd.ritz_ws[1 - flip].p : nullptr;
         a.nev = nev; a.K = K; a.maxiter = maxiter; a.tol = tol;
-        a.vn_max = vn_max; a.use_bi = lz_bi_; a.stop_above = lz_stop_above_; a.strict = lz_strict_; a.poll_ns = 0; a.arrow_restart = lz_arrow_;
+        a.vn_max = vn_max; a.use_bi = lz_bi_; a.stop_above = lz_stop_above_; a.strict = lz_strict_; a.eager = (opt.krylovkit_eager && lz_stop_above_ >= 1e300) ? 1 : 0; a.poll_ns = 0; a.arrow_restart = lz_arrow_;
         a.debug = getenv("PROXSDP_B200_LZ_DEBUG") ? 1 : 0;
         a.rbase = nside / C; a.rrem = nside % C; a.vbase = nside / C; a.vrem = nside % C;
         a.vals = cd.vals.p; a.info = cd.info.p; a.scal = scal_target_; a.cone = cone_idx;

@@ -585,3 +585,28 @@ def test_log_verbose_output_and_extended_log_control_flow(gpu, oracle_mod, capfd
     # silent by default
     gpu.chambolle_pock(aff, con, Options(tol_gap=1e-4, tol_feasibility=1e-4))
     assert capfd.readouterr().out == ""
+
+
+@pytest.mark.parametrize("n,rank,nev", [(150, 3, 5), (260, 6, 2), (400, 9, 11), (700, 5, 4)])
+def test_krylovkit_eager_schedule(gpu, oracle_mod, n, rank, nev):
+    """`krylovkit_eager = true` (reference src/eigsolver.jl:809 -> KrylovKit `Lanczos(...; eager = true)`): the Ritz analysis
+    runs after every expansion step once the basis holds `howmany` vectors and the eigsolve stops at the first step at which
+    `howmany` pairs have converged — fewer mat-vecs, and only the pairs converged by then come back.  Sides on the resident
+    single-cluster kernel and on the grid-wide one; counts identical to the oracle's."""
+    rng = np.random.default_rng(n)
+    Q, _ = np.linalg.qr(rng.standard_normal((n, n)))
+    lam = np.concatenate([np.linspace(40.0, 8.0, rank), -np.abs(rng.standard_normal(n - rank)) * 3.0 - 0.05])
+    A = (Q * lam) @ Q.T
+    A = 0.5 * (A + A.T)
+    ii, jj = np.triu_indices(n)
+    order = np.lexsort((ii, jj))
+    ii, jj = ii[order], jj[order]
+    x = np.where(ii != jj, A[ii, jj] * np.sqrt(2.0), A[ii, jj])
+    opt = Options(krylovkit_eager=True)
+    xo, co, mo, cvo, no = oracle_mod.psd_project([n], x, [nev], opt)
+    xg, cg, mg, cvg, ng, _ = gpu.psd_project([n], x, [nev], opt)
+    _, _, _, _, n_plain, _ = gpu.psd_project([n], x, [nev], Options())
+    assert list(co) == list(cg) and list(cvo) == list(cvg) and no == ng
+    assert ng <= n_plain
+    assert np.abs(xo - xg).max() <= 1e-9 * max(1.0, np.abs(xo).max())
+    assert np.allclose(mo, mg, rtol=1e-9, atol=1e-9)
