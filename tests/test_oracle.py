@@ -313,3 +313,22 @@ def test_exact_spectral_norm_vs_arpack_svds(oracle_mod, which):
     plain = oracle_mod.chambolle_pock(aff, con, Options(full_eig_decomp=True, trace_cap=200, max_iter=200))
     if which != "C1":        # C1: M = 4 unit rows, sigma_max = 1 but ||M||_F = 2
         assert plain.trace[0, 7] != ro.trace[0, 7]
+
+
+@pytest.mark.parametrize("n,rank,nev", [(150, 3, 5), (260, 6, 2), (400, 9, 11)])
+def test_krylovkit_eager_schedule_oracle(oracle_mod, n, rank, nev):
+    """`krylovkit_eager` (reference src/eigsolver.jl:809): never more mat-vecs than the plain schedule, the same projection
+    (both stop at tol = 1e-12), and at most as many converged pairs come back."""
+    rng = np.random.default_rng(n)
+    Q, _ = np.linalg.qr(rng.standard_normal((n, n)))
+    lam = np.concatenate([np.linspace(40.0, 8.0, rank), -np.abs(rng.standard_normal(n - rank)) * 3.0 - 0.05])
+    A = (Q * lam) @ Q.T
+    A = 0.5 * (A + A.T)
+    ii, jj = np.triu_indices(n)
+    order = np.lexsort((ii, jj))
+    ii, jj = ii[order], jj[order]
+    x = np.where(ii != jj, A[ii, jj] * np.sqrt(2.0), A[ii, jj])
+    x0, c0, m0, cv0, n0 = oracle_mod.psd_project([n], x, [nev], Options())
+    x1, c1, m1, cv1, n1 = oracle_mod.psd_project([n], x, [nev], Options(krylovkit_eager=True))
+    assert n1 <= n0 and cv1[0] <= cv0[0] and cv1[0] >= min(nev, cv0[0]) and list(c0) == list(c1)
+    assert np.abs(x0 - x1).max() <= 1e-9 * np.abs(x0).max()
