@@ -139,3 +139,51 @@ def test_mimo_certified_optimum(oracle_mod):
     scale = 1.0 + abs(k["primal"])
     assert lower <= k["primal"] + 1e-5 * scale
     assert k["primal"] - lower <= 1e-3 * scale, k
+
+
+def test_soc_projection_vs_closed_form(oracle_mod):
+    """soc_projection! (reference src/prox_operators.jl:138-158) against the textbook projection onto {(t, v): ||v|| <= t}."""
+    rng = np.random.default_rng(3)
+    lens = [1, 2, 3, 7, 50, 300, 4, 4, 4]
+    x = rng.standard_normal(sum(lens)) * 3.0
+    # force the three branches on the last three cones: inside, polar, outside
+    off = sum(lens[:-3])
+    x[off:off + 4] = [5.0, 1.0, 1.0, 1.0]
+    x[off + 4:off + 8] = [-5.0, 1.0, 1.0, 1.0]
+    x[off + 8:off + 12] = [0.5, 2.0, -1.0, 0.5]
+    out = oracle_mod.soc_project(lens, x)
+    o = 0
+    for ln in lens:
+        t, v = x[o], x[o + 1:o + ln]
+        nv = np.linalg.norm(v)
+        if nv <= -t:
+            want = np.zeros(ln)
+        elif nv <= t:
+            want = x[o:o + ln]
+        else:
+            a = 0.5 * (1.0 + t / nv)
+            want = np.concatenate([[a * nv], a * v])
+        assert np.abs(out[o:o + ln] - want).max() <= 1e-14 * max(1.0, np.abs(want).max())
+        o += ln
+
+
+@pytest.mark.parametrize("sides", [[1, 1], [2, 3, 7], [40, 65], [130]])
+def test_exact_projection_vs_lapack(oracle_mod, sides):
+    """full_eig! (reference src/prox_operators.jl:111-126) on ragged batches: X+ = V max(lam, 0) V' from LAPACK dsyevr,
+    current_rank = #{lam > tol_psd}, min_eig = 0."""
+    rng = np.random.default_rng(sum(sides))
+    xs, wants, ranks = [], [], []
+    for n in sides:
+        B = rng.standard_normal((n, n))
+        A = B + B.T
+        xs.append(_svec_scaled(A))
+        w, V = sla.eigh(A, driver="evr")
+        keep = w > 0
+        wants.append(_svec_scaled((V[:, keep] * w[keep]) @ V[:, keep].T))
+        ranks.append(int((w > Options().tol_psd).sum()))
+    x = np.concatenate(xs)
+    out, cur, mineig, conv, nops = oracle_mod.psd_project(sides, x, [2] * len(sides), Options(full_eig_decomp=True))
+    want = np.concatenate(wants)
+    assert np.abs(out - want).max() <= 1e-11 * max(1.0, np.abs(want).max())
+    assert [int(c) for c in cur] == [r if n > 1 else int(c) for r, n, c in zip(ranks, sides, cur)]
+    assert nops == 0
