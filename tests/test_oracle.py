@@ -332,3 +332,23 @@ def test_krylovkit_eager_schedule_oracle(oracle_mod, n, rank, nev):
     x1, c1, m1, cv1, n1 = oracle_mod.psd_project([n], x, [nev], Options(krylovkit_eager=True))
     assert n1 <= n0 and cv1[0] <= cv0[0] and cv1[0] >= min(nev, cv0[0]) and list(c0) == list(c1)
     assert np.abs(x0 - x1).max() <= 1e-9 * np.abs(x0).max()
+
+
+def test_oracle_vs_numpy_mirror_permuted_mixed_cones(oracle_mod):
+    """preprocess! with a real permutation (reference src/scaling.jl:2-26: [PSD | SOC | free] order, undone for the
+    result at src/pdhg.jl:768-769) on a problem with a PSD cone, an SOC cone and free variables: the C oracle against the
+    numpy mirror, and against its own solve of the un-permuted problem."""
+    from oracle import oracle_np
+    from test_gpu_parity_full import _scrambled
+    aff, con = sensorloc_problem(1, 8, soc_variant=True)
+    aff2, con2, new_of_old = _scrambled(aff, con, 5)
+    opt = Options(full_eig_decomp=True, trace_cap=300, max_iter=300)
+    ro = oracle_mod.chambolle_pock(aff2, con2, opt)
+    rn = oracle_np.solve_exact(aff2, con2, opt, 300)
+    r1 = oracle_mod.chambolle_pock(aff, con, opt)
+    assert ro.iter == rn["iter"] == r1.iter
+    k = len(rn["trace"])
+    assert np.abs(ro.trace[:k, 1:9] - rn["trace"][:k, 1:9]).max() <= 1e-6 * max(1.0, np.abs(rn["trace"][:k, 1:9]).max())
+    assert np.abs(ro.primal - rn["primal"]).max() < 1e-8
+    assert np.abs(ro.primal[new_of_old] - r1.primal).max() < 1e-9
+    assert np.abs(ro.dual_cone[new_of_old] - r1.dual_cone).max() < 1e-9
